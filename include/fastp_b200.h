@@ -1,0 +1,282 @@
+/*
+ * fastp_b200.h -- C-ABI of the B200-native per-read FASTQ preprocessing hot path.
+ *
+ * This library replaces the worker body of the reference (OpenGene/fastp v1.3.6)
+ *   bool SingleEndProcessor::processSingleEnd(ReadPack*, ThreadConfig*)   src/seprocessor.cpp:197-325
+ *   bool PairEndProcessor::processPairEnd(ReadPack*, ReadPack*, ThreadConfig*)   src/peprocessor.cpp:362-708
+ * i.e. the per-read operator chain
+ *   Stats::statRead (pre)      src/stats.cpp:191-291
+ *   Filter::trimAndCut         src/filter.cpp:68-207
+ *   PolyX::trimPolyG           src/polyx.cpp:16-42
+ *   OverlapAnalysis::analyze   src/overlapanalysis.cpp:17-146          (PE)
+ *   statInsertSize             src/peprocessor.cpp:710-723             (PE)
+ *   BaseCorrector::correctByOverlapAnalysis  src/basecorrector.cpp:16-83   (PE)
+ *   AdapterTrimmer::trimByOverlapAnalysis    src/adaptertrimmer.cpp:17-46  (PE)
+ *   AdapterTrimmer::trimBySequence / trimByMultiSequences  src/adaptertrimmer.cpp:48-157
+ *   PolyX::trimPolyX           src/polyx.cpp:49-116
+ *   max_len clip (Read::resize src/read.cpp:62-67)
+ *   Filter::passFilter         src/filter.cpp:15-57
+ *   FilterResult counters      src/filterresult.cpp:28-36,99-107,124-203
+ *   Stats::statRead (post)
+ *
+ * The reference has no plugin/FFI boundary; the seam is those two private member
+ * functions.  INTEGRATION.md shows the host shim a maintainer adds (stage ReadPacks
+ * into the SoA batch below, call fp_process_*, unstage fp_read_result back into
+ * Read::mSeq/mQuality, fill Stats/FilterResult from fp_counters_fetch).
+ *
+ * Plain C: pointers and sizes only.  Every function returns 0 on success or a
+ * negative FP_E_* code; nothing calls exit().  Semantics are those of
+ * `fastp --thread 1` unless fp_params.thread0_semantics == 0.
+ */
+#ifndef FASTP_B200_H
+#define FASTP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- verdict codes: src/common.h:43-51 ---- */
+#define FP_PASS_FILTER         0
+#define FP_FAIL_POLY_X         4
+#define FP_FAIL_OVERLAP        8
+#define FP_FAIL_N_BASE        12
+#define FP_FAIL_LENGTH        16
+#define FP_FAIL_TOO_LONG      17
+#define FP_FAIL_QUALITY       20
+#define FP_FAIL_COMPLEXITY    24
+#define FP_FAIL_ADAPTER_DIMER 28
+#define FP_FILTER_RESULT_TYPES 32
+
+/* ---- error codes ---- */
+#define FP_OK              0
+#define FP_E_INVAL        -1   /* bad argument / unsupported parameter combination */
+#define FP_E_CUDA         -2   /* CUDA runtime error (see fp_last_error)             */
+#define FP_E_NOMEM        -3
+#define FP_E_TOOLARGE     -4   /* batch larger than ctx capacity                       */
+#define FP_E_UNSUPPORTED  -5   /* option the device path does not implement            */
+
+/* ---- limits ---- */
+#define FP_MAX_STRIDE       512   /* bytes per read row (multiple of 16)              */
+#define FP_MAX_ADAPTER_LEN  255   /* per adapter sequence                             */
+#define FP_MAX_ADAPTERS     512   /* r1 + r2 + fasta list                             */
+#define FP_KMER_BINS       1024   /* 5-mers; reference allocates 2048 (stats.cpp:45), upper half stays 0 */
+#define FP_QUAL_BINS        128   /* stats.h:85                                       */
+#define FP_CYCLE_KINDS       34   /* Q30[8] Q20[8] content[8] qualsum[8] totalBase totalQual (stats.cpp:54-63) */
+
+/* POD mirror of the Options fields the chain reads (src/options.h). */
+typedef struct fp_params {
+    int32_t paired;                 /* 0 = SE (processSingleEnd), 1 = PE (processPairEnd) */
+    int32_t thread0_semantics;      /* 1: behave as worker thread 0 of `--thread 1`: overlap analysis + insert size on every pair
+                                       (peprocessor.cpp:438,449,497). 0: as worker tid!=0.                                    */
+    /* TrimmingOptions  options.h:223-246 */
+    int32_t trim_front1, trim_tail1, trim_front2, trim_tail2, max_len1, max_len2;
+    /* QualityCutOptions options.h:132-170 */
+    int32_t cut_front, cut_tail, cut_right;
+    int32_t cut_front_window, cut_front_quality;
+    int32_t cut_tail_window,  cut_tail_quality;
+    int32_t cut_right_window, cut_right_quality;
+    /* PolyGTrimmerOptions / PolyXTrimmerOptions options.h:82-102 */
+    int32_t polyg_enabled, polyg_min_len;
+    int32_t polyx_enabled, polyx_min_len;
+    /* AdapterOptions options.h:197-221 */
+    int32_t adapter_enabled;
+    int32_t has_seq_r1, has_seq_r2;         /* adapter.hasSeqR1 / hasSeqR2                     */
+    const char* adapter_seq_r1;             /* adapter.sequence   (NUL terminated, may be NULL) */
+    const char* adapter_seq_r2;             /* adapter.sequenceR2                               */
+    int32_t n_fasta_adapters;               /* adapter.hasFasta <=> n_fasta_adapters > 0        */
+    const char* const* fasta_adapters;      /* adapter.seqsInFasta                              */
+    int32_t allow_gap_overlap_trimming;     /* must be 0 (FP_E_UNSUPPORTED otherwise)           */
+    int32_t dimer_max_len;                  /* adapter.dimerMaxLen (default 2)                  */
+    /* CorrectionOptions + overlap thresholds options.h:123-130,376-379 (defaults 30/5/20 options.cpp:24-26) */
+    int32_t correction_enabled;
+    int32_t overlap_require, overlap_diff_limit, overlap_diff_percent_limit;
+    /* QualityFilteringOptions options.h:248-268 */
+    int32_t qual_filter_enabled;
+    int32_t qualified_qual;                 /* ASCII char, num2qual(15) = '0' by default        */
+    int32_t unqualified_percent_limit, n_base_limit, avg_qual_req;
+    /* ReadLengthFilteringOptions options.h:270-284 */
+    int32_t length_filter_enabled, length_required, length_limit;
+    /* LowComplexityFilterOptions options.h:60-69 */
+    int32_t complexity_filter_enabled;
+    double  complexity_threshold;           /* int/100.0 as main.cpp:343 builds it              */
+    /* insert size histogram  options.cpp:23, peprocessor.cpp:24-26 */
+    int32_t insert_size_max;                /* default 512                                      */
+    /* sequence lengths from the pre-scan; only sizes the reference's Stats buffers */
+    int32_t seq_len1, seq_len2;
+} fp_params;
+
+/* Fill with the reference's defaults: Options::Options() (options.cpp:9-32) + nested
+ * ctors (options.h) + what main.cpp sets with no flags (length filter on, main.cpp:337). */
+void fp_params_default(fp_params* p, int paired);
+
+/* One batch of reads (SE) or read pairs (PE) in fixed-stride SoA form.
+ * Row i of seq1 starts at seq1 + i*stride and holds len1[i] valid bytes.
+ * Bytes in [len, stride) are ignored. seq/qual are MODIFIED IN PLACE by base correction. */
+typedef struct fp_batch {
+    int64_t   n;            /* reads (SE) or pairs (PE)                     */
+    int32_t   stride;       /* multiple of 16, <= FP_MAX_STRIDE             */
+    int32_t   _pad;
+    uint8_t  *seq1, *qual1; /* [n][stride] bases (ASCII) / phred+33 quals    */
+    uint16_t *len1;         /* [n]                                          */
+    uint8_t  *seq2, *qual2; /* PE only                                      */
+    uint16_t *len2;
+} fp_batch;
+
+/* flags */
+#define FP_F_DROPPED          0x01  /* trimAndCut returned NULL (filter.cpp:78,101,134,170,196) */
+#define FP_F_ADAPTER_TRIMMED  0x02  /* counted by incTrimmedAdapterRead                        */
+#define FP_F_POLYX_TRIMMED    0x04  /* addPolyXTrimmed was called                              */
+#define FP_F_CORRECTED        0x08  /* at least one base of this read was overwritten          */
+#define FP_F_POLYG_TRIMMED    0x10  /* trimPolyG shortened the read                            */
+#define FP_F_ADAPTER_DIMER    0x20
+
+typedef struct fp_read_result {
+    uint16_t front;        /* frontTrimmed: bases removed at the 5' end by trimAndCut          */
+    uint16_t len;          /* final length; the kept window is [front, front+len) of the input */
+    uint8_t  verdict;      /* this read's passFilter code after the dimer override             */
+    uint8_t  flags;        /* FP_F_*                                                           */
+    int16_t  adapter_pos;  /* last trimBySequence hit position (trimmed coords; <0: A-tail skip), else 0 */
+    uint16_t adapter_len;  /* adapter bases of this read added to mTrimmedAdapterBases         */
+    uint8_t  polyx_base;   /* 0..3 = A,T,C,G (ATCG_BASES common.h:25); 255 = none              */
+    uint8_t  pair_verdict; /* code passed to addFilterResult: SE = verdict, PE = max(r1,r2)    */
+    uint16_t polyx_len;    /* bases removed by trimPolyX                                       */
+    uint16_t reserved;
+} fp_read_result;          /* 16 bytes */
+
+/* mirror of OverlapResult src/overlapanalysis.h:15-22 */
+typedef struct fp_ov_result {
+    uint8_t overlapped, has_gap;
+    int16_t offset, overlap_len, diff;
+} fp_ov_result;            /* 8 bytes */
+
+/* A base overwritten by BaseCorrector (basecorrector.cpp:44-60). */
+typedef struct fp_patch {
+    uint32_t pair;         /* index in the batch                 */
+    uint16_t pos;          /* position in the ORIGINAL read row  */
+    uint8_t  which;        /* 0 = read1, 1 = read2               */
+    uint8_t  base;         /* new base                           */
+    uint8_t  qual;         /* new quality                        */
+    uint8_t  _pad[3];
+} fp_patch;                /* 12 bytes */
+
+/* ---------------- packed counter block (all int64, plain sums) ----------------
+ * stats[s], s in {0:pre1, 1:post1, 2:pre2, 3:post2}  (SE uses 0,1):
+ *     cycle[34][C]   kinds in the reference's order (stats.cpp:54-63); slot = base & 7
+ *     kmer[1024]     code = base-4 digits A0 T1 C2 G3, first base most significant (stats.cpp:228-266)
+ *     qualhist[128]  indexed by the raw quality char (stats.cpp:213)
+ *     reads, lengthSum (stats.cpp:194,290)
+ * filter:  filterReadStats[32] | trimmedAdapterRead | trimmedAdapterBases | polyXReads[4] | polyXBases[4]
+ *          | correction[64] | correctedReads | mergedPairs          (filterresult.h:66-79)
+ * isize:   insertSizeHist[insert_size_max+1]                          (peprocessor.cpp:24-26)
+ */
+#define FP_STATS_PRE1  0
+#define FP_STATS_POST1 1
+#define FP_STATS_PRE2  2
+#define FP_STATS_POST2 3
+
+typedef struct fp_counter_layout {
+    int32_t cycles;        /* C: capacity of the per-cycle arrays (>= longest read)   */
+    int32_t n_stats;       /* 2 (SE) or 4 (PE)                                        */
+    int32_t isize_bins;    /* insert_size_max + 1                                     */
+    int32_t _pad;
+    int64_t stats_stride;  /* int64 words per Stats block                             */
+    int64_t off_kmer, off_qualhist, off_reads, off_length_sum;   /* inside a Stats block */
+    int64_t off_filter;    /* start of the FilterResult block                         */
+    int64_t off_isize;     /* start of the insert-size histogram                      */
+    int64_t total;         /* total int64 words                                       */
+} fp_counter_layout;
+
+/* offsets inside the FilterResult block */
+#define FP_FR_READSTATS        0
+#define FP_FR_ADAPTER_READS   32
+#define FP_FR_ADAPTER_BASES   33
+#define FP_FR_POLYX_READS     34
+#define FP_FR_POLYX_BASES     38
+#define FP_FR_CORRECTION      42
+#define FP_FR_CORRECTED_READS 106
+#define FP_FR_MERGED_PAIRS    107
+#define FP_FR_WORDS           108
+
+void fp_counter_layout_make(fp_counter_layout* L, int paired, int cycles, int insert_size_max);
+/* ABI self-check for bindings: sizeof of 0:fp_params 1:fp_batch 2:fp_read_result 3:fp_ov_result 4:fp_patch 5:fp_counter_layout */
+size_t fp_abi_sizeof(int which);
+
+static inline int64_t fp_off_cycle(const fp_counter_layout* L, int stats, int kind, int cycle) {
+    return (int64_t)stats * L->stats_stride + (int64_t)kind * L->cycles + cycle;
+}
+static inline int64_t fp_off_kmer(const fp_counter_layout* L, int stats, int code) {
+    return (int64_t)stats * L->stats_stride + L->off_kmer + code;
+}
+static inline int64_t fp_off_qualhist(const fp_counter_layout* L, int stats, int q) {
+    return (int64_t)stats * L->stats_stride + L->off_qualhist + q;
+}
+static inline int64_t fp_off_reads(const fp_counter_layout* L, int stats) {
+    return (int64_t)stats * L->stats_stride + L->off_reads;
+}
+static inline int64_t fp_off_length_sum(const fp_counter_layout* L, int stats) {
+    return (int64_t)stats * L->stats_stride + L->off_length_sum;
+}
+
+/* ---------------- device context ---------------- */
+typedef struct fp_ctx fp_ctx;
+
+/* Create a context on CUDA device `device` for batches of up to max_batch reads/pairs of
+ * `stride` bytes per row; per-cycle counters cover `cycles` cycles (>= longest read).
+ * Fails with FP_E_CUDA if no usable device / the CUDA kernels cannot be loaded: there is no CPU fallback. */
+int  fp_ctx_create(const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles, fp_ctx** out);
+void fp_ctx_destroy(fp_ctx* ctx);
+const char* fp_last_error(void);
+
+int  fp_ctx_layout(const fp_ctx* ctx, fp_counter_layout* out);
+
+/* HBM-resident entry points: every pointer in `b`, and out1/out2/ov/patches, is DEVICE memory on the
+ * ctx's device. Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own
+ * stream) and NOT synchronised. Counters accumulate inside the ctx until fp_counters_reset.
+ * ov / patches / n_patches may be NULL.  patches capacity = patch_cap entries; *n_patches counts all
+ * corrections (may exceed patch_cap: extra ones are applied in place but not listed).               */
+int  fp_process_se(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, void* stream);
+int  fp_process_pe(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2,
+                   fp_ov_result* ov, fp_patch* patches, uint32_t patch_cap, uint32_t* n_patches, void* stream);
+
+/* Host-buffer entry points (the call the reference-side shim makes): every pointer is HOST memory
+ * (pinned or pageable). Copies inputs H2D in chunks on two streams, runs the kernels, copies the
+ * per-read records back and applies base-correction patches to the host seq/qual rows. Synchronous. */
+int  fp_process_se_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1);
+int  fp_process_pe_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2,
+                        fp_ov_result* ov);
+
+/* Counter block. fetch synchronises the ctx's streams, finalises (totals per cycle) and copies
+ * layout.total int64 words to host_out. */
+int  fp_counters_reset(fp_ctx* ctx);
+int  fp_counters_fetch(fp_ctx* ctx, int64_t* host_out);
+/* Device pointer to the finalised int64 block (layout.total words) for an in-place
+ * ncclAllReduce(ncclInt64, ncclSum) / torch.distributed.all_reduce by the caller (Stats::merge
+ * src/stats.cpp:877-955 and FilterResult::merge src/filterresult.cpp:38-89 are element-wise sums). */
+int  fp_counters_device_ptr(fp_ctx* ctx, int64_t** dev_ptr, int64_t* n_words);
+/* Collective form: `comm` is an ncclComm_t (void*); no-op when comm == NULL. */
+int  fp_counters_allreduce(fp_ctx* ctx, void* comm, void* stream);
+
+/* Pinned host memory helpers for the staging shim. */
+int  fp_host_alloc(void** p, size_t bytes);
+int  fp_host_free(void* p);
+
+/* Synthetic input generator: fills DEVICE rows for reads/pairs
+ * [first_index, first_index + b->n) of the stream identified by (seed, profile).  The same generator
+ * compiled for the host (fastp_b200/csrc/synth.h via oracle/synth_host.c) regenerates any batch for the CPU oracle.
+ * profile: 0 = ref-style (scripts/bench_e2e.sh:41-86), 1 = enriched fragment model.            */
+int  fp_synth_fill(fp_ctx* ctx, const fp_batch* b, int64_t first_index, uint64_t seed,
+                   int32_t profile, int32_t read_len, void* stream);
+
+/* Timing hook: average duration in ms of the hot kernel launches recorded with CUDA events on the
+ * launching stream since the last reset; returns number of launches through *n. */
+int  fp_kernel_time_ms(fp_ctx* ctx, double* total_ms, int64_t* n_launches, int reset);
+
+int  fp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTP_B200_H */

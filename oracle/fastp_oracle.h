@@ -1,0 +1,26 @@
+/*
+ * fastp_oracle.h -- CPU oracle of the per-read hot path.  TEST INFRASTRUCTURE ONLY (see fastp_oracle.c).
+ */
+#ifndef FASTP_ORACLE_H
+#define FASTP_ORACLE_H
+#include "fastp_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Runs processSingleEnd / processPairEnd semantics over a HOST batch; per-read records to out1/out2
+ * (out2, ov may be NULL for SE / if unwanted); counters are ADDED into counters[L->total].
+ * seq/qual rows are modified in place by base correction. */
+int fp_oracle_process(const fp_params* p, const fp_counter_layout* L, const fp_batch* b,
+                      fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov, int64_t* counters);
+
+/* single-operator entry points for known-answer tests */
+int fp_oracle_trim_and_cut(const fp_params* p, uint8_t* seq, uint8_t* qual, int len, int front, int tail, int* frontOut, int* lenOut);
+int fp_oracle_trim_polyg(uint8_t* seq, int len, int minLen);
+int fp_oracle_trim_polyx(uint8_t* seq, int len, int minLen, int* poly, int* plen);
+int fp_oracle_trim_by_sequence(uint8_t* seq, int len, const char* adapter, int* trimmed);
+fp_ov_result fp_oracle_analyze(uint8_t* seq1, int len1, uint8_t* seq2, int len2, int diffLimit, int overlapRequire, double diffPercentLimit);
+int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int len);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,210 @@
+"""Test infrastructure: loaders for the CPU checkers under oracle/ and comparison helpers.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use oracle/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from fastp_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libfastp_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libfastp_ref.so")
+REF_CLI = os.path.join(ORACLE_DIR, "_ref", "fastp_ref")
+
+TRUSEQ_R1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+TRUSEQ_R2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+
+_PROC_ARGS = [C.POINTER(capi.Params), C.POINTER(capi.CounterLayout), C.POINTER(capi.Batch),
+              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+_oracle = None
+_ref = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "libfastp_oracle.so"], check=True)
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        capi.bind(lib, ["fp_params_default", "fp_counter_layout_make", "fp_abi_sizeof"])
+        lib.fp_oracle_process.restype = C.c_int
+        lib.fp_oracle_process.argtypes = _PROC_ARGS
+        lib.fp_synth_fill_host.restype = C.c_int
+        lib.fp_synth_fill_host.argtypes = [C.POINTER(capi.Batch), C.c_int64, C.c_uint64, C.c_int32, C.c_int32]
+        lib.fp_oracle_trim_and_cut.restype = C.c_int
+        lib.fp_oracle_trim_and_cut.argtypes = [C.POINTER(capi.Params), C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.fp_oracle_trim_polyg.restype = C.c_int
+        lib.fp_oracle_trim_polyg.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        lib.fp_oracle_trim_polyx.restype = C.c_int
+        lib.fp_oracle_trim_polyx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.fp_oracle_trim_by_sequence.restype = C.c_int
+        lib.fp_oracle_trim_by_sequence.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+
+        class OV(C.Structure):
+            _fields_ = [("overlapped", C.c_uint8), ("has_gap", C.c_uint8), ("offset", C.c_int16),
+                        ("overlap_len", C.c_int16), ("diff", C.c_int16)]
+        lib.fp_oracle_analyze.restype = OV
+        lib.fp_oracle_analyze.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double]
+        lib.fp_oracle_pass_filter.restype = C.c_int
+        lib.fp_oracle_pass_filter.argtypes = [C.POINTER(capi.Params), C.c_char_p, C.c_char_p, C.c_int]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        lib.fp_ref_process.restype = C.c_int
+        lib.fp_ref_process.argtypes = _PROC_ARGS
+        lib.fp_ref_process_mt.restype = C.c_int
+        lib.fp_ref_process_mt.argtypes = _PROC_ARGS + [C.c_int]
+        _ref = lib
+    return _ref
+
+
+def copy_arrays(arrs):
+    return {k: v.copy() for k, v in arrs.items()}
+
+
+def synth_host(n, stride, paired, first_index, seed, profile, read_len):
+    b, arrs = capi.host_batch(n, stride, paired)
+    rc = oracle().fp_synth_fill_host(C.byref(b), first_index, seed, profile, read_len)
+    assert rc == 0
+    return b, arrs
+
+
+def run_cpu(which, params, arrs, cycles, nthreads=0):
+    """Run the C port ('oracle') or the reference harness ('ref') over a COPY of arrs.
+    Returns dict(out1, out2, ov, counters(CounterView), arrs(after correction))."""
+    a = copy_arrays(arrs)
+    b = capi.batch_from_arrays(a)
+    paired = bool(params.paired)
+    L = capi.make_layout(oracle(), paired, cycles, params.insert_size_max)
+    n = b.n
+    out1 = np.zeros(n, capi.READ_RESULT_DTYPE)
+    out2 = np.zeros(n, capi.READ_RESULT_DTYPE)
+    ov = np.zeros(n, capi.OV_RESULT_DTYPE)
+    cnt = np.zeros(L.total, np.int64)
+    args = (C.byref(params), C.byref(L), C.byref(b), out1.ctypes.data, out2.ctypes.data if paired else None,
+            ov.ctypes.data if paired else None, cnt.ctypes.data)
+    if which == "oracle":
+        rc = oracle().fp_oracle_process(*args)
+    elif nthreads:
+        rc = ref().fp_ref_process_mt(*args, nthreads)
+    else:
+        rc = ref().fp_ref_process(*args)
+    assert rc == 0, rc
+    return {"out1": out1, "out2": out2, "ov": ov, "counters": capi.CounterView(L, cnt), "arrs": a, "layout": L}
+
+
+RESULT_FIELDS = ("front", "len", "verdict", "flags", "adapter_pos", "adapter_len", "polyx_base", "pair_verdict", "polyx_len")
+
+
+def first_diff(a, b):
+    idx = np.nonzero(a != b)[0]
+    return int(idx[0]) if idx.size else -1
+
+
+def assert_results_equal(x, y, paired, skip=(), what=""):
+    """Bit-exact comparison of per-read records, overlap records, corrected bases and all counters."""
+    outs = ("out1", "out2") if paired else ("out1",)
+    for o in outs:
+        for f in RESULT_FIELDS:
+            if f in skip:
+                continue
+            xa, ya = x[o][f], y[o][f]
+            if f in ("front", "len") :
+                # a dropped read (trimAndCut -> NULL) has no window
+                pass
+            i = first_diff(xa, ya)
+            assert i < 0, f"{what} {o}.{f} differs at read {i}: {xa[i]} vs {ya[i]} (rec {x[o][i]} vs {y[o][i]})"
+    if paired and "ov" not in skip:
+        for f in ("overlapped", "has_gap", "offset", "overlap_len", "diff"):
+            i = first_diff(x["ov"][f], y["ov"][f])
+            assert i < 0, f"{what} ov.{f} differs at pair {i}: {x['ov'][i]} vs {y['ov'][i]}"
+    for k in x["arrs"]:
+        if k.startswith("len"):
+            continue
+        i = first_diff((x["arrs"][k] != y["arrs"][k]).any(axis=1), np.zeros(x["arrs"][k].shape[0], bool))
+        if i >= 0:
+            # only the valid part of the row matters
+            ln = x["arrs"]["len" + k[-1]][i]
+            assert (x["arrs"][k][i, :ln] == y["arrs"][k][i, :ln]).all(), f"{what} {k} row {i} differs after correction"
+    assert_counters_equal(x["counters"], y["counters"], what)
+
+
+def assert_counters_equal(cx, cy, what=""):
+    L = cx.L
+    assert cx.data.size == cy.data.size
+    if (cx.data == cy.data).all():
+        return
+    names = {0: "pre1", 1: "post1", 2: "pre2", 3: "post2"}
+    for s in range(L.n_stats):
+        sx, sy = cx.stats(s), cy.stats(s)
+        for key in ("cycle", "kmer", "qualhist"):
+            if not (sx[key] == sy[key]).all():
+                idx = np.argwhere(sx[key] != sy[key])[0]
+                raise AssertionError(f"{what} stats[{names[s]}].{key}{tuple(idx)}: {sx[key][tuple(idx)]} vs {sy[key][tuple(idx)]}")
+        for key in ("reads", "length_sum"):
+            assert sx[key] == sy[key], f"{what} stats[{names[s]}].{key}: {sx[key]} vs {sy[key]}"
+    if not (cx.filter == cy.filter).all():
+        i = int(np.nonzero(cx.filter != cy.filter)[0][0])
+        raise AssertionError(f"{what} filter[{i}]: {cx.filter[i]} vs {cy.filter[i]}")
+    if not (cx.isize == cy.isize).all():
+        i = int(np.nonzero(cx.isize != cy.isize)[0][0])
+        raise AssertionError(f"{what} isize[{i}]: {cx.isize[i]} vs {cy.isize[i]}")
+    raise AssertionError(f"{what} counter blocks differ")
+
+
+# Parameter sets exercised by the parity tests (names follow the fastp CLI flags they model).
+def config_params(name, paired, lib=None):
+    lib = lib or oracle()
+    P = lambda **kw: capi.default_params(paired, lib=lib, **kw)  # noqa: E731
+    if name == "default":
+        return P()
+    if name == "cfg2_cut_right_polyg":        # BASELINE config 2: --cut_right --trim_poly_g -A
+        return P(cut_right=1, polyg_enabled=1, adapter_enabled=0)
+    if name == "cfg3_overlap_correction":     # BASELINE config 3: overlap adapter trimming + --correction
+        return P(correction_enabled=1)
+    if name == "cfg4_full":                   # BASELINE config 4: --cut_right -g -x -c + adapter seqs
+        return P(cut_right=1, polyg_enabled=1, polyx_enabled=1, correction_enabled=1,
+                 adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
+    if name == "cut_front_tail":
+        return P(cut_front=1, cut_tail=1, cut_front_window=4, cut_front_quality=20, cut_tail_window=5, cut_tail_quality=18)
+    if name == "trim_fixed":
+        return P(trim_front1=3, trim_tail1=2, trim_front2=5, trim_tail2=1, max_len1=100, max_len2=90)
+    if name == "all_cuts":
+        return P(cut_front=1, cut_right=1, cut_tail=1, trim_front1=2, trim_tail2=3, cut_right_window=6, cut_right_quality=25,
+                 polyx_enabled=1, polyg_enabled=1, polyx_min_len=8, polyg_min_len=12,
+                 adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
+    if name == "filters":
+        return P(complexity_filter_enabled=1, complexity_threshold=30 / 100.0, avg_qual_req=25, length_required=40,
+                 length_limit=148, n_base_limit=2, unqualified_percent_limit=20, qualified_qual=ord('5'))
+    if name == "no_filters":
+        return P(qual_filter_enabled=0, length_filter_enabled=0, adapter_enabled=0)
+    if name == "fasta_adapters":
+        return P(fasta_adapters=[TRUSEQ_R1, "CTGTCTCTTATACACATCT", TRUSEQ_R2[:20], "AAAAAAAAAAAA", "GGGGGGGGGG"],
+                 adapter_seq_r1=TRUSEQ_R1[:12])
+    if name == "tid_nonzero":
+        return P(thread0_semantics=0, adapter_enabled=0)
+    if name == "short_adapter":
+        return P(adapter_seq_r1="AGATCGGAAG", adapter_seq_r2="AGATCGG", polyx_enabled=1)
+    raise KeyError(name)
+
+
+CONFIG_NAMES = ["default", "cfg2_cut_right_polyg", "cfg3_overlap_correction", "cfg4_full", "cut_front_tail", "trim_fixed",
+                "all_cuts", "filters", "no_filters", "fasta_adapters", "tid_nonzero", "short_adapter"]
