@@ -1,0 +1,516 @@
+/*
+ * fp_api.cu -- host side of libfastp_b200.so: the C-ABI of include/fastp_b200.h.
+ *
+ * Context creation precomputes (with the reference's own double expressions) the integer LUTs the
+ * kernels use, uploads adapters, sizes the shared-memory tile and the persistent grid.  The
+ * fp_process_* entry points enqueue the fused sm_100a kernel (fp_device.cuh); the *_host variants wrap
+ * it in a two-stream chunked H2D -> kernel -> D2H pipeline for callers holding host buffers (the
+ * reference-side shim of INTEGRATION.md).  No CPU fallback anywhere: without a CUDA device every
+ * call fails with FP_E_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fastp_b200.h"
+#include "fp_device.cuh"
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return set_err(FP_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* fp_last_error(void) { return g_err; }
+extern "C" int fp_version(void) { return 100; }
+
+struct EvPair { cudaEvent_t a, b; };
+
+struct fp_ctx {
+    int device = 0;
+    fp_params p{};
+    std::string ad1, ad2;
+    std::vector<std::string> fasta;
+    fp_dev_params dp{};
+    fp_counter_layout L{};
+    int64_t max_batch = 0;
+    int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
+    fp_smem_layout sl{};
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    /* device tables */
+    int16_t *d_ovlimit = nullptr, *d_lowq = nullptr, *d_mindiff = nullptr;
+    uint8_t* d_adapters = nullptr;
+    int32_t *d_fasta_off = nullptr, *d_fasta_len = nullptr;
+    long long *d_raw = nullptr, *d_fin = nullptr;
+    /* host-mode staging (allocated lazily) */
+    int64_t chunk = 0;
+    uint8_t* d_stage[2][4] = {{nullptr}};      /* seq1 qual1 seq2 qual2 */
+    uint16_t* d_stage_len[2][2] = {{nullptr}};
+    fp_read_result* d_out[2][2] = {{nullptr}};
+    fp_ov_result* d_ov[2] = {nullptr, nullptr};
+    fp_patch* d_patch[2] = {nullptr, nullptr};
+    unsigned int* d_npatch[2] = {nullptr, nullptr};
+    fp_patch* h_patch[2] = {nullptr, nullptr};
+    unsigned int* h_npatch[2] = {nullptr, nullptr};
+    uint32_t patch_cap = 0;
+    /* kernel timing */
+    std::vector<EvPair> evs;
+    std::vector<EvPair> ev_pool;
+    double ev_ms = 0.0;
+    int64_t ev_n = 0;
+};
+
+static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov, std::vector<int16_t>& lowq, std::vector<int16_t>& mind) {
+    ov.assign(stride + 2, 0); lowq.assign(stride + 2, 0); mind.assign(stride + 2, 0);
+    const double diffPercentLimit = p->overlap_diff_percent_limit / 100.0;        /* peprocessor.cpp:439 */
+    for (int ol = 0; ol <= stride; ol++) {
+        int v = std::min(p->overlap_diff_limit, (int)(ol * diffPercentLimit));    /* overlapanalysis.cpp:51 */
+        ov[ol] = (int16_t)v;
+    }
+    for (int rlen = 0; rlen <= stride; rlen++) {
+        /* lowQualNum > (unqualifiedPercentLimit * rlen / 100.0)   filter.cpp:37 : largest int NOT exceeding the bound */
+        double bound = p->unqualified_percent_limit * rlen / 100.0;
+        int n = 0;
+        while (n <= stride && !((double)n > bound)) n++;       /* first n with n > bound */
+        lowq[rlen] = (int16_t)(n - 1);
+    }
+    for (int len = 0; len <= stride; len++) {
+        /* pass iff (double)diff/(double)(len-1) >= threshold   filter.cpp:65 */
+        int d = len + 1;
+        if (len > 1) {
+            for (int k = 0; k <= len - 1; k++)
+                if ((double)k / (double)(len - 1) >= p->complexity_threshold) { d = k; break; }
+        }
+        mind[len] = (int16_t)d;
+    }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void make_smem_layout(fp_ctx* c) {
+    const int sides = c->p.paired ? 2 : 1;
+    const int S = c->stride;
+    int T = (int)((48 * 1024) / (size_t)(sides * 2 * S));
+    T = std::min(T, 128);
+    T = std::max(T / 8 * 8, 8);
+    c->tile = T;
+    fp_smem_layout& sl = c->sl;
+    size_t off = 0;
+    sl.off_mbar = (int)off; off += 16;
+    off = align_up(off, 128);
+    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 16;
+    off = align_up(off, 16);
+    sl.off_len = (int)off; off += (size_t)sides * T * 2;
+    sl.off_clean = (int)off; off += (size_t)sides * T;
+    off = align_up(off, 16);
+    sl.rc_bytes = (int)align_up(S + 16, 16);
+    sl.off_rc = (int)off; off += (size_t)FP_WARPS * sl.rc_bytes;
+    sl.scratch_ints = std::max(S + 2, 2 * (FP_MAX_ADAPTER_LEN + 2));
+    sl.off_scratch = (int)off; off += (size_t)FP_WARPS * sl.scratch_ints * 4;
+    sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
+    sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
+    sl.off_bc = (int)off; off += sizeof(BlockCounters);
+    off = align_up(off, 8);
+    sl.off_rl = (int)off; off += 8 * 8;
+    sl.total = (int)align_up(off, 128);
+}
+
+extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles, fp_ctx** out) {
+    if (!p || !out) return set_err(FP_E_INVAL, "null argument");
+    if (stride <= 0 || stride % 16 || stride > FP_MAX_STRIDE) return set_err(FP_E_INVAL, "stride must be a multiple of 16 and <= FP_MAX_STRIDE");
+    if (cycles <= 0) cycles = stride;
+    if (p->allow_gap_overlap_trimming) return set_err(FP_E_UNSUPPORTED, "allow_gap_overlap_trimming is not implemented on the device path");
+    if (p->insert_size_max < 0 || p->insert_size_max > (1 << 20)) return set_err(FP_E_INVAL, "insert_size_max out of range");
+    if ((p->paired ? 2 : 1) * (stride / 4) > FP_THREADS) return set_err(FP_E_INVAL, "stride too large for the column pass");
+    if (p->cut_front_window < 1 || p->cut_tail_window < 1 || p->cut_right_window < 1) return set_err(FP_E_INVAL, "cut window must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(FP_E_CUDA, "no CUDA device: fastp_b200 has no CPU fallback (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return set_err(FP_E_INVAL, "bad device index");
+    CK(cudaSetDevice(device));
+    fp_ctx* c = new fp_ctx();
+    c->device = device;
+    c->p = *p;
+    if (p->has_seq_r1 && p->adapter_seq_r1) c->ad1 = p->adapter_seq_r1;
+    if (p->has_seq_r2 && p->adapter_seq_r2) c->ad2 = p->adapter_seq_r2;
+    for (int i = 0; i < p->n_fasta_adapters; i++) c->fasta.push_back(p->fasta_adapters[i]);
+    c->p.adapter_seq_r1 = c->ad1.c_str(); c->p.adapter_seq_r2 = c->ad2.c_str(); c->p.fasta_adapters = nullptr;
+    if ((int)c->fasta.size() > FP_MAX_ADAPTERS) { delete c; return set_err(FP_E_INVAL, "too many adapters"); }
+    for (auto& s : c->fasta) if (s.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
+    if (c->ad1.size() > FP_MAX_ADAPTER_LEN || c->ad2.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
+    c->max_batch = max_batch; c->stride = stride; c->cycles = cycles;
+    fp_counter_layout_make(&c->L, p->paired, cycles, p->insert_size_max);
+    make_smem_layout(c);
+
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+
+    /* LUTs */
+    std::vector<int16_t> ov, lowq, mind;
+    build_luts(p, stride, ov, lowq, mind);
+    CK(cudaMalloc(&c->d_ovlimit, ov.size() * 2)); CK(cudaMalloc(&c->d_lowq, lowq.size() * 2)); CK(cudaMalloc(&c->d_mindiff, mind.size() * 2));
+    CK(cudaMemcpy(c->d_ovlimit, ov.data(), ov.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_lowq, lowq.data(), lowq.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mindiff, mind.data(), mind.size() * 2, cudaMemcpyHostToDevice));
+    /* adapters blob: each adapter at a 16-byte aligned offset, zero padded (+8 readable bytes) */
+    std::vector<uint8_t> blob;
+    std::vector<int32_t> foff, flen;
+    auto put = [&](const std::string& s) { size_t off = blob.size(); blob.insert(blob.end(), s.begin(), s.end()); blob.resize(align_up(blob.size() + 8, 16), 0); return (int)off; };
+    fp_dev_params& d = c->dp;
+    d.adapter_r1_off = put(c->ad1); d.adapter_r1_len = (int)c->ad1.size();
+    d.adapter_r2_off = put(c->ad2); d.adapter_r2_len = (int)c->ad2.size();
+    for (auto& s : c->fasta) { foff.push_back(put(s)); flen.push_back((int)s.size()); }
+    blob.resize(blob.size() + 16, 0);
+    CK(cudaMalloc(&c->d_adapters, blob.size()));
+    CK(cudaMemcpy(c->d_adapters, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    if (!foff.empty()) {
+        CK(cudaMalloc(&c->d_fasta_off, foff.size() * 4)); CK(cudaMalloc(&c->d_fasta_len, flen.size() * 4));
+        CK(cudaMemcpy(c->d_fasta_off, foff.data(), foff.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_fasta_len, flen.data(), flen.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&c->d_raw, c->L.total * 8)); CK(cudaMalloc(&c->d_fin, c->L.total * 8));
+    CK(cudaMemset(c->d_raw, 0, c->L.total * 8)); CK(cudaMemset(c->d_fin, 0, c->L.total * 8));
+
+    d.paired = p->paired; d.thread0 = p->thread0_semantics;
+    d.trim_front1 = p->trim_front1; d.trim_tail1 = p->trim_tail1; d.trim_front2 = p->trim_front2; d.trim_tail2 = p->trim_tail2;
+    d.max_len1 = p->max_len1; d.max_len2 = p->max_len2;
+    d.cut_front = p->cut_front; d.cut_tail = p->cut_tail; d.cut_right = p->cut_right;
+    d.cf_w = p->cut_front_window; d.cf_thr = p->cut_front_window * (33 + p->cut_front_quality);      /* filter.cpp:117 */
+    d.ct_w = p->cut_tail_window;  d.ct_thr = p->cut_tail_window * (33 + p->cut_tail_quality);        /* filter.cpp:184 */
+    d.cr_w = p->cut_right_window; d.cr_thr = p->cut_right_window * (33 + p->cut_right_quality);      /* filter.cpp:151 */
+    d.cr_q = 33 + p->cut_right_quality;                                                              /* filter.cpp:159 */
+    d.polyg = p->polyg_enabled; d.polyg_min = p->polyg_min_len; d.polyx = p->polyx_enabled; d.polyx_min = p->polyx_min_len;
+    d.adapter_enabled = p->adapter_enabled; d.has_r1 = p->has_seq_r1 && !c->ad1.empty() ? 1 : (p->has_seq_r1 ? 1 : 0);
+    d.has_r2 = p->has_seq_r2 ? 1 : 0;
+    d.n_fasta = (int)c->fasta.size();
+    d.fasta_match_req = d.n_fasta > 256 ? 6 : d.n_fasta > 16 ? 5 : 4;                                /* adaptertrimmer.cpp:49-53 */
+    d.dimer_max_len = p->dimer_max_len;
+    d.correction = p->correction_enabled; d.ov_require = p->overlap_require;
+    d.qual_filter = p->qual_filter_enabled; d.qualified_qual = p->qualified_qual & 0xFF; d.n_base_limit = p->n_base_limit; d.avg_qual_req = p->avg_qual_req;
+    d.length_filter = p->length_filter_enabled; d.length_required = p->length_required; d.length_limit = p->length_limit;
+    d.complexity_filter = p->complexity_filter_enabled;
+    d.isize_max = p->insert_size_max;
+    d.stride = stride; d.cycles = cycles; d.tile = c->tile; d.n_stats = c->L.n_stats;
+    d.lut_ovlimit = c->d_ovlimit; d.lut_lowq = c->d_lowq; d.lut_mindiff = c->d_mindiff;
+    d.adapters = c->d_adapters; d.fasta_off = c->d_fasta_off; d.fasta_len = c->d_fasta_len;
+    d.L = c->L;
+
+    /* kernel attributes + persistent grid size */
+    int occ = 0;
+    if (p->paired) {
+        CK(cudaFuncSetAttribute(fp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain_kernel<true>, FP_THREADS, c->sl.total));
+    } else {
+        CK(cudaFuncSetAttribute(fp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain_kernel<false>, FP_THREADS, c->sl.total));
+    }
+    if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
+    c->grid_max = occ * c->num_sms;
+    *out = c;
+    return FP_OK;
+}
+
+static void free_staging(fp_ctx* c) {
+    for (int i = 0; i < 2; i++) {
+        for (int k = 0; k < 4; k++) { cudaFree(c->d_stage[i][k]); c->d_stage[i][k] = nullptr; }
+        for (int k = 0; k < 2; k++) { cudaFree(c->d_stage_len[i][k]); c->d_stage_len[i][k] = nullptr; cudaFree(c->d_out[i][k]); c->d_out[i][k] = nullptr; }
+        cudaFree(c->d_ov[i]); c->d_ov[i] = nullptr;
+        cudaFree(c->d_patch[i]); c->d_patch[i] = nullptr;
+        cudaFree(c->d_npatch[i]); c->d_npatch[i] = nullptr;
+        if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
+        if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
+    }
+    c->chunk = 0;
+}
+
+extern "C" void fp_ctx_destroy(fp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_staging(c);
+    cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
+    cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
+    for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    delete c;
+}
+
+extern "C" int fp_ctx_layout(const fp_ctx* c, fp_counter_layout* out) {
+    if (!c || !out) return set_err(FP_E_INVAL, "null argument");
+    *out = c->L;
+    return FP_OK;
+}
+
+static int drain_events(fp_ctx* c) {
+    for (auto& e : c->evs) {
+        CK(cudaEventSynchronize(e.b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        c->ev_ms += ms; c->ev_n++;
+        c->ev_pool.push_back(e);
+    }
+    c->evs.clear();
+    return FP_OK;
+}
+
+static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                        fp_patch* patches, uint32_t patch_cap, uint32_t* n_patches, cudaStream_t st) {
+    if (b->n == 0) return FP_OK;
+    if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    if (b->n > (int64_t)1 << 31) return set_err(FP_E_TOOLARGE, "batch larger than 2^31 (split it)");
+    auto mis = [](const void* q) { return ((uintptr_t)q & 15) != 0; };
+    if (mis(b->seq1) || mis(b->qual1) || (c->p.paired && (mis(b->seq2) || mis(b->qual2)))) return set_err(FP_E_INVAL, "seq/qual pointers must be 16-byte aligned");
+    fp_launch_args a;
+    memset(&a, 0, sizeof(a));
+    a.b = *b; a.out1 = out1; a.out2 = out2; a.ov = ov;
+    a.sink.patches = patches; a.sink.cap = patches ? patch_cap : 0; a.sink.count = n_patches;
+    a.counters = reinterpret_cast<unsigned long long*>(c->d_raw);
+    a.n_tiles = (b->n + c->tile - 1) / c->tile;
+    a.sl = c->sl;
+    int grid = (int)std::min<long long>(a.n_tiles, c->grid_max);
+    CK(cudaMemcpyToSymbolAsync(c_p, &c->dp, sizeof(fp_dev_params), 0, cudaMemcpyHostToDevice, st));
+    EvPair ev;
+    if (!c->ev_pool.empty()) { ev = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
+    if (c->evs.size() > 4096) { int rc = drain_events(c); if (rc) return rc; }
+    CK(cudaEventRecord(ev.a, st));
+    if (c->p.paired) fp_chain_kernel<true><<<grid, FP_THREADS, c->sl.total, st>>>(a);
+    else fp_chain_kernel<false><<<grid, FP_THREADS, c->sl.total, st>>>(a);
+    CK(cudaEventRecord(ev.b, st));
+    c->evs.push_back(ev);
+    CK(cudaGetLastError());
+    return FP_OK;
+}
+
+extern "C" int fp_process_se(fp_ctx* c, const fp_batch* b, fp_read_result* out1, void* stream) {
+    if (!c || !b || !out1) return set_err(FP_E_INVAL, "null argument");
+    if (c->p.paired) return set_err(FP_E_INVAL, "ctx was created for paired-end data");
+    CK(cudaSetDevice(c->device));
+    return launch_chain(c, b, out1, nullptr, nullptr, nullptr, 0, nullptr, stream ? (cudaStream_t)stream : c->stream[0]);
+}
+
+extern "C" int fp_process_pe(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                             fp_patch* patches, uint32_t patch_cap, uint32_t* n_patches, void* stream) {
+    if (!c || !b || !out1 || !out2) return set_err(FP_E_INVAL, "null argument");
+    if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
+    CK(cudaSetDevice(c->device));
+    return launch_chain(c, b, out1, out2, ov, patches, patch_cap, n_patches, stream ? (cudaStream_t)stream : c->stream[0]);
+}
+
+/* ---------------- host-buffer pipeline ---------------- */
+static int ensure_staging(fp_ctx* c) {
+    if (c->chunk) return FP_OK;
+    const int sides = c->p.paired ? 2 : 1;
+    int64_t chunk = std::min<int64_t>(std::max<int64_t>(c->max_batch, 1), (int64_t)1 << 18);
+    chunk = (chunk + c->tile - 1) / c->tile * c->tile;
+    c->chunk = chunk;
+    c->patch_cap = (uint32_t)std::min<int64_t>(chunk * 2 + 1024, (int64_t)1 << 22);
+    for (int i = 0; i < 2; i++) {
+        for (int k = 0; k < 2 * sides; k++) CK(cudaMalloc(&c->d_stage[i][k], (size_t)chunk * c->stride + 64));
+        for (int k = 0; k < sides; k++) { CK(cudaMalloc(&c->d_stage_len[i][k], (size_t)chunk * 2)); CK(cudaMalloc(&c->d_out[i][k], (size_t)chunk * sizeof(fp_read_result))); }
+        if (c->p.paired) {
+            CK(cudaMalloc(&c->d_ov[i], (size_t)chunk * sizeof(fp_ov_result)));
+            CK(cudaMalloc(&c->d_patch[i], (size_t)c->patch_cap * sizeof(fp_patch)));
+            CK(cudaMalloc(&c->d_npatch[i], 4));
+            CK(cudaMallocHost(&c->h_patch[i], (size_t)c->patch_cap * sizeof(fp_patch)));
+            CK(cudaMallocHost(&c->h_npatch[i], 4));
+        }
+    }
+    return FP_OK;
+}
+
+static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov) {
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_staging(c);
+    if (rc) return rc;
+    if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    const bool pe = c->p.paired;
+    const int S = c->stride;
+    const int64_t n = b->n, CH = c->chunk;
+    const int64_t nchunks = (n + CH - 1) / CH;
+    struct Pending { int64_t lo, cnt; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    auto finish = [&](int slot) -> int {
+        if (!pend[slot].active) return FP_OK;
+        CK(cudaStreamSynchronize(c->stream[slot]));
+        if (pe && c->p.correction_enabled) {
+            uint32_t np = *c->h_npatch[slot];
+            const int64_t lo = pend[slot].lo;
+            if (np <= c->patch_cap) {
+                for (uint32_t k = 0; k < np; k++) {
+                    const fp_patch& pt = c->h_patch[slot][k];
+                    uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * S;
+                    uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * S;
+                    sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
+                }
+            } else {   /* patch list overflow: take the corrected rows wholesale */
+                const size_t bytes = (size_t)pend[slot].cnt * S;
+                CK(cudaMemcpy(b->seq1 + lo * S, c->d_stage[slot][0], bytes, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(b->qual1 + lo * S, c->d_stage[slot][1], bytes, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(b->seq2 + lo * S, c->d_stage[slot][2], bytes, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(b->qual2 + lo * S, c->d_stage[slot][3], bytes, cudaMemcpyDeviceToHost));
+            }
+        }
+        pend[slot].active = false;
+        return FP_OK;
+    };
+    for (int64_t ci = 0; ci < nchunks; ci++) {
+        const int slot = (int)(ci & 1);
+        rc = finish(slot);
+        if (rc) return rc;
+        const int64_t lo = ci * CH, cnt = std::min(CH, n - lo);
+        cudaStream_t st = c->stream[slot];
+        const size_t bytes = (size_t)cnt * S;
+        CK(cudaMemcpyAsync(c->d_stage[slot][0], b->seq1 + lo * S, bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_stage[slot][1], b->qual1 + lo * S, bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_stage_len[slot][0], b->len1 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+        if (pe) {
+            CK(cudaMemcpyAsync(c->d_stage[slot][2], b->seq2 + lo * S, bytes, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_stage[slot][3], b->qual2 + lo * S, bytes, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_stage_len[slot][1], b->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st));
+        }
+        fp_batch db;
+        memset(&db, 0, sizeof(db));
+        db.n = cnt; db.stride = S;
+        db.seq1 = c->d_stage[slot][0]; db.qual1 = c->d_stage[slot][1]; db.len1 = c->d_stage_len[slot][0];
+        if (pe) { db.seq2 = c->d_stage[slot][2]; db.qual2 = c->d_stage[slot][3]; db.len2 = c->d_stage_len[slot][1]; }
+        rc = launch_chain(c, &db, c->d_out[slot][0], pe ? c->d_out[slot][1] : nullptr, pe ? c->d_ov[slot] : nullptr,
+                          pe ? c->d_patch[slot] : nullptr, c->patch_cap, pe ? c->d_npatch[slot] : nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out1 + lo, c->d_out[slot][0], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
+        if (pe) {
+            CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
+            if (ov) CK(cudaMemcpyAsync(ov + lo, c->d_ov[slot], (size_t)cnt * sizeof(fp_ov_result), cudaMemcpyDeviceToHost, st));
+            if (c->p.correction_enabled) {
+                CK(cudaMemcpyAsync(c->h_npatch[slot], c->d_npatch[slot], 4, cudaMemcpyDeviceToHost, st));
+                /* the list is usually tiny; copy the whole capacity only when it is small, else size it after the count */
+                CK(cudaStreamSynchronize(st));
+                uint32_t np = std::min(*c->h_npatch[slot], c->patch_cap);
+                if (np) CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)np * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        pend[slot].lo = lo; pend[slot].cnt = cnt; pend[slot].active = true;
+    }
+    for (int s = 0; s < 2; s++) { rc = finish(s); if (rc) return rc; }
+    return FP_OK;
+}
+
+extern "C" int fp_process_se_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1) {
+    if (!c || !b || !out1) return set_err(FP_E_INVAL, "null argument");
+    if (c->p.paired) return set_err(FP_E_INVAL, "ctx was created for paired-end data");
+    return process_host(c, b, out1, nullptr, nullptr);
+}
+
+extern "C" int fp_process_pe_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov) {
+    if (!c || !b || !out1 || !out2) return set_err(FP_E_INVAL, "null argument");
+    if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
+    return process_host(c, b, out1, out2, ov);
+}
+
+/* ---------------- counters ---------------- */
+extern "C" int fp_counters_reset(fp_ctx* c) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(c->d_raw, 0, c->L.total * 8));
+    return FP_OK;
+}
+
+static int finalize(fp_ctx* c, cudaStream_t st) {
+    const int threads = 256;
+    const int blocks = (int)((c->L.total + threads - 1) / threads);
+    fp_finalize_kernel<<<blocks, threads, 0, st>>>(c->d_raw, c->d_fin, c->L);
+    CK(cudaGetLastError());
+    return FP_OK;
+}
+
+extern "C" int fp_counters_fetch(fp_ctx* c, int64_t* host_out) {
+    if (!c || !host_out) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    int rc = finalize(c, c->stream[0]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(host_out, c->d_fin, c->L.total * 8, cudaMemcpyDeviceToHost, c->stream[0]));
+    CK(cudaStreamSynchronize(c->stream[0]));
+    return FP_OK;
+}
+
+extern "C" int fp_counters_device_ptr(fp_ctx* c, int64_t** dev_ptr, int64_t* n_words) {
+    if (!c || !dev_ptr) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    /* the RAW block is what gets summed across ranks (totals are derived afterwards by fetch) */
+    *dev_ptr = reinterpret_cast<int64_t*>(c->d_raw);
+    if (n_words) *n_words = c->L.total;
+    return FP_OK;
+}
+
+/* ncclAllReduce resolved at run time from the NCCL already in the process (torch bundles libnccl.so.2) */
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+extern "C" int fp_counters_allreduce(fp_ctx* c, void* comm, void* stream) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    if (!comm) return FP_OK;
+    static nccl_allreduce_fn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+        if (h) fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+        if (!fn) return set_err(FP_E_UNSUPPORTED, "ncclAllReduce not found (libnccl.so.2 not loadable)");
+    }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
+    CK(cudaDeviceSynchronize());
+    /* ncclInt64 = 4, ncclSum = 0 (nccl.h) */
+    int rc = fn(c->d_raw, c->d_raw, (size_t)c->L.total, 4, 0, comm, st);
+    if (rc != 0) return set_err(FP_E_CUDA, "ncclAllReduce failed");
+    CK(cudaStreamSynchronize(st));
+    return FP_OK;
+}
+
+extern "C" int fp_host_alloc(void** p, size_t bytes) {
+    if (!p) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaMallocHost(p, bytes));
+    return FP_OK;
+}
+extern "C" int fp_host_free(void* p) {
+    CK(cudaFreeHost(p));
+    return FP_OK;
+}
+
+extern "C" int fp_synth_fill(fp_ctx* c, const fp_batch* b, int64_t first_index, uint64_t seed, int32_t profile, int32_t read_len, void* stream) {
+    if (!c || !b) return set_err(FP_E_INVAL, "null argument");
+    if (read_len > b->stride || read_len < 16) return set_err(FP_E_INVAL, "read_len must be in [16, stride]");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
+    if (b->n == 0) return FP_OK;
+    const int threads = 128;
+    const int blocks = (int)((b->n + threads - 1) / threads);
+    fp_synth_kernel<<<blocks, threads, 0, st>>>(*b, first_index, seed, profile, read_len);
+    CK(cudaGetLastError());
+    return FP_OK;
+}
+
+extern "C" int fp_kernel_time_ms(fp_ctx* c, double* total_ms, int64_t* n_launches, int reset) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = drain_events(c);
+    if (rc) return rc;
+    if (total_ms) *total_ms = c->ev_ms;
+    if (n_launches) *n_launches = c->ev_n;
+    if (reset) { c->ev_ms = 0; c->ev_n = 0; }
+    return FP_OK;
+}

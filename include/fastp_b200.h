@@ -204,19 +204,24 @@ void fp_counter_layout_make(fp_counter_layout* L, int paired, int cycles, int in
 /* ABI self-check for bindings: sizeof of 0:fp_params 1:fp_batch 2:fp_read_result 3:fp_ov_result 4:fp_patch 5:fp_counter_layout */
 size_t fp_abi_sizeof(int which);
 
-static inline int64_t fp_off_cycle(const fp_counter_layout* L, int stats, int kind, int cycle) {
+#ifdef __CUDACC__
+#define FP_INLINE static __host__ __device__ __forceinline__
+#else
+#define FP_INLINE static inline
+#endif
+FP_INLINE int64_t fp_off_cycle(const fp_counter_layout* L, int stats, int kind, int cycle) {
     return (int64_t)stats * L->stats_stride + (int64_t)kind * L->cycles + cycle;
 }
-static inline int64_t fp_off_kmer(const fp_counter_layout* L, int stats, int code) {
+FP_INLINE int64_t fp_off_kmer(const fp_counter_layout* L, int stats, int code) {
     return (int64_t)stats * L->stats_stride + L->off_kmer + code;
 }
-static inline int64_t fp_off_qualhist(const fp_counter_layout* L, int stats, int q) {
+FP_INLINE int64_t fp_off_qualhist(const fp_counter_layout* L, int stats, int q) {
     return (int64_t)stats * L->stats_stride + L->off_qualhist + q;
 }
-static inline int64_t fp_off_reads(const fp_counter_layout* L, int stats) {
+FP_INLINE int64_t fp_off_reads(const fp_counter_layout* L, int stats) {
     return (int64_t)stats * L->stats_stride + L->off_reads;
 }
-static inline int64_t fp_off_length_sum(const fp_counter_layout* L, int stats) {
+FP_INLINE int64_t fp_off_length_sum(const fp_counter_layout* L, int stats) {
     return (int64_t)stats * L->stats_stride + L->off_length_sum;
 }
 

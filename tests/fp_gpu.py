@@ -1,0 +1,114 @@
+"""GPU-side test helper: runs the C-ABI of libfastp_b200.so on cuda:0.
+torch is used for device memory only (plumbing); every compute call goes through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+
+from fastp_b200 import capi
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class GpuCtx:
+    def __init__(self, params, max_batch, stride, cycles, device=0):
+        self.lib = capi.load()
+        self.params = params
+        self.h = C.c_void_p()
+        capi.check(self.lib.fp_ctx_create(C.byref(params), device, max_batch, stride, cycles, C.byref(self.h)), self.lib)
+        self.L = capi.CounterLayout()
+        capi.check(self.lib.fp_ctx_layout(self.h, C.byref(self.L)), self.lib)
+        self.stride = stride
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.fp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def counters(self):
+        out = np.zeros(self.L.total, np.int64)
+        capi.check(self.lib.fp_counters_fetch(self.h, out.ctypes.data), self.lib)
+        return capi.CounterView(self.L, out)
+
+    def reset(self):
+        capi.check(self.lib.fp_counters_reset(self.h), self.lib)
+
+    def kernel_time_ms(self, reset=True):
+        ms = C.c_double()
+        n = C.c_int64()
+        capi.check(self.lib.fp_kernel_time_ms(self.h, C.byref(ms), C.byref(n), 1 if reset else 0), self.lib)
+        return ms.value, n.value
+
+
+def device_batch(arrs, device=0):
+    """Copy numpy host arrays to torch cuda tensors; returns (Batch with device pointers, tensors)."""
+    torch = _torch()
+    t = {k: torch.from_numpy(v).to(f"cuda:{device}") for k, v in arrs.items()}
+    b = capi.Batch()
+    b.n = arrs["seq1"].shape[0]
+    b.stride = arrs["seq1"].shape[1]
+    for k, v in t.items():
+        setattr(b, k, v.data_ptr())
+    b._keepalive = t
+    return b, t
+
+
+def run_gpu(params, arrs, cycles, mode="device", ctx=None):
+    """Run the CUDA hot path over a COPY of arrs; same return shape as fp_testlib.run_cpu."""
+    torch = _torch()
+    paired = bool(params.paired)
+    n, stride = arrs["seq1"].shape
+    own = ctx is None
+    if own:
+        ctx = GpuCtx(params, max(n, 1), stride, cycles)
+    lib = ctx.lib
+    ctx.reset()
+    a = {k: v.copy() for k, v in arrs.items()}
+    out1 = np.zeros(n, capi.READ_RESULT_DTYPE)
+    out2 = np.zeros(n, capi.READ_RESULT_DTYPE)
+    ov = np.zeros(n, capi.OV_RESULT_DTYPE)
+    if mode == "device":
+        b, t = device_batch(a)
+        d_out1 = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device="cuda:0")
+        d_out2 = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device="cuda:0")
+        d_ov = torch.zeros(max(n, 1) * 8, dtype=torch.uint8, device="cuda:0")
+        if paired:
+            cap = 4 * n + 16
+            d_patch = torch.zeros(cap * 12, dtype=torch.uint8, device="cuda:0")
+            d_np = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+            capi.check(lib.fp_process_pe(ctx.h, C.byref(b), d_out1.data_ptr(), d_out2.data_ptr(), d_ov.data_ptr(),
+                                         d_patch.data_ptr(), cap, d_np.data_ptr(), None), lib)
+        else:
+            capi.check(lib.fp_process_se(ctx.h, C.byref(b), d_out1.data_ptr(), None), lib)
+        torch.cuda.synchronize()
+        out1 = d_out1.cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n].copy()
+        if paired:
+            out2 = d_out2.cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n].copy()
+            ov = d_ov.cpu().numpy().view(capi.OV_RESULT_DTYPE)[:n].copy()
+            npatch = int(d_np.cpu().item())
+            patches = d_patch.cpu().numpy().view(capi.PATCH_DTYPE)[:min(npatch, cap)].copy()
+        for k in a:
+            a[k] = t[k].cpu().numpy()
+        extra = {"patches": patches, "n_patches": npatch} if paired else {}
+    else:
+        b = capi.batch_from_arrays(a)
+        if paired:
+            capi.check(lib.fp_process_pe_host(ctx.h, C.byref(b), out1.ctypes.data, out2.ctypes.data, ov.ctypes.data), lib)
+        else:
+            capi.check(lib.fp_process_se_host(ctx.h, C.byref(b), out1.ctypes.data), lib)
+        extra = {}
+    cnt = ctx.counters()
+    res = {"out1": out1, "out2": out2, "ov": ov, "counters": cnt, "arrs": a, "layout": ctx.L}
+    res.update(extra)
+    if own:
+        ctx.close()
+    return res
