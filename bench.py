@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native fastp hot path.
+
+A "step" is one pass of the per-read operator chain over one batch of synthetic 2x150 bp read pairs
+(BASELINE.json configs[2]: PE, overlap adapter trimming + --correction) that is already resident in
+HBM.  N GPUs: every rank processes its own shard of the same size (weak scaling, no data-path
+collective) and the int64 counter block is all-reduced (NCCL sum) once per step.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference ...                     # the reference's own CPU code (oracle/_ref)
+
+Prints ONE JSON line (rank 0).  torch is plumbing only (device memory, streams, torch.distributed).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRUSEQ_R1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+TRUSEQ_R2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+READ_LEN, STRIDE = 150, 160
+BYTES_PER_PAIR = 4 * READ_LEN + 32          # 4*L in + two 16-byte fp_read_result out
+SEED = 42
+
+
+def workload_params(capi, lib, name):
+    """fp_params of the named BASELINE.json config."""
+    if name == "pe150_overlap_correction":      # configs[2]
+        return capi.default_params(1, lib=lib, correction_enabled=1)
+    if name == "pe150_full":                    # configs[3]
+        return capi.default_params(1, lib=lib, cut_right=1, polyg_enabled=1, polyx_enabled=1, correction_enabled=1,
+                                   adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
+    if name == "se150_cut_right_polyg":         # configs[1]
+        return capi.default_params(0, lib=lib, cut_right=1, polyg_enabled=1, adapter_enabled=0)
+    raise KeyError(name)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places bench.py touches oracle/): cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def load_cpu_checker():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fp_testlib as T
+    if T.have_ref():
+        return T, "reference"
+    return T, "port"
+
+
+def synth_host_parallel(T, n, paired, first, profile, threads):
+    from fastp_b200 import capi
+    b, arrs = capi.host_batch(n, STRIDE, paired)
+    lib = T.oracle()
+    bounds = [n * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi <= lo:
+            return
+        sub = {k: v[lo:hi] for k, v in arrs.items()}
+        sb = capi.batch_from_arrays(sub)
+        lib.fp_synth_fill_host(C.byref(sb), first + lo, SEED, profile, READ_LEN)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return b, arrs
+
+
+def cpu_run(T, kind, params, arrs, threads):
+    """One pass of the reference worker body over the sample on `threads` host threads; returns seconds."""
+    from fastp_b200 import capi
+    paired = bool(params.paired)
+    a = {k: v.copy() for k, v in arrs.items()}
+    b = capi.batch_from_arrays(a)
+    L = capi.make_layout(T.oracle(), paired, STRIDE, params.insert_size_max)
+    cnt = np.zeros(L.total, np.int64)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        rc = T.ref().fp_ref_process_mt(C.byref(params), C.byref(L), C.byref(b), None, None, None, cnt.ctypes.data, threads)
+        assert rc == 0
+    else:
+        # the C port is single-threaded per call: shard over python threads (ctypes drops the GIL)
+        n = b.n
+        bounds = [n * i // threads for i in range(threads + 1)]
+        outs = []
+
+        def work(i):
+            lo, hi = bounds[i], bounds[i + 1]
+            if hi <= lo:
+                return
+            sub = {k: v[lo:hi] for k, v in a.items()}
+            sb = capi.batch_from_arrays(sub)
+            o1 = np.zeros(hi - lo, capi.READ_RESULT_DTYPE); o2 = np.zeros(hi - lo, capi.READ_RESULT_DTYPE)
+            c = np.zeros(L.total, np.int64)
+            T.oracle().fp_oracle_process(C.byref(params), C.byref(L), C.byref(sb), o1.ctypes.data, o2.ctypes.data if paired else None,
+                                         None, c.ctypes.data)
+            outs.append(c)
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(workload, profile, target_seconds=12.0):
+    from fastp_b200 import capi
+    T, kind = load_cpu_checker()
+    params = workload_params(capi, T.oracle(), workload)
+    paired = bool(params.paired)
+    cores = os.cpu_count() or 1
+    probe_n = 20000 * max(1, min(cores, 16))
+    _, arrs = synth_host_parallel(T, probe_n, paired, 0, profile, min(cores, 32))
+    dt = cpu_run(T, kind, params, arrs, cores)
+    rate = probe_n / dt
+    n = int(min(max(rate * target_seconds, probe_n), 6_000_000))
+    if n > probe_n:
+        _, arrs = synth_host_parallel(T, n, paired, 0, profile, min(cores, 32))
+        dt = cpu_run(T, kind, params, arrs, cores)
+    else:
+        n = probe_n
+    return {"value": n / dt, "unit": "pairs/s" if paired else "reads/s", "cores": cores, "kind": kind,
+            "sample": f"first {n} units of the same synthetic stream (seed {SEED}, profile {profile}), in-memory batches, "
+                      f"{cores} worker threads each with private Stats/FilterResult, {dt:.2f} s"}, (T, kind, params, arrs)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fastp_b200 import capi  # noqa: F401  (ctypes structs only; no CUDA is touched on this arm)
+    profile = args.profile
+    base, (T, kind, params, arrs) = cpu_baseline(args.workload, profile, target_seconds=6.0)
+    cores = base["cores"]
+    n = arrs["seq1"].shape[0]
+    for _ in range(args.warmup):
+        cpu_run(T, kind, params, arrs, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_run(T, kind, params, arrs, cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    unit = "pairs/s" if params.paired else "reads/s"
+    line = {
+        "impl": "reference", "metric": f"{unit.split('/')[0]} per second, 150 bp {'PE' if params.paired else 'SE'} synthetic, reference worker body on host CPUs",
+        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "units_per_step": n, "read_len": READ_LEN, "profile": profile, "threads": cores},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind,
+                         "sample": f"{n} units per step x {args.steps} steps, in-memory batches, {cores} threads"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pe150_overlap_correction",
+                    choices=["pe150_overlap_correction", "pe150_full", "se150_cut_right_polyg"])
+    ap.add_argument("--units", type=int, default=0, help="reads/pairs per GPU per step (default: BASELINE config size)")
+    ap.add_argument("--e2e-units", type=int, default=4_000_000, help="host-buffer batch for the e2e measurement")
+    ap.add_argument("--profile", type=int, default=1, help="synthetic profile: 1 = enriched fragment model, 0 = ref-style")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fastp_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (fastp_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = f"cuda:{local_rank}"
+    lib = capi.load()
+    params = workload_params(capi, lib, args.workload)
+    paired = bool(params.paired)
+    unit = "pairs/s" if paired else "reads/s"
+    default_units = {"pe150_overlap_correction": 100_000_000, "pe150_full": 125_000_000, "se150_cut_right_polyg": 10_000_000}
+    n = args.units or default_units[args.workload]
+    free_b, _ = torch.cuda.mem_get_info()
+    per_unit = (4 if paired else 2) * STRIDE + (2 if paired else 1) * (2 + 16) + (8 if paired else 0)
+    n = int(min(n, 0.85 * free_b / per_unit))
+    bytes_per_unit = BYTES_PER_PAIR if paired else 2 * READ_LEN + 16
+
+    h = C.c_void_p()
+    capi.check(lib.fp_ctx_create(C.byref(params), local_rank, min(n, 1 << 18), STRIDE, STRIDE, C.byref(h)), lib)
+    L = capi.CounterLayout()
+    capi.check(lib.fp_ctx_layout(h, C.byref(L)), lib)
+
+    def alloc(nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    t = {"seq1": alloc(n * STRIDE), "qual1": alloc(n * STRIDE), "len1": alloc(n * 2)}
+    if paired:
+        t.update(seq2=alloc(n * STRIDE), qual2=alloc(n * STRIDE), len2=alloc(n * 2))
+    out1 = alloc(n * 16)
+    out2 = alloc(n * 16) if paired else None
+    ov = alloc(n * 8) if paired else None
+    b = capi.Batch()
+    b.n, b.stride = n, STRIDE
+    for k, v in t.items():
+        setattr(b, k, v.data_ptr())
+    # inputs are generated ON the device: each rank owns global indices [rank*n, (rank+1)*n)
+    first = rank * n
+    capi.check(lib.fp_synth_fill(h, C.byref(b), first, SEED, args.profile, READ_LEN, None), lib)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    cnt_ptr = C.c_void_p(); cnt_words = C.c_int64()
+
+    class _Raw:  # expose the raw device counter block to torch (for the NCCL all-reduce)
+        def __init__(self, ptr, nwords):
+            self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    def step():
+        capi.check(lib.fp_counters_reset(h), lib)
+        if paired:
+            capi.check(lib.fp_process_pe(h, C.byref(b), out1.data_ptr(), out2.data_ptr(), ov.data_ptr(), None, 0, None,
+                                         C.c_void_p(stream.cuda_stream)), lib)
+        else:
+            capi.check(lib.fp_process_se(h, C.byref(b), out1.data_ptr(), C.c_void_p(stream.cuda_stream)), lib)
+        if world > 1:
+            stream.synchronize()
+            capi.check(lib.fp_counters_device_ptr(h, C.byref(cnt_ptr), C.byref(cnt_words)), lib)
+            raw = torch.as_tensor(_Raw(cnt_ptr.value, cnt_words.value), device=dev)
+            dist.all_reduce(raw, op=dist.ReduceOp.SUM)      # Stats::merge / FilterResult::merge are plain sums
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ms_tmp = C.c_double(); nl = C.c_int64()
+    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)   # reset kernel timers
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)
+    kernel_ms = ms_tmp.value / max(nl.value, 1)
+
+    # sanity invariants on the full-size run (size-independent properties; the parity tests proper live in tests/)
+    cnt = np.zeros(L.total, np.int64)
+    capi.check(lib.fp_counters_fetch(h, cnt.ctypes.data), lib)
+    cv = capi.CounterView(L, cnt)
+    total_units = n * world
+    checks = {
+        "pre_reads_eq_units": cv.stats(capi.STATS_PRE1)["reads"] == total_units,
+        "verdicts_sum": int(cv.filter[:32].sum()) == total_units * (2 if paired else 1),
+        "post_le_pre": cv.stats(capi.STATS_POST1)["reads"] <= cv.stats(capi.STATS_PRE1)["reads"],
+        "qualhist_eq_bases": int(cv.stats(capi.STATS_PRE1)["qualhist"].sum()) == cv.stats(capi.STATS_PRE1)["length_sum"],
+    }
+
+    value = total_units * args.steps / (elapsed_ms / 1e3)
+    peak, peak_src = measured_peak()
+    achieved = n * bytes_per_unit / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(args.workload)
+            if tj:
+                traffic = tj["dram_bytes_per_unit"] * n     # ncu --set full capture, scaled per launch
+        except Exception:
+            pass
+
+    line = {
+        "metric": f"{unit.split('/')[0]} per second, 150 bp {'PE' if paired else 'SE'} synthetic FASTQ resident in HBM",
+        "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": "configs[2]" if args.workload == "pe150_overlap_correction" else args.workload,
+                   "units_per_gpu": n, "read_len": READ_LEN, "stride": STRIDE, "profile": "enriched" if args.profile == 1 else "ref-style",
+                   "seed": SEED, "parallelism": f"shard{world}", "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n * (4 if paired else 2) * STRIDE / 1e9),
+                   "note": "base correction rewrites <1% of bases in place during warm-up; timed steps see the corrected rows"},
+        "gpu_launches": int(nl.value),
+        "checks": checks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "fp_chain_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_unit": bytes_per_unit,
+                     "peak_source": peak_src},
+    }
+    if rank == 0:
+        line["clocks"] = clocks
+
+    # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region) ----
+    if not args.no_e2e:
+        ne = int(min(args.e2e_units, n))
+        hb = {}
+        keys = ["seq1", "qual1"] + (["seq2", "qual2"] if paired else [])
+        for k in keys:
+            hb[k] = torch.empty(ne * STRIDE, dtype=torch.uint8).pin_memory()
+            hb[k].copy_(t[k][: ne * STRIDE])
+        for k in (["len1", "len2"] if paired else ["len1"]):
+            hb[k] = torch.empty(ne * 2, dtype=torch.uint8).pin_memory()
+            hb[k].copy_(t[k][: ne * 2])
+        ho1 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory()
+        ho2 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory() if paired else None
+        hov = torch.empty(ne * 8, dtype=torch.uint8).pin_memory() if paired else None
+        hbt = capi.Batch()
+        hbt.n, hbt.stride = ne, STRIDE
+        for k, v in hb.items():
+            setattr(hbt, k, v.data_ptr())
+
+        def e2e_step():
+            if paired:
+                capi.check(lib.fp_process_pe_host(h, C.byref(hbt), ho1.data_ptr(), ho2.data_ptr(), hov.data_ptr()), lib)
+            else:
+                capi.check(lib.fp_process_se_host(h, C.byref(hbt), ho1.data_ptr()), lib)
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        h2d = ne * ((4 if paired else 2) * STRIDE + (4 if paired else 2))
+        d2h = ne * ((32 + 8) if paired else 16)
+        line["e2e"] = {"value": ne * world * args.steps / dt, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "units_per_step_per_gpu": ne, "api": "fp_process_pe_host" if paired else "fp_process_se_host",
+                       "note": "pinned host SoA buffers -> chunked H2D on two streams -> kernel -> D2H of per-read records (+ correction patches)"}
+
+    lib.fp_ctx_destroy(h)
+    del t, out1, out2, ov
+    torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"], _ = cpu_baseline(args.workload, args.profile)
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -689,3 +689,6 @@ int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int l
     oread r = {seq, qual, len, 0};
     return pass_filter(p, &r);
 }
+int fp_oracle_match_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit) {
+    return match_with_one_insertion(insData, normalData, cmplen, diffLimit);
+}

@@ -20,6 +20,7 @@ int fp_oracle_trim_polyx(uint8_t* seq, int len, int minLen, int* poly, int* plen
 int fp_oracle_trim_by_sequence(uint8_t* seq, int len, const char* adapter, int* trimmed);
 fp_ov_result fp_oracle_analyze(uint8_t* seq1, int len1, uint8_t* seq2, int len2, int diffLimit, int overlapRequire, double diffPercentLimit);
 int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int len);
+int fp_oracle_match_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit);
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,8 @@ def oracle():
         lib.fp_oracle_analyze.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double]
         lib.fp_oracle_pass_filter.restype = C.c_int
         lib.fp_oracle_pass_filter.argtypes = [C.POINTER(capi.Params), C.c_char_p, C.c_char_p, C.c_int]
+        lib.fp_oracle_match_with_one_insertion.restype = C.c_int
+        lib.fp_oracle_match_with_one_insertion.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _oracle = lib
     return _oracle
 

@@ -1,0 +1,40 @@
+"""Pins the plain-C port (oracle/fastp_oracle.c) against the REFERENCE's own objects compiled into
+oracle/_ref/libfastp_ref.so (recipe: oracle/Makefile) on seeded synthetic batches: every per-read record,
+overlap record, corrected base and counter, for every option set the parity tests use.
+Skipped where oracle/_ref is absent (it is rebuilt wherever /root/reference exists)."""
+import pytest
+
+import fp_testlib as T
+
+pytestmark = pytest.mark.reference
+needs_ref = pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("paired", [1, 0])
+@pytest.mark.parametrize("name", T.CONFIG_NAMES)
+def test_port_equals_reference_objects(name, paired):
+    p = T.config_params(name, paired)
+    n = 4000 if name == "fasta_adapters" else 12000
+    _, arrs = T.synth_host(n, 160, paired, 5000, 2024, 1, 150)
+    x = T.run_cpu("oracle", p, arrs, 160)
+    y = T.run_cpu("ref", p, arrs, 160)
+    T.assert_results_equal(x, y, paired, skip=("adapter_pos",), what=name)
+
+
+@needs_ref
+@pytest.mark.parametrize("L,stride", [(250, 256), (100, 112), (36, 48)])
+def test_port_equals_reference_other_lengths(L, stride):
+    p = T.config_params("cfg4_full", 1)
+    _, arrs = T.synth_host(5000, stride, 1, 0, 7, 1, L)
+    T.assert_results_equal(T.run_cpu("oracle", p, arrs, stride), T.run_cpu("ref", p, arrs, stride), 1, skip=("adapter_pos",), what=f"L{L}")
+
+
+@needs_ref
+def test_reference_mt_equals_single_thread():
+    """Stats::merge / FilterResult::merge are plain sums: the multi-threaded CPU baseline must give the same block."""
+    p = T.config_params("cfg4_full", 1)
+    _, arrs = T.synth_host(6000, 160, 1, 0, 11, 1, 150)
+    a = T.run_cpu("ref", p, arrs, 160)
+    b = T.run_cpu("ref", p, arrs, 160, nthreads=5)
+    T.assert_results_equal(a, b, 1, what="mt")
