@@ -1,0 +1,88 @@
+"""-m gpu: the drop-in boundary end to end.  Plain FASTQ -> fastp_gpu_cli (C++ GpuChainWorker::processPairEnd /
+processSingleEnd: stage -> C-ABI -> unstage) -> output FASTQ + summary, compared with
+  * the UNMODIFIED reference CLI's outputs on the reference's own testdata (committed golden, config 1), and
+  * the oracle on a synthetic batch with the full option set (byte-identical output reads: the reference's own
+    definition of parity, scripts/bench_e2e.sh:183-225)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fp_testlib as T
+from fastp_b200 import capi
+from test_golden import load_fixture
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "fastp_b200", "host", "fastp_gpu_cli")
+
+
+def write_fastq(path, seq, qual, lens):
+    with open(path, "w") as f:
+        for i in range(seq.shape[0]):
+            n = int(lens[i])
+            f.write(f"@r{i}\n{bytes(seq[i, :n]).decode()}\n+\n{bytes(qual[i, :n]).decode()}\n")
+
+
+def read_fastq(path):
+    lines = open(path).read().split("\n")
+    return [[lines[i + 1], lines[i + 3]] for i in range(0, len(lines) - 3, 4)]
+
+
+@pytest.fixture(scope="module")
+def cli():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required")
+    assert os.path.exists(CLI), "build with __graft_entry__.build()"
+    return CLI
+
+
+def test_testdata_equals_reference_cli(cli, tmp_path):
+    meta, p, arrs, want = load_fixture(os.path.join(ROOT, "tests", "golden", "testdata_pe.npz"))
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "testdata_cli.json")))
+    write_fastq(tmp_path / "r1.fq", arrs["seq1"], arrs["qual1"], arrs["len1"])
+    write_fastq(tmp_path / "r2.fq", arrs["seq2"], arrs["qual2"], arrs["len2"])
+    subprocess.run([cli, "-i", str(tmp_path / "r1.fq"), "-I", str(tmp_path / "r2.fq"), "-o", str(tmp_path / "o1.fq"), "-O", str(tmp_path / "o2.fq"),
+                    "-j", str(tmp_path / "s.json"), "-g"], check=True, timeout=300)
+    assert read_fastq(tmp_path / "o1.fq") == ref["out1"]
+    assert read_fastq(tmp_path / "o2.fq") == ref["out2"]
+    js = json.load(open(tmp_path / "s.json"))
+    for part in ("before_filtering", "after_filtering"):
+        for k in ("total_reads", "total_bases", "q20_bases", "q30_bases"):
+            assert js[part][k] == ref["summary"][part][k], (part, k)
+    for k in ("passed_filter_reads", "low_quality_reads", "too_many_N_reads", "too_short_reads"):
+        assert js["filtering_result"][k] == ref["filtering_result"][k]
+
+
+@pytest.mark.parametrize("paired", [1, 0])
+def test_synthetic_full_chain_output_reads(cli, tmp_path, paired):
+    n = 20000
+    p = T.config_params("cfg4_full", paired)
+    _, arrs = T.synth_host(n, 160, paired, 0, 77, 1, 150)
+    want = T.run_cpu("oracle", p, arrs, 160)
+    write_fastq(tmp_path / "r1.fq", arrs["seq1"], arrs["qual1"], arrs["len1"])
+    cmd = [cli, "-i", str(tmp_path / "r1.fq"), "-o", str(tmp_path / "o1.fq"), "-j", str(tmp_path / "s.json"),
+           "--cut_right", "-g", "-x", "-a", T.TRUSEQ_R1, "--pack_size", "4096", "--max_read_len", "150"]
+    if paired:
+        write_fastq(tmp_path / "r2.fq", arrs["seq2"], arrs["qual2"], arrs["len2"])
+        cmd += ["-I", str(tmp_path / "r2.fq"), "-O", str(tmp_path / "o2.fq"), "-c", "--adapter_sequence_r2", T.TRUSEQ_R2]
+    subprocess.run(cmd, check=True, timeout=600)
+    keep = np.nonzero(want["out1"]["pair_verdict"] == 0)[0]
+    for side, key, fn in (("1", "out1", "o1.fq"), ("2", "out2", "o2.fq"))[: 2 if paired else 1]:
+        got = read_fastq(tmp_path / fn)
+        assert len(got) == len(keep)
+        for j, i in enumerate(keep):
+            r = want[key][i]
+            s = bytes(want["arrs"]["seq" + side][i, r["front"]: r["front"] + r["len"]]).decode()
+            q = bytes(want["arrs"]["qual" + side][i, r["front"]: r["front"] + r["len"]]).decode()
+            assert got[j] == [s, q], (side, i)
+    js = json.load(open(tmp_path / "s.json"))
+    c = want["counters"]
+    assert js["filtering_result"]["passed_filter_reads"] == c.filter[0]
+    assert js["adapter_cutting"]["adapter_trimmed_reads"] == c.filter[capi.FR_ADAPTER_READS]
+    assert js["adapter_cutting"]["adapter_trimmed_bases"] == c.filter[capi.FR_ADAPTER_BASES]
+    posts = (capi.STATS_POST1, capi.STATS_POST2) if paired else (capi.STATS_POST1,)
+    assert js["after_filtering"]["total_bases"] == sum(c.summary(s)["bases"] for s in posts)
