@@ -50,6 +50,8 @@ struct fp_ctx {
     int16_t *d_ovlimit = nullptr, *d_lowq = nullptr, *d_mindiff = nullptr;
     uint8_t* d_adapters = nullptr;
     int32_t *d_fasta_off = nullptr, *d_fasta_len = nullptr;
+    uint32_t* d_aplanes = nullptr;
+    uint8_t* d_aclean = nullptr;
     long long *d_raw = nullptr, *d_fin = nullptr;
     /* host-mode staging (allocated lazily) */
     int64_t chunk = 0;
@@ -100,7 +102,7 @@ static void make_smem_layout(fp_ctx* c) {
     const int sides = c->p.paired ? 2 : 1;
     const int S = c->stride;
     int T = (int)((48 * 1024) / (size_t)(sides * 2 * S));
-    T = std::min(T, 128);
+    T = std::min(T, 64 * (3 - sides));
     T = std::max(T / 8 * 8, 8);
     c->tile = T;
     fp_smem_layout& sl = c->sl;
@@ -121,6 +123,13 @@ static void make_smem_layout(fp_ctx* c) {
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
     off = align_up(off, 8);
     sl.off_rl = (int)off; off += 8 * 8;
+    sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
+    sl.off_delta = (int)off; off += (size_t)sides * ((size_t)S * 20 + FP_KMER_BINS + FP_QUAL_BINS) * 4;
+    sl.off_next = (int)off; off += 16;
+    sl.plane_words = S / 32 + 3;
+    off = align_up(off, 16);
+    sl.off_planes = (int)off; off += (size_t)sides * T * 4 * sl.plane_words * 4;
+    sl.off_rcplanes = (int)off; off += (size_t)FP_WARPS * 3 * sl.plane_words * 4;
     sl.total = (int)align_up(off, 128);
 }
 
@@ -180,6 +189,25 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         CK(cudaMemcpy(c->d_fasta_off, foff.data(), foff.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_fasta_len, flen.data(), flen.size() * 4, cudaMemcpyHostToDevice));
     }
+    {   /* bit planes of every adapter (fp_device.cuh Planes): index 0 = r1, 1 = r2, 2+i = fasta i */
+        std::vector<std::string> all = {c->ad1, c->ad2};
+        for (auto& s : c->fasta) all.push_back(s);
+        std::vector<uint32_t> pl(all.size() * 24, 0);
+        std::vector<uint8_t> cl(all.size(), 1);
+        for (size_t a = 0; a < all.size(); a++)
+            for (size_t k = 0; k < all[a].size(); k++) {
+                const unsigned char ch = (unsigned char)all[a][k];
+                if (ch == 'N') pl[a * 24 + 16 + (k >> 5)] |= 1u << (k & 31);
+                else if (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') {
+                    const int c2 = (ch >> 1) & 3;
+                    if (c2 & 1) pl[a * 24 + 0 + (k >> 5)] |= 1u << (k & 31);
+                    if (c2 & 2) pl[a * 24 + 8 + (k >> 5)] |= 1u << (k & 31);
+                } else cl[a] = 0;
+            }
+        CK(cudaMalloc(&c->d_aplanes, pl.size() * 4)); CK(cudaMalloc(&c->d_aclean, cl.size()));
+        CK(cudaMemcpy(c->d_aplanes, pl.data(), pl.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_aclean, cl.data(), cl.size(), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&c->d_raw, c->L.total * 8)); CK(cudaMalloc(&c->d_fin, c->L.total * 8));
     CK(cudaMemset(c->d_raw, 0, c->L.total * 8)); CK(cudaMemset(c->d_fin, 0, c->L.total * 8));
 
@@ -205,6 +233,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     d.stride = stride; d.cycles = cycles; d.tile = c->tile; d.n_stats = c->L.n_stats;
     d.lut_ovlimit = c->d_ovlimit; d.lut_lowq = c->d_lowq; d.lut_mindiff = c->d_mindiff;
     d.adapters = c->d_adapters; d.fasta_off = c->d_fasta_off; d.fasta_len = c->d_fasta_len;
+    d.adapter_planes = c->d_aplanes; d.adapter_clean = c->d_aclean;
     d.L = c->L;
 
     /* kernel attributes + persistent grid size */
@@ -242,6 +271,7 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     free_staging(c);
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
+    cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);

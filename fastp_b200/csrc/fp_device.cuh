@@ -21,7 +21,7 @@
 #include <stdint.h>
 #include "fastp_b200.h"
 
-#define FP_THREADS 256
+#define FP_THREADS 512
 #define FP_WARPS (FP_THREADS / 32)
 #define FULL_MASK 0xffffffffu
 #define FP_MAX_ISIZE_SMEM 1025
@@ -50,6 +50,8 @@ struct fp_dev_params {
     const uint8_t* adapters;        /* blob of adapter strings, each padded to a multiple of 4 + 8               */
     const int32_t* fasta_off;       /* [n_fasta] offsets into blob */
     const int32_t* fasta_len;       /* [n_fasta] */
+    const uint32_t* adapter_planes; /* [2 + n_fasta][3][8] lo/hi/nn bit planes of each adapter (index 0 = r1, 1 = r2, 2+i = fasta i) */
+    const uint8_t* adapter_clean;   /* [2 + n_fasta] 1 if the adapter holds only A,C,G,T,N */
     /* counter layout */
     fp_counter_layout L;
 };
@@ -72,6 +74,10 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
     uint32_t lo = w[0], hi = w[1];
     return __funnelshift_r(lo, hi, (unsigned)(a & 3) * 8);
+}
+/* fire-and-forget 64-bit add to the global counter block (two's complement for negative deltas): RED, not ATOM */
+__device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint8_t dev_complement(uint8_t b) {   /* util.h:16-33 */
     switch (b) {
@@ -291,6 +297,194 @@ __device__ __noinline__ bool dev_trim_polyx(WRead& r, int minLen, int& polyOut, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Bit planes of a read ROW (clean rows only: every base in {A,C,G,T,N}).  Bit p = row position p.
+ * code = (base>>1)&3 : A0 C1 T2 G3;  lo = code bit0, hi = code bit1, both 0 under N;  nn = N mask;
+ * lq = (qual < qualified_qual).  Two bases differ iff (lo^lo') | (hi^hi') | (nn^nn').
+ * Each plane holds pw = stride/32 + 2 words, zero beyond the row, so any 32-bit field is one funnel
+ * shift (plane_bits).  Planes of every row of a tile are built once, word-parallel (phase 0.5); users
+ * address the trimmed window as bit (front + k) and mask by the current length.
+ * ------------------------------------------------------------------------------------------------ */
+struct Planes { uint32_t *lo, *hi, *nn, *lq; };
+
+__device__ __forceinline__ uint32_t plane_bits(const uint32_t* P, int bit) {
+    const int w = bit >> 5;
+    return __funnelshift_r(P[w], P[w + 1], bit & 31);
+}
+__device__ __forceinline__ uint32_t low_mask(int nbits) {     /* mask of min(max(nbits,0),32) low bits */
+    return nbits >= 32 ? 0xffffffffu : (nbits <= 0 ? 0u : ((1u << nbits) - 1u));
+}
+/* 4 bytes holding 0/1 -> 4-bit nibble, byte k -> bit k */
+__device__ __forceinline__ uint32_t pack_nibble(uint32_t v01) { return ((v01 * 0x01020408u) >> 24) & 0xFu; }
+
+/* One plane word (32 bases = 8 seq words + 8 qual words) of one row: returns false if a valid byte is outside
+ * {A,C,G,T,N} or a quality has bit 7 set.  x/q: the 8 words; n = number of valid bases in this word (0..32). */
+__device__ __forceinline__ bool plane_word_from_bytes(const uint32_t (&x)[8], const uint32_t (&q)[8], int n, uint32_t qq4,
+                                                      uint32_t& lo, uint32_t& hi, uint32_t& nn, uint32_t& lq) {
+    const uint32_t K = 0x01010101u;
+    lo = hi = nn = lq = 0;
+    uint32_t bad = 0;
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int nv = n - 4 * k;                                   /* valid bytes of this word */
+        const uint32_t vm = nv >= 4 ? K : (nv <= 0 ? 0u : (K & ((1u << (8 * nv)) - 1u)));
+        const uint32_t w = x[k];
+        const uint32_t c0 = w & K, c1 = (w >> 1) & K, c2 = (w >> 2) & K, b3 = (w >> 3) & K, b4 = (w >> 4) & K;
+        const uint32_t up = (~(w >> 5)) & (w >> 6) & (~(w >> 7)) & K;         /* bits 7..5 == 010 */
+        const uint32_t isACG = c0 & (~c2 | c1) & ~b3 & ~b4;                     /* 0x41 0x43 0x47 */
+        const uint32_t isT = ~c0 & ~c1 & c2 & ~b3 & b4;                          /* 0x54 */
+        const uint32_t isN = ~c0 & c1 & c2 & b3 & ~b4 & up & vm;                 /* 0x4E */
+        const uint32_t acgt = (isACG | isT) & up & vm;
+        bad |= vm & ~(acgt | isN);
+        bad |= (q[k] >> 7) & vm;
+        /* q < qualified_qual  <=>  bit7 of (q | 0x80) - qq is clear (q, qq < 128) */
+        const uint32_t ql = (~(((q[k] | 0x80808080u) - qq4) >> 7)) & vm;
+        lo |= pack_nibble(c1 & acgt) << (4 * k);
+        hi |= pack_nibble(c2 & acgt) << (4 * k);
+        nn |= pack_nibble(isN) << (4 * k);
+        lq |= pack_nibble(ql) << (4 * k);
+    }
+    return bad == 0;
+}
+
+/* ballot-based rebuild of one row's planes (used after base correction rewrote the row; rare) */
+__device__ __noinline__ void dev_rebuild_planes(const uint8_t* seq, const uint8_t* qual, int len, int pw, Planes P) {
+    const int lane = lane_id();
+    const uint8_t qq = (uint8_t)c_p.qualified_qual;
+    for (int w = 0; w < pw; w++) {
+        const int i = w * 32 + lane;
+        const bool valid = i < len;
+        uint8_t b = 0, q = 255;
+        if (valid) { b = seq[i]; q = qual[i]; }
+        const bool isN = (b == 'N');
+        const int c2 = (b >> 1) & 3;
+        const bool acgt = valid && !isN;
+        const unsigned mlo = __ballot_sync(FULL_MASK, acgt && (c2 & 1));
+        const unsigned mhi = __ballot_sync(FULL_MASK, acgt && (c2 & 2));
+        const unsigned mn = __ballot_sync(FULL_MASK, isN);
+        const unsigned mq = __ballot_sync(FULL_MASK, valid && q < qq);
+        if (lane == 0) { P.lo[w] = mlo; P.hi[w] = mhi; P.nn[w] = mn; P.lq[w] = mq; }
+    }
+    __syncwarp();
+}
+
+/* reverseComplement(r2 window) as planes RC (relative to bit 0), from r2's row planes by bit reversal:
+ * RC[k] = complement(row2[e - k]), e = front2 + len2 - 1.  complement flips code bit1 (A0<->T2, C1<->G3), N stays N. */
+__device__ __forceinline__ void dev_rc_planes(const Planes& P2, int front2, int len2, int pw, Planes RC) {
+    const int lane = lane_id();
+    if (lane < pw) {
+        const int e = front2 + len2 - 1;
+        const int s0 = e - 32 * lane - 31;                           /* row position of the field's bit 0 (before reversal) */
+        uint32_t flo, fhi, fnn;
+        if (s0 >= 0) { flo = plane_bits(P2.lo, s0); fhi = plane_bits(P2.hi, s0); fnn = plane_bits(P2.nn, s0); }
+        else if (s0 > -32) { flo = P2.lo[0] << (-s0); fhi = P2.hi[0] << (-s0); fnn = P2.nn[0] << (-s0); }
+        else { flo = fhi = fnn = 0; }
+        const uint32_t vm = low_mask(len2 - 32 * lane);
+        const uint32_t n = __brev(fnn) & vm;
+        RC.nn[lane] = n;
+        RC.lo[lane] = __brev(flo) & vm & ~n;
+        RC.hi[lane] = ~__brev(fhi) & vm & ~n;
+    }
+    __syncwarp();
+}
+
+/* OverlapAnalysis::analyze on bit planes (both rows clean).  Same candidate order and acceptance rule as the byte
+ * version below (overlapanalysis.cpp:34-89); per candidate offset: funnel shifts + xor/or + 2 popc, no loop. */
+__device__ __noinline__ fp_ov_result dev_analyze_planes(int len1, int front1, int len2, int front2, Planes A, Planes P2, Planes RC, int pw, const int16_t* lut) {
+    const int lane = lane_id();
+    dev_rc_planes(P2, front2, len2, pw, RC);
+    const int req = c_p.ov_require;
+    fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+    const int nfwd = max(len1 - req, 0), nbwd = max(len2 - req, 0);
+    /* constant sides: first 64 bases of rc(r2) (forward scan) and of r1 (backward scan) */
+    const uint32_t blo0 = RC.lo[0], blo1 = RC.lo[1], bhi0 = RC.hi[0], bhi1 = RC.hi[1], bnn0 = RC.nn[0], bnn1 = RC.nn[1];
+    const uint32_t alo0 = plane_bits(A.lo, front1), alo1 = plane_bits(A.lo, front1 + 32), ahi0 = plane_bits(A.hi, front1), ahi1 = plane_bits(A.hi, front1 + 32),
+                   ann0 = plane_bits(A.nn, front1), ann1 = plane_bits(A.nn, front1 + 32);
+    for (int dir = 0; dir < 2; dir++) {
+        const int ncand = dir == 0 ? nfwd : nbwd;
+        for (int base = 0; base < ncand; base += 32) {
+            const int o = base + lane;
+            const bool valid = o < ncand;
+            int ol = 0, limit = -1, mm = 0;
+            if (valid) {
+                ol = dir == 0 ? min(len1 - o, len2) : min(len1, len2 - o);
+                limit = lut[ol];
+                const int pp = min(ol, 50);                                /* complete_compare_require :29 */
+                uint32_t x0, x1;
+                if (dir == 0) {
+                    const int bit = front1 + o, w = bit >> 5, sh = bit & 31;
+                    x0 = (__funnelshift_r(A.lo[w], A.lo[w + 1], sh) ^ blo0) | (__funnelshift_r(A.hi[w], A.hi[w + 1], sh) ^ bhi0) | (__funnelshift_r(A.nn[w], A.nn[w + 1], sh) ^ bnn0);
+                    x1 = (__funnelshift_r(A.lo[w + 1], A.lo[w + 2], sh) ^ blo1) | (__funnelshift_r(A.hi[w + 1], A.hi[w + 2], sh) ^ bhi1) | (__funnelshift_r(A.nn[w + 1], A.nn[w + 2], sh) ^ bnn1);
+                } else {
+                    const int w = o >> 5, sh = o & 31;
+                    x0 = (__funnelshift_r(RC.lo[w], RC.lo[w + 1], sh) ^ alo0) | (__funnelshift_r(RC.hi[w], RC.hi[w + 1], sh) ^ ahi0) | (__funnelshift_r(RC.nn[w], RC.nn[w + 1], sh) ^ ann0);
+                    x1 = (__funnelshift_r(RC.lo[w + 1], RC.lo[w + 2], sh) ^ alo1) | (__funnelshift_r(RC.hi[w + 1], RC.hi[w + 2], sh) ^ ahi1) | (__funnelshift_r(RC.nn[w + 1], RC.nn[w + 2], sh) ^ ann1);
+                }
+                mm = __popc(x0 & low_mask(pp)) + __popc(x1 & low_mask(pp - 32));
+            }
+            const unsigned am = __ballot_sync(FULL_MASK, valid && mm <= limit);
+            if (am) {
+                const int wl = __ffs(am) - 1;
+                const int wo = base + wl;
+                const int wol = __shfl_sync(FULL_MASK, ol, wl);
+                int diff = __shfl_sync(FULL_MASK, mm, wl);
+                if (wol > 50) {                                            /* :41-43 full recount, lanes over words */
+                    int d = 0;
+                    const int abit = front1 + (dir == 0 ? wo : 0), bbit = dir == 0 ? 0 : wo;
+                    for (int w = lane; w * 32 < wol; w += 32) {
+                        const uint32_t x = (plane_bits(A.lo, abit + 32 * w) ^ plane_bits(RC.lo, bbit + 32 * w)) | (plane_bits(A.hi, abit + 32 * w) ^ plane_bits(RC.hi, bbit + 32 * w)) |
+                                           (plane_bits(A.nn, abit + 32 * w) ^ plane_bits(RC.nn, bbit + 32 * w));
+                        d += __popc(x & low_mask(wol - 32 * w));
+                    }
+                    diff = warp_sum(d);
+                }
+                ov.overlapped = 1; ov.offset = (int16_t)(dir == 0 ? wo : -wo); ov.overlap_len = (int16_t)wol; ov.diff = (int16_t)diff;
+                return ov;
+            }
+        }
+    }
+    return ov;
+}
+
+/* Filter::passFilter on bit planes (clean row; window = bits [front, front+rlen)).  filter.cpp:15-57 */
+__device__ __noinline__ int dev_pass_filter_planes(const uint8_t* qual, int rlen, bool null, Planes P, int front, int pw, const int16_t* lut) {
+    if (null || rlen == 0) return FP_FAIL_LENGTH;
+    const int lane = lane_id();
+    int lowq = 0, nb = 0, adj = 0;
+    if (lane * 32 < rlen) {
+        const int bit = front + 32 * lane;
+        const uint32_t m = low_mask(rlen - 32 * lane);
+        const uint32_t lo = plane_bits(P.lo, bit), hi = plane_bits(P.hi, bit), nn = plane_bits(P.nn, bit);
+        lowq = __popc(plane_bits(P.lq, bit) & m);
+        nb = __popc(nn & m);
+        const uint32_t m1 = low_mask(rlen - 1 - 32 * lane);                /* pairs (i, i+1), i < rlen-1 */
+        const uint32_t d = (lo ^ plane_bits(P.lo, bit + 1)) | (hi ^ plane_bits(P.hi, bit + 1)) | (nn ^ plane_bits(P.nn, bit + 1));
+        adj = __popc(d & m1);
+    }
+    if (c_p.qual_filter) {
+        lowq = warp_sum(lowq);
+        if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
+        if (c_p.avg_qual_req > 0) {
+            int tq = 0;
+            for (int i = lane; i < rlen; i += 32) tq += (int)qual[i] - 33;
+            tq = warp_sum(tq);
+            if ((tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
+        }
+        nb = warp_sum(nb);
+        if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
+    }
+    if (c_p.length_filter) {
+        if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
+        if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
+    }
+    if (c_p.complexity_filter) {
+        if (rlen <= 1) return FP_FAIL_COMPLEXITY;
+        adj = warp_sum(adj);
+        if (adj < (int)lut[2 * (c_p.stride + 2) + rlen]) return FP_FAIL_COMPLEXITY;
+    }
+    return FP_PASS_FILTER;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * OverlapAnalysis::analyze  (overlapanalysis.cpp:17-146, allowGap=false).
  * rc = per-warp scratch holding reverseComplement(r2) (simd.cpp:297-310), padded by 8 readable bytes.
  * Lanes enumerate 32 candidate offsets at a time in the reference's order (forward 0,1,.. then
@@ -304,7 +498,7 @@ __device__ __forceinline__ int dev_count_mismatch_coop(const uint8_t* a, const u
     return warp_sum(d);
 }
 
-__device__ __noinline__ fp_ov_result dev_analyze(const WRead& r1, const WRead& r2, uint8_t* rc) {
+__device__ __noinline__ fp_ov_result dev_analyze(const WRead& r1, const WRead& r2, uint8_t* rc, const int16_t* lut) {
     const int lane = lane_id();
     const int len1 = r1.len, len2 = r2.len;
     for (int i = lane; i < len2; i += 32) rc[i] = dev_complement(r2.seq[len2 - 1 - i]);
@@ -323,7 +517,7 @@ __device__ __noinline__ fp_ov_result dev_analyze(const WRead& r1, const WRead& r
             int ol = 0, limit = 0, pp = 0, mm = 0;
             if (valid) {
                 ol = dir == 0 ? min(len1 - o, len2) : min(len1, len2 - o);
-                limit = c_p.lut_ovlimit[ol];
+                limit = lut[ol];
                 pp = min(ol, 50);                                          /* complete_compare_require :29 */
             }
             bool active = valid && pp > 0;
@@ -472,7 +666,7 @@ __device__ __noinline__ int dev_gap_scan(const uint8_t* ins, int ins_n, const ui
 }
 
 __device__ __noinline__ bool dev_trim_by_sequence(WRead& r, const uint8_t* adata, int alen, int matchReq, int* A,
-                                                  int& posOut, int& basesOut, BlockCounters* bc) {
+                                                  int& posOut, int& basesOut, BlockCounters* bc, int aidx, const Planes* RP) {
     const int lane = lane_id();
     const int rlen = r.len;
     const uint8_t* rdata = r.seq;
@@ -489,8 +683,30 @@ __device__ __noinline__ bool dev_trim_by_sequence(WRead& r, const uint8_t* adata
         int mism = dev_count_mismatch_coop(adata + so, rdata, cmplen - so);
         if (mism <= allowed) { found = true; pos = p; break; }
     }
-    /* scan 1, pos >= 0: lanes over pos, 4 bytes per step, early exit */
-    if (!found) {
+    /* scan 1, pos >= 0 on bit planes (clean read, clean adapter): lanes over pos, 32 bases per popc */
+    if (!found && RP != nullptr && c_p.adapter_clean[aidx]) {
+        const int npos = rlen - matchReq;
+        const uint32_t* alo = c_p.adapter_planes + aidx * 24; const uint32_t* ahi = alo + 8; const uint32_t* ann = alo + 16;
+        const int nw = (alen + 31) >> 5;
+        for (int base = 0; base < npos; base += 32) {
+            const int p = base + lane;
+            const bool valid = p < npos;
+            int allowed = -1, mm = 0;
+            if (valid) {
+                const int cmplen = min(rlen - p, alen);
+                allowed = cmplen / 8;
+                for (int k = 0; k < nw; k++) {
+                    if (32 * k >= cmplen) break;
+                    const int bit = r.front + p + 32 * k;
+                    const uint32_t x = (plane_bits(RP->lo, bit) ^ __ldg(alo + k)) | (plane_bits(RP->hi, bit) ^ __ldg(ahi + k)) |
+                                       (plane_bits(RP->nn, bit) ^ __ldg(ann + k));
+                    mm += __popc(x & low_mask(cmplen - 32 * k));
+                }
+            }
+            const unsigned am = __ballot_sync(FULL_MASK, valid && mm <= allowed);
+            if (am) { found = true; pos = base + __ffs(am) - 1; break; }
+        }
+    } else if (!found) {
         const int npos = rlen - matchReq;                                  /* pos in [0, npos) */
         const uint32_t* aw = reinterpret_cast<const uint32_t*>(adata);
         for (int base = 0; base < npos; base += 32) {
@@ -541,10 +757,10 @@ __device__ __noinline__ bool dev_trim_by_sequence(WRead& r, const uint8_t* adata
     return false;
 }
 
-__device__ __forceinline__ bool dev_trim_by_multi(WRead& r, int* A, int& posOut, int& basesOut, BlockCounters* bc) {
+__device__ __forceinline__ bool dev_trim_by_multi(WRead& r, int* A, int& posOut, int& basesOut, BlockCounters* bc, const Planes* RP) {
     bool trimmed = false;                                                 /* adaptertrimmer.cpp:48-62 */
     for (int i = 0; i < c_p.n_fasta; i++)
-        trimmed |= dev_trim_by_sequence(r, c_p.adapters + c_p.fasta_off[i], c_p.fasta_len[i], c_p.fasta_match_req, A, posOut, basesOut, bc);
+        trimmed |= dev_trim_by_sequence(r, c_p.adapters + c_p.fasta_off[i], c_p.fasta_len[i], c_p.fasta_match_req, A, posOut, basesOut, bc, 2 + i, RP);
     return trimmed;
 }
 
@@ -552,7 +768,7 @@ __device__ __forceinline__ bool dev_trim_by_multi(WRead& r, int* A, int& posOut,
  * Filter::passFilter  (filter.cpp:15-57) + countQualityMetrics (simd.cpp:281-295) +
  * passLowComplexityFilter (filter.cpp:59-66)
  * ------------------------------------------------------------------------------------------------ */
-__device__ __noinline__ int dev_pass_filter(const WRead& r) {
+__device__ __noinline__ int dev_pass_filter(const WRead& r, const int16_t* lut) {
     if (r.null || r.len == 0) return FP_FAIL_LENGTH;
     const int lane = lane_id();
     const int rlen = r.len;
@@ -569,7 +785,7 @@ __device__ __noinline__ int dev_pass_filter(const WRead& r) {
     if (need_metrics) { lowq = warp_sum(lowq); nb = warp_sum(nb); tq = warp_sum(tq); }
     else { lowq = nb = tq = 0; }
     if (c_p.qual_filter) {
-        if (lowq > (int)c_p.lut_lowq[rlen]) return FP_FAIL_QUALITY;
+        if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
         else if (c_p.avg_qual_req > 0 && (tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
         else if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
     }
@@ -580,7 +796,7 @@ __device__ __noinline__ int dev_pass_filter(const WRead& r) {
     if (c_p.complexity_filter) {
         if (rlen <= 1) return FP_FAIL_COMPLEXITY;
         adj = warp_sum(adj);
-        if (adj < (int)c_p.lut_mindiff[rlen]) return FP_FAIL_COMPLEXITY;
+        if (adj < (int)lut[2 * (c_p.stride + 2) + rlen]) return FP_FAIL_COMPLEXITY;
     }
     return FP_PASS_FILTER;
 }
@@ -657,10 +873,10 @@ __device__ __noinline__ void slow_cycle_byte(unsigned long long* G, int stats, i
     const fp_counter_layout& L = c_p.L;
     int b = base & 7;
     if (cycle >= L.cycles) return;
-    if (q >= '?') { atomicAdd(&G[fp_off_cycle(&L, stats, 0 * 8 + b, cycle)], 1ull); atomicAdd(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cycle)], 1ull); }
-    else if (q >= '5') atomicAdd(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cycle)], 1ull);
-    atomicAdd(&G[fp_off_cycle(&L, stats, 2 * 8 + b, cycle)], 1ull);
-    atomicAdd(&G[fp_off_cycle(&L, stats, 3 * 8 + b, cycle)], (unsigned long long)(long long)((int)q - 33));
+    if (q >= '?') { red_add64(&G[fp_off_cycle(&L, stats, 0 * 8 + b, cycle)], 1ull); red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cycle)], 1ull); }
+    else if (q >= '5') red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cycle)], 1ull);
+    red_add64(&G[fp_off_cycle(&L, stats, 2 * 8 + b, cycle)], 1ull);
+    red_add64(&G[fp_off_cycle(&L, stats, 3 * 8 + b, cycle)], (unsigned long long)(long long)((int)q - 33));
 }
 
 /* 2-bit value of a base for the 5-mer code (stats.cpp:293-318): A0 T1 C2 G3, -1 otherwise */
@@ -685,21 +901,76 @@ __device__ __noinline__ void dev_stat_positions(unsigned long long* G, int stats
         const uint8_t base = seq[i], q = qual[i];
         const int b = base & 7;
         const int cyc = i - ctx0;
-        if (q < FP_QUAL_BINS) atomicAdd(&G[fp_off_qualhist(&L, stats, q)], one);
+        if (q < FP_QUAL_BINS) red_add64(&G[fp_off_qualhist(&L, stats, q)], one);
         if (cyc < L.cycles) {
             const unsigned long long qv = (unsigned long long)((long long)sign * ((int)q - 33));
-            if (q >= '?') { atomicAdd(&G[fp_off_cycle(&L, stats, 0 * 8 + b, cyc)], one); atomicAdd(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cyc)], one); }
-            else if (q >= '5') atomicAdd(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cyc)], one);
-            atomicAdd(&G[fp_off_cycle(&L, stats, 2 * 8 + b, cyc)], one);
-            atomicAdd(&G[fp_off_cycle(&L, stats, 3 * 8 + b, cyc)], qv);
+            if (q >= '?') { red_add64(&G[fp_off_cycle(&L, stats, 0 * 8 + b, cyc)], one); red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cyc)], one); }
+            else if (q >= '5') red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, cyc)], one);
+            red_add64(&G[fp_off_cycle(&L, stats, 2 * 8 + b, cyc)], one);
+            red_add64(&G[fp_off_cycle(&L, stats, 3 * 8 + b, cyc)], qv);
         }
         if (i - 4 >= ctx0) {
             int code = 0; bool ok = true;
             #pragma unroll
             for (int k = 0; k < 5; k++) { int v = dev_base2val(seq[i - 4 + k]); ok = ok && (v >= 0); code = (code << 2) | (v & 3); }
-            if (ok) atomicAdd(&G[fp_off_kmer(&L, stats, code)], one);
+            if (ok) red_add64(&G[fp_off_kmer(&L, stats, code)], one);
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-private form of the same engine for CLEAN rows (bases in {A,C,G,T,N}): signed 32-bit shared-memory
+ * accumulators instead of global atomics (the global block would serialise on its few hot addresses).
+ *   D.cyc [side][cycle][bin A,C,T,N,G][kind count,q20,q30,qualsum]   D.kmer [side][1024]   D.qh [side][128]
+ * Flushed once per CTA into the POST stats of that side.
+ * ------------------------------------------------------------------------------------------------ */
+struct DeltaAcc { int* cyc; int* kmer; int* qh; int cycles; };
+
+__device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side, const uint8_t* seq, const uint8_t* qual,
+                                                    int ctx0, int lo, int hi, int sign) {
+    const int lane = lane_id();
+    int* cy = D.cyc + side * D.cycles * 20;
+    int* km = D.kmer + side * FP_KMER_BINS;
+    int* qh = D.qh + side * FP_QUAL_BINS;
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < hi;
+        uint8_t b = 0, q = 0;
+        if (valid) { b = seq[i]; q = qual[i]; }
+        /* quality histogram: aggregate equal values inside the warp first (few distinct qualities) */
+        const unsigned peers = __match_any_sync(FULL_MASK, valid ? (int)q : -1);
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&qh[q], sign * __popc(peers));
+        if (valid) {
+            const int cyc = i - ctx0;
+            if (cyc < D.cycles) {
+                const int bin = (0x43F21F0Fu >> (4 * (b & 7))) & 0xF;       /* base&7: A1 C3 T4 N6 G7 -> 0..4 */
+                int* c4 = cy + (cyc * 5 + bin) * 4;
+                atomicAdd(&c4[0], sign);
+                if (q >= '5') atomicAdd(&c4[1], sign);
+                if (q >= '?') atomicAdd(&c4[2], sign);
+                atomicAdd(&c4[3], sign * ((int)q - 33));
+            }
+            if (i - 4 >= ctx0) {
+                /* 5-mer ending at i: two unaligned 32-bit loads cover bases i-4..i */
+                const uint32_t w0 = ld_u32_unaligned(seq + i - 4);             /* bases i-4..i-1 */
+                const uint32_t K = 0x01010101u;
+                const uint32_t c0 = w0 & K, c1 = (w0 >> 1) & K, c2 = (w0 >> 2) & K;
+                const uint32_t ok4 = (c0 & ~c1 & ~c2) | (c0 & c1) | (~c0 & ~c1 & c2);       /* A C G T by base&7 */
+                const uint32_t v4 = (w0 & 0x02020202u) | c2;
+                const int vb = ((b >> 1) & 1) * 2 + ((b >> 2) & 1);
+                const bool okb = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T');
+                if (ok4 == K && okb) atomicAdd(&km[((((v4 * 0x40100401u) >> 24) << 2) | vb) & 0x3FF], sign);
+            }
+        }
+    }
+}
+
+/* post-filter delta: block-private for clean rows, exact global path otherwise */
+__device__ __forceinline__ void post_delta(bool clean, const DeltaAcc& D, unsigned long long* G, int side, const uint8_t* seq, const uint8_t* qual,
+                                           int ctx0, int lo, int hi, int sign) {
+    if (hi <= lo) return;
+    if (clean) dev_stat_positions_smem(D, side, seq, qual, ctx0, lo, hi, sign);
+    else dev_stat_positions(G, side * 2 + 1, seq, qual, ctx0, lo, hi, sign);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -707,7 +978,7 @@ __device__ __noinline__ void dev_stat_positions(unsigned long long* G, int stats
  * ------------------------------------------------------------------------------------------------ */
 struct fp_smem_layout {
     int off_mbar, off_tile, tile_array_bytes, off_len, off_clean, off_rc, rc_bytes, off_scratch, scratch_ints,
-        off_kmer, off_qhist, off_bc, off_rl, total;
+        off_kmer, off_qhist, off_bc, off_rl, off_next, off_planes, off_rcplanes, off_lut, off_delta, plane_words, total;
 };
 
 struct fp_launch_args {
@@ -744,7 +1015,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
  * The fused kernel.
  * ------------------------------------------------------------------------------------------------ */
 template <bool PAIRED>
-__global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch_args a) {
+__global__ void __launch_bounds__(FP_THREADS, 1) fp_chain_kernel(const fp_launch_args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int SIDES = PAIRED ? 2 : 1;
     const fp_smem_layout& sl = a.sl;
@@ -766,13 +1037,24 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
     unsigned int* s_kmer = reinterpret_cast<unsigned int*>(smem + sl.off_kmer);    /* [SIDES][1024] */
     unsigned int* s_qhist = reinterpret_cast<unsigned int*>(smem + sl.off_qhist);  /* [SIDES][128]  */
     BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem + sl.off_bc);
-    unsigned long long* s_rl = reinterpret_cast<unsigned long long*>(smem + sl.off_rl);   /* [4][2] reads, lengthSum */
+    DeltaAcc D;
+    D.cycles = S;
+    D.cyc = reinterpret_cast<int*>(smem + sl.off_delta);                                   /* [SIDES][S][5][4] */
+    D.kmer = D.cyc + SIDES * S * 20;                                                       /* [SIDES][1024]    */
+    D.qh = D.kmer + SIDES * FP_KMER_BINS;                                                  /* [SIDES][128]     */
+    int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);                        /* [3][S+2]: ovlimit, lowq, mindiff */
+    int* s_next = reinterpret_cast<int*>(smem + sl.off_next);                              /* dynamic row claim of phase 2 */
+    const int PW = sl.plane_words;
+    uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T][4][PW] */
+    uint32_t* my_rcp = reinterpret_cast<uint32_t*>(smem + sl.off_rcplanes) + warp * (3 * PW);
+    Planes PRC = {my_rcp, my_rcp + PW, my_rcp + 2 * PW, nullptr};
 
     /* zero block-level accumulators */
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
     for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) s_qhist[i] = 0;
+    for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
     for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
-    if (tid < 8) s_rl[tid] = 0;
+    for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership */
@@ -790,6 +1072,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
             #pragma unroll
             for (int k = 0; k < 4; k++) acc.v[c][b][k] = 0;
 
+    unsigned long long rl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* per-warp (uniform) reads / lengthSum of pre1 post1 pre2 post2 */
     __syncthreads();
     uint32_t parity = 0;
 
@@ -798,6 +1081,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
         const int rows = (int)min((long long)T, a.b.n - row0);
         /* ---------------- phase 0: TMA bulk loads ---------------- */
         if (tid == 0) {
+            *s_next = 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const uint32_t bytes = (uint32_t)rows * (uint32_t)S;
             mbar_expect_tx(mbar, bytes * 2 * SIDES);
@@ -818,25 +1102,30 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
         parity ^= 1;
         __syncthreads();
 
-        /* ---------------- phase 0.5: validate rows (clean = only A,C,G,T,N and quals < 128) ---------------- */
-        for (int i = warp; i < SIDES * T; i += FP_WARPS) {
-            int sd = i / T, r = i % T;
-            const int ln = s_len[i];
-            const uint8_t* sq = tile_seq[sd] + r * S; const uint8_t* ql = tile_qual[sd] + r * S;
-            bool bad = false;
-            for (int k = lane * 4; k < ln; k += 128) {
-                uint32_t x = *reinterpret_cast<const uint32_t*>(sq + k);
-                uint32_t q = *reinterpret_cast<const uint32_t*>(ql + k);
-                uint32_t wm = window_mask(k, 0, ln);
-                uint32_t okA = ~nz_bytes(x ^ 0x41414141u), okC = ~nz_bytes(x ^ 0x43434343u), okG = ~nz_bytes(x ^ 0x47474747u),
-                         okT = ~nz_bytes(x ^ 0x54545454u), okN = ~nz_bytes(x ^ 0x4E4E4E4Eu);
-                uint32_t ok = (okA | okC | okG | okT | okN) & 0x80808080u;
-                uint32_t need = wm & 0x80808080u;
-                if ((ok & need) != need) bad = true;
-                if (q & wm & 0x80808080u) bad = true;
+        /* ---------------- phase 0.5: bit planes of every row + validation (clean = only A,C,G,T,N, quals < 128) ---------------- */
+        for (int i = tid; i < SIDES * T; i += FP_THREADS) s_clean[i] = 1;
+        __syncthreads();
+        {
+            const int nwords = (S + 31) >> 5;                     /* plane words holding bases; the rest of PW is zero padding */
+            const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
+            for (int it = tid; it < SIDES * T * PW; it += FP_THREADS) {
+                const int j = it % PW, rr = (it / PW) % T, sd = it / (PW * T);
+                uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
+                if (j < nwords && rr < rows) {
+                    const int ln = s_len[sd * T + rr];
+                    const int n = ln - 32 * j;
+                    if (n > 0) {
+                        const uint4* sp = reinterpret_cast<const uint4*>(tile_seq[sd] + rr * S + 32 * j);
+                        const uint4* qp = reinterpret_cast<const uint4*>(tile_qual[sd] + rr * S + 32 * j);
+                        const uint4 s0 = sp[0], s1 = sp[1], q0 = qp[0], q1 = qp[1];
+                        const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr] = 0;
+                    }
+                }
+                uint32_t* pr = tile_planes + ((sd * T + rr) * 4) * PW + j;
+                pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
             }
-            bad = __any_sync(FULL_MASK, bad);
-            if (lane == 0) s_clean[i] = bad ? 0 : 1;
         }
         __syncthreads();
 
@@ -891,25 +1180,32 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
         }
         __syncthreads();
 
-        /* ---------------- phase 2: per-read operator chain, one warp per read / pair ---------------- */
-        for (int r = warp; r < rows; r += FP_WARPS) {
+        /* ---------------- phase 2: per-read operator chain, one warp per read / pair (dynamic claim) ---------------- */
+        for (;;) {
+            int r = 0;
+            if (lane == 0) r = atomicAdd(s_next, 1);
+            r = __shfl_sync(FULL_MASK, r, 0);
+            if (r >= rows) break;
             const long long gi = row0 + r;
             if (!PAIRED) {
                 /* SingleEndProcessor::processSingleEnd loop body  seprocessor.cpp:204-296 */
                 uint8_t* rs = tile_seq[0] + r * S; uint8_t* rq = tile_qual[0] + r * S;
                 const int len0 = s_len[r];
                 const bool clean = s_clean[r];
-                if (lane == 0) { atomicAdd(&s_rl[0], 1ull); atomicAdd(&s_rl[1], (unsigned long long)len0); }
+                rl[0] += 1; rl[1] += len0;
                 if (!clean) dev_stat_positions(G, FP_STATS_PRE1, rs, rq, 0, 0, len0, +1);
                 WRead r1 = {rs, rq, len0, 0, false};
                 int flags = 0, apos = 0, abases = 0, pbase = 255, plen = 0;
                 dev_trim_and_cut(r1, c_p.trim_front1, c_p.trim_tail1, my_scratch);               /* :235 */
                 if (!r1.null && c_p.polyg) { if (dev_trim_polyg(r1, c_p.polyg_min)) flags |= FP_F_POLYG_TRIMMED; }   /* :237-240 */
+                const bool usep = clean && !r1.null;
+                uint32_t* pr1 = tile_planes + (r * 4) * PW;
+                Planes P1 = {pr1, pr1 + PW, pr1 + 2 * PW, pr1 + 3 * PW};
                 bool dimer = false;
                 if (!r1.null && c_p.adapter_enabled) {                                            /* :243-260 */
                     bool trimmed = false;
-                    if (c_p.has_r1) trimmed = dev_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, my_scratch, apos, abases, bc);
-                    if (c_p.n_fasta > 0) trimmed |= dev_trim_by_multi(r1, my_scratch, apos, abases, bc);
+                    if (c_p.has_r1) trimmed = dev_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, my_scratch, apos, abases, bc, 0, usep ? &P1 : nullptr);
+                    if (c_p.n_fasta > 0) trimmed |= dev_trim_by_multi(r1, my_scratch, apos, abases, bc, usep ? &P1 : nullptr);
                     if (trimmed) { if (lane == 0) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags |= FP_F_ADAPTER_TRIMMED; }
                     if (trimmed && r1.len <= c_p.dimer_max_len) dimer = true;
                 }
@@ -920,19 +1216,19 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                     }
                 }
                 if (!r1.null && c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;   /* :268-271 */
-                int result = dev_pass_filter(r1);                                                 /* :273 */
+                int result = usep ? dev_pass_filter_planes(r1.qual, r1.len, r1.null, P1, r1.front, PW, s_lut) : dev_pass_filter(r1, s_lut);   /* :273 */
                 if (dimer) { result = FP_FAIL_ADAPTER_DIMER; flags |= FP_F_ADAPTER_DIMER; }
                 if (lane == 0) atomicAdd(&bc->fr[FP_FR_READSTATS + result], 1u);                   /* :278 */
                 const bool counted = !r1.null && result == FP_PASS_FILTER;                        /* :281-286 */
                 /* post stats as a delta against pre */
                 if (counted) {
-                    if (lane == 0) { atomicAdd(&s_rl[2], 1ull); atomicAdd(&s_rl[3], (unsigned long long)r1.len); }
-                    if (r1.front == 0 && clean) { if (r1.len < len0) dev_stat_positions(G, FP_STATS_POST1, rs, rq, 0, r1.len, len0, -1); }
+                    rl[2] += 1; rl[3] += r1.len;
+                    if (r1.front == 0 && clean) post_delta(true, D, G, 0, rs, rq, 0, r1.len, len0, -1);
                     else {
-                        if (clean) dev_stat_positions(G, FP_STATS_POST1, rs, rq, 0, 0, len0, -1);
-                        dev_stat_positions(G, FP_STATS_POST1, rs, rq, r1.front, r1.front, r1.front + r1.len, +1);
+                        if (clean) post_delta(true, D, G, 0, rs, rq, 0, 0, len0, -1);
+                        post_delta(clean, D, G, 0, rs, rq, r1.front, r1.front, r1.front + r1.len, +1);
                     }
-                } else if (clean) dev_stat_positions(G, FP_STATS_POST1, rs, rq, 0, 0, len0, -1);
+                } else if (clean) post_delta(true, D, G, 0, rs, rq, 0, 0, len0, -1);
                 if (lane == 0) a.out1[gi] = make_result(r1, result, result, flags, apos, abases, pbase, plen);
             } else {
                 /* PairEndProcessor::processPairEnd loop body  peprocessor.cpp:383-643 */
@@ -940,10 +1236,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                 uint8_t* rs2 = tile_seq[1] + r * S; uint8_t* rq2 = tile_qual[1] + r * S;
                 const int l1 = s_len[r], l2 = s_len[T + r];
                 const bool clean1 = s_clean[r], clean2 = s_clean[T + r];
-                if (lane == 0) {
-                    atomicAdd(&s_rl[0], 1ull); atomicAdd(&s_rl[1], (unsigned long long)l1);
-                    atomicAdd(&s_rl[4], 1ull); atomicAdd(&s_rl[5], (unsigned long long)l2);
-                }
+                rl[0] += 1; rl[1] += l1; rl[4] += 1; rl[5] += l2;
                 if (!clean1) dev_stat_positions(G, FP_STATS_PRE1, rs1, rq1, 0, 0, l1, +1);
                 if (!clean2) dev_stat_positions(G, FP_STATS_PRE2, rs2, rq2, 0, 0, l2, +1);
                 WRead r1 = {rs1, rq1, l1, 0, false}, r2 = {rs2, rq2, l2, 0, false};
@@ -955,11 +1248,14 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                     if (dev_trim_polyg(r1, c_p.polyg_min)) flags1 |= FP_F_POLYG_TRIMMED;
                     if (dev_trim_polyg(r2, c_p.polyg_min)) flags2 |= FP_F_POLYG_TRIMMED;
                 }
+                const bool usep1 = clean1 && !r1.null, usep2 = clean2 && !r2.null;
+                uint32_t* pr1 = tile_planes + (r * 4) * PW; uint32_t* pr2 = tile_planes + ((T + r) * 4) * PW;
+                Planes P1 = {pr1, pr1 + PW, pr1 + 2 * PW, pr1 + 3 * PW}, P2 = {pr2, pr2 + PW, pr2 + 2 * PW, pr2 + 3 * PW};
                 bool dimer = false;
                 bool removed1 = false, removed2 = false;      /* whole read already subtracted from post (before correction) */
                 fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
                 if (both && (c_p.adapter_enabled || c_p.correction || c_p.thread0)) {             /* :438-441 */
-                    ov = dev_analyze(r1, r2, my_rc);
+                    ov = (usep1 && usep2) ? dev_analyze_planes(r1.len, r1.front, r2.len, r2.front, P1, P2, PRC, PW, s_lut) : dev_analyze(r1, r2, my_rc, s_lut);
                     if (c_p.thread0) {                                                            /* statInsertSize :449-452 / :497-504, :710-723 */
                         int isize = c_p.isize_max;
                         if (ov.overlapped) {
@@ -969,7 +1265,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                         if (isize > c_p.isize_max) isize = c_p.isize_max;
                         if (lane == 0) {
                             if (c_p.isize_max < FP_MAX_ISIZE_SMEM) atomicAdd(&bc->isize[isize], 1u);
-                            else atomicAdd(&G[L.off_isize + isize], 1ull);
+                            else red_add64(&G[L.off_isize + isize], 1ull);
                         }
                     }
                 }
@@ -977,15 +1273,15 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                     if (c_p.correction && ov.overlapped && ov.diff != 0) {                        /* :453-456 */
                         /* the post stats are kept as a delta against the ORIGINAL bases: take the two reads out
                            before any base is overwritten; they are re-added below if the pair passes */
-                        if (clean1) dev_stat_positions(G, FP_STATS_POST1, rs1, rq1, 0, 0, l1, -1);
-                        if (clean2) dev_stat_positions(G, FP_STATS_POST2, rs2, rq2, 0, 0, l2, -1);
+                        if (clean1) post_delta(true, D, G, 0, rs1, rq1, 0, 0, l1, -1);
+                        if (clean2) post_delta(true, D, G, 1, rs2, rq2, 0, 0, l2, -1);
                         removed1 = removed2 = true;
                         __syncwarp();
                         bool c1, c2;
                         dev_correct(r1, r2, ov, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
                                     a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, c1, c2);
-                        if (c1) flags1 |= FP_F_CORRECTED;
-                        if (c2) flags2 |= FP_F_CORRECTED;
+                        if (c1) { flags1 |= FP_F_CORRECTED; if (usep1) dev_rebuild_planes(rs1, rq1, l1, PW, P1); }
+                        if (c2) { flags2 |= FP_F_CORRECTED; if (usep2) dev_rebuild_planes(rs2, rq2, l2, PW, P2); }
                     }
                     if (c_p.adapter_enabled) {                                                    /* :457-485 */
                         bool trimmed = false;
@@ -1000,12 +1296,12 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                         }
                         bool t1 = trimmed, t2 = trimmed;
                         if (!trimmed) {                                                           /* :461-466 */
-                            if (c_p.has_r1) t1 = dev_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, my_scratch, apos1, ab1, bc);
-                            if (c_p.has_r2) t2 = dev_trim_by_sequence(r2, c_p.adapters + c_p.adapter_r2_off, c_p.adapter_r2_len, 4, my_scratch, apos2, ab2, bc);
+                            if (c_p.has_r1) t1 = dev_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, my_scratch, apos1, ab1, bc, 0, usep1 ? &P1 : nullptr);
+                            if (c_p.has_r2) t2 = dev_trim_by_sequence(r2, c_p.adapters + c_p.adapter_r2_off, c_p.adapter_r2_len, 4, my_scratch, apos2, ab2, bc, 1, usep2 ? &P2 : nullptr);
                         }
                         if (c_p.n_fasta > 0) {                                                    /* :467-470 */
-                            t1 |= dev_trim_by_multi(r1, my_scratch, apos1, ab1, bc);
-                            t2 |= dev_trim_by_multi(r2, my_scratch, apos2, ab2, bc);
+                            t1 |= dev_trim_by_multi(r1, my_scratch, apos1, ab1, bc, usep1 ? &P1 : nullptr);
+                            t2 |= dev_trim_by_multi(r2, my_scratch, apos2, ab2, bc, usep2 ? &P2 : nullptr);
                         }
                         if (t1) { if (lane == 0) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags1 |= FP_F_ADAPTER_TRIMMED; }   /* :472-475 */
                         if (t2) { if (lane == 0) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags2 |= FP_F_ADAPTER_TRIMMED; }
@@ -1026,15 +1322,13 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                     if (c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;
                     if (c_p.max_len2 > 0 && c_p.max_len2 < r2.len) r2.len = c_p.max_len2;
                 }
-                int res1 = dev_pass_filter(r1), res2 = dev_pass_filter(r2);                       /* :565-566 */
+                int res1 = usep1 ? dev_pass_filter_planes(r1.qual, r1.len, r1.null, P1, r1.front, PW, s_lut) : dev_pass_filter(r1, s_lut);   /* :565-566 */
+                int res2 = usep2 ? dev_pass_filter_planes(r2.qual, r2.len, r2.null, P2, r2.front, PW, s_lut) : dev_pass_filter(r2, s_lut);
                 if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
                 const int pv = max(res1, res2);
                 if (lane == 0) atomicAdd(&bc->fr[FP_FR_READSTATS + pv], 2u);                       /* :573 */
                 const bool counted = !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER;   /* :577-591 */
-                if (counted && lane == 0) {
-                    atomicAdd(&s_rl[2], 1ull); atomicAdd(&s_rl[3], (unsigned long long)r1.len);
-                    atomicAdd(&s_rl[6], 1ull); atomicAdd(&s_rl[7], (unsigned long long)r2.len);
-                }
+                if (counted) { rl[2] += 1; rl[3] += r1.len; rl[6] += 1; rl[7] += r2.len; }
                 /* post stats as a delta against pre (per side) */
                 #pragma unroll
                 for (int sd = 0; sd < 2; sd++) {
@@ -1042,14 +1336,13 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                     uint8_t* rs = sd ? rs2 : rs1; uint8_t* rq = sd ? rq2 : rq1;
                     const int l0 = sd ? l2 : l1;
                     const bool clean = sd ? clean2 : clean1, removed = sd ? removed2 : removed1;
-                    const int st = sd ? FP_STATS_POST2 : FP_STATS_POST1;
                     if (counted) {
-                        if (rr.front == 0 && clean && !removed) { if (rr.len < l0) dev_stat_positions(G, st, rs, rq, 0, rr.len, l0, -1); }
+                        if (rr.front == 0 && clean && !removed) post_delta(true, D, G, sd, rs, rq, 0, rr.len, l0, -1);
                         else {
-                            if (clean && !removed) dev_stat_positions(G, st, rs, rq, 0, 0, l0, -1);
-                            dev_stat_positions(G, st, rs, rq, rr.front, rr.front, rr.front + rr.len, +1);
+                            if (clean && !removed) post_delta(true, D, G, sd, rs, rq, 0, 0, l0, -1);
+                            post_delta(clean, D, G, sd, rs, rq, rr.front, rr.front, rr.front + rr.len, +1);
                         }
-                    } else if (clean && !removed) dev_stat_positions(G, st, rs, rq, 0, 0, l0, -1);
+                    } else if (clean && !removed) post_delta(true, D, G, sd, rs, rq, 0, 0, l0, -1);
                 }
                 if (lane == 0) {
                     a.out1[gi] = make_result(r1, res1, pv, flags1, apos1, ab1, pb1, pl1);
@@ -1076,30 +1369,42 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch
                 #pragma unroll
                 for (int pp = 0; pp < 2; pp++) {       /* dense pass feeds pre AND post (post gets deltas on top) */
                     const int st = my_side * 2 + pp;
-                    if (n30) atomicAdd(&G[fp_off_cycle(&L, st, 0 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n30);
-                    if (n20) atomicAdd(&G[fp_off_cycle(&L, st, 1 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n20);
-                    atomicAdd(&G[fp_off_cycle(&L, st, 2 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n);
-                    atomicAdd(&G[fp_off_cycle(&L, st, 3 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)qs);
+                    if (n30) red_add64(&G[fp_off_cycle(&L, st, 0 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n30);
+                    if (n20) red_add64(&G[fp_off_cycle(&L, st, 1 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n20);
+                    red_add64(&G[fp_off_cycle(&L, st, 2 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n);
+                    red_add64(&G[fp_off_cycle(&L, st, 3 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)qs);
                 }
             }
         }
     }
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) {
         unsigned int v = s_kmer[i];
-        if (v) { int sd = i / FP_KMER_BINS, k = i % FP_KMER_BINS; atomicAdd(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); atomicAdd(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
+        if (v) { int sd = i / FP_KMER_BINS, k = i % FP_KMER_BINS; red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) {
         unsigned int v = s_qhist[i];
-        if (v) { int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; atomicAdd(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); atomicAdd(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
+        if (v) { int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
-    for (int i = tid; i < FP_FR_WORDS; i += FP_THREADS) { unsigned int v = bc->fr[i]; if (v) atomicAdd(&G[L.off_filter + i], (unsigned long long)v); }
+    {   /* block-private post-filter deltas -> POST stats of each side */
+        const int BIN_SLOT[NB] = {1, 3, 4, 6, 7};
+        for (int i = tid; i < SIDES * S * 20; i += FP_THREADS) {
+            const int v = D.cyc[i];
+            if (v == 0) continue;
+            const int sd = i / (S * 20), rem = i % (S * 20), cyc = rem / 20, bin = (rem % 20) / 4, kind = rem & 3;
+            if (cyc >= L.cycles) continue;
+            const int gk = kind == 0 ? 2 : kind == 1 ? 1 : kind == 2 ? 0 : 3;       /* count->content, q20, q30, qualsum */
+            red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
+        }
+        for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, i % FP_KMER_BINS)], (unsigned long long)(long long)v); }
+        for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
+    }
+    for (int i = tid; i < FP_FR_WORDS; i += FP_THREADS) { unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
     if (c_p.isize_max < FP_MAX_ISIZE_SMEM)
-        for (int i = tid; i <= c_p.isize_max; i += FP_THREADS) { unsigned int v = bc->isize[i]; if (v) atomicAdd(&G[L.off_isize + i], (unsigned long long)v); }
-    if (tid < 2 * L.n_stats) {
-        /* s_rl index: stats s -> [2s] reads, [2s+1] lengthSum with s order pre1, post1, pre2, post2 */
-        unsigned long long v = s_rl[tid];
-        int st = tid >> 1;
-        if (v) atomicAdd(&G[(tid & 1) ? fp_off_length_sum(&L, st) : fp_off_reads(&L, st)], v);
+        for (int i = tid; i <= c_p.isize_max; i += FP_THREADS) { unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
+    if (lane == 0) {
+        #pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < 2 * L.n_stats && rl[k]) red_add64(&G[(k & 1) ? fp_off_length_sum(&L, k >> 1) : fp_off_reads(&L, k >> 1)], rl[k]);
     }
 }
 
