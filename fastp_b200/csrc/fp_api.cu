@@ -18,6 +18,7 @@
 
 #include "fastp_b200.h"
 #include "fp_device.cuh"
+#include "fp_chain2.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
@@ -98,14 +99,9 @@ static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov,
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void make_smem_layout(fp_ctx* c) {
+static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     const int sides = c->p.paired ? 2 : 1;
     const int S = c->stride;
-    int T = (int)((48 * 1024) / (size_t)(sides * 2 * S));
-    T = std::min(T, 64 * (3 - sides));
-    T = std::max(T / 8 * 8, 8);
-    c->tile = T;
-    fp_smem_layout& sl = c->sl;
     size_t off = 0;
     sl.off_mbar = (int)off; off += 16;
     off = align_up(off, 128);
@@ -116,7 +112,11 @@ static void make_smem_layout(fp_ctx* c) {
     off = align_up(off, 16);
     sl.rc_bytes = (int)align_up(S + 16, 16);
     sl.off_rc = (int)off; off += (size_t)FP_WARPS * sl.rc_bytes;
-    sl.scratch_ints = std::max(S + 2, 2 * (FP_MAX_ADAPTER_LEN + 2));
+    /* per-warp int scratch: prefix sums of quals (only when a sliding-window cut is on, filter.cpp:97-194) and the
+       two arrays of the one-gap adapter scans (only when adapters are trimmed by sequence, adaptertrimmer.cpp:105-135) */
+    const bool need_cut = c->p.cut_front || c->p.cut_tail || c->p.cut_right;
+    const bool need_gap = c->p.adapter_enabled && (c->p.has_seq_r1 || c->p.has_seq_r2 || c->p.n_fasta_adapters > 0);
+    sl.scratch_ints = std::max(need_cut ? S + 2 : 4, need_gap ? 2 * (FP_MAX_ADAPTER_LEN + 2) : 4);
     sl.off_scratch = (int)off; off += (size_t)FP_WARPS * sl.scratch_ints * 4;
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
     sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
@@ -126,11 +126,23 @@ static void make_smem_layout(fp_ctx* c) {
     sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
     sl.off_delta = (int)off; off += (size_t)sides * ((size_t)S * 20 + FP_KMER_BINS + FP_QUAL_BINS) * 4;
     sl.off_next = (int)off; off += 16;
-    sl.plane_words = S / 32 + 3;
+    sl.plane_words = (S + 31) / 32 + 2;
+    sl.plane_stride = (4 * sl.plane_words) | 1;                      /* odd: one thread per row without bank conflicts */
     off = align_up(off, 16);
-    sl.off_planes = (int)off; off += (size_t)sides * T * 4 * sl.plane_words * 4;
-    sl.off_rcplanes = (int)off; off += (size_t)FP_WARPS * 3 * sl.plane_words * 4;
+    sl.off_planes = (int)off; off += (size_t)sides * T * sl.plane_stride * 4;
+    sl.off_rcplanes = (int)off;
     sl.total = (int)align_up(off, 128);
+    return (size_t)sl.total;
+}
+
+/* tile size: as large as possible (<= 64 pairs / 128 reads) while TWO CTAs still fit one SM's shared memory */
+static void make_smem_layout(fp_ctx* c) {
+    const int sides = c->p.paired ? 2 : 1;
+    const size_t budget = (227 * 1024 - 2 * 1024) / 2;
+    int T = 64 * (3 - sides);
+    while (T > 16 && smem_layout_for_tile(c, T, c->sl) > budget) T -= 8;
+    c->tile = T;
+    smem_layout_for_tile(c, T, c->sl);
 }
 
 extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles, fp_ctx** out) {
@@ -139,7 +151,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     if (cycles <= 0) cycles = stride;
     if (p->allow_gap_overlap_trimming) return set_err(FP_E_UNSUPPORTED, "allow_gap_overlap_trimming is not implemented on the device path");
     if (p->insert_size_max < 0 || p->insert_size_max > (1 << 20)) return set_err(FP_E_INVAL, "insert_size_max out of range");
-    if ((p->paired ? 2 : 1) * (stride / 4) > FP_THREADS) return set_err(FP_E_INVAL, "stride too large for the column pass");
+    if ((p->paired ? 2 : 1) * (stride / 2) > FP_THREADS) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
     if (p->cut_front_window < 1 || p->cut_tail_window < 1 || p->cut_right_window < 1) return set_err(FP_E_INVAL, "cut window must be >= 1");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -239,11 +251,11 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     /* kernel attributes + persistent grid size */
     int occ = 0;
     if (p->paired) {
-        CK(cudaFuncSetAttribute(fp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain_kernel<true>, FP_THREADS, c->sl.total));
+        CK(cudaFuncSetAttribute(fp_chain2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<true>, FP_THREADS, c->sl.total));
     } else {
-        CK(cudaFuncSetAttribute(fp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain_kernel<false>, FP_THREADS, c->sl.total));
+        CK(cudaFuncSetAttribute(fp_chain2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<false>, FP_THREADS, c->sl.total));
     }
     if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
     c->grid_max = occ * c->num_sms;
@@ -317,8 +329,8 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
     if (c->evs.size() > 4096) { int rc = drain_events(c); if (rc) return rc; }
     CK(cudaEventRecord(ev.a, st));
-    if (c->p.paired) fp_chain_kernel<true><<<grid, FP_THREADS, c->sl.total, st>>>(a);
-    else fp_chain_kernel<false><<<grid, FP_THREADS, c->sl.total, st>>>(a);
+    if (c->p.paired) fp_chain2_kernel<true><<<grid, FP_THREADS, c->sl.total, st>>>(a);
+    else fp_chain2_kernel<false><<<grid, FP_THREADS, c->sl.total, st>>>(a);
     CK(cudaEventRecord(ev.b, st));
     c->evs.push_back(ev);
     CK(cudaGetLastError());

@@ -1,0 +1,924 @@
+/*
+ * fp_chain2.cuh -- second-generation fused kernel (fp_chain2_kernel).
+ *
+ * Same tile pipeline as before (TMA bulk loads -> bit planes + validation -> dense column pass), but
+ *   * the dense pass gives each thread TWO cycles (half a word column) so only 40 accumulator registers stay
+ *     live across the persistent loop, and
+ *   * the operator chain runs ONE THREAD PER READ / PAIR on the bit planes: with lo/hi/N/low-quality planes a
+ *     150-base read is 5 words, so overlap analysis, adapter scans, the pass/fail filter and base correction are
+ *     a few word operations per candidate and a warp handles 32 pairs at once instead of one.  Byte-level work
+ *     that is genuinely per base (post-filter statistics of removed / re-added bases) stays warp-cooperative:
+ *     lanes flag what they need and the warp walks the flagged lanes.
+ * Rows holding bytes outside {A,C,G,T,N} use scalar byte-exact twins of every operator.
+ * Reference semantics are cited per operator (file:line under /root/reference/src), as in fp_device.cuh.
+ */
+#pragma once
+#include "fp_device.cuh"
+
+/* thread-level view of one read: row pointers (smem), plane pointers, current window */
+struct TRead {
+    uint8_t* seq;          /* row start in the shared-memory tile */
+    uint8_t* qual;
+    const uint32_t* pl;    /* planes of the row: lo = pl, hi = pl+PW, nn = pl+2PW, lq = pl+3PW */
+    int front, len;
+    bool null, clean;
+};
+
+__device__ __forceinline__ uint32_t tp_bits(const uint32_t* P, int bit) {      /* 32 bits of a plane starting at `bit` */
+    const int w = bit >> 5;
+    return __funnelshift_r(P[w], P[w + 1], bit & 31);
+}
+
+/* A read / pair is served by a GROUP of g adjacent lanes (g = 4 for PE, 2 for SE): all lanes run the scalar operators
+ * redundantly (same shared-memory addresses -> broadcasts), the long candidate scans (overlap offsets, adapter
+ * positions) are split round-robin over the g lanes and combined with group_min, and every side effect (atomics,
+ * stores) is done by the group's lane 0 only. */
+__device__ __forceinline__ unsigned group_mask(int g) { return (g >= 32 ? 0xffffffffu : ((1u << g) - 1u)) << (lane_id() & ~(g - 1)); }
+__device__ __forceinline__ int group_min(int v, int g) {
+    const unsigned gm = group_mask(g);          /* only the group's lanes take part: groups of one warp may diverge */
+    for (int o = g >> 1; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(gm, v, o));
+    return v;
+}
+/* value of `v` held by the lane of my group for which `mine` is true (exactly one lane, or none -> returns own v) */
+__device__ __forceinline__ int group_pick(int v, bool mine, int g) {
+    const unsigned gm = group_mask(g);
+    const unsigned b = __ballot_sync(gm, mine);
+    const int src = b ? __ffs(b) - 1 : lane_id();
+    return __shfl_sync(gm, v, src);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Filter::trimAndCut  (filter.cpp:68-207), scalar per thread.  Returns false for NULL.
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut) {
+    frontOut = 0; lenOut = l0;
+    const bool anycut = c_p.cut_front || c_p.cut_tail || c_p.cut_right;
+    if (front == 0 && tail == 0 && !anycut) return true;                  /* :71-72 */
+    int rlen = l0 - front - tail;                                         /* :75 */
+    if (rlen < 0) return false;
+    if (!anycut) { frontOut = front; lenOut = rlen; return true; }        /* :79-89 (front==0: resize only) */
+    const int l = l0;
+    const signed char* q = reinterpret_cast<const signed char*>(qualu);
+    if (c_p.cut_front) {                                                  /* :97-127 */
+        const int w = c_p.cf_w;
+        int s = front;
+        if (l - front - tail - w <= 0) return false;
+        int total = 0;
+        for (int i = 0; i < w - 1; i++) total += q[s + i];
+        for (s = front; s + w < l - tail; s++) {
+            total += q[s + w - 1];
+            if (s > front) total -= q[s - 1];
+            if (total >= c_p.cf_thr) break;
+        }
+        if (s > 0) s = s + w - 1;
+        while (s < l && seq[s] == 'N') s++;
+        front = s;
+        rlen = l - front - tail;
+    }
+    if (c_p.cut_right) {                                                  /* :130-163 */
+        const int w = c_p.cr_w;
+        int s = front;
+        if (l - front - tail - w <= 0) return false;
+        int total = 0;
+        for (int i = 0; i < w - 1; i++) total += q[s + i];
+        bool found = false;
+        for (s = front; s + w < l - tail; s++) {
+            total += q[s + w - 1];
+            if (s > front) total -= q[s - 1];
+            if (total < c_p.cr_thr) { found = true; break; }
+        }
+        if (found) {
+            while (s < l - 1 && q[s] >= c_p.cr_q) s++;
+            rlen = s - front;
+        }
+    }
+    if (!c_p.cut_right && c_p.cut_tail) {                                 /* :166-194 */
+        const int w = c_p.ct_w;
+        if (l - front - tail - w <= 0) return false;
+        int total = 0;
+        int t = l - tail - 1;
+        for (int i = 0; i < w - 1; i++) total += q[t - i];
+        for (t = l - tail - 1; t - w >= front; t--) {
+            total += q[t - w + 1];
+            if (t < l - tail - 1) total -= q[t + 1];
+            if (total >= c_p.ct_thr) break;
+        }
+        if (t < l - 1) t = t - w + 1;
+        while (t >= 0 && seq[t] == 'N') t--;
+        rlen = t - front + 1;
+    }
+    if (rlen <= 0 || front >= l - 1) return false;                        /* :196-197 */
+    frontOut = front; lenOut = rlen;
+    return true;
+}
+
+/* PolyX::trimPolyG  (polyx.cpp:16-42): returns the new length */
+__device__ __noinline__ int t_trim_polyg(const uint8_t* data, int rlen, int minLen) {
+    int mismatch = 0, i = 0, firstGPos = rlen - 1;
+    for (i = 0; i < rlen; i++) {
+        if (data[rlen - i - 1] != 'G') mismatch++; else firstGPos = rlen - i - 1;
+        const int allowed = (i + 1) / 8;
+        if (mismatch > 5 || (mismatch > allowed && i >= minLen - 1)) break;
+    }
+    if (i >= minLen && firstGPos >= 0 && firstGPos <= rlen) return firstGPos;
+    return rlen;
+}
+
+/* PolyX::trimPolyX  (polyx.cpp:49-116): returns true if addPolyXTrimmed is called */
+__device__ __noinline__ bool t_trim_polyx(const uint8_t* data, int rlen, int minLen, int& newLen, int& polyOut, int& nOut) {
+    int a = 0, t = 0, c = 0, g = 0, pos = 0;
+    for (pos = 0; pos < rlen; pos++) {
+        const uint8_t ch = data[rlen - pos - 1];
+        const int n = (ch == 'N');
+        a += (ch == 'A') | n; t += (ch == 'T') | n; c += (ch == 'C') | n; g += (ch == 'G') | n;
+        const int cmp = pos + 1;
+        const int allowed = min(5, cmp / 8);
+        const bool need = (cmp - a > allowed) && (cmp - t > allowed) && (cmp - c > allowed) && (cmp - g > allowed);
+        if (need && (pos >= 8 || pos + 1 >= minLen - 1)) break;
+    }
+    newLen = rlen;
+    if (pos + 1 >= minLen) {
+        int poly = 0, mx = a;
+        if (t > mx) { mx = t; poly = 1; }
+        if (c > mx) { mx = c; poly = 2; }
+        if (g > mx) { mx = g; poly = 3; }
+        const uint8_t pb = poly == 0 ? 'A' : poly == 1 ? 'T' : poly == 2 ? 'C' : 'G';
+        for (;;) {                                                        /* :107-108; data[-1] / data[rlen] never match */
+            const int idx = rlen - pos - 1;
+            const uint8_t ch = (idx < 0 || idx >= rlen) ? 0 : data[idx];
+            if (ch != pb && pos >= 0) pos--; else break;
+        }
+        const int nl = rlen - pos - 1;
+        if (nl >= 0 && nl <= rlen) newLen = nl;
+        polyOut = poly; nOut = pos + 1;
+        return true;
+    }
+    return false;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * OverlapAnalysis::analyze  (overlapanalysis.cpp:17-146) on bit planes, one thread per pair, no scratch.
+ * rc(r2)[k] = complement(row2[e-k]), e = front2+len2-1:  a 32-bit field of rc(r2) is the bit-reversal of a field
+ * of row2's planes (complement flips code bit 1, N stays N).
+ *   forward  offset o: r1[o+k] vs rc(r2)[k], k < pp  -> r1 field at a moving position vs two constant rc words
+ *   backward offset o: r1[k] vs rc(r2)[o+k]          -> equivalently comp(r1[pp-1-t]) vs row2[s+t], s = e-o-pp+1:
+ *                      the reversed-complemented r1 prefix Y is constant, row2's field moves (never negative).
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t tp_bits_z(const uint32_t* P, int s0) {   /* tp_bits with zeros below bit 0 */
+    if (s0 >= 0) return tp_bits(P, s0);
+    if (s0 > -32) return P[0] << (-s0);
+    return 0u;
+}
+__device__ __forceinline__ unsigned long long tp_bits64(const uint32_t* P, int bit) {
+    const int w = bit >> 5, sh = bit & 31;
+    const uint32_t lo = __funnelshift_r(P[w], P[w + 1], sh), hi = __funnelshift_r(P[w + 1], P[w + 2], sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long mask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
+
+__device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRead r2, int PW, const int16_t* lut, int sub, int g) {
+    const uint32_t *alo = r1.pl, *ahi = r1.pl + PW, *ann = r1.pl + 2 * PW;
+    const uint32_t *plo = r2.pl, *phi = r2.pl + PW, *pnn = r2.pl + 2 * PW;
+    const int len1 = r1.len, len2 = r2.len, f1 = r1.front;
+    const int e = r2.front + len2 - 1;
+    const int req = c_p.ov_require;
+    fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+    /* any N in either window? (lets the scans skip the N plane) */
+    uint32_t anyN = 0;
+    for (int k = 0; k * 32 < len1; k++) anyN |= tp_bits(ann, f1 + 32 * k) & low_mask(len1 - 32 * k);
+    for (int k = 0; k * 32 < len2; k++) anyN |= tp_bits(pnn, r2.front + 32 * k) & low_mask(len2 - 32 * k);
+    int found_dir = -1, found_o = 0, found_mm = 0, found_ol = 0;
+    /* ---- forward: offset 0 .. len1-req-1 (:48-65) ---- */
+    {
+        const unsigned long long bnn = ((unsigned long long)__brev(tp_bits_z(pnn, e - 63)) << 32) | __brev(tp_bits_z(pnn, e - 31));
+        const unsigned long long blo = ((unsigned long long)__brev(tp_bits_z(plo, e - 63)) << 32) | __brev(tp_bits_z(plo, e - 31));
+        const unsigned long long bhi = ~(((unsigned long long)__brev(tp_bits_z(phi, e - 63)) << 32) | __brev(tp_bits_z(phi, e - 31))) & ~bnn;
+        const int nfwd = len1 - req;
+        int my_o = 1 << 20, my_mm = 0, my_ol = 0;
+        for (int o = sub; o < nfwd; o += g) {
+            const int ol = min(len1 - o, len2);
+            const int pp = min(ol, 50);
+            const int bit = f1 + o;
+            unsigned long long x = (tp_bits64(alo, bit) ^ blo) | (tp_bits64(ahi, bit) ^ bhi);
+            if (anyN) x |= tp_bits64(ann, bit) ^ bnn;
+            const int mm = __popcll(x & mask64(pp));
+            if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+        }
+        const int best = group_min(my_o, g);                               /* first accepted offset in the reference's order */
+        if (best < (1 << 20)) {
+            found_dir = 0; found_o = best;
+            found_mm = group_pick(my_mm, my_o == best, g); found_ol = group_pick(my_ol, my_o == best, g);
+        }
+    }
+    /* ---- backward: offset 0 .. -(len2-req-1) (:73-89) ---- */
+    if (found_dir < 0) {
+        const unsigned long long a_nn = tp_bits64(ann, f1), a_lo = tp_bits64(alo, f1), a_hi = tp_bits64(ahi, f1);
+        /* Y50[t] = comp(r1[49-t]) : 64-bit reversal >> 14 */
+        const unsigned long long ynn = __brevll(a_nn) >> 14, ylo = __brevll(a_lo) >> 14, yhi = ~(__brevll(a_hi) >> 14) & ~ynn;
+        const int nbwd = len2 - req;
+        int my_o = 1 << 20, my_mm = 0, my_ol = 0;
+        for (int o = sub; o < nbwd; o += g) {
+            const int ol = min(len1, len2 - o);
+            const int pp = min(ol, 50);
+            const int sbit = e - o - pp + 1;                               /* >= front2 >= 0 */
+            const int ysh = 50 - pp;
+            unsigned long long x = (tp_bits64(plo, sbit) ^ (ylo >> ysh)) | (tp_bits64(phi, sbit) ^ (yhi >> ysh));
+            if (anyN) x |= tp_bits64(pnn, sbit) ^ (ynn >> ysh);
+            const int mm = __popcll(x & mask64(pp));
+            if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+        }
+        const int best = group_min(my_o, g);
+        if (best < (1 << 20)) {
+            found_dir = 1; found_o = best;
+            found_mm = group_pick(my_mm, my_o == best, g); found_ol = group_pick(my_ol, my_o == best, g);
+        }
+    }
+    if (found_dir >= 0) {
+        int diff = found_mm;
+        if (found_ol > 50) {                                               /* :41-43 full recount over the whole overlap */
+            diff = 0;
+            const int abit = f1 + (found_dir == 0 ? found_o : 0), bbit = found_dir == 0 ? 0 : found_o;
+            for (int k = 0; k * 32 < found_ol; k++) {
+                const int s0 = e - (bbit + 32 * k) - 31;
+                const uint32_t rn = __brev(tp_bits_z(pnn, s0));
+                const uint32_t rl_ = __brev(tp_bits_z(plo, s0)), rh = ~__brev(tp_bits_z(phi, s0)) & ~rn;
+                const uint32_t x = (tp_bits(alo, abit + 32 * k) ^ rl_) | (tp_bits(ahi, abit + 32 * k) ^ rh) | (tp_bits(ann, abit + 32 * k) ^ rn);
+                diff += __popc(x & low_mask(found_ol - 32 * k));
+            }
+        }
+        ov.overlapped = 1; ov.offset = (int16_t)(found_dir == 0 ? found_o : -found_o); ov.overlap_len = (int16_t)found_ol; ov.diff = (int16_t)diff;
+    }
+    return ov;
+}
+
+/* byte-exact twin for rows with bytes outside {A,C,G,T,N} */
+__device__ __noinline__ fp_ov_result t_analyze_bytes(const TRead r1, const TRead r2, const int16_t* lut) {
+    const uint8_t* s1 = r1.seq + r1.front; const uint8_t* s2 = r2.seq + r2.front;
+    const int len1 = r1.len, len2 = r2.len, req = c_p.ov_require;
+    fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+    for (int dir = 0; dir < 2; dir++) {
+        const int ncand = dir == 0 ? len1 - req : len2 - req;
+        for (int o = 0; o < ncand; o++) {
+            const int ol = dir == 0 ? min(len1 - o, len2) : min(len1, len2 - o);
+            const int limit = lut[ol], pp = min(ol, 50);
+            int mm = 0;
+            for (int k = 0; k < pp; k++) {
+                const uint8_t a = dir == 0 ? s1[o + k] : s1[k];
+                const uint8_t b = dev_complement(dir == 0 ? s2[len2 - 1 - k] : s2[len2 - 1 - o - k]);
+                mm += (a != b);
+            }
+            if (mm <= limit) {
+                int diff = mm;
+                if (ol > 50) {
+                    diff = 0;
+                    for (int k = 0; k < ol; k++) {
+                        const uint8_t a = dir == 0 ? s1[o + k] : s1[k];
+                        const uint8_t b = dev_complement(dir == 0 ? s2[len2 - 1 - k] : s2[len2 - 1 - o - k]);
+                        diff += (a != b);
+                    }
+                }
+                ov.overlapped = 1; ov.offset = (int16_t)(dir == 0 ? o : -o); ov.overlap_len = (int16_t)ol; ov.diff = (int16_t)diff;
+                return ov;
+            }
+        }
+    }
+    return ov;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * BaseCorrector::correctByOverlapAnalysis  (basecorrector.cpp:21-83), one thread per pair, scalar over the overlap.
+ * Writes the shared-memory rows, the HBM rows, the patch list and (for clean rows) updates the bit planes.
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void t_plane_set_base(uint32_t* pl, int PW, int pos, uint8_t base, uint8_t q) {
+    const int w = pos >> 5; const uint32_t m = 1u << (pos & 31);
+    const int c2 = (base >> 1) & 3; const bool n = (base == 'N');
+    pl[w] = (pl[w] & ~m) | ((!n && (c2 & 1)) ? m : 0u);
+    pl[PW + w] = (pl[PW + w] & ~m) | ((!n && (c2 & 2)) ? m : 0u);
+    pl[2 * PW + w] = (pl[2 * PW + w] & ~m) | (n ? m : 0u);
+    pl[3 * PW + w] = (pl[3 * PW + w] & ~m) | ((q < (uint8_t)c_p.qualified_qual) ? m : 0u);
+}
+
+__device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t* pl1, uint32_t* pl2, int PW, const fp_ov_result ov,
+                                       uint8_t* g1s, uint8_t* g1q, uint8_t* g2s, uint8_t* g2q, unsigned int pair_index, const PatchSink& sink,
+                                       BlockCounters* bc, bool& c1, bool& c2) {
+    c1 = c2 = false;
+    if (ov.diff == 0 || !ov.overlapped) return;                           /* :23-24 */
+    const int ol = ov.overlap_len;
+    const int start1 = max(0, (int)ov.offset);
+    const int start2 = r2.len - max(0, -(int)ov.offset) - 1;
+    uint8_t* s1 = r1.seq + r1.front; uint8_t* q1p = r1.qual + r1.front;
+    uint8_t* s2 = r2.seq + r2.front; uint8_t* q2p = r2.qual + r2.front;
+    const signed char GOOD = 33 + 30, BAD = 33 + 14;
+    int corrected = 0;
+    for (int i = 0; i < ol; i++) {
+        const int p1 = start1 + i, p2 = start2 - i;
+        const uint8_t b1 = s1[p1], b2 = s2[p2];
+        if (b1 != dev_complement(b2)) {
+            const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
+            if (q1 >= GOOD && q2 <= BAD) {                                 /* use R1 :42-50 */
+                const uint8_t nb = dev_complement(b1);
+                s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
+                if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
+                corrected++; c2 = true;
+                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);   /* diagonal only, SURVEY App. A.6 */
+                if (sink.count) {
+                    const unsigned int slot = atomicAdd(sink.count, 1u);
+                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                }
+            } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
+                const uint8_t nb = dev_complement(b2);
+                s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
+                if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
+                corrected++; c1 = true;
+                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
+                if (sink.count) {
+                    const unsigned int slot = atomicAdd(sink.count, 1u);
+                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                }
+            }
+        }
+    }
+    if (corrected > 0) atomicAdd(&bc->fr[FP_FR_CORRECTED_READS], (c1 && c2) ? 2u : 1u);   /* :75-80 */
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * AdapterTrimmer::trimBySequence  (adaptertrimmer.cpp:64-157), one thread per read.
+ * Scan 1 on planes (clean read + clean adapter) or bytes; scans 2/3 in the closed form of dev_gap_scan,
+ * evaluated sequentially (O(alen)).
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ int t_gap_scan(const uint8_t* ins, const uint8_t* norm, int cmax, int cmin) {
+    /* largest c in [cmin,cmax] with min_{1<=i<=c-1}(P1[i]-P2[i]) + P2[c] <= c/8 - 1, else -1 (see dev_gap_scan) */
+    if (cmax < cmin || cmax < 2) return -1;
+    int p1 = 0, p2 = 0, runmin = 1 << 20, best = -1;
+    for (int j = 0; j < cmax; j++) {
+        /* here p1 = P1[j], p2 = P2[j]; M[j+1] = runmin = min_{1<=i<=j} */
+        const int c = j + 1;                                               /* evaluate c = j+1 needs M[c] (i<=c-1=j) and P2[c] */
+        p1 += (ins[j] != norm[j]);
+        const int p2n = p2 + (ins[j + 1] != norm[j]);                      /* P2[j+1] */
+        if (c >= 2 && c >= cmin && runmin + p2n <= c / 8 - 1) best = c;
+        /* extend runmin with i = j+1: P1[j+1] - P2[j+1] */
+        runmin = min(runmin, p1 - p2n);
+        p2 = p2n;
+    }
+    return best;
+}
+
+__device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, int alen, int matchReq, int aidx, int PW,
+                                                int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
+    const int rlen = r.len;
+    const uint8_t* rdata = r.seq + r.front;
+    if (alen < matchReq) return false;                                    /* :73-74 */
+    int start = 0;
+    if (alen >= 16) start = -4; else if (alen >= 12) start = -3; else if (alen >= 8) start = -2;
+    bool found = false;
+    int pos = 0;
+    const bool planes = r.clean && c_p.adapter_clean[aidx];
+    /* scan 1 (:87-100) */
+    for (int p = start; p < 0 && p < rlen - matchReq && !found; p++) {
+        const int cmplen = min(rlen - p, alen), so = -p, n = cmplen - so;
+        int mm = 0;
+        for (int k = 0; k < n; k++) mm += (adata[so + k] != rdata[k]);
+        if (mm <= cmplen / 8) { found = true; pos = p; }
+    }
+    if (!found) {
+        const int npos = rlen - matchReq;
+        int my_p = 1 << 20;
+        if (planes) {
+            const uint32_t* alo = c_p.adapter_planes + aidx * 24; const uint32_t* ahi = alo + 8; const uint32_t* ann = alo + 16;
+            const uint32_t *plo = r.pl, *phi = r.pl + PW, *pnn = r.pl + 2 * PW;
+            const int nw = (alen + 31) >> 5;
+            for (int p = sub; p < npos; p += g) {
+                const int cmplen = min(rlen - p, alen);
+                int mm = 0;
+                for (int k = 0; k < nw && 32 * k < cmplen; k++) {
+                    const int bit = r.front + p + 32 * k;
+                    const uint32_t x = (tp_bits(plo, bit) ^ __ldg(alo + k)) | (tp_bits(phi, bit) ^ __ldg(ahi + k)) | (tp_bits(pnn, bit) ^ __ldg(ann + k));
+                    mm += __popc(x & low_mask(cmplen - 32 * k));
+                }
+                if (mm <= cmplen / 8) { my_p = p; break; }
+            }
+        } else {
+            for (int p = sub; p < npos; p += g) {
+                const int cmplen = min(rlen - p, alen), allowed = cmplen / 8;
+                int mm = 0;
+                for (int k = 0; k < cmplen && mm <= allowed; k++) mm += (adata[k] != rdata[p + k]);
+                if (mm <= allowed) { my_p = p; break; }
+            }
+        }
+        const int best = group_min(my_p, g);
+        if (best < (1 << 20)) { found = true; pos = best; }
+    }
+    if (!found && rlen - matchReq - 1 > 0) {                              /* scan 2 (:105-118) */
+        const int cmax = min(rlen - 1, alen);
+        const int c = t_gap_scan(rdata, adata, cmax, matchReq + 1);
+        if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - 1 - c; }
+    }
+    if (!found && rlen - matchReq > 0) {                                  /* scan 3 (:122-135) */
+        const int cmax = min(rlen, alen - 1);
+        const int c = t_gap_scan(adata, rdata, cmax, matchReq + 1);
+        if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - c; }
+    }
+    if (found) {                                                          /* :137-154 */
+        int abases;
+        if (pos < 0) { abases = alen + pos; r.len = 0; }
+        else { abases = rlen - pos; if (pos <= r.len) r.len = pos; }
+        if (abases > 0 && sub == 0) atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)abases);
+        posOut = pos; basesOut += max(abases, 0);
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool t_trim_by_multi(TRead& r, int PW, int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
+    bool trimmed = false;                                                 /* adaptertrimmer.cpp:48-62 */
+    for (int i = 0; i < c_p.n_fasta; i++)
+        trimmed |= t_trim_by_sequence(r, c_p.adapters + c_p.fasta_off[i], c_p.fasta_len[i], c_p.fasta_match_req, 2 + i, PW, posOut, basesOut, bc, sub, g);
+    return trimmed;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Filter::passFilter  (filter.cpp:15-57), one thread per read: planes for clean rows, bytes otherwise.
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __noinline__ int t_pass_filter(const TRead r, int PW, const int16_t* lut) {
+    if (r.null || r.len == 0) return FP_FAIL_LENGTH;
+    const int rlen = r.len;
+    int lowq = 0, nb = 0, adj = 0;
+    if (r.clean) {
+        const uint32_t *plo = r.pl, *phi = r.pl + PW, *pnn = r.pl + 2 * PW, *plq = r.pl + 3 * PW;
+        for (int k = 0; k * 32 < rlen; k++) {
+            const int bit = r.front + 32 * k;
+            const uint32_t m = low_mask(rlen - 32 * k);
+            const uint32_t nn = tp_bits(pnn, bit);
+            lowq += __popc(tp_bits(plq, bit) & m);
+            nb += __popc(nn & m);
+            if (c_p.complexity_filter) {
+                const uint32_t d = (tp_bits(plo, bit) ^ tp_bits(plo, bit + 1)) | (tp_bits(phi, bit) ^ tp_bits(phi, bit + 1)) | (nn ^ tp_bits(pnn, bit + 1));
+                adj += __popc(d & low_mask(rlen - 1 - 32 * k));
+            }
+        }
+    } else {
+        const uint8_t* s = r.seq + r.front; const uint8_t* q = r.qual + r.front;
+        const uint8_t qq = (uint8_t)c_p.qualified_qual;
+        for (int i = 0; i < rlen; i++) {
+            lowq += (q[i] < qq); nb += (s[i] == 'N');
+            if (i + 1 < rlen) adj += (s[i] != s[i + 1]);
+        }
+    }
+    if (c_p.qual_filter) {
+        if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
+        if (c_p.avg_qual_req > 0) {
+            const uint8_t* q = r.qual + r.front;
+            int tq = 0;
+            for (int i = 0; i < rlen; i++) tq += (int)q[i] - 33;
+            if ((tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
+        }
+        if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
+    }
+    if (c_p.length_filter) {
+        if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
+        if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
+    }
+    if (c_p.complexity_filter) {
+        if (rlen <= 1) return FP_FAIL_COMPLEXITY;
+        if (adj < (int)lut[2 * (c_p.stride + 2) + rlen]) return FP_FAIL_COMPLEXITY;
+    }
+    return FP_PASS_FILTER;
+}
+
+__device__ __forceinline__ fp_read_result t_make_result(const TRead& r, int verdict, int pv, int flags, int apos, int abases, int pbase, int plen) {
+    fp_read_result o;
+    if (r.null) { o.front = 0; o.len = 0; flags |= FP_F_DROPPED; }
+    else { o.front = (uint16_t)r.front; o.len = (uint16_t)r.len; }
+    o.verdict = (uint8_t)verdict; o.flags = (uint8_t)flags; o.adapter_pos = (int16_t)apos; o.adapter_len = (uint16_t)abases;
+    o.polyx_base = (uint8_t)pbase; o.pair_verdict = (uint8_t)pv; o.polyx_len = (uint16_t)plen; o.reserved = 0;
+    return o;
+}
+
+/* warp-cooperative execution of per-lane statistics requests: every lane may ask for the contribution of positions
+ * [lo,hi) of one row (context start ctx0, sign +-1); the warp serves the requests one lane at a time. */
+__device__ __forceinline__ void warp_serve_delta(bool want, bool clean, const DeltaAcc& D, unsigned long long* G, int side,
+                                                 const uint8_t* seq, const uint8_t* qual, int ctx0, int lo, int hi, int sign) {
+    unsigned m = __ballot_sync(FULL_MASK, want && hi > lo);
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const bool cl = __shfl_sync(FULL_MASK, (int)clean, l) != 0;
+        const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)seq, l));
+        const uint8_t* ql = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)qual, l));
+        const int c0 = __shfl_sync(FULL_MASK, ctx0, l), a = __shfl_sync(FULL_MASK, lo, l), b = __shfl_sync(FULL_MASK, hi, l), sg = __shfl_sync(FULL_MASK, sign, l);
+        if (cl) dev_stat_positions_smem(D, side, sq, ql, c0, a, b, sg);
+        else dev_stat_positions(G, side * 2 + 1, sq, ql, c0, a, b, sg);
+    }
+}
+/* pre-filter stats of unclean rows (global path, sign +1) */
+__device__ __forceinline__ void warp_serve_pre(bool want, unsigned long long* G, int stats, const uint8_t* seq, const uint8_t* qual, int len) {
+    unsigned m = __ballot_sync(FULL_MASK, want && len > 0);
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)seq, l));
+        const uint8_t* ql = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)qual, l));
+        const int n = __shfl_sync(FULL_MASK, len, l);
+        dev_stat_positions(G, stats, sq, ql, 0, 0, n, +1);
+    }
+}
+
+/* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
+struct ColAcc2 { unsigned int v[2][NB][4]; };
+
+/* ------------------------------------------------------------------------------------------------
+ * The fused kernel, generation 2.
+ * ------------------------------------------------------------------------------------------------ */
+template <bool PAIRED>
+__global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launch_args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int SIDES = PAIRED ? 2 : 1;
+    const fp_smem_layout& sl = a.sl;
+    const int S = c_p.stride, T = c_p.tile;
+    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    unsigned long long* G = a.counters;
+    const fp_counter_layout& L = c_p.L;
+
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sl.off_mbar);
+    uint8_t* tile_seq[2]; uint8_t* tile_qual[2];
+    tile_seq[0] = smem + sl.off_tile;
+    tile_qual[0] = tile_seq[0] + sl.tile_array_bytes;
+    tile_seq[1] = tile_qual[0] + sl.tile_array_bytes;
+    tile_qual[1] = tile_seq[1] + sl.tile_array_bytes;
+    uint16_t* s_len = reinterpret_cast<uint16_t*>(smem + sl.off_len);       /* [SIDES][T] */
+    uint8_t* s_clean = smem + sl.off_clean;                                 /* [SIDES][T] */
+    unsigned int* s_kmer = reinterpret_cast<unsigned int*>(smem + sl.off_kmer);    /* [SIDES][1024] */
+    unsigned int* s_qhist = reinterpret_cast<unsigned int*>(smem + sl.off_qhist);  /* [SIDES][128]  */
+    BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem + sl.off_bc);
+    DeltaAcc D;
+    D.cycles = S;
+    D.cyc = reinterpret_cast<int*>(smem + sl.off_delta);
+    D.kmer = D.cyc + SIDES * S * 20;
+    D.qh = D.kmer + SIDES * FP_KMER_BINS;
+    int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);
+    const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free thread-per-row access */
+    uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
+
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) s_qhist[i] = 0;
+    for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
+    for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
+    for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
+    if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+    /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
+    const int HPR = S >> 1;                       /* half-words per row */
+    const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_THREADS */
+    const bool col_active = tid < ncols;
+    const int my_side = col_active ? tid / HPR : 0, my_hc = col_active ? tid % HPR : 0;
+    const int my_w = my_hc >> 1, my_half = my_hc & 1;
+    ColAcc2 acc;
+    #pragma unroll
+    for (int c = 0; c < 2; c++)
+        #pragma unroll
+        for (int b = 0; b < NB; b++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) acc.v[c][b][k] = 0;
+    unsigned long long rl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* per-thread reads / lengthSum of pre1 post1 pre2 post2 */
+
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (long long tix = blockIdx.x; tix < a.n_tiles; tix += gridDim.x) {
+        const long long row0 = tix * T;
+        const int rows = (int)min((long long)T, a.b.n - row0);
+        /* ---------------- phase 0: TMA bulk loads ---------------- */
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)S;
+            mbar_expect_tx(mbar, bytes * 2 * SIDES);
+            tma_bulk_g2s(tile_seq[0], a.b.seq1 + row0 * S, bytes, mbar);
+            tma_bulk_g2s(tile_qual[0], a.b.qual1 + row0 * S, bytes, mbar);
+            if (PAIRED) {
+                tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
+                tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
+            }
+        }
+        for (int i = tid; i < SIDES * T; i += FP_THREADS) {
+            const int sd = i / T, r = i % T;
+            uint16_t ln = 0;
+            if (r < rows) { ln = (sd == 0 ? a.b.len1 : a.b.len2)[row0 + r]; if (ln > S) ln = (uint16_t)S; }
+            s_len[i] = ln;
+            s_clean[i] = 1;
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        __syncthreads();
+
+        /* ---------------- phase 0.5: bit planes of every row + validation ---------------- */
+        {
+            const int nwords = (S + 31) >> 5;
+            const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
+            #pragma unroll 1
+            for (int it = tid; it < SIDES * T * PW; it += FP_THREADS) {
+                const int j = it % PW, rr = (it / PW) % T, sd = it / (PW * T);
+                uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
+                if (j < nwords && rr < rows) {
+                    const int n = (int)s_len[sd * T + rr] - 32 * j;
+                    if (n > 0) {
+                        const uint4* sp = reinterpret_cast<const uint4*>(tile_seq[sd] + rr * S + 32 * j);
+                        const uint4* qp = reinterpret_cast<const uint4*>(tile_qual[sd] + rr * S + 32 * j);
+                        const uint4 s0 = sp[0], s1 = sp[1], q0 = qp[0], q1 = qp[1];
+                        const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr] = 0;
+                    }
+                }
+                uint32_t* pr = tile_planes + (sd * T + rr) * PSTR + j;
+                pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
+            }
+        }
+        __syncthreads();
+
+        /* ---------------- phase 1: dense column pass (pre-filter stats of clean rows), two cycles per thread ---------------- */
+        if (col_active) {
+            const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
+            const uint16_t* lens = s_len + my_side * T; const uint8_t* cl = s_clean + my_side * T;
+            unsigned int* kh = s_kmer + my_side * FP_KMER_BINS; unsigned int* qh = s_qhist + my_side * FP_QUAL_BINS;
+            const int w4 = my_w * 4;
+            #pragma unroll 1
+            for (int r0 = 0; r0 < rows; r0 += 4) {
+                uint32_t xs[4], xq[4];
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int r = r0 + k;
+                    const int hi = (r < rows && cl[r]) ? lens[r] : 0;
+                    const uint32_t m = window_mask(w4, 0, hi);
+                    uint32_t x = 0, q = 0;
+                    if (m) {
+                        x = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;
+                        q = *reinterpret_cast<const uint32_t*>(tq + r * S + w4) & m;
+                        /* this thread's two bytes of the word: quality histogram (stats.cpp:213) + 5-mers (stats.cpp:228-266) */
+                        const int j0 = my_half * 2;
+                        const int nb = min(hi - w4, 4);
+                        if (j0 < nb) atomicAdd(&qh[(q >> (8 * j0)) & 0xFF], 1u);
+                        if (j0 + 1 < nb) atomicAdd(&qh[(q >> (8 * j0 + 8)) & 0xFF], 1u);
+                        if (my_w > 0) {
+                            const uint32_t xp = *reinterpret_cast<const uint32_t*>(ts + r * S + w4 - 4);
+                            const uint32_t K = 0x01010101u;
+                            const uint32_t c0 = x & K, c1 = (x >> 1) & K, c2 = (x >> 2) & K;
+                            const uint32_t okc = (c0 & ~c1 & ~c2) | (c0 & c1) | (~c0 & ~c1 & c2);
+                            const uint32_t p0 = xp & K, p1 = (xp >> 1) & K, p2 = (xp >> 2) & K;
+                            const uint32_t okp = (p0 & ~p1 & ~p2) | (p0 & p1) | (~p0 & ~p1 & p2);
+                            const uint32_t vc = (x & 0x02020202u) | c2, vp = (xp & 0x02020202u) | p2;
+                            const uint32_t s16 = (((vp * 0x40100401u) >> 24) << 8) | ((vc * 0x40100401u) >> 24);
+                            const uint32_t ok8 = ((((okp * 0x08040201u) >> 24) & 0xF) << 4) | (((okc * 0x08040201u) >> 24) & 0xF);
+                            if (((ok8 >> (3 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (3 - j0))) & 0x3FF], 1u);
+                            if (((ok8 >> (2 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (2 - j0))) & 0x3FF], 1u);
+                        }
+                    }
+                    xs[k] = x; xq[k] = q;
+                }
+                /* 4x4 byte transpose restricted to this thread's two cycles */
+                const unsigned sel = my_half ? 0x7362u : 0x5140u;
+                const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+                const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+                acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
+                acc_cycle(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
+            }
+        }
+        __syncthreads();
+
+        /* ---------------- phase 2: operator chain, one lane GROUP per read / pair ---------------- */
+        constexpr int GL = PAIRED ? 4 : 2;            /* lanes per unit */
+        constexpr int UPW = 32 / GL;                  /* units per warp */
+        const int sub = lane % GL;
+        const bool lead = sub == 0;
+        const unsigned gmask = group_mask(GL);
+        const int glead = lane & ~(GL - 1);
+        #pragma unroll 1
+        for (int rbase = warp * UPW; rbase < rows; rbase += FP_WARPS * UPW) {
+            const int r = rbase + lane / GL;
+            const bool active = r < rows;
+            const int rr = active ? r : 0;
+            const long long gi = row0 + rr;
+            if (!PAIRED) {
+                /* SingleEndProcessor::processSingleEnd loop body  seprocessor.cpp:204-296 */
+                uint8_t* rs = tile_seq[0] + rr * S; uint8_t* rq = tile_qual[0] + rr * S;
+                const int len0 = active ? s_len[rr] : 0;
+                const bool clean = s_clean[rr] != 0;
+                if (active && lead) { rl[0] += 1; rl[1] += len0; }
+                warp_serve_pre(active && lead && !clean, G, FP_STATS_PRE1, rs, rq, len0);
+                TRead r1; r1.seq = rs; r1.qual = rq; r1.pl = tile_planes + rr * PSTR; r1.front = 0; r1.len = len0; r1.null = false; r1.clean = clean;
+                int flags = 0, apos = 0, abases = 0, pbase = 255, plen = 0, result = FP_FAIL_LENGTH;
+                bool counted = false;
+                if (active) {
+                    r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len);   /* :235 */
+                    if (!r1.null && c_p.polyg) { const int nl = t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
+                    bool dimer = false;
+                    if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
+                        bool trimmed = false;
+                        if (c_p.has_r1) trimmed = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos, abases, bc, sub, GL);
+                        if (c_p.n_fasta > 0) trimmed |= t_trim_by_multi(r1, PW, apos, abases, bc, sub, GL);
+                        if (trimmed) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags |= FP_F_ADAPTER_TRIMMED; }
+                        if (trimmed && r1.len <= c_p.dimer_max_len) dimer = true;
+                    }
+                    if (!r1.null && c_p.polyx) {                                                  /* :263-266 */
+                        int nl;
+                        if (t_trim_polyx(rs + r1.front, r1.len, c_p.polyx_min, nl, pbase, plen)) {
+                            r1.len = nl;
+                            if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pbase], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pbase], (unsigned)plen); }
+                            flags |= FP_F_POLYX_TRIMMED;
+                        }
+                    }
+                    if (!r1.null && c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;   /* :268-271 */
+                    result = t_pass_filter(r1, PW, s_lut);                                        /* :273 */
+                    if (dimer) { result = FP_FAIL_ADAPTER_DIMER; flags |= FP_F_ADAPTER_DIMER; }
+                    counted = !r1.null && result == FP_PASS_FILTER;                               /* :281-286 */
+                    if (lead) {
+                        atomicAdd(&bc->fr[FP_FR_READSTATS + result], 1u);                          /* :278 */
+                        if (counted) { rl[2] += 1; rl[3] += r1.len; }
+                        a.out1[gi] = t_make_result(r1, result, result, flags, apos, abases, pbase, plen);
+                    }
+                }
+                /* post stats as a delta against pre (warp-cooperative) */
+                const bool keep_tail = counted && r1.front == 0 && clean;
+                warp_serve_delta(active && lead && clean, true, D, G, 0, rs, rq, 0, keep_tail ? r1.len : 0, len0, -1);
+                warp_serve_delta(active && lead && counted && !keep_tail, clean, D, G, 0, rs, rq, r1.front, r1.front, r1.front + r1.len, +1);
+            } else {
+                /* PairEndProcessor::processPairEnd loop body  peprocessor.cpp:383-643 */
+                uint8_t* rs1 = tile_seq[0] + rr * S; uint8_t* rq1 = tile_qual[0] + rr * S;
+                uint8_t* rs2 = tile_seq[1] + rr * S; uint8_t* rq2 = tile_qual[1] + rr * S;
+                const int l1 = active ? s_len[rr] : 0, l2 = active ? s_len[T + rr] : 0;
+                const bool clean1 = s_clean[rr] != 0, clean2 = s_clean[T + rr] != 0;
+                if (active && lead) { rl[0] += 1; rl[1] += l1; rl[4] += 1; rl[5] += l2; }
+                warp_serve_pre(active && lead && !clean1, G, FP_STATS_PRE1, rs1, rq1, l1);
+                warp_serve_pre(active && lead && !clean2, G, FP_STATS_PRE2, rs2, rq2, l2);
+                uint32_t* pl1 = tile_planes + rr * PSTR; uint32_t* pl2 = tile_planes + (T + rr) * PSTR;
+                TRead r1, r2;
+                r1.seq = rs1; r1.qual = rq1; r1.pl = pl1; r1.front = 0; r1.len = l1; r1.null = false; r1.clean = clean1;
+                r2.seq = rs2; r2.qual = rq2; r2.pl = pl2; r2.front = 0; r2.len = l2; r2.null = false; r2.clean = clean2;
+                int flags1 = 0, flags2 = 0, apos1 = 0, apos2 = 0, ab1 = 0, ab2 = 0, pb1 = 255, pb2 = 255, pl1n = 0, pl2n = 0;
+                fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+                bool both = false, need_correct = false;
+                if (active) {
+                    r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len);   /* :425-426 */
+                    r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len);
+                    both = !r1.null && !r2.null;
+                    if (both && c_p.polyg) {                                                      /* :428-431 */
+                        int nl = t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; }
+                        nl = t_trim_polyg(rs2 + r2.front, r2.len, c_p.polyg_min); if (nl != r2.len) { r2.len = nl; flags2 |= FP_F_POLYG_TRIMMED; }
+                    }
+                    if (both && (c_p.adapter_enabled || c_p.correction || c_p.thread0)) {         /* :438-441 */
+                        ov = (clean1 && clean2) ? t_analyze_planes(r1, r2, PW, s_lut, sub, GL) : t_analyze_bytes(r1, r2, s_lut);
+                        if (c_p.thread0 && lead) {                                                /* statInsertSize :449-452 / :497-504, :710-723 */
+                            int isize = c_p.isize_max;
+                            if (ov.overlapped) {
+                                if (ov.offset > 0) isize = r1.len + r2.len - ov.overlap_len + r1.front + r2.front;
+                                else isize = ov.overlap_len + r1.front + r2.front;
+                            }
+                            if (isize > c_p.isize_max) isize = c_p.isize_max;
+                            if (c_p.isize_max < FP_MAX_ISIZE_SMEM) atomicAdd(&bc->isize[isize], 1u);
+                            else red_add64(&G[L.off_isize + isize], 1ull);
+                        }
+                    }
+                    need_correct = both && (c_p.adapter_enabled || c_p.correction) && c_p.correction && ov.overlapped && ov.diff != 0;   /* :443,:453-456 */
+                }
+                /* the post stats are a delta against the ORIGINAL bases: take reads that are about to be corrected out first */
+                warp_serve_delta(need_correct && lead && clean1, true, D, G, 0, rs1, rq1, 0, 0, l1, -1);
+                warp_serve_delta(need_correct && lead && clean2, true, D, G, 1, rs2, rq2, 0, 0, l2, -1);
+                int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
+                bool counted = false;
+                if (active) {
+                    bool dimer = false;
+                    if (need_correct) {
+                        int cf = 0;
+                        if (lead) {
+                            bool c1, c2;
+                            t_correct(r1, r2, pl1, pl2, PW, ov, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
+                                      a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, c1, c2);
+                            cf = (c1 ? 1 : 0) | (c2 ? 2 : 0);
+                        }
+                        __syncwarp(gmask);                                                        /* corrected bytes / planes visible to the whole group */
+                        cf = __shfl_sync(gmask, cf, glead);
+                        if (cf & 1) flags1 |= FP_F_CORRECTED;
+                        if (cf & 2) flags2 |= FP_F_CORRECTED;
+                    }
+                    if (both && c_p.adapter_enabled) {                                            /* :457-485 */
+                        bool trimmed = false;
+                        if (ov.overlapped && ov.offset < 0) {                                     /* trimByOverlapAnalysis adaptertrimmer.cpp:17-46 */
+                            const int ol = ov.overlap_len;
+                            const int nl1 = min(r1.len, ol + r2.front), nl2 = min(r2.len, ol + r1.front);
+                            const int a1 = r1.len - nl1, a2 = r2.len - nl2;
+                            r1.len = nl1; r2.len = nl2;
+                            if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)(a1 + a2));
+                            ab1 += a1; ab2 += a2;
+                            trimmed = true;
+                        }
+                        bool t1 = trimmed, t2 = trimmed;
+                        if (!trimmed) {                                                           /* :461-466 */
+                            if (c_p.has_r1) t1 = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos1, ab1, bc, sub, GL);
+                            if (c_p.has_r2) t2 = t_trim_by_sequence(r2, c_p.adapters + c_p.adapter_r2_off, c_p.adapter_r2_len, 4, 1, PW, apos2, ab2, bc, sub, GL);
+                        }
+                        if (c_p.n_fasta > 0) { t1 |= t_trim_by_multi(r1, PW, apos1, ab1, bc, sub, GL); t2 |= t_trim_by_multi(r2, PW, apos2, ab2, bc, sub, GL); }   /* :467-470 */
+                        if (t1) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags1 |= FP_F_ADAPTER_TRIMMED; }   /* :472-475 */
+                        if (t2) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags2 |= FP_F_ADAPTER_TRIMMED; }
+                        if ((t1 || t2) && r1.len <= c_p.dimer_max_len && r2.len <= c_p.dimer_max_len) dimer = true;   /* :480-484 */
+                    }
+                    if (both && c_p.polyx) {                                                      /* :506-509 */
+                        int nl;
+                        if (t_trim_polyx(rs1 + r1.front, r1.len, c_p.polyx_min, nl, pb1, pl1n)) {
+                            r1.len = nl; flags1 |= FP_F_POLYX_TRIMMED;
+                            if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pb1], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pb1], (unsigned)pl1n); }
+                        }
+                        if (t_trim_polyx(rs2 + r2.front, r2.len, c_p.polyx_min, nl, pb2, pl2n)) {
+                            r2.len = nl; flags2 |= FP_F_POLYX_TRIMMED;
+                            if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pb2], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pb2], (unsigned)pl2n); }
+                        }
+                    }
+                    if (both) {                                                                   /* :511-516 */
+                        if (c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;
+                        if (c_p.max_len2 > 0 && c_p.max_len2 < r2.len) r2.len = c_p.max_len2;
+                    }
+                    res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);      /* :565-566 */
+                    if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
+                    const int pv = max(res1, res2);
+                    counted = !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER;   /* :577-591 */
+                    if (lead) {
+                        atomicAdd(&bc->fr[FP_FR_READSTATS + pv], 2u);                              /* :573 */
+                        if (counted) { rl[2] += 1; rl[3] += r1.len; rl[6] += 1; rl[7] += r2.len; }
+                        a.out1[gi] = t_make_result(r1, res1, pv, flags1, apos1, ab1, pb1, pl1n);
+                        a.out2[gi] = t_make_result(r2, res2, pv, flags2, apos2, ab2, pb2, pl2n);
+                        if (a.ov) a.ov[gi] = ov;
+                    }
+                }
+                /* post stats as a delta against pre, per side (warp-cooperative) */
+                {
+                    const bool removed = need_correct;
+                    const bool keep1 = counted && r1.front == 0 && clean1 && !removed;
+                    warp_serve_delta(active && lead && clean1 && !removed, true, D, G, 0, rs1, rq1, 0, keep1 ? r1.len : 0, l1, -1);
+                    warp_serve_delta(active && lead && counted && !keep1, clean1, D, G, 0, rs1, rq1, r1.front, r1.front, r1.front + r1.len, +1);
+                    const bool keep2 = counted && r2.front == 0 && clean2 && !removed;
+                    warp_serve_delta(active && lead && clean2 && !removed, true, D, G, 1, rs2, rq2, 0, keep2 ? r2.len : 0, l2, -1);
+                    warp_serve_delta(active && lead && counted && !keep2, clean2, D, G, 1, rs2, rq2, r2.front, r2.front, r2.front + r2.len, +1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    /* ---------------- flush block-level accumulators ---------------- */
+    const int BIN_SLOT[NB] = {1, 3, 4, 6, 7};      /* base & 7 of A C T N G */
+    if (col_active) {
+        #pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int cyc = my_hc * 2 + c;
+            if (cyc >= L.cycles) continue;
+            #pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const unsigned int n = acc.v[c][b][0], n20 = acc.v[c][b][1], n30 = acc.v[c][b][2], sq = acc.v[c][b][3];
+                if (n == 0) continue;
+                const long long qs = (long long)sq - 33ll * (long long)n;
+                #pragma unroll 1
+                for (int pp = 0; pp < 2; pp++) {       /* dense pass feeds pre AND post (post gets deltas on top) */
+                    const int st = my_side * 2 + pp;
+                    if (n30) red_add64(&G[fp_off_cycle(&L, st, 0 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n30);
+                    if (n20) red_add64(&G[fp_off_cycle(&L, st, 1 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n20);
+                    red_add64(&G[fp_off_cycle(&L, st, 2 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)n);
+                    red_add64(&G[fp_off_cycle(&L, st, 3 * 8 + BIN_SLOT[b], cyc)], (unsigned long long)qs);
+                }
+            }
+        }
+    }
+    #pragma unroll 1
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) {
+        const unsigned int v = s_kmer[i];
+        if (v) { const int sd = i / FP_KMER_BINS, k = i % FP_KMER_BINS; red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
+    }
+    #pragma unroll 1
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) {
+        const unsigned int v = s_qhist[i];
+        if (v) { const int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
+    }
+    #pragma unroll 1
+    for (int i = tid; i < SIDES * S * 20; i += FP_THREADS) {
+        const int v = D.cyc[i];
+        if (v == 0) continue;
+        const int sd = i / (S * 20), rem = i % (S * 20), cyc = rem / 20, bin = (rem % 20) / 4, kind = rem & 3;
+        if (cyc >= L.cycles) continue;
+        const int gk = kind == 0 ? 2 : kind == 1 ? 1 : kind == 2 ? 0 : 3;       /* count->content, q20, q30, qualsum */
+        red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
+    }
+    #pragma unroll 1
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, i % FP_KMER_BINS)], (unsigned long long)(long long)v); }
+    #pragma unroll 1
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
+    #pragma unroll 1
+    for (int i = tid; i < FP_FR_WORDS; i += FP_THREADS) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
+    if (c_p.isize_max < FP_MAX_ISIZE_SMEM) {
+        #pragma unroll 1
+        for (int i = tid; i <= c_p.isize_max; i += FP_THREADS) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
+    }
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned long long v = rl[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+        if (lane == 0 && k < 2 * L.n_stats && v) red_add64(&G[(k & 1) ? fp_off_length_sum(&L, k >> 1) : fp_off_reads(&L, k >> 1)], v);
+    }
+}

@@ -21,7 +21,7 @@
 #include <stdint.h>
 #include "fastp_b200.h"
 
-#define FP_THREADS 512
+#define FP_THREADS 256
 #define FP_WARPS (FP_THREADS / 32)
 #define FULL_MASK 0xffffffffu
 #define FP_MAX_ISIZE_SMEM 1025
@@ -449,19 +449,22 @@ __device__ __noinline__ fp_ov_result dev_analyze_planes(int len1, int front1, in
 __device__ __noinline__ int dev_pass_filter_planes(const uint8_t* qual, int rlen, bool null, Planes P, int front, int pw, const int16_t* lut) {
     if (null || rlen == 0) return FP_FAIL_LENGTH;
     const int lane = lane_id();
-    int lowq = 0, nb = 0, adj = 0;
+    int packed = 0;                                                        /* lowq | nb << 10 | adj << 20 (each <= 512) */
     if (lane * 32 < rlen) {
         const int bit = front + 32 * lane;
         const uint32_t m = low_mask(rlen - 32 * lane);
-        const uint32_t lo = plane_bits(P.lo, bit), hi = plane_bits(P.hi, bit), nn = plane_bits(P.nn, bit);
-        lowq = __popc(plane_bits(P.lq, bit) & m);
-        nb = __popc(nn & m);
-        const uint32_t m1 = low_mask(rlen - 1 - 32 * lane);                /* pairs (i, i+1), i < rlen-1 */
-        const uint32_t d = (lo ^ plane_bits(P.lo, bit + 1)) | (hi ^ plane_bits(P.hi, bit + 1)) | (nn ^ plane_bits(P.nn, bit + 1));
-        adj = __popc(d & m1);
+        const uint32_t nn = plane_bits(P.nn, bit);
+        packed = __popc(plane_bits(P.lq, bit) & m) | (__popc(nn & m) << 10);
+        if (c_p.complexity_filter) {
+            const uint32_t lo = plane_bits(P.lo, bit), hi = plane_bits(P.hi, bit);
+            const uint32_t m1 = low_mask(rlen - 1 - 32 * lane);            /* pairs (i, i+1), i < rlen-1 */
+            const uint32_t d = (lo ^ plane_bits(P.lo, bit + 1)) | (hi ^ plane_bits(P.hi, bit + 1)) | (nn ^ plane_bits(P.nn, bit + 1));
+            packed |= __popc(d & m1) << 20;
+        }
     }
+    packed = warp_sum(packed);
+    const int lowq = packed & 0x3FF, nb = (packed >> 10) & 0x3FF, adj = packed >> 20;
     if (c_p.qual_filter) {
-        lowq = warp_sum(lowq);
         if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
         if (c_p.avg_qual_req > 0) {
             int tq = 0;
@@ -469,10 +472,21 @@ __device__ __noinline__ int dev_pass_filter_planes(const uint8_t* qual, int rlen
             tq = warp_sum(tq);
             if ((tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
         }
-        nb = warp_sum(nb);
         if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
     }
     if (c_p.length_filter) {
+        if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
+        if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
+    }
+    if (c_p.complexity_filter) {
+        if (rlen <= 1) return FP_FAIL_COMPLEXITY;
+        if (adj < (int)lut[2 * (c_p.stride + 2) + rlen]) return FP_FAIL_COMPLEXITY;
+    }
+    return FP_PASS_FILTER;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * OverlapAnalysis::analyze    if (c_p.length_filter) {
         if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
         if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
     }
@@ -978,7 +992,7 @@ __device__ __forceinline__ void post_delta(bool clean, const DeltaAcc& D, unsign
  * ------------------------------------------------------------------------------------------------ */
 struct fp_smem_layout {
     int off_mbar, off_tile, tile_array_bytes, off_len, off_clean, off_rc, rc_bytes, off_scratch, scratch_ints,
-        off_kmer, off_qhist, off_bc, off_rl, off_next, off_planes, off_rcplanes, off_lut, off_delta, plane_words, total;
+        off_kmer, off_qhist, off_bc, off_rl, off_next, off_planes, off_rcplanes, off_lut, off_delta, plane_words, plane_stride, total;
 };
 
 struct fp_launch_args {
@@ -1015,7 +1029,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
  * The fused kernel.
  * ------------------------------------------------------------------------------------------------ */
 template <bool PAIRED>
-__global__ void __launch_bounds__(FP_THREADS, 1) fp_chain_kernel(const fp_launch_args a) {
+__global__ void __launch_bounds__(FP_THREADS, 2) fp_chain_kernel(const fp_launch_args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int SIDES = PAIRED ? 2 : 1;
     const fp_smem_layout& sl = a.sl;

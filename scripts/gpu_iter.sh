@@ -11,7 +11,7 @@ import json;d=json.load(open('gpurun_out/bench_iter.json'))
 print('VALUE %.1f M/s  kernel_ms %.2f  frac %.4f  e2e %.1f M/s' % (d['value']/1e6, d['roofline']['kernel_ms'], d['roofline']['frac'], d.get('e2e',{}).get('value',0)/1e6), d['checks'], d['clocks'])"
 tail -3 gpurun_out/bench_iter.err
 if [ -n "$NCU" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:fp_chain_kernel -s 1 -c 1 -o gpurun_out/prof_iter \
+  ncu --set full --clock-control none --import-source on -k regex:fp_chain -s 1 -c 1 -o gpurun_out/prof_iter \
     python bench.py --units 1000000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e ${BENCH_ARGS} > gpurun_out/ncu_iter.log 2>&1
   ls -la gpurun_out/prof_iter.ncu-rep
 fi
