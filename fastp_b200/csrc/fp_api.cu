@@ -131,6 +131,8 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     off = align_up(off, 16);
     sl.off_planes = (int)off; off += (size_t)sides * T * sl.plane_stride * 4;
     sl.off_rcplanes = (int)off;
+    off = align_up(off, 16);
+    sl.off_queue = (int)off; off += (size_t)sides * T * 2 * 16;
     sl.total = (int)align_up(off, 128);
     return (size_t)sl.total;
 }

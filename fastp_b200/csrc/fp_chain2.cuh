@@ -310,30 +310,44 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
     uint8_t* s2 = r2.seq + r2.front; uint8_t* q2p = r2.qual + r2.front;
     const signed char GOOD = 33 + 30, BAD = 33 + 14;
     int corrected = 0;
-    for (int i = 0; i < ol; i++) {
-        const int p1 = start1 + i, p2 = start2 - i;
-        const uint8_t b1 = s1[p1], b2 = s2[p2];
-        if (b1 != dev_complement(b2)) {
-            const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
-            if (q1 >= GOOD && q2 <= BAD) {                                 /* use R1 :42-50 */
-                const uint8_t nb = dev_complement(b1);
-                s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
-                if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
-                corrected++; c2 = true;
-                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);   /* diagonal only, SURVEY App. A.6 */
-                if (sink.count) {
-                    const unsigned int slot = atomicAdd(sink.count, 1u);
-                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
-                }
-            } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
-                const uint8_t nb = dev_complement(b2);
-                s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
-                if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
-                corrected++; c1 = true;
-                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
-                if (sink.count) {
-                    const unsigned int slot = atomicAdd(sink.count, 1u);
-                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+    const bool use_planes = r1.clean && r2.clean;
+    const int e = r2.front + r2.len - 1, jb = r2.len - 1 - start2;          /* rc(r2) index of overlap position 0 */
+    for (int k = 0; k * 32 < ol; k++) {
+        /* positions of this 32-chunk whose bases differ: from the planes (clean rows) or all of them (byte path decides) */
+        uint32_t todo = low_mask(ol - 32 * k);
+        if (use_planes) {
+            const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
+            const uint32_t rn = __brev(tp_bits_z(pl2 + 2 * PW, s0));
+            const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
+            todo &= (tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn);
+        }
+        while (todo) {
+            const int i = 32 * k + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int p1 = start1 + i, p2 = start2 - i;
+            const uint8_t b1 = s1[p1], b2 = s2[p2];
+            if (b1 != dev_complement(b2)) {
+                const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
+                if (q1 >= GOOD && q2 <= BAD) {                                 /* use R1 :42-50 */
+                    const uint8_t nb = dev_complement(b1);
+                    s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
+                    if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
+                    corrected++; c2 = true;
+                    atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);   /* diagonal only, SURVEY App. A.6 */
+                    if (sink.count) {
+                        const unsigned int slot = atomicAdd(sink.count, 1u);
+                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                    }
+                } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
+                    const uint8_t nb = dev_complement(b2);
+                    s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
+                    if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
+                    corrected++; c1 = true;
+                    atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
+                    if (sink.count) {
+                        const unsigned int slot = atomicAdd(sink.count, 1u);
+                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                    }
                 }
             }
         }
@@ -526,8 +540,31 @@ __device__ __forceinline__ void warp_serve_pre(bool want, unsigned long long* G,
 /* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
 struct ColAcc2 { unsigned int v[2][NB][4]; };
 
+/* exact "byte is one of A,C,G,T" per byte (0/1 bytes): class by base&7 plus the upper-bit pattern */
+__device__ __forceinline__ uint32_t exact_acgt(uint32_t w) {
+    const uint32_t K = 0x01010101u;
+    const uint32_t c0 = w & K, c1 = (w >> 1) & K, c2 = (w >> 2) & K, b3 = (w >> 3) & K, b4 = (w >> 4) & K;
+    const uint32_t up = (~(w >> 5)) & (w >> 6) & (~(w >> 7)) & K;
+    return ((c0 & (~c2 | c1) & ~b3 & ~b4) | (~c0 & ~c1 & c2 & ~b3 & b4)) & up;
+}
+
+/* deferred post-filter statistics request (phase C): contribution of positions [lo,hi) of one tile row */
+struct DeltaReq { int row_side; int ctx0, lo, hi; };        /* row_side = row | side<<16 | clean<<17 | (sign<0)<<18 */
+
+__device__ __forceinline__ void push_delta(DeltaReq* q, int* qn, bool want, bool clean, int side, int row, int ctx0, int lo, int hi, int sign) {
+    if (want && hi > lo) {
+        const int slot = atomicAdd(qn, 1);
+        DeltaReq r; r.row_side = row | (side << 16) | ((clean ? 1 : 0) << 17) | ((sign < 0 ? 1 : 0) << 18); r.ctx0 = ctx0; r.lo = lo; r.hi = hi;
+        q[slot] = r;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
- * The fused kernel, generation 2.
+ * The fused kernel, generation 2.  Per tile, separated by CTA barriers (phase-synchronous execution keeps the
+ * instruction cache warm; two CTAs per SM overlap each other's barriers):
+ *   A  dense column pass (warps holding columns)  ||  bit planes + validation (the other warps)
+ *   B  operator chain, one lane group per read / pair; post-stat requests go to a shared-memory queue
+ *   C  the queue is drained by all warps (balanced), then the tile buffer is free for the next TMA load
  * ------------------------------------------------------------------------------------------------ */
 template <bool PAIRED>
 __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launch_args a) {
@@ -556,20 +593,23 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     D.kmer = D.cyc + SIDES * S * 20;
     D.qh = D.kmer + SIDES * FP_KMER_BINS;
     int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);
-    const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free thread-per-row access */
+    const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free lane-group-per-row access */
     uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
+    DeltaReq* s_queue = reinterpret_cast<DeltaReq*>(smem + sl.off_queue);    /* [SIDES * T * 2] */
+    int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
 
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
     for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) s_qhist[i] = 0;
     for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
     for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
     for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
-    if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
-    const int HPR = S >> 1;                       /* half-words per row */
+    const int HPR = S >> 1;
     const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_THREADS */
     const bool col_active = tid < ncols;
+    const int ndense_warps = (ncols + 31) >> 5;
     const int my_side = col_active ? tid / HPR : 0, my_hc = col_active ? tid % HPR : 0;
     const int my_w = my_hc >> 1, my_half = my_hc & 1;
     ColAcc2 acc;
@@ -581,13 +621,21 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
             for (int k = 0; k < 4; k++) acc.v[c][b][k] = 0;
     unsigned long long rl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* per-thread reads / lengthSum of pre1 post1 pre2 post2 */
 
+    constexpr int GL = PAIRED ? 4 : 2;            /* lanes per unit */
+    constexpr int UPW = 32 / GL;                  /* units per warp step */
+    const int sub = lane % GL;
+    const bool lead = sub == 0;
+    const unsigned gmask = group_mask(GL);
+    const int glead = lane & ~(GL - 1);
+
     __syncthreads();
     uint32_t parity = 0;
 
+    #pragma unroll 1
     for (long long tix = blockIdx.x; tix < a.n_tiles; tix += gridDim.x) {
         const long long row0 = tix * T;
         const int rows = (int)min((long long)T, a.b.n - row0);
-        /* ---------------- phase 0: TMA bulk loads ---------------- */
+        /* ---------------- TMA bulk loads ---------------- */
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const uint32_t bytes = (uint32_t)rows * (uint32_t)S;
@@ -598,6 +646,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
+            s_qn[0] = 0; s_qn[1] = 0;
         }
         for (int i = tid; i < SIDES * T; i += FP_THREADS) {
             const int sd = i / T, r = i % T;
@@ -610,87 +659,97 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         parity ^= 1;
         __syncthreads();
 
-        /* ---------------- phase 0.5: bit planes of every row + validation ---------------- */
-        {
+        /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
+        const bool split_roles = ndense_warps < FP_WARPS;
+        if (!split_roles || warp < ndense_warps) {
+        /* ---------------- dense column pass: pre-filter stats of every row, two cycles per thread, exact for any byte ---------------- */
+            if (col_active) {
+                const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
+                const uint16_t* lens = s_len + my_side * T;
+                unsigned int* kh = s_kmer + my_side * FP_KMER_BINS; unsigned int* qh = s_qhist + my_side * FP_QUAL_BINS;
+                const int w4 = my_w * 4;
+                const int j0 = my_half * 2;
+                #pragma unroll 1
+                for (int r0 = 0; r0 < rows; r0 += 4) {
+                    uint32_t xs[4], xq[4];
+                    #pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int r = r0 + kk;
+                        const int hi = (r < rows) ? lens[r] : 0;
+                        const uint32_t m = window_mask(w4, 0, hi);
+                        uint32_t x = 0, q = 0;
+                        if (m) {
+                            const uint32_t K = 0x01010101u;
+                            x = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;
+                            q = *reinterpret_cast<const uint32_t*>(tq + r * S + w4) & m;
+                            /* bytes the register fast path cannot represent: base&7 in {0,2,5} or quality >= 128 -> exact global path */
+                            const uint32_t c0 = x & K, c1 = (x >> 1) & K, c2 = (x >> 2) & K;
+                            const uint32_t present = (m & K);
+                            uint32_t bad = present & (((~c0) & (~c2)) | (c0 & (~c1) & c2) | (q >> 7));
+                            if (bad) {
+                                #pragma unroll 1
+                                for (int j = j0; j < j0 + 2; j++)
+                                    if ((bad >> (8 * j)) & 1) {
+                                        const uint8_t bb = (uint8_t)(x >> (8 * j)), qb = (uint8_t)(q >> (8 * j));
+                                        slow_cycle_byte(G, my_side * 2, w4 + j, bb, qb);           /* dense feeds pre AND post */
+                                        slow_cycle_byte(G, my_side * 2 + 1, w4 + j, bb, qb);
+                                    }
+                                x &= ~(bad * 0xFFu);                                              /* drop them from the fast path */
+                            }
+                            /* this thread's two bytes: quality histogram (stats.cpp:213) + 5-mers (stats.cpp:228-266) */
+                            const int nb = min(hi - w4, 4);
+                            if (j0 < nb && !((q >> (8 * j0 + 7)) & 1)) atomicAdd(&qh[(q >> (8 * j0)) & 0x7F], 1u);
+                            if (j0 + 1 < nb && !((q >> (8 * j0 + 15)) & 1)) atomicAdd(&qh[(q >> (8 * j0 + 8)) & 0x7F], 1u);
+                            if (my_w > 0) {
+                                const uint32_t xc = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;   /* unfiltered bases for 5-mers */
+                                const uint32_t xp = *reinterpret_cast<const uint32_t*>(ts + r * S + w4 - 4);
+                                const uint32_t okc = exact_acgt(xc), okp = exact_acgt(xp);
+                                const uint32_t vc = (xc & 0x02020202u) | ((xc >> 2) & K), vp = (xp & 0x02020202u) | ((xp >> 2) & K);
+                                const uint32_t s16 = (((vp * 0x40100401u) >> 24) << 8) | ((vc * 0x40100401u) >> 24);
+                                const uint32_t ok8 = ((((okp * 0x08040201u) >> 24) & 0xF) << 4) | (((okc * 0x08040201u) >> 24) & 0xF);
+                                if (((ok8 >> (3 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (3 - j0))) & 0x3FF], 1u);
+                                if (((ok8 >> (2 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (2 - j0))) & 0x3FF], 1u);
+                            }
+                        }
+                        xs[kk] = x; xq[kk] = q;
+                    }
+                    const unsigned sel = my_half ? 0x7362u : 0x5140u;
+                    const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+                    const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+                    acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
+                    acc_cycle(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
+                }
+            }
+
+        }
+        if (!split_roles) __syncthreads();
+        if (!split_roles || warp >= ndense_warps) {
+            const int pt0 = split_roles ? tid - ndense_warps * 32 : tid;
+            const int pstep = split_roles ? FP_THREADS - ndense_warps * 32 : FP_THREADS;
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
             #pragma unroll 1
-            for (int it = tid; it < SIDES * T * PW; it += FP_THREADS) {
-                const int j = it % PW, rr = (it / PW) % T, sd = it / (PW * T);
+            for (int it = pt0; it < SIDES * T * PW; it += pstep) {
+                const int j = it % PW, rr2 = (it / PW) % T, sd = it / (PW * T);
                 uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
-                if (j < nwords && rr < rows) {
-                    const int n = (int)s_len[sd * T + rr] - 32 * j;
+                if (j < nwords && rr2 < rows) {
+                    const int n = (int)s_len[sd * T + rr2] - 32 * j;
                     if (n > 0) {
-                        const uint4* sp = reinterpret_cast<const uint4*>(tile_seq[sd] + rr * S + 32 * j);
-                        const uint4* qp = reinterpret_cast<const uint4*>(tile_qual[sd] + rr * S + 32 * j);
-                        const uint4 s0 = sp[0], s1 = sp[1], q0 = qp[0], q1 = qp[1];
+                        const uint4* s4 = reinterpret_cast<const uint4*>(tile_seq[sd] + rr2 * S + 32 * j);
+                        const uint4* q4 = reinterpret_cast<const uint4*>(tile_qual[sd] + rr2 * S + 32 * j);
+                        const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
                         const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                         const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr] = 0;
+                        if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr2] = 0;
                     }
                 }
-                uint32_t* pr = tile_planes + (sd * T + rr) * PSTR + j;
+                uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;
                 pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
             }
         }
         __syncthreads();
 
-        /* ---------------- phase 1: dense column pass (pre-filter stats of clean rows), two cycles per thread ---------------- */
-        if (col_active) {
-            const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
-            const uint16_t* lens = s_len + my_side * T; const uint8_t* cl = s_clean + my_side * T;
-            unsigned int* kh = s_kmer + my_side * FP_KMER_BINS; unsigned int* qh = s_qhist + my_side * FP_QUAL_BINS;
-            const int w4 = my_w * 4;
-            #pragma unroll 1
-            for (int r0 = 0; r0 < rows; r0 += 4) {
-                uint32_t xs[4], xq[4];
-                #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int r = r0 + k;
-                    const int hi = (r < rows && cl[r]) ? lens[r] : 0;
-                    const uint32_t m = window_mask(w4, 0, hi);
-                    uint32_t x = 0, q = 0;
-                    if (m) {
-                        x = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;
-                        q = *reinterpret_cast<const uint32_t*>(tq + r * S + w4) & m;
-                        /* this thread's two bytes of the word: quality histogram (stats.cpp:213) + 5-mers (stats.cpp:228-266) */
-                        const int j0 = my_half * 2;
-                        const int nb = min(hi - w4, 4);
-                        if (j0 < nb) atomicAdd(&qh[(q >> (8 * j0)) & 0xFF], 1u);
-                        if (j0 + 1 < nb) atomicAdd(&qh[(q >> (8 * j0 + 8)) & 0xFF], 1u);
-                        if (my_w > 0) {
-                            const uint32_t xp = *reinterpret_cast<const uint32_t*>(ts + r * S + w4 - 4);
-                            const uint32_t K = 0x01010101u;
-                            const uint32_t c0 = x & K, c1 = (x >> 1) & K, c2 = (x >> 2) & K;
-                            const uint32_t okc = (c0 & ~c1 & ~c2) | (c0 & c1) | (~c0 & ~c1 & c2);
-                            const uint32_t p0 = xp & K, p1 = (xp >> 1) & K, p2 = (xp >> 2) & K;
-                            const uint32_t okp = (p0 & ~p1 & ~p2) | (p0 & p1) | (~p0 & ~p1 & p2);
-                            const uint32_t vc = (x & 0x02020202u) | c2, vp = (xp & 0x02020202u) | p2;
-                            const uint32_t s16 = (((vp * 0x40100401u) >> 24) << 8) | ((vc * 0x40100401u) >> 24);
-                            const uint32_t ok8 = ((((okp * 0x08040201u) >> 24) & 0xF) << 4) | (((okc * 0x08040201u) >> 24) & 0xF);
-                            if (((ok8 >> (3 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (3 - j0))) & 0x3FF], 1u);
-                            if (((ok8 >> (2 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (2 - j0))) & 0x3FF], 1u);
-                        }
-                    }
-                    xs[k] = x; xq[k] = q;
-                }
-                /* 4x4 byte transpose restricted to this thread's two cycles */
-                const unsigned sel = my_half ? 0x7362u : 0x5140u;
-                const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
-                const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
-                acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
-                acc_cycle(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
-            }
-        }
-        __syncthreads();
-
-        /* ---------------- phase 2: operator chain, one lane GROUP per read / pair ---------------- */
-        constexpr int GL = PAIRED ? 4 : 2;            /* lanes per unit */
-        constexpr int UPW = 32 / GL;                  /* units per warp */
-        const int sub = lane % GL;
-        const bool lead = sub == 0;
-        const unsigned gmask = group_mask(GL);
-        const int glead = lane & ~(GL - 1);
+        /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
         for (int rbase = warp * UPW; rbase < rows; rbase += FP_WARPS * UPW) {
             const int r = rbase + lane / GL;
@@ -703,7 +762,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 const int len0 = active ? s_len[rr] : 0;
                 const bool clean = s_clean[rr] != 0;
                 if (active && lead) { rl[0] += 1; rl[1] += len0; }
-                warp_serve_pre(active && lead && !clean, G, FP_STATS_PRE1, rs, rq, len0);
                 TRead r1; r1.seq = rs; r1.qual = rq; r1.pl = tile_planes + rr * PSTR; r1.front = 0; r1.len = len0; r1.null = false; r1.clean = clean;
                 int flags = 0, apos = 0, abases = 0, pbase = 255, plen = 0, result = FP_FAIL_LENGTH;
                 bool counted = false;
@@ -736,10 +794,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                         a.out1[gi] = t_make_result(r1, result, result, flags, apos, abases, pbase, plen);
                     }
                 }
-                /* post stats as a delta against pre (warp-cooperative) */
-                const bool keep_tail = counted && r1.front == 0 && clean;
-                warp_serve_delta(active && lead && clean, true, D, G, 0, rs, rq, 0, keep_tail ? r1.len : 0, len0, -1);
-                warp_serve_delta(active && lead && counted && !keep_tail, clean, D, G, 0, rs, rq, r1.front, r1.front, r1.front + r1.len, +1);
+                /* post stats as a delta against pre (warp-cooperative): drop what was trimmed / failed, re-add shifted windows */
+                const bool keep_tail = counted && r1.front == 0;
+                push_delta(s_queue, &s_qn[0], active && lead, clean, 0, rr, 0, keep_tail ? r1.len : 0, len0, -1);
+                push_delta(s_queue, &s_qn[0], active && lead && counted && !keep_tail, clean, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
             } else {
                 /* PairEndProcessor::processPairEnd loop body  peprocessor.cpp:383-643 */
                 uint8_t* rs1 = tile_seq[0] + rr * S; uint8_t* rq1 = tile_qual[0] + rr * S;
@@ -747,8 +805,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 const int l1 = active ? s_len[rr] : 0, l2 = active ? s_len[T + rr] : 0;
                 const bool clean1 = s_clean[rr] != 0, clean2 = s_clean[T + rr] != 0;
                 if (active && lead) { rl[0] += 1; rl[1] += l1; rl[4] += 1; rl[5] += l2; }
-                warp_serve_pre(active && lead && !clean1, G, FP_STATS_PRE1, rs1, rq1, l1);
-                warp_serve_pre(active && lead && !clean2, G, FP_STATS_PRE2, rs2, rq2, l2);
                 uint32_t* pl1 = tile_planes + rr * PSTR; uint32_t* pl2 = tile_planes + (T + rr) * PSTR;
                 TRead r1, r2;
                 r1.seq = rs1; r1.qual = rq1; r1.pl = pl1; r1.front = 0; r1.len = l1; r1.null = false; r1.clean = clean1;
@@ -777,11 +833,11 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             else red_add64(&G[L.off_isize + isize], 1ull);
                         }
                     }
-                    need_correct = both && (c_p.adapter_enabled || c_p.correction) && c_p.correction && ov.overlapped && ov.diff != 0;   /* :443,:453-456 */
+                    need_correct = both && c_p.correction && ov.overlapped && ov.diff != 0;       /* :443,:453-456 */
                 }
                 /* the post stats are a delta against the ORIGINAL bases: take reads that are about to be corrected out first */
-                warp_serve_delta(need_correct && lead && clean1, true, D, G, 0, rs1, rq1, 0, 0, l1, -1);
-                warp_serve_delta(need_correct && lead && clean2, true, D, G, 1, rs2, rq2, 0, 0, l2, -1);
+                warp_serve_delta(need_correct && lead, clean1, D, G, 0, rs1, rq1, 0, 0, l1, -1);
+                warp_serve_delta(need_correct && lead, clean2, D, G, 1, rs2, rq2, 0, 0, l2, -1);
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
                 if (active) {
@@ -850,13 +906,32 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 /* post stats as a delta against pre, per side (warp-cooperative) */
                 {
                     const bool removed = need_correct;
-                    const bool keep1 = counted && r1.front == 0 && clean1 && !removed;
-                    warp_serve_delta(active && lead && clean1 && !removed, true, D, G, 0, rs1, rq1, 0, keep1 ? r1.len : 0, l1, -1);
-                    warp_serve_delta(active && lead && counted && !keep1, clean1, D, G, 0, rs1, rq1, r1.front, r1.front, r1.front + r1.len, +1);
-                    const bool keep2 = counted && r2.front == 0 && clean2 && !removed;
-                    warp_serve_delta(active && lead && clean2 && !removed, true, D, G, 1, rs2, rq2, 0, keep2 ? r2.len : 0, l2, -1);
-                    warp_serve_delta(active && lead && counted && !keep2, clean2, D, G, 1, rs2, rq2, r2.front, r2.front, r2.front + r2.len, +1);
+                    const bool keep1 = counted && r1.front == 0 && !removed;
+                    push_delta(s_queue, &s_qn[0], active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
+                    push_delta(s_queue, &s_qn[0], active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
+                    const bool keep2 = counted && r2.front == 0 && !removed;
+                    push_delta(s_queue, &s_qn[0], active && lead && !removed, clean2, 1, rr, 0, keep2 ? r2.len : 0, l2, -1);
+                    push_delta(s_queue, &s_qn[0], active && lead && counted && !keep2, clean2, 1, rr, r2.front, r2.front, r2.front + r2.len, +1);
                 }
+            }
+        }
+
+        __syncthreads();
+
+        /* ---------------- phase C: drain the post-stat request queue (all warps, dynamic) ---------------- */
+        {
+            const int nreq = s_qn[0];
+            #pragma unroll 1
+            for (;;) {
+                int qi = 0;
+                if (lane == 0) qi = atomicAdd(&s_qn[1], 1);
+                qi = __shfl_sync(FULL_MASK, qi, 0);
+                if (qi >= nreq) break;
+                const DeltaReq rq = s_queue[qi];
+                const int row = rq.row_side & 0xFFFF, side = (rq.row_side >> 16) & 1, sign = ((rq.row_side >> 18) & 1) ? -1 : +1;
+                const uint8_t* sq = tile_seq[side] + row * S; const uint8_t* ql = tile_qual[side] + row * S;
+                if ((rq.row_side >> 17) & 1) dev_stat_positions_smem(D, side, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
+                else dev_stat_positions(G, side * 2 + 1, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
             }
         }
         __syncthreads();

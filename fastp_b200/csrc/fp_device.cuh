@@ -992,7 +992,7 @@ __device__ __forceinline__ void post_delta(bool clean, const DeltaAcc& D, unsign
  * ------------------------------------------------------------------------------------------------ */
 struct fp_smem_layout {
     int off_mbar, off_tile, tile_array_bytes, off_len, off_clean, off_rc, rc_bytes, off_scratch, scratch_ints,
-        off_kmer, off_qhist, off_bc, off_rl, off_next, off_planes, off_rcplanes, off_lut, off_delta, plane_words, plane_stride, total;
+        off_kmer, off_qhist, off_bc, off_rl, off_next, off_planes, off_rcplanes, off_lut, off_delta, off_queue, plane_words, plane_stride, total;
 };
 
 struct fp_launch_args {
