@@ -376,6 +376,8 @@ static int ensure_staging(fp_ctx* c) {
     return FP_OK;
 }
 
+static const uint32_t PFAST = 16384;   /* patches copied back without waiting for their count */
+
 static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_staging(c);
@@ -392,6 +394,8 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         if (pe && c->p.correction_enabled) {
             uint32_t np = *c->h_npatch[slot];
             const int64_t lo = pend[slot].lo;
+            if (np > PFAST && np <= c->patch_cap)
+                CK(cudaMemcpy(c->h_patch[slot] + PFAST, c->d_patch[slot] + PFAST, (size_t)(np - PFAST) * sizeof(fp_patch), cudaMemcpyDeviceToHost));
             if (np <= c->patch_cap) {
                 for (uint32_t k = 0; k < np; k++) {
                     const fp_patch& pt = c->h_patch[slot][k];
@@ -439,11 +443,9 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
             if (ov) CK(cudaMemcpyAsync(ov + lo, c->d_ov[slot], (size_t)cnt * sizeof(fp_ov_result), cudaMemcpyDeviceToHost, st));
             if (c->p.correction_enabled) {
+                /* count + the first PFAST patches ride along asynchronously (corrections are sparse); finish() fetches the rest if any */
                 CK(cudaMemcpyAsync(c->h_npatch[slot], c->d_npatch[slot], 4, cudaMemcpyDeviceToHost, st));
-                /* the list is usually tiny; copy the whole capacity only when it is small, else size it after the count */
-                CK(cudaStreamSynchronize(st));
-                uint32_t np = std::min(*c->h_npatch[slot], c->patch_cap);
-                if (np) CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)np * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)std::min<uint32_t>(PFAST, c->patch_cap) * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
             }
         }
         pend[slot].lo = lo; pend[slot].cnt = cnt; pend[slot].active = true;

@@ -195,7 +195,30 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
         const unsigned long long bhi = ~(((unsigned long long)__brev(tp_bits_z(phi, e - 63)) << 32) | __brev(tp_bits_z(phi, e - 31))) & ~bnn;
         const int nfwd = len1 - req;
         int my_o = 1 << 20, my_mm = 0, my_ol = 0;
-        for (int o = sub; o < nfwd; o += g) {
+        int o = sub;
+        /* fast range: overlap >= 50 bases, so the protected prefix is exactly 50 bits; the three words under the
+           sliding window stay in registers while the offset moves inside one 32-bit word */
+        const int nfast = len2 >= 50 ? min(max(len1 - 49, 0), nfwd) : 0;
+        {
+            const uint32_t b_lo0 = (uint32_t)blo, b_lo1 = (uint32_t)(blo >> 32), b_hi0 = (uint32_t)bhi, b_hi1 = (uint32_t)(bhi >> 32),
+                           b_nn0 = (uint32_t)bnn, b_nn1 = (uint32_t)(bnn >> 32);
+            while (o < nfast && my_o == (1 << 20)) {
+                int c = f1 + o;
+                const int w = c >> 5;
+                const uint32_t L0 = alo[w], L1 = alo[w + 1], L2 = alo[w + 2], H0 = ahi[w], H1 = ahi[w + 1], H2 = ahi[w + 2],
+                               N0 = ann[w], N1 = ann[w + 1], N2 = ann[w + 2];
+                do {
+                    const int sh = c & 31;
+                    const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
+                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
+                    const int mm = __popc(x0) + __popc(x1);
+                    const int ol = min(len1 - o, len2);
+                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    o += g; c += g;
+                } while (o < nfast && (c >> 5) == w);
+            }
+        }
+        for (; o < nfwd && my_o == (1 << 20); o += g) {
             const int ol = min(len1 - o, len2);
             const int pp = min(ol, 50);
             const int bit = f1 + o;
@@ -217,7 +240,28 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
         const unsigned long long ynn = __brevll(a_nn) >> 14, ylo = __brevll(a_lo) >> 14, yhi = ~(__brevll(a_hi) >> 14) & ~ynn;
         const int nbwd = len2 - req;
         int my_o = 1 << 20, my_mm = 0, my_ol = 0;
-        for (int o = sub; o < nbwd; o += g) {
+        int o = sub;
+        const int nfast = len1 >= 50 ? min(max(len2 - 49, 0), nbwd) : 0;   /* overlap >= 50: row2's 50-bit field starts at e-49-o */
+        {
+            const uint32_t y_lo0 = (uint32_t)ylo, y_lo1 = (uint32_t)(ylo >> 32), y_hi0 = (uint32_t)yhi, y_hi1 = (uint32_t)(yhi >> 32),
+                           y_nn0 = (uint32_t)ynn, y_nn1 = (uint32_t)(ynn >> 32);
+            while (o < nfast && my_o == (1 << 20)) {
+                int c = e - 49 - o;                                        /* >= front2 >= 0 */
+                const int w = c >> 5;
+                const uint32_t L0 = plo[w], L1 = plo[w + 1], L2 = plo[w + 2], H0 = phi[w], H1 = phi[w + 1], H2 = phi[w + 2],
+                               N0 = pnn[w], N1 = pnn[w + 1], N2 = pnn[w + 2];
+                do {
+                    const int sh = c & 31;
+                    const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
+                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
+                    const int mm = __popc(x0) + __popc(x1);
+                    const int ol = min(len1, len2 - o);
+                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    o += g; c -= g;
+                } while (o < nfast && c >= 0 && (c >> 5) == w);
+            }
+        }
+        for (; o < nbwd && my_o == (1 << 20); o += g) {
             const int ol = min(len1, len2 - o);
             const int pp = min(ol, 50);
             const int sbit = e - o - pp + 1;                               /* >= front2 >= 0 */
