@@ -102,35 +102,26 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     const int sides = c->p.paired ? 2 : 1;
     const int S = c->stride;
+    memset(&sl, 0, sizeof(sl));
     size_t off = 0;
     sl.off_mbar = (int)off; off += 16;
+    sl.off_next = (int)off; off += 16;                                     /* delta queue length + pop cursor */
     off = align_up(off, 128);
-    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 16;
+    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
     off = align_up(off, 16);
     sl.off_len = (int)off; off += (size_t)sides * T * 2;
     sl.off_clean = (int)off; off += (size_t)sides * T;
     off = align_up(off, 16);
-    sl.rc_bytes = (int)align_up(S + 16, 16);
-    sl.off_rc = (int)off; off += (size_t)FP_WARPS * sl.rc_bytes;
-    /* per-warp int scratch: prefix sums of quals (only when a sliding-window cut is on, filter.cpp:97-194) and the
-       two arrays of the one-gap adapter scans (only when adapters are trimmed by sequence, adaptertrimmer.cpp:105-135) */
-    const bool need_cut = c->p.cut_front || c->p.cut_tail || c->p.cut_right;
-    const bool need_gap = c->p.adapter_enabled && (c->p.has_seq_r1 || c->p.has_seq_r2 || c->p.n_fasta_adapters > 0);
-    sl.scratch_ints = std::max(need_cut ? S + 2 : 4, need_gap ? 2 * (FP_MAX_ADAPTER_LEN + 2) : 4);
-    sl.off_scratch = (int)off; off += (size_t)FP_WARPS * sl.scratch_ints * 4;
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
     sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
-    off = align_up(off, 8);
-    sl.off_rl = (int)off; off += 8 * 8;
+    off = align_up(off, 16);
     sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
     sl.off_delta = (int)off; off += (size_t)sides * ((size_t)S * 20 + FP_KMER_BINS + FP_QUAL_BINS) * 4;
-    sl.off_next = (int)off; off += 16;
     sl.plane_words = (S + 31) / 32 + 2;
-    sl.plane_stride = (4 * sl.plane_words) | 1;                      /* odd: one thread per row without bank conflicts */
+    sl.plane_stride = (4 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
     off = align_up(off, 16);
     sl.off_planes = (int)off; off += (size_t)sides * T * sl.plane_stride * 4;
-    sl.off_rcplanes = (int)off;
     off = align_up(off, 16);
     sl.off_queue = (int)off; off += (size_t)sides * T * 2 * 16;
     sl.total = (int)align_up(off, 128);

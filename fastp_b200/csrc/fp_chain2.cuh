@@ -568,19 +568,6 @@ __device__ __forceinline__ void warp_serve_delta(bool want, bool clean, const De
         else dev_stat_positions(G, side * 2 + 1, sq, ql, c0, a, b, sg);
     }
 }
-/* pre-filter stats of unclean rows (global path, sign +1) */
-__device__ __forceinline__ void warp_serve_pre(bool want, unsigned long long* G, int stats, const uint8_t* seq, const uint8_t* qual, int len) {
-    unsigned m = __ballot_sync(FULL_MASK, want && len > 0);
-    while (m) {
-        const int l = __ffs(m) - 1;
-        m &= m - 1;
-        const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)seq, l));
-        const uint8_t* ql = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)qual, l));
-        const int n = __shfl_sync(FULL_MASK, len, l);
-        dev_stat_positions(G, stats, sq, ql, 0, 0, n, +1);
-    }
-}
-
 /* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
 struct ColAcc2 { unsigned int v[2][NB][4]; };
 
