@@ -368,7 +368,7 @@ def main():
         "gpu_launches": int(nl.value),
         "checks": checks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fp_chain_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_unit": bytes_per_unit,
+                     "traffic": traffic, "kernel": "fp_chain2_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_unit": bytes_per_unit,
                      "peak_source": peak_src},
     }
     if rank == 0:
