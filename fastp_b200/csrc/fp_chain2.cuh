@@ -329,6 +329,56 @@ __device__ __noinline__ fp_ov_result t_analyze_bytes(const TRead r1, const TRead
     return ov;
 }
 
+/* Effect of ONE corrected base on the post-filter statistics, in full-read context (cycle = row position P, 5-mers of
+ * the whole original row): -(old base, old quality) +(new base, new quality).  The dense pass credited the ORIGINAL row to
+ * pre and post; with this delta the block-private (or, for unclean rows, global) post accumulators describe the CURRENT row,
+ * so the end-of-chain tail/whole-read removal can use the current bytes for corrected and uncorrected reads alike.
+ * Called by one thread while seq[P] still holds the old base. */
+__device__ __noinline__ void t_patch_delta(const DeltaAcc D, unsigned long long* G, bool clean, int side, const uint8_t* seq, int l0, int P,
+                                           uint8_t ob, uint8_t oq, uint8_t nb, uint8_t nq) {
+    const fp_counter_layout& L = c_p.L;
+    #pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const uint8_t b = pass ? nb : ob, q = pass ? nq : oq;
+        const int sg = pass ? +1 : -1;
+        if (clean) {
+            if (q < FP_QUAL_BINS) atomicAdd(&D.qh[side * FP_QUAL_BINS + q], sg);
+            if (P < D.cycles) {
+                int* c4 = D.cyc + side * D.cycles * 20 + (P * 5 + ((0x43F21F0Fu >> (4 * (b & 7))) & 0xF)) * 4;
+                atomicAdd(&c4[0], sg);
+                if (q >= '5') atomicAdd(&c4[1], sg);
+                if (q >= '?') atomicAdd(&c4[2], sg);
+                atomicAdd(&c4[3], sg * ((int)q - 33));
+            }
+        } else {
+            const unsigned long long one = (unsigned long long)(long long)sg;
+            const int st = side * 2 + 1, bb = b & 7;
+            if (q < FP_QUAL_BINS) red_add64(&G[fp_off_qualhist(&L, st, q)], one);
+            if (P < L.cycles) {
+                if (q >= '?') { red_add64(&G[fp_off_cycle(&L, st, 0 * 8 + bb, P)], one); red_add64(&G[fp_off_cycle(&L, st, 1 * 8 + bb, P)], one); }
+                else if (q >= '5') red_add64(&G[fp_off_cycle(&L, st, 1 * 8 + bb, P)], one);
+                red_add64(&G[fp_off_cycle(&L, st, 2 * 8 + bb, P)], one);
+                red_add64(&G[fp_off_cycle(&L, st, 3 * 8 + bb, P)], (unsigned long long)((long long)sg * ((int)q - 33)));
+            }
+        }
+        /* 5-mers ending at i = P .. P+4 (stats.cpp:228-266) with the base at P set to b */
+        #pragma unroll 1
+        for (int i = max(P, 4); i <= min(P + 4, l0 - 1); i++) {
+            int code = 0; bool ok = true;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int pos = i - 4 + k;
+                const int v = dev_base2val(pos == P ? b : seq[pos]);
+                ok = ok && (v >= 0); code = (code << 2) | (v & 3);
+            }
+            if (ok) {
+                if (clean) atomicAdd(&D.kmer[side * FP_KMER_BINS + code], sg);
+                else red_add64(&G[fp_off_kmer(&L, side * 2 + 1, code)], (unsigned long long)(long long)sg);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * BaseCorrector::correctByOverlapAnalysis  (basecorrector.cpp:21-83), one thread per pair, scalar over the overlap.
  * Writes the shared-memory rows, the HBM rows, the patch list and (for clean rows) updates the bit planes.
@@ -344,7 +394,7 @@ __device__ __forceinline__ void t_plane_set_base(uint32_t* pl, int PW, int pos, 
 
 __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t* pl1, uint32_t* pl2, int PW, const fp_ov_result ov,
                                        uint8_t* g1s, uint8_t* g1q, uint8_t* g2s, uint8_t* g2q, unsigned int pair_index, const PatchSink& sink,
-                                       BlockCounters* bc, bool& c1, bool& c2) {
+                                       BlockCounters* bc, const DeltaAcc D, unsigned long long* G, int l1, int l2, bool& c1, bool& c2) {
     c1 = c2 = false;
     if (ov.diff == 0 || !ov.overlapped) return;                           /* :23-24 */
     const int ol = ov.overlap_len;
@@ -374,6 +424,7 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
                 const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
                 if (q1 >= GOOD && q2 <= BAD) {                                 /* use R1 :42-50 */
                     const uint8_t nb = dev_complement(b1);
+                    t_patch_delta(D, G, r2.clean, 1, r2.seq, l2, r2.front + p2, b2, (uint8_t)q2, nb, (uint8_t)q1);
                     s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
                     if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
                     corrected++; c2 = true;
@@ -384,6 +435,7 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
                     }
                 } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
                     const uint8_t nb = dev_complement(b2);
+                    t_patch_delta(D, G, r1.clean, 0, r1.seq, l1, r1.front + p1, b1, (uint8_t)q1, nb, (uint8_t)q2);
                     s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
                     if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
                     corrected++; c1 = true;
@@ -634,7 +686,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
     for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
     for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
-    if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
     const int HPR = S >> 1;
@@ -677,7 +729,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
-            s_qn[0] = 0; s_qn[1] = 0;
+            s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0;
         }
         for (int i = tid; i < SIDES * T; i += FP_THREADS) {
             const int sd = i / T, r = i % T;
@@ -691,8 +743,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         __syncthreads();
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
-        const bool split_roles = ndense_warps < FP_WARPS;
-        if (!split_roles || warp < ndense_warps) {
+        if (warp < ndense_warps) {
         /* ---------------- dense column pass: pre-filter stats of every row, two cycles per thread, exact for any byte ---------------- */
             if (col_active) {
                 const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
@@ -753,29 +804,34 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
             }
 
         }
-        if (!split_roles) __syncthreads();
-        if (!split_roles || warp >= ndense_warps) {
-            const int pt0 = split_roles ? tid - ndense_warps * 32 : tid;
-            const int pstep = split_roles ? FP_THREADS - ndense_warps * 32 : FP_THREADS;
+        {   /* bit planes + validation: 32-item batches claimed dynamically -- warps without columns start at once, the dense warps join */
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
+            const int total = SIDES * T * PW;
             #pragma unroll 1
-            for (int it = pt0; it < SIDES * T * PW; it += pstep) {
-                const int j = it % PW, rr2 = (it / PW) % T, sd = it / (PW * T);
-                uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
-                if (j < nwords && rr2 < rows) {
-                    const int n = (int)s_len[sd * T + rr2] - 32 * j;
-                    if (n > 0) {
-                        const uint4* s4 = reinterpret_cast<const uint4*>(tile_seq[sd] + rr2 * S + 32 * j);
-                        const uint4* q4 = reinterpret_cast<const uint4*>(tile_qual[sd] + rr2 * S + 32 * j);
-                        const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
-                        const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                        const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr2] = 0;
+            for (;;) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_qn[2], 32);
+                base = __shfl_sync(FULL_MASK, base, 0);
+                if (base >= total) break;
+                const int it = base + lane;
+                if (it < total) {
+                    const int j = it % PW, rr2 = (it / PW) % T, sd = it / (PW * T);
+                    uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
+                    if (j < nwords && rr2 < rows) {
+                        const int n = (int)s_len[sd * T + rr2] - 32 * j;
+                        if (n > 0) {
+                            const uint4* s4 = reinterpret_cast<const uint4*>(tile_seq[sd] + rr2 * S + 32 * j);
+                            const uint4* q4 = reinterpret_cast<const uint4*>(tile_qual[sd] + rr2 * S + 32 * j);
+                            const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
+                            const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                            const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                            if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr2] = 0;
+                        }
                     }
+                    uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;
+                    pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
                 }
-                uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;
-                pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
             }
         }
         __syncthreads();
@@ -866,9 +922,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                     }
                     need_correct = both && c_p.correction && ov.overlapped && ov.diff != 0;       /* :443,:453-456 */
                 }
-                /* the post stats are a delta against the ORIGINAL bases: take reads that are about to be corrected out first */
-                warp_serve_delta(need_correct && lead, clean1, D, G, 0, rs1, rq1, 0, 0, l1, -1);
-                warp_serve_delta(need_correct && lead, clean2, D, G, 1, rs2, rq2, 0, 0, l2, -1);
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
                 if (active) {
@@ -878,7 +931,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                         if (lead) {
                             bool c1, c2;
                             t_correct(r1, r2, pl1, pl2, PW, ov, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
-                                      a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, c1, c2);
+                                      a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, D, G, l1, l2, c1, c2);
                             cf = (c1 ? 1 : 0) | (c2 ? 2 : 0);
                         }
                         __syncwarp(gmask);                                                        /* corrected bytes / planes visible to the whole group */
@@ -936,7 +989,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 }
                 /* post stats as a delta against pre, per side (warp-cooperative) */
                 {
-                    const bool removed = need_correct;
+                    const bool removed = false;        /* corrections were folded into the accumulators base by base (t_patch_delta) */
                     const bool keep1 = counted && r1.front == 0 && !removed;
                     push_delta(s_queue, &s_qn[0], active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
                     push_delta(s_queue, &s_qn[0], active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
