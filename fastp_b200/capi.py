@@ -48,6 +48,9 @@ class Params(C.Structure):
         ("length_filter_enabled", C.c_int32), ("length_required", C.c_int32), ("length_limit", C.c_int32),
         ("complexity_filter_enabled", C.c_int32), ("complexity_threshold", C.c_double),
         ("insert_size_max", C.c_int32), ("seq_len1", C.c_int32), ("seq_len2", C.c_int32),
+        ("overrep_enabled", C.c_int32), ("overrep_sampling", C.c_int32),
+        ("n_overrep1", C.c_int32), ("overrep_seqs1", C.POINTER(C.c_char_p)),
+        ("n_overrep2", C.c_int32), ("overrep_seqs2", C.POINTER(C.c_char_p)),
     ]
 
 
@@ -64,7 +67,9 @@ class CounterLayout(C.Structure):
         ("cycles", C.c_int32), ("n_stats", C.c_int32), ("isize_bins", C.c_int32), ("_pad", C.c_int32),
         ("stats_stride", C.c_int64), ("off_kmer", C.c_int64), ("off_qualhist", C.c_int64),
         ("off_reads", C.c_int64), ("off_length_sum", C.c_int64),
-        ("off_filter", C.c_int64), ("off_isize", C.c_int64), ("total", C.c_int64),
+        ("off_filter", C.c_int64), ("off_isize", C.c_int64),
+        ("n_overrep", C.c_int32 * 2), ("overrep_len", C.c_int32 * 2), ("off_overrep", C.c_int64 * 4),
+        ("total", C.c_int64),
     ]
 
 
@@ -85,6 +90,7 @@ assert READ_RESULT_DTYPE.itemsize == 16 and OV_RESULT_DTYPE.itemsize == 8 and PA
 SYMBOLS = {
     "fp_params_default": (None, [C.POINTER(Params), C.c_int]),
     "fp_counter_layout_make": (None, [C.POINTER(CounterLayout), C.c_int, C.c_int, C.c_int]),
+    "fp_counter_layout_make_overrep": (None, [C.POINTER(CounterLayout), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fp_abi_sizeof": (C.c_size_t, [C.c_int]),
     "fp_ctx_create": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "fp_ctx_destroy": (None, [C.c_void_p]),
@@ -149,6 +155,14 @@ def set_params(p, **kw):
             b = v.encode() if isinstance(v, str) else v
             setattr(p, k, b)
             setattr(p, "has_seq_" + k[-2:], 1 if b else 0)
+        elif k in ("overrep_seqs1", "overrep_seqs2"):
+            items = [a.encode() if isinstance(a, str) else a for a in v]
+            arr = (C.c_char_p * max(len(items), 1))(*items)
+            keep = getattr(p, "_overrep_keepalive", {})
+            keep[k] = (arr, items)
+            p._overrep_keepalive = keep
+            setattr(p, k, C.cast(arr, C.POINTER(C.c_char_p)))
+            setattr(p, "n_overrep" + k[-1], len(items))
         elif k == "fasta_adapters":
             items = [a.encode() if isinstance(a, str) else a for a in v]
             arr = (C.c_char_p * len(items))(*items)
@@ -162,9 +176,14 @@ def set_params(p, **kw):
     return p
 
 
-def make_layout(lib, paired, cycles, insert_size_max=512):
+def make_layout(lib, paired, cycles, insert_size_max=512, params=None):
+    """Counter layout; with `params` the over-representation regions follow its candidate lists."""
     L = CounterLayout()
-    lib.fp_counter_layout_make(C.byref(L), 1 if paired else 0, cycles, insert_size_max)
+    if params is not None and params.overrep_enabled:
+        lib.fp_counter_layout_make_overrep(C.byref(L), 1 if paired else 0, cycles, insert_size_max,
+                                           params.n_overrep1, params.seq_len1, params.n_overrep2, params.seq_len2)
+    else:
+        lib.fp_counter_layout_make(C.byref(L), 1 if paired else 0, cycles, insert_size_max)
     return L
 
 
@@ -187,6 +206,14 @@ class CounterView:
             "reads": int(d[base + L.off_reads]),
             "length_sum": int(d[base + L.off_length_sum]),
         }
+
+    def overrep(self, s):
+        """(count[K], dist[K][seqLen]) of Stats s (stats.cpp:270-288)."""
+        L = self.L
+        side = s >> 1
+        k, ln = L.n_overrep[side], L.overrep_len[side]
+        base = L.off_overrep[s]
+        return self.data[base: base + k], self.data[base + k: base + k + k * ln].reshape(k, ln) if k else self.data[base:base].reshape(0, max(ln, 1))
 
     @property
     def filter(self):

@@ -53,6 +53,17 @@ struct fp_ctx {
     int32_t *d_fasta_off = nullptr, *d_fasta_len = nullptr;
     uint32_t* d_aplanes = nullptr;
     uint8_t* d_aclean = nullptr;
+    /* over-representation analysis (stats.cpp:270-288) */
+    std::vector<std::string> overrep[2];
+    fp_overrep_side ovr_side[2] = {};
+    uint8_t* d_ovr_blob[2] = {nullptr, nullptr};
+    int32_t *d_ovr_off[2] = {nullptr, nullptr}, *d_ovr_len[2] = {nullptr, nullptr}, *d_ovr_tidx[2] = {nullptr, nullptr};
+    unsigned long long* d_ovr_thash[2] = {nullptr, nullptr};
+    unsigned int *d_ovr_blocksum = nullptr, *d_ovr_list = nullptr, *d_ovr_list_n = nullptr;
+    unsigned long long* d_ovr_base = nullptr;      /* [2] ping-pong: counted reads seen before this batch */
+    int ovr_base_cur = 0;
+    int64_t ovr_scratch_n = 0;
+    int64_t reads_seen = 0;
     long long *d_raw = nullptr, *d_fin = nullptr;
     /* host-mode staging (allocated lazily) */
     int64_t chunk = 0;
@@ -163,7 +174,14 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     for (auto& s : c->fasta) if (s.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
     if (c->ad1.size() > FP_MAX_ADAPTER_LEN || c->ad2.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
     c->max_batch = max_batch; c->stride = stride; c->cycles = cycles;
-    fp_counter_layout_make(&c->L, p->paired, cycles, p->insert_size_max);
+    if (p->overrep_enabled) {
+        if (p->overrep_sampling < 1) { delete c; return set_err(FP_E_INVAL, "overrep_sampling must be >= 1"); }
+        for (int i = 0; i < p->n_overrep1; i++) c->overrep[0].push_back(p->overrep_seqs1[i]);
+        if (p->paired) for (int i = 0; i < p->n_overrep2; i++) c->overrep[1].push_back(p->overrep_seqs2[i]);
+    }
+    c->p.overrep_seqs1 = nullptr; c->p.overrep_seqs2 = nullptr;
+    fp_counter_layout_make_overrep(&c->L, p->paired, cycles, p->insert_size_max, (int)c->overrep[0].size(), p->seq_len1,
+                                   (int)c->overrep[1].size(), p->seq_len2);
     make_smem_layout(c);
 
     cudaDeviceProp prop;
@@ -212,6 +230,35 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         CK(cudaMalloc(&c->d_aplanes, pl.size() * 4)); CK(cudaMalloc(&c->d_aclean, cl.size()));
         CK(cudaMemcpy(c->d_aplanes, pl.data(), pl.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_aclean, cl.data(), cl.size(), cudaMemcpyHostToDevice));
+    }
+    if (p->overrep_enabled) {
+        for (int sd = 0; sd < 2; sd++) {
+            const auto& cs = c->overrep[sd];
+            fp_overrep_side& S = c->ovr_side[sd];
+            S.K = (int)cs.size(); S.eval_len = sd ? p->seq_len2 : p->seq_len1;
+            if (S.K == 0) continue;
+            std::vector<uint8_t> blob; std::vector<int32_t> off, len;
+            for (auto& q : cs) { off.push_back((int32_t)blob.size()); len.push_back((int32_t)q.size()); blob.insert(blob.end(), q.begin(), q.end()); }
+            int tsize = 64; while (tsize < 4 * S.K) tsize <<= 1;
+            std::vector<unsigned long long> th(tsize, 0); std::vector<int32_t> ti(tsize, -1);
+            for (int k = 0; k < S.K; k++) {
+                unsigned long long h = 0;
+                for (unsigned char ch : cs[k]) h = h * FP_OVERREP_HASH_B + (unsigned long long)(ch + 1);
+                if (h == 0) h = 1;
+                unsigned int slot = (unsigned int)(h ^ (h >> 32)) & (tsize - 1);
+                while (th[slot] != 0) slot = (slot + 1) & (tsize - 1);
+                th[slot] = h; ti[slot] = k;
+            }
+            S.table_mask = tsize - 1;
+            CK(cudaMalloc(&c->d_ovr_blob[sd], blob.size() + 16)); CK(cudaMemcpy(c->d_ovr_blob[sd], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_ovr_off[sd], off.size() * 4)); CK(cudaMemcpy(c->d_ovr_off[sd], off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_ovr_len[sd], len.size() * 4)); CK(cudaMemcpy(c->d_ovr_len[sd], len.data(), len.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_ovr_thash[sd], (size_t)tsize * 8)); CK(cudaMemcpy(c->d_ovr_thash[sd], th.data(), (size_t)tsize * 8, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_ovr_tidx[sd], (size_t)tsize * 4)); CK(cudaMemcpy(c->d_ovr_tidx[sd], ti.data(), (size_t)tsize * 4, cudaMemcpyHostToDevice));
+            S.blob = c->d_ovr_blob[sd]; S.off = c->d_ovr_off[sd]; S.len = c->d_ovr_len[sd]; S.thash = c->d_ovr_thash[sd]; S.tidx = c->d_ovr_tidx[sd];
+        }
+        CK(cudaMalloc(&c->d_ovr_base, 16)); CK(cudaMemset(c->d_ovr_base, 0, 16));
+        CK(cudaMalloc(&c->d_ovr_list_n, 4));
     }
     CK(cudaMalloc(&c->d_raw, c->L.total * 8)); CK(cudaMalloc(&c->d_fin, c->L.total * 8));
     CK(cudaMemset(c->d_raw, 0, c->L.total * 8)); CK(cudaMemset(c->d_fin, 0, c->L.total * 8));
@@ -277,6 +324,8 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
     cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
+    for (int sd = 0; sd < 2; sd++) { cudaFree(c->d_ovr_blob[sd]); cudaFree(c->d_ovr_off[sd]); cudaFree(c->d_ovr_len[sd]); cudaFree(c->d_ovr_thash[sd]); cudaFree(c->d_ovr_tidx[sd]); }
+    cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list); cudaFree(c->d_ovr_list_n); cudaFree(c->d_ovr_base);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -317,6 +366,28 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     a.sl = c->sl;
     int grid = (int)std::min<long long>(a.n_tiles, c->grid_max);
     CK(cudaMemcpyToSymbolAsync(c_p, &c->dp, sizeof(fp_dev_params), 0, cudaMemcpyHostToDevice, st));
+    fp_overrep_args oa;
+    const bool ovr = c->p.overrep_enabled && (c->ovr_side[0].K > 0 || c->ovr_side[1].K > 0);
+    if (ovr) {
+        const int64_t nblk = (b->n + FP_RANK_ITEMS - 1) / FP_RANK_ITEMS;
+        const int64_t cap = b->n / c->p.overrep_sampling + 64;
+        if (b->n > c->ovr_scratch_n) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list);
+            CK(cudaMalloc(&c->d_ovr_blocksum, (size_t)(nblk + 1) * 4)); CK(cudaMalloc(&c->d_ovr_list, (size_t)cap * 4));
+            c->ovr_scratch_n = b->n;
+        }
+        memset(&oa, 0, sizeof(oa));
+        oa.b = *b; oa.side[0] = c->ovr_side[0]; oa.side[1] = c->ovr_side[1];
+        oa.counters = reinterpret_cast<unsigned long long*>(c->d_raw); oa.L = c->L;
+        oa.sides = c->p.paired ? 2 : 1; oa.sampling = c->p.overrep_sampling;
+        /* pre-filter stats: the ORIGINAL rows, i.e. before the chain kernel may correct bases in place */
+        oa.post = 0; oa.first_index = c->reads_seen;
+        const long long units = (b->n + oa.sampling - 1) / oa.sampling + 1;
+        const long long warps = units * oa.sides;
+        fp_overrep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(oa);
+        CK(cudaGetLastError());
+    }
     EvPair ev;
     if (!c->ev_pool.empty()) { ev = c->ev_pool.back(); c->ev_pool.pop_back(); }
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
@@ -327,6 +398,22 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     CK(cudaEventRecord(ev.b, st));
     c->evs.push_back(ev);
     CK(cudaGetLastError());
+    if (ovr) {
+        /* post-filter stats: rank the counted reads (verdict records), emit the sampled ones, scan their trimmed windows */
+        const int64_t nblk = (b->n + FP_RANK_ITEMS - 1) / FP_RANK_ITEMS;
+        const unsigned int cap = (unsigned int)(b->n / c->p.overrep_sampling + 64);
+        unsigned long long* base_cur = c->d_ovr_base + c->ovr_base_cur; unsigned long long* base_next = c->d_ovr_base + (c->ovr_base_cur ^ 1);
+        CK(cudaMemsetAsync(c->d_ovr_list_n, 0, 4, st));
+        fp_overrep_blocksum_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum);
+        fp_overrep_scan_kernel<<<1, 32, 0, st>>>(c->d_ovr_blocksum, (int)nblk, base_cur, base_next);
+        fp_overrep_emit_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum, base_cur, c->p.overrep_sampling, c->d_ovr_list, c->d_ovr_list_n, cap);
+        oa.post = 1; oa.res[0] = out1; oa.res[1] = out2; oa.list = c->d_ovr_list; oa.list_n = c->d_ovr_list_n;
+        const long long warps = (long long)cap * oa.sides;
+        fp_overrep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(oa);
+        CK(cudaGetLastError());
+        c->ovr_base_cur ^= 1;
+        c->reads_seen += b->n;
+    }
     return FP_OK;
 }
 
@@ -463,6 +550,8 @@ extern "C" int fp_counters_reset(fp_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemset(c->d_raw, 0, c->L.total * 8));
+    c->reads_seen = 0;
+    if (c->d_ovr_base) CK(cudaMemset(c->d_ovr_base, 0, 16));
     return FP_OK;
 }
 

@@ -748,7 +748,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
             if (col_active) {
                 const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
                 const uint16_t* lens = s_len + my_side * T;
-                unsigned int* kh = s_kmer + my_side * FP_KMER_BINS; unsigned int* qh = s_qhist + my_side * FP_QUAL_BINS;
                 const int w4 = my_w * 4;
                 const int j0 = my_half * 2;
                 #pragma unroll 1
@@ -777,20 +776,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                                         slow_cycle_byte(G, my_side * 2 + 1, w4 + j, bb, qb);
                                     }
                                 x &= ~(bad * 0xFFu);                                              /* drop them from the fast path */
-                            }
-                            /* this thread's two bytes: quality histogram (stats.cpp:213) + 5-mers (stats.cpp:228-266) */
-                            const int nb = min(hi - w4, 4);
-                            if (j0 < nb && !((q >> (8 * j0 + 7)) & 1)) atomicAdd(&qh[(q >> (8 * j0)) & 0x7F], 1u);
-                            if (j0 + 1 < nb && !((q >> (8 * j0 + 15)) & 1)) atomicAdd(&qh[(q >> (8 * j0 + 8)) & 0x7F], 1u);
-                            if (my_w > 0) {
-                                const uint32_t xc = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;   /* unfiltered bases for 5-mers */
-                                const uint32_t xp = *reinterpret_cast<const uint32_t*>(ts + r * S + w4 - 4);
-                                const uint32_t okc = exact_acgt(xc), okp = exact_acgt(xp);
-                                const uint32_t vc = (xc & 0x02020202u) | ((xc >> 2) & K), vp = (xp & 0x02020202u) | ((xp >> 2) & K);
-                                const uint32_t s16 = (((vp * 0x40100401u) >> 24) << 8) | ((vc * 0x40100401u) >> 24);
-                                const uint32_t ok8 = ((((okp * 0x08040201u) >> 24) & 0xF) << 4) | (((okc * 0x08040201u) >> 24) & 0xF);
-                                if (((ok8 >> (3 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (3 - j0))) & 0x3FF], 1u);
-                                if (((ok8 >> (2 - j0)) & 0x1F) == 0x1F) atomicAdd(&kh[(s16 >> (2 * (2 - j0))) & 0x3FF], 1u);
                             }
                         }
                         xs[kk] = x; xq[kk] = q;
@@ -827,6 +812,41 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                             const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                             if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr2] = 0;
+                            /* pre-filter quality histogram (stats.cpp:213) and 5-mer counts (stats.cpp:228-266) of these bases */
+                            unsigned int* kh = s_kmer + sd * FP_KMER_BINS; unsigned int* qh = s_qhist + sd * FP_QUAL_BINS;
+                            const int nv = min(n, 32);
+                            int kmer = 0, run = 0;
+                            if (j > 0) {                                   /* context: the 4 bases before this chunk */
+                                const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tile_seq[sd] + rr2 * S + 32 * j - 4);
+                                const uint32_t okp = exact_acgt(pw_);
+                                #pragma unroll
+                                for (int b4 = 0; b4 < 4; b4++) {
+                                    const uint32_t xx = (pw_ >> (8 * b4 + 1)) & 3u;
+                                    kmer = ((kmer << 2) | ((0xD8u >> (2 * xx)) & 3u)) & 0x3FF;
+                                    run = ((okp >> (8 * b4)) & 1u) ? run + 1 : 0;
+                                }
+                            }
+                            int curq = -1, cnt = 0;
+                            #pragma unroll 1
+                            for (int k8 = 0; k8 < 8; k8++) {
+                                if (4 * k8 >= nv) break;
+                                const uint32_t w = *reinterpret_cast<const uint32_t*>(tile_seq[sd] + rr2 * S + 32 * j + 4 * k8);
+                                const uint32_t qw = *reinterpret_cast<const uint32_t*>(tile_qual[sd] + rr2 * S + 32 * j + 4 * k8);
+                                const uint32_t okw = exact_acgt(w);
+                                #pragma unroll
+                                for (int b4 = 0; b4 < 4; b4++) {
+                                    if (4 * k8 + b4 < nv) {
+                                        const uint32_t xx = (w >> (8 * b4 + 1)) & 3u;
+                                        kmer = ((kmer << 2) | ((0xD8u >> (2 * xx)) & 3u)) & 0x3FF;      /* A0 T1 C2 G3 */
+                                        run = ((okw >> (8 * b4)) & 1u) ? run + 1 : 0;
+                                        if (run >= 5) atomicAdd(&kh[kmer], 1u);
+                                        const int qb = (int)((qw >> (8 * b4)) & 0xFFu);
+                                        if (qb == curq) cnt++;
+                                        else { if (cnt && curq < FP_QUAL_BINS) atomicAdd(&qh[curq], (unsigned)cnt); curq = qb; cnt = 1; }
+                                    }
+                                }
+                            }
+                            if (cnt && curq < FP_QUAL_BINS) atomicAdd(&qh[curq], (unsigned)cnt);
                         }
                     }
                     uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;

@@ -34,9 +34,15 @@ void fp_params_default(fp_params* p, int paired) {
     p->complexity_threshold = 30 / 100.0;                                   /* main.cpp:343  */
     p->insert_size_max = 512;                                               /* options.cpp:23 */
     p->seq_len1 = p->seq_len2 = 151;                                        /* options.cpp:28-29 */
+    p->overrep_enabled = 0;                                                 /* options.h:74  */
+    p->overrep_sampling = 20;                                               /* options.h:75  */
 }
 
 void fp_counter_layout_make(fp_counter_layout* L, int paired, int cycles, int insert_size_max) {
+    fp_counter_layout_make_overrep(L, paired, cycles, insert_size_max, 0, 0, 0, 0);
+}
+
+void fp_counter_layout_make_overrep(fp_counter_layout* L, int paired, int cycles, int insert_size_max, int k1, int len1, int k2, int len2) {
     memset(L, 0, sizeof(*L));
     L->cycles = cycles;
     L->n_stats = paired ? 4 : 2;
@@ -48,7 +54,14 @@ void fp_counter_layout_make(fp_counter_layout* L, int paired, int cycles, int in
     L->stats_stride = L->off_length_sum + 1;
     L->off_filter = (int64_t)L->n_stats * L->stats_stride;
     L->off_isize = L->off_filter + FP_FR_WORDS;
-    L->total = L->off_isize + L->isize_bins;
+    L->n_overrep[0] = k1; L->n_overrep[1] = paired ? k2 : 0;
+    L->overrep_len[0] = len1; L->overrep_len[1] = len2;
+    int64_t off = L->off_isize + L->isize_bins;
+    for (int s = 0; s < 4; s++) {
+        L->off_overrep[s] = off;
+        if (s < L->n_stats) off += (int64_t)L->n_overrep[s >> 1] * (1 + L->overrep_len[s >> 1]);
+    }
+    L->total = off;
 }
 
 /* ABI self-check for foreign-language bindings (ctypes / cgo): sizeof of each public struct. */

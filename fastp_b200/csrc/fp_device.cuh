@@ -369,3 +369,161 @@ __global__ void fp_synth_kernel(fp_batch b, long long first_index, unsigned long
     fp_synth_pair(seed, (uint64_t)(first_index + i), profile, read_len, b.stride, b.seq1 + o, b.qual1 + o, b.len1 + i,
                   b.seq2 ? b.seq2 + o : nullptr, b.seq2 ? b.qual2 + o : nullptr, b.seq2 ? b.len2 + i : nullptr);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Over-representation scan  (Stats::statRead, stats.cpp:270-288), its own small kernels: only 1 of every
+ * `sampling` reads is scanned, so it stays out of the fused kernel.
+ *   for step in {10, 20, 40, 100, min(150, evalLen-2)}:  slide i over [0, len-step); if seq[i, i+step) is a
+ *   candidate: count++, dist[p]++ for p in [i, i+step) and p < evalLen, then i += step (plus the loop's i++).
+ * Candidates sit in an open-addressing table keyed by a 64-bit polynomial hash of the bytes (verified byte by byte
+ * on a hash hit).  One warp per sampled read: prefix hashes once, every position's substring hash in O(1), hits
+ * found in parallel and then accepted in increasing i under the skip rule.
+ * pre-filter stats sample by the read's global index; post-filter stats by its rank among the counted reads
+ * (an exclusive scan of the verdicts, fp_overrep_rank_kernel).
+ * ------------------------------------------------------------------------------------------------ */
+#define FP_OVERREP_HASH_B 0x9E3779B97F4A7C15ull
+
+struct fp_overrep_side {
+    const uint8_t* blob;              /* candidate strings back to back                     */
+    const int32_t* off;               /* [K] offset into blob                               */
+    const int32_t* len;               /* [K]                                                */
+    const unsigned long long* thash;  /* [table_size] hash of the candidate, 0 = empty slot */
+    const int32_t* tidx;              /* [table_size] candidate index                       */
+    int table_mask, K, eval_len;
+};
+
+struct fp_overrep_args {
+    fp_batch b;
+    const fp_read_result* res[2];     /* post: trimmed windows; pre: nullptr                */
+    fp_overrep_side side[2];
+    unsigned long long* counters;
+    fp_counter_layout L;
+    int post;                         /* 0: pre-filter stats (original rows), 1: post-filter stats */
+    int sides, sampling;
+    long long first_index;            /* pre: global index of row 0 of this batch           */
+    const unsigned int* list;         /* post: batch-local indices of the sampled counted reads */
+    const unsigned int* list_n;
+};
+
+__device__ __forceinline__ unsigned long long overrep_pow(int step) {
+    unsigned long long r = 1, b = FP_OVERREP_HASH_B;
+    for (int e = step; e; e >>= 1) { if (e & 1) r *= b; b *= b; }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) fp_overrep_kernel(const fp_overrep_args a) {
+    __shared__ unsigned long long s_pref[8][FP_MAX_STRIDE + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * 8 + warp;             /* one warp per (sampled read, side) */
+    const long long unit = gw / a.sides;
+    const int sd = (int)(gw % a.sides);
+    long long row;
+    if (a.post) { if (unit >= (long long)*a.list_n) return; row = a.list[unit]; }
+    else {
+        /* rows with (first_index + row) % sampling == 0 */
+        const long long r0 = (a.sampling - (a.first_index % a.sampling)) % a.sampling;
+        row = r0 + unit * a.sampling;
+        if (row >= a.b.n) return;
+    }
+    const fp_overrep_side& S = a.side[sd];
+    if (S.K == 0) return;
+    const uint8_t* seq = (sd ? a.b.seq2 : a.b.seq1) + row * a.b.stride;
+    int len = (sd ? a.b.len2 : a.b.len1)[row];
+    if (a.post) { const fp_read_result r = a.res[sd][row]; seq += r.front; len = r.len; }
+    if (len > a.b.stride) len = a.b.stride;
+    unsigned long long* pref = s_pref[warp];
+    if (lane == 0) {
+        unsigned long long h = 0;
+        pref[0] = 0;
+        for (int i = 0; i < len; i++) { h = h * FP_OVERREP_HASH_B + (unsigned long long)(seq[i] + 1); pref[i + 1] = h; }
+    }
+    __syncwarp();
+    const int stats = sd * 2 + a.post;
+    const int steps[5] = {10, 20, 40, 100, min(150, S.eval_len - 2)};
+    for (int s5 = 0; s5 < 5; s5++) {
+        const int step = steps[s5];
+        if (step <= 0) continue;
+        const unsigned long long bp = overrep_pow(step);
+        const int npos = len - step;                                   /* i in [0, npos) */
+        int allowed = 0;
+        for (int base = 0; base < npos; base += 32) {
+            const int i = base + lane;
+            int hit = -1;
+            if (i < npos) {
+                unsigned long long h = pref[i + step] - pref[i] * bp;
+                if (h == 0) h = 1;
+                for (unsigned int slot = (unsigned int)(h ^ (h >> 32)) & S.table_mask;; slot = (slot + 1) & S.table_mask) {
+                    const unsigned long long th = S.thash[slot];
+                    if (th == 0) break;
+                    if (th == h) {
+                        const int k = S.tidx[slot];
+                        if (S.len[k] == step) {
+                            const uint8_t* c = S.blob + S.off[k];
+                            bool eq = true;
+                            for (int j = 0; j < step && eq; j++) eq = (c[j] == seq[i + j]);
+                            if (eq) { hit = k; break; }
+                        }
+                    }
+                }
+            }
+            unsigned m = __ballot_sync(FULL_MASK, hit >= 0);
+            while (m) {                                                /* accept hits in increasing i under the skip rule */
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int hi = base + bit;
+                if (hi >= allowed) {
+                    const int k = __shfl_sync(FULL_MASK, hit, bit);
+                    if (lane == 0) red_add64(&a.counters[fp_off_overrep_count(&a.L, stats, k)], 1ull);
+                    for (int q = hi + lane; q < hi + step && q < S.eval_len; q += 32) red_add64(&a.counters[fp_off_overrep_dist(&a.L, stats, k, q)], 1ull);
+                    allowed = hi + step + 1;
+                }
+            }
+        }
+    }
+}
+
+/* rank of every counted read among the counted reads (exclusive scan of pair_verdict == PASS), in three steps;
+ * emits the batch-local indices whose (base + rank) % sampling == 0 and advances *base by the batch's count. */
+#define FP_RANK_ITEMS 2048
+__global__ void __launch_bounds__(256) fp_overrep_blocksum_kernel(const fp_read_result* res, long long n, unsigned int* blocksum) {
+    __shared__ unsigned int s[8];
+    const long long b0 = (long long)blockIdx.x * FP_RANK_ITEMS;
+    unsigned int c = 0;
+    for (int k = threadIdx.x; k < FP_RANK_ITEMS; k += 256) { const long long i = b0 + k; if (i < n) c += (res[i].pair_verdict == FP_PASS_FILTER); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < 8; w++) t += s[w]; blocksum[blockIdx.x] = t; }
+}
+__global__ void fp_overrep_scan_kernel(unsigned int* blocksum, int nblocks, unsigned long long* base, unsigned long long* base_next) {
+    /* single thread: nblocks <= n / 2048 (a few tens of thousands at most); turns sums into exclusive offsets */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < nblocks; i++) { const unsigned int v = blocksum[i]; blocksum[i] = (unsigned int)run; run += v; }
+        *base_next = *base + run;
+    }
+}
+__global__ void __launch_bounds__(256) fp_overrep_emit_kernel(const fp_read_result* res, long long n, const unsigned int* blockoff,
+                                                              const unsigned long long* base, int sampling, unsigned int* list, unsigned int* list_n, unsigned int cap) {
+    __shared__ unsigned int s_run;
+    const long long b0 = (long long)blockIdx.x * FP_RANK_ITEMS;
+    if (threadIdx.x == 0) s_run = blockoff[blockIdx.x];
+    __syncthreads();
+    const unsigned long long gbase = *base;
+    for (int k0 = 0; k0 < FP_RANK_ITEMS; k0 += 256) {                  /* keep the items in order: 256 at a time */
+        const long long i = b0 + k0 + threadIdx.x;
+        const bool cnt = i < n && res[i].pair_verdict == FP_PASS_FILTER;
+        const unsigned m = __ballot_sync(FULL_MASK, cnt);
+        __shared__ unsigned int s_w[8];
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        unsigned int before = s_run;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += s_w[w];
+        const unsigned int rank = before + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        if (cnt && (gbase + rank) % (unsigned long long)sampling == 0) { const unsigned int slot = atomicAdd(list_n, 1u); if (slot < cap) list[slot] = (unsigned int)i; }
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; s_run += t; }
+        __syncthreads();
+    }
+}

@@ -104,8 +104,16 @@ typedef struct fp_params {
     double  complexity_threshold;           /* int/100.0 as main.cpp:343 builds it              */
     /* insert size histogram  options.cpp:23, peprocessor.cpp:24-26 */
     int32_t insert_size_max;                /* default 512                                      */
-    /* sequence lengths from the pre-scan; only sizes the reference's Stats buffers */
+    /* sequence lengths from the pre-scan (Options::seqLen1/2, options.h:366-367): Stats::mEvaluatedSeqLen */
     int32_t seq_len1, seq_len2;
+    /* OverrepresentedSequenceAnasysOptions options.h:71-80 + the candidate lists the Evaluator pre-scan produced
+     * (Options::overRepSeqs1/2, options.h:364-365; Evaluator::computeOverRepSeq evaluator.cpp:78-169 stays on the host) */
+    int32_t overrep_enabled;
+    int32_t overrep_sampling;               /* default 20 */
+    int32_t n_overrep1;
+    const char* const* overrep_seqs1;       /* keys of overRepSeqs1 (any order; the layout keeps this order) */
+    int32_t n_overrep2;
+    const char* const* overrep_seqs2;
 } fp_params;
 
 /* Fill with the reference's defaults: Options::Options() (options.cpp:9-32) + nested
@@ -186,6 +194,10 @@ typedef struct fp_counter_layout {
     int64_t off_kmer, off_qualhist, off_reads, off_length_sum;   /* inside a Stats block */
     int64_t off_filter;    /* start of the FilterResult block                         */
     int64_t off_isize;     /* start of the insert-size histogram                      */
+    /* over-representation (stats.cpp:270-288): per Stats s: count[K_s] then dist[K_s][seqLen_s]; K/seqLen per SIDE */
+    int32_t n_overrep[2];  /* candidates of read1 / read2                             */
+    int32_t overrep_len[2];/* mEvaluatedSeqLen of read1 / read2                       */
+    int64_t off_overrep[4];/* start of each Stats' over-representation region         */
     int64_t total;         /* total int64 words                                       */
 } fp_counter_layout;
 
@@ -201,6 +213,8 @@ typedef struct fp_counter_layout {
 #define FP_FR_WORDS           108
 
 void fp_counter_layout_make(fp_counter_layout* L, int paired, int cycles, int insert_size_max);
+/* same, with over-representation regions for k1/k2 candidates and evaluated sequence lengths len1/len2 */
+void fp_counter_layout_make_overrep(fp_counter_layout* L, int paired, int cycles, int insert_size_max, int k1, int len1, int k2, int len2);
 /* ABI self-check for bindings: sizeof of 0:fp_params 1:fp_batch 2:fp_read_result 3:fp_ov_result 4:fp_patch 5:fp_counter_layout */
 size_t fp_abi_sizeof(int which);
 
@@ -223,6 +237,13 @@ FP_INLINE int64_t fp_off_reads(const fp_counter_layout* L, int stats) {
 }
 FP_INLINE int64_t fp_off_length_sum(const fp_counter_layout* L, int stats) {
     return (int64_t)stats * L->stats_stride + L->off_length_sum;
+}
+FP_INLINE int64_t fp_off_overrep_count(const fp_counter_layout* L, int stats, int k) {
+    return L->off_overrep[stats] + k;
+}
+FP_INLINE int64_t fp_off_overrep_dist(const fp_counter_layout* L, int stats, int k, int pos) {
+    const int side = stats >> 1;
+    return L->off_overrep[stats] + L->n_overrep[side] + (int64_t)k * L->overrep_len[side] + pos;
 }
 
 /* ---------------- device context ---------------- */

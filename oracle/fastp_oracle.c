@@ -51,7 +51,7 @@ static inline int base2val(uint8_t b) {  /* stats.cpp:293-318 */
     switch (b) { case 'A': return 0; case 'T': return 1; case 'C': return 2; case 'G': return 3; default: return -1; }
 }
 
-static void stat_read(int64_t* C, const fp_counter_layout* L, int s, const uint8_t* seq, const uint8_t* qual, int len) {
+static void stat_read(const fp_params* p, int64_t* C, const fp_counter_layout* L, int s, const uint8_t* seq, const uint8_t* qual, int len) {
     C[fp_off_length_sum(L, s)] += len;                                  /* stats.cpp:194 */
     int kmer = 0;
     int needFullCompute = 1;
@@ -90,6 +90,28 @@ static void stat_read(int64_t* C, const fp_counter_layout* L, int s, const uint8
             if (!valid) { needFullCompute = 1; continue; }
             C[fp_off_kmer(L, s, kmer)]++;
             needFullCompute = 0;
+        }
+    }
+    /* over-representation analysis for 1 of every `sampling` reads  stats.cpp:270-288 */
+    if (p->overrep_enabled) {
+        if (C[fp_off_reads(L, s)] % p->overrep_sampling == 0) {
+            const int side = s >> 1;
+            const int K = L->n_overrep[side], evalLen = L->overrep_len[side];
+            const char* const* cands = side ? p->overrep_seqs2 : p->overrep_seqs1;
+            const int steps[5] = {10, 20, 40, 100, imin(150, evalLen - 2)};
+            for (int s5 = 0; s5 < 5; s5++) {
+                const int step = steps[s5];
+                for (int i = 0; i < len - step; i++) {
+                    int hit = -1;                                       /* mOverRepSeq.count(seq) > 0 */
+                    for (int k = 0; k < K && hit < 0; k++)
+                        if ((int)strlen(cands[k]) == step && memcmp(cands[k], seq + i, (size_t)step) == 0) hit = k;
+                    if (hit >= 0) {
+                        C[fp_off_overrep_count(L, s, hit)]++;
+                        for (int q = i; q < step + i && q < evalLen; q++) C[fp_off_overrep_dist(L, s, hit, q)]++;
+                        i += step;
+                    }
+                }
+            }
         }
     }
     C[fp_off_reads(L, s)]++;                                            /* stats.cpp:290 */
@@ -495,7 +517,7 @@ static void fill_result(fp_read_result* o, const oread* r, const uint8_t* row, i
 static void process_se_one(const fp_params* p, const fp_counter_layout* L, int64_t* C,
                            uint8_t* seq, uint8_t* qual, int len, fp_read_result* out) {
     int64_t* FR = C + L->off_filter;
-    stat_read(C, L, FP_STATS_PRE1, seq, qual, len);                     /* :211 */
+    stat_read(p, C, L, FP_STATS_PRE1, seq, qual, len);                     /* :211 */
     oread r = {seq, qual, len, 0};
     int frontTrimmed = 0, flags = 0, apos = 0, abases = 0, polyBase = 255, polyLen = 0;
     if (!trim_and_cut(p, &r, p->trim_front1, p->trim_tail1, &frontTrimmed)) r.is_null = 1;   /* :235 */
@@ -523,7 +545,7 @@ static void process_se_one(const fp_params* p, const fp_counter_layout* L, int64
     if (isAdapterDimer) { result = FP_FAIL_ADAPTER_DIMER; flags |= FP_F_ADAPTER_DIMER; }   /* :275-276 */
     FR[FP_FR_READSTATS + result] += 1;                                  /* :278 */
     if (!r.is_null && result == FP_PASS_FILTER)                         /* :281-286 */
-        stat_read(C, L, FP_STATS_POST1, r.seq, r.qual, r.len);
+        stat_read(p, C, L, FP_STATS_POST1, r.seq, r.qual, r.len);
     fill_result(out, &r, seq, result, result, flags, apos, abases, polyBase, polyLen);
 }
 
@@ -536,8 +558,8 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
                            fp_read_result* out1, fp_read_result* out2, fp_ov_result* ovOut) {
     int64_t* FR = C + L->off_filter;
     int64_t* ISZ = C + L->off_isize;
-    stat_read(C, L, FP_STATS_PRE1, seq1, qual1, len1);                  /* :393-394 */
-    stat_read(C, L, FP_STATS_PRE2, seq2, qual2, len2);
+    stat_read(p, C, L, FP_STATS_PRE1, seq1, qual1, len1);                  /* :393-394 */
+    stat_read(p, C, L, FP_STATS_PRE2, seq2, qual2, len2);
     oread r1 = {seq1, qual1, len1, 0}, r2 = {seq2, qual2, len2, 0};
     int ft1 = 0, ft2 = 0;
     int flags1 = 0, flags2 = 0, apos1 = 0, apos2 = 0, ab1 = 0, ab2 = 0, pb1 = 255, pb2 = 255, pl1 = 0, pl2 = 0;
@@ -636,8 +658,8 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
     int pv = imax(result1, result2);
     FR[FP_FR_READSTATS + pv] += 2;                                      /* :573 */
     if (!r1.is_null && result1 == FP_PASS_FILTER && !r2.is_null && result2 == FP_PASS_FILTER) {   /* :577-591 */
-        stat_read(C, L, FP_STATS_POST1, r1.seq, r1.qual, r1.len);
-        stat_read(C, L, FP_STATS_POST2, r2.seq, r2.qual, r2.len);
+        stat_read(p, C, L, FP_STATS_POST1, r1.seq, r1.qual, r1.len);
+        stat_read(p, C, L, FP_STATS_POST2, r2.seq, r2.qual, r2.len);
     }
     fill_result(out1, &r1, seq1, result1, pv, flags1, apos1, ab1, pb1, pl1);
     fill_result(out2, &r2, seq2, result2, pv, flags2, apos2, ab2, pb2, pl2);

@@ -63,7 +63,10 @@ void fill_options(Options& o, const fp_params* p) {
     o.complexityFilter.enabled = p->complexity_filter_enabled; o.complexityFilter.threshold = p->complexity_threshold;
     o.insertSizeMax = p->insert_size_max;
     o.seqLen1 = p->seq_len1; o.seqLen2 = p->seq_len2;
-    o.overRepAnalysis.enabled = false;
+    o.overRepAnalysis.enabled = p->overrep_enabled; o.overRepAnalysis.sampling = p->overrep_sampling;
+    o.overRepSeqs1.clear(); o.overRepSeqs2.clear();
+    for (int i = 0; i < p->n_overrep1; i++) o.overRepSeqs1[p->overrep_seqs1[i]] = 0;
+    for (int i = 0; i < p->n_overrep2; i++) o.overRepSeqs2[p->overrep_seqs2[i]] = 0;
     o.duplicate.enabled = false;
     if (p->paired) { o.in1 = "r1"; o.in2 = "r2"; } else { o.in1 = "r1"; }
 }
@@ -271,7 +274,7 @@ void pe_one(Worker& w, const fp_params* p, uint8_t* seq1, uint8_t* qual1, int le
     delete or1; delete or2;
 }
 
-void dump_stats(Stats* s, const fp_counter_layout* L, int idx, int64_t* C) {
+void dump_stats(Stats* s, const fp_params* p, const fp_counter_layout* L, int idx, int64_t* C) {
     int n = std::min(s->mBufLen, L->cycles);
     for (int k = 0; k < 8; k++)
         for (int c = 0; c < n; c++) {
@@ -288,12 +291,23 @@ void dump_stats(Stats* s, const fp_counter_layout* L, int idx, int64_t* C) {
     for (int q = 0; q < FP_QUAL_BINS; q++) C[fp_off_qualhist(L, idx, q)] += s->mBaseQualHistogram[q];
     C[fp_off_reads(L, idx)] += s->mReads;
     C[fp_off_length_sum(L, idx)] += s->mLengthSum;
+    if (p->overrep_enabled) {                                                 // Stats::mOverRepSeq / mOverRepSeqDist (stats.h:91-92)
+        const int side = idx >> 1;
+        const char* const* cands = side ? p->overrep_seqs2 : p->overrep_seqs1;
+        for (int k = 0; k < L->n_overrep[side]; k++) {
+            std::string key(cands[k]);
+            if (s->mOverRepSeq.count(key) == 0) continue;
+            C[fp_off_overrep_count(L, idx, k)] += s->mOverRepSeq[key];
+            long* dist = s->mOverRepSeqDist[key];
+            for (int q = 0; q < L->overrep_len[side] && q < s->mEvaluatedSeqLen; q++) C[fp_off_overrep_dist(L, idx, k, q)] += dist[q];
+        }
+    }
 }
 
 void dump_worker(Worker& w, const fp_params* p, const fp_counter_layout* L, int64_t* C) {
-    dump_stats(w.pre1, L, FP_STATS_PRE1, C);
-    dump_stats(w.post1, L, FP_STATS_POST1, C);
-    if (p->paired) { dump_stats(w.pre2, L, FP_STATS_PRE2, C); dump_stats(w.post2, L, FP_STATS_POST2, C); }
+    dump_stats(w.pre1, p, L, FP_STATS_PRE1, C);
+    dump_stats(w.post1, p, L, FP_STATS_POST1, C);
+    if (p->paired) { dump_stats(w.pre2, p, L, FP_STATS_PRE2, C); dump_stats(w.post2, p, L, FP_STATS_POST2, C); }
     int64_t* FR = C + L->off_filter;
     for (int i = 0; i < FILTER_RESULT_TYPES; i++) FR[FP_FR_READSTATS + i] += w.fr->mFilterReadStats[i];
     FR[FP_FR_ADAPTER_READS] += w.fr->mTrimmedAdapterRead;

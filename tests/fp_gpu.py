@@ -62,7 +62,7 @@ def device_batch(arrs, device=0):
     return b, t
 
 
-def run_gpu(params, arrs, cycles, mode="device", ctx=None):
+def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
     """Run the CUDA hot path over a COPY of arrs; same return shape as fp_testlib.run_cpu."""
     torch = _torch()
     paired = bool(params.paired)
@@ -85,10 +85,18 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None):
             cap = 4 * n + 16
             d_patch = torch.zeros(cap * 12, dtype=torch.uint8, device="cuda:0")
             d_np = torch.zeros(1, dtype=torch.int32, device="cuda:0")
-            capi.check(lib.fp_process_pe(ctx.h, C.byref(b), d_out1.data_ptr(), d_out2.data_ptr(), d_ov.data_ptr(),
-                                         d_patch.data_ptr(), cap, d_np.data_ptr(), None), lib)
-        else:
-            capi.check(lib.fp_process_se(ctx.h, C.byref(b), d_out1.data_ptr(), None), lib)
+        bounds = [n * i // splits for i in range(splits + 1)]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):          # consecutive sub-batches of one stream (counters accumulate)
+            sb = capi.Batch()
+            sb.n, sb.stride = hi - lo, stride
+            for k, v in t.items():
+                setattr(sb, k, v.data_ptr() + lo * (2 if k.startswith("len") else stride))
+            if paired:
+                assert splits == 1 or not params.correction_enabled, "patch indices are batch-local"
+                capi.check(lib.fp_process_pe(ctx.h, C.byref(sb), d_out1.data_ptr() + lo * 16, d_out2.data_ptr() + lo * 16, d_ov.data_ptr() + lo * 8,
+                                             d_patch.data_ptr(), cap, d_np.data_ptr(), None), lib)
+            else:
+                capi.check(lib.fp_process_se(ctx.h, C.byref(sb), d_out1.data_ptr() + lo * 16, None), lib)
         torch.cuda.synchronize()
         out1 = d_out1.cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n].copy()
         if paired:

@@ -34,7 +34,7 @@ def oracle():
         if not os.path.exists(ORACLE_SO):
             build_oracle()
         lib = C.CDLL(ORACLE_SO)
-        capi.bind(lib, ["fp_params_default", "fp_counter_layout_make", "fp_abi_sizeof"])
+        capi.bind(lib, ["fp_params_default", "fp_counter_layout_make", "fp_counter_layout_make_overrep", "fp_abi_sizeof"])
         lib.fp_oracle_process.restype = C.c_int
         lib.fp_oracle_process.argtypes = _PROC_ARGS
         lib.fp_synth_fill_host.restype = C.c_int
@@ -95,7 +95,7 @@ def run_cpu(which, params, arrs, cycles, nthreads=0):
     a = copy_arrays(arrs)
     b = capi.batch_from_arrays(a)
     paired = bool(params.paired)
-    L = capi.make_layout(oracle(), paired, cycles, params.insert_size_max)
+    L = capi.make_layout(oracle(), paired, cycles, params.insert_size_max, params)
     n = b.n
     out1 = np.zeros(n, capi.READ_RESULT_DTYPE)
     out2 = np.zeros(n, capi.READ_RESULT_DTYPE)
@@ -163,6 +163,14 @@ def assert_counters_equal(cx, cy, what=""):
                 raise AssertionError(f"{what} stats[{names[s]}].{key}{tuple(idx)}: {sx[key][tuple(idx)]} vs {sy[key][tuple(idx)]}")
         for key in ("reads", "length_sum"):
             assert sx[key] == sy[key], f"{what} stats[{names[s]}].{key}: {sx[key]} vs {sy[key]}"
+    for s in range(L.n_stats):
+        (xc, xd), (yc, yd) = cx.overrep(s), cy.overrep(s)
+        if not (xc == yc).all():
+            i = int(np.nonzero(xc != yc)[0][0])
+            raise AssertionError(f"{what} stats[{names[s]}].overrep_count[{i}]: {xc[i]} vs {yc[i]}")
+        if not (xd == yd).all():
+            idx = np.argwhere(xd != yd)[0]
+            raise AssertionError(f"{what} stats[{names[s]}].overrep_dist{tuple(idx)}: {xd[tuple(idx)]} vs {yd[tuple(idx)]}")
     if not (cx.filter == cy.filter).all():
         i = int(np.nonzero(cx.filter != cy.filter)[0][0])
         raise AssertionError(f"{what} filter[{i}]: {cx.filter[i]} vs {cy.filter[i]}")
@@ -206,6 +214,31 @@ def config_params(name, paired, lib=None):
     if name == "short_adapter":
         return P(adapter_seq_r1="AGATCGGAAG", adapter_seq_r2="AGATCGG", polyx_enabled=1)
     raise KeyError(name)
+
+
+def overrep_candidates(arrs, side, L, seed=1, per_step=6):
+    """Candidate list for over-representation tests: substrings of the batch itself at the five step lengths the
+    reference scans (stats.cpp:274), plus candidates that can never match (wrong length) or match by chance."""
+    rng = np.random.default_rng(seed)
+    out = set()
+    n = arrs["seq" + side].shape[0]
+    for step in (10, 20, 40, 100, min(150, L - 2)):
+        for _ in range(per_step):
+            r = int(rng.integers(0, n)); ln = int(arrs["len" + side][r])
+            if ln > step + 1:
+                i = int(rng.integers(0, ln - step))
+                out.add(bytes(arrs["seq" + side][r, i:i + step]).decode())
+    out.update(["ACGTACGTAC", "G" * 20, "A" * 15, "G" * 10, "A" * 10])
+    return sorted(out)
+
+
+def overrep_params(name, paired, arrs, L, sampling=20, lib=None):
+    p = config_params(name, paired, lib)
+    kw = dict(overrep_enabled=1, overrep_sampling=sampling, seq_len1=L, seq_len2=L, overrep_seqs1=overrep_candidates(arrs, "1", L))
+    if paired:
+        kw["overrep_seqs2"] = overrep_candidates(arrs, "2", L, seed=2)
+    capi.set_params(p, **kw)
+    return p
 
 
 CONFIG_NAMES = ["default", "cfg2_cut_right_polyg", "cfg3_overlap_correction", "cfg4_full", "cut_front_tail", "trim_fixed",

@@ -19,6 +19,9 @@ def load_fixture(path):
     if meta["config"] == "testdata_cli_defaults":
         p = capi.default_params(1, lib=T.oracle(), polyg_enabled=1, seq_len1=151, seq_len2=151)
         arrs = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    elif "overrep_sampling" in meta:
+        _, arrs = T.synth_host(meta["n"], meta["stride"], meta["paired"], 0, meta["seed"], meta["profile"], meta["read_len"])
+        p = T.overrep_params(meta["base_config"], meta["paired"], arrs, meta["read_len"], meta["overrep_sampling"])
     else:
         p = T.config_params(meta["config"], meta["paired"])
         _, arrs = T.synth_host(meta["n"], meta["stride"], meta["paired"], 0, meta["seed"], meta["profile"], meta["read_len"])
@@ -29,13 +32,13 @@ def load_fixture(path):
         if "patch_" + k in z.files:
             for r, c, v in z["patch_" + k]:
                 after[k][r, c] = v
-    L = capi.make_layout(T.oracle(), meta["paired"], meta["cycles"], p.insert_size_max)
+    L = capi.make_layout(T.oracle(), meta["paired"], meta["cycles"], p.insert_size_max, p)
     want = {"out1": z["out1"], "out2": z["out2"], "ov": z["ov"], "counters": capi.CounterView(L, cnt), "arrs": after}
     return meta, p, arrs, want
 
 
 def test_fixture_count():
-    assert len(GOLDEN) >= 28
+    assert len(GOLDEN) >= 31
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

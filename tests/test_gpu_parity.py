@@ -68,3 +68,27 @@ def test_patch_list_matches_corrected_rows(gpu):
         rebuilt["qual" + side][pt["pair"], pt["pos"]] = pt["qual"]
     for k in ("seq1", "qual1", "seq2", "qual2"):
         assert (rebuilt[k] == got["arrs"][k]).all()
+
+
+@pytest.mark.parametrize("paired", [1, 0])
+@pytest.mark.parametrize("L,stride,sampling", [(150, 160, 20), (100, 112, 7), (250, 256, 20)])
+def test_overrepresentation_analysis(gpu, paired, L, stride, sampling):
+    """config 5's scan (stats.cpp:270-288): candidate substrings counted on 1 of every `sampling` reads, pre-filter by
+    read index, post-filter by rank among the counted reads; one batch, and the same stream cut into 3 launches."""
+    _, arrs = T.synth_host(7000, stride, paired, 0, 5, 1, L)
+    p = T.overrep_params("cfg2_cut_right_polyg" if not paired else "all_cuts", paired, arrs, L, sampling)
+    p.correction_enabled = 0
+    want = T.run_cpu("oracle", p, arrs, stride)
+    assert sum(int(want["counters"].overrep(s)[0].sum()) for s in range(4 if paired else 2)) > 10
+    got = gpu.run_gpu(p, arrs, stride, mode="device")
+    T.assert_results_equal(got, want, paired, what="overrep")
+    got = gpu.run_gpu(p, arrs, stride, mode="device", splits=3)
+    T.assert_results_equal(got, want, paired, what="overrep-3-launches")
+
+
+def test_overrepresentation_with_correction_host_mode(gpu):
+    _, arrs = T.synth_host(600000, 160, 1, 0, 9, 1, 150)      # > one host chunk (262144): sampling state crosses chunks
+    p = T.overrep_params("cfg3_overlap_correction", 1, arrs, 150)
+    want = T.run_cpu("oracle", p, arrs, 160)
+    got = gpu.run_gpu(p, arrs, 160, mode="host")
+    T.assert_results_equal(got, want, 1, what="overrep-host")

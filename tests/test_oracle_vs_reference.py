@@ -38,3 +38,16 @@ def test_reference_mt_equals_single_thread():
     a = T.run_cpu("ref", p, arrs, 160)
     b = T.run_cpu("ref", p, arrs, 160, nthreads=5)
     T.assert_results_equal(a, b, 1, what="mt")
+
+
+@needs_ref
+@pytest.mark.parametrize("paired", [1, 0])
+@pytest.mark.parametrize("L,stride,sampling", [(150, 160, 20), (100, 112, 7), (250, 256, 3)])
+def test_port_equals_reference_overrepresentation(paired, L, stride, sampling):
+    """Stats::statRead's over-representation scan (stats.cpp:270-288) incl. the post-filter sampling by counted rank."""
+    _, arrs = T.synth_host(6000, stride, paired, 0, 5, 1, L)
+    p = T.overrep_params("cfg4_full", paired, arrs, L, sampling)
+    x = T.run_cpu("oracle", p, arrs, stride)
+    y = T.run_cpu("ref", p, arrs, stride)
+    T.assert_results_equal(x, y, paired, skip=("adapter_pos",), what="overrep")
+    assert sum(int(x["counters"].overrep(s)[0].sum()) for s in range(4 if paired else 2)) > 10
