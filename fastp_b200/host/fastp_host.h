@@ -12,6 +12,7 @@
  */
 #ifndef FASTP_HOST_H
 #define FASTP_HOST_H
+#include <map>
 #include <string>
 #include <vector>
 #include <cstdint>
@@ -47,10 +48,12 @@ struct Options {
     struct { bool enabled = true; char qualifiedQual = '0'; int unqualifiedPercentLimit = 40, nBaseLimit = 5, avgQualReq = 0; } qualfilter;
     struct { bool enabled = true; int requiredLength = 15, maxLength = 0; } lengthFilter;
     struct { bool enabled = false; double threshold = 0.3; } complexityFilter;
+    struct { bool enabled = false; int sampling = 20; } overRepAnalysis;           /* options.h:71-80 */
+    std::map<std::string, long> overRepSeqs1, overRepSeqs2;                        /* options.h:364-365, filled by the Evaluator pre-scan */
     int insertSizeMax = 512, overlapRequire = 30, overlapDiffLimit = 5, overlapDiffPercentLimit = 20;
     int seqLen1 = 151, seqLen2 = 151;
     bool paired = false;
-    void toParams(fp_params* p, std::vector<const char*>& fastaKeep) const;
+    void toParams(fp_params* p, std::vector<const char*>& fastaKeep, std::vector<const char*>& ovr1Keep, std::vector<const char*>& ovr2Keep) const;
 };
 
 /* Merged counters, filled from the device block (fp_counters_fetch). */
@@ -67,6 +70,9 @@ struct Stats {                        /* src/stats.h:77-101, summarize() src/sta
     std::vector<long> mCycleQ30Bases[8], mCycleQ20Bases[8], mCycleBaseContents[8], mCycleBaseQual[8], mCycleTotalBase, mCycleTotalQual;
     std::vector<long> mKmer;          /* 1024 used bins */
     long mBaseQualHistogram[128] = {0};
+    std::map<std::string, long> mOverRepSeq;                     /* stats.h:91 */
+    std::map<std::string, std::vector<long>> mOverRepSeqDist;    /* stats.h:92 */
+    void fillOverRep(const int64_t* block, const fp_counter_layout& L, int which, const std::vector<const char*>& keys);
     void fill(const int64_t* block, const fp_counter_layout& L, int which);
 };
 
@@ -93,7 +99,7 @@ private:
     const Options* mOptions;
     fp_ctx* mCtx = nullptr;
     fp_params mParams;
-    std::vector<const char*> mFastaKeep;
+    std::vector<const char*> mFastaKeep, mOvr1Keep, mOvr2Keep;
     int mStride = 0;
     int64_t mCap = 0;
     uint8_t *mSeq[2] = {nullptr, nullptr}, *mQual[2] = {nullptr, nullptr};    /* pinned SoA staging */

@@ -12,7 +12,7 @@
 
 namespace fastp_b200 {
 
-void Options::toParams(fp_params* p, std::vector<const char*>& fastaKeep) const {
+void Options::toParams(fp_params* p, std::vector<const char*>& fastaKeep, std::vector<const char*>& ovr1Keep, std::vector<const char*>& ovr2Keep) const {
     fp_params_default(p, paired ? 1 : 0);
     p->trim_front1 = trim.front1; p->trim_tail1 = trim.tail1; p->trim_front2 = trim.front2; p->trim_tail2 = trim.tail2;
     p->max_len1 = trim.maxLen1; p->max_len2 = trim.maxLen2;
@@ -35,6 +35,22 @@ void Options::toParams(fp_params* p, std::vector<const char*>& fastaKeep) const 
     p->length_filter_enabled = lengthFilter.enabled; p->length_required = lengthFilter.requiredLength; p->length_limit = lengthFilter.maxLength;
     p->complexity_filter_enabled = complexityFilter.enabled; p->complexity_threshold = complexityFilter.threshold;
     p->insert_size_max = insertSizeMax; p->seq_len1 = seqLen1; p->seq_len2 = seqLen2;
+    p->overrep_enabled = overRepAnalysis.enabled; p->overrep_sampling = overRepAnalysis.sampling;
+    ovr1Keep.clear(); ovr2Keep.clear();
+    for (auto& kv : overRepSeqs1) ovr1Keep.push_back(kv.first.c_str());
+    for (auto& kv : overRepSeqs2) ovr2Keep.push_back(kv.first.c_str());
+    p->n_overrep1 = (int)ovr1Keep.size(); p->overrep_seqs1 = ovr1Keep.empty() ? nullptr : ovr1Keep.data();
+    p->n_overrep2 = (int)ovr2Keep.size(); p->overrep_seqs2 = ovr2Keep.empty() ? nullptr : ovr2Keep.data();
+}
+
+void Stats::fillOverRep(const int64_t* B, const fp_counter_layout& L, int which, const std::vector<const char*>& keys) {
+    const int side = which >> 1;
+    for (int k = 0; k < L.n_overrep[side] && k < (int)keys.size(); k++) {
+        mOverRepSeq[keys[k]] = B[fp_off_overrep_count(&L, which, k)];
+        std::vector<long>& d = mOverRepSeqDist[keys[k]];
+        d.assign(L.overrep_len[side], 0);
+        for (int q = 0; q < L.overrep_len[side]; q++) d[q] = B[fp_off_overrep_dist(&L, which, k, q)];
+    }
 }
 
 void Stats::fill(const int64_t* B, const fp_counter_layout& L, int which) {
@@ -63,7 +79,7 @@ void Stats::fill(const int64_t* B, const fp_counter_layout& L, int which) {
 }
 
 GpuChainWorker::GpuChainWorker(const Options* opt, int maxReadLen, int device, int64_t maxBatch) : mOptions(opt) {
-    opt->toParams(&mParams, mFastaKeep);
+    opt->toParams(&mParams, mFastaKeep, mOvr1Keep, mOvr2Keep);
     mStride = std::max(16, (maxReadLen + 15) / 16 * 16);
     mCap = maxBatch;
     int rc = fp_ctx_create(&mParams, device, maxBatch, mStride, mStride, &mCtx);
@@ -151,9 +167,12 @@ bool GpuChainWorker::finish(Stats* pre1, Stats* post1, Stats* pre2, Stats* post2
     fp_ctx_layout(mCtx, &L);
     std::vector<int64_t> B(L.total);
     if (fp_counters_fetch(mCtx, B.data()) != FP_OK) { mError = fp_last_error(); return false; }
-    if (pre1) pre1->fill(B.data(), L, FP_STATS_PRE1);
-    if (post1) post1->fill(B.data(), L, FP_STATS_POST1);
-    if (L.n_stats == 4) { if (pre2) pre2->fill(B.data(), L, FP_STATS_PRE2); if (post2) post2->fill(B.data(), L, FP_STATS_POST2); }
+    if (pre1) { pre1->fill(B.data(), L, FP_STATS_PRE1); pre1->fillOverRep(B.data(), L, FP_STATS_PRE1, mOvr1Keep); }
+    if (post1) { post1->fill(B.data(), L, FP_STATS_POST1); post1->fillOverRep(B.data(), L, FP_STATS_POST1, mOvr1Keep); }
+    if (L.n_stats == 4) {
+        if (pre2) { pre2->fill(B.data(), L, FP_STATS_PRE2); pre2->fillOverRep(B.data(), L, FP_STATS_PRE2, mOvr2Keep); }
+        if (post2) { post2->fill(B.data(), L, FP_STATS_POST2); post2->fillOverRep(B.data(), L, FP_STATS_POST2, mOvr2Keep); }
+    }
     if (fr) {
         const int64_t* F = B.data() + L.off_filter;
         for (int i = 0; i < FP_FILTER_RESULT_TYPES; i++) fr->mFilterReadStats[i] = F[FP_FR_READSTATS + i];
