@@ -153,7 +153,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     if (!p || !out) return set_err(FP_E_INVAL, "null argument");
     if (stride <= 0 || stride % 16 || stride > FP_MAX_STRIDE) return set_err(FP_E_INVAL, "stride must be a multiple of 16 and <= FP_MAX_STRIDE");
     if (cycles <= 0) cycles = stride;
-    if (p->allow_gap_overlap_trimming) return set_err(FP_E_UNSUPPORTED, "allow_gap_overlap_trimming is not implemented on the device path");
+    if (p->allow_gap_overlap_trimming && p->overlap_require < 2) return set_err(FP_E_INVAL, "allow_gap_overlap_trimming needs overlap_require >= 2");
     if (p->insert_size_max < 0 || p->insert_size_max > (1 << 20)) return set_err(FP_E_INVAL, "insert_size_max out of range");
     if ((p->paired ? 2 : 1) * (stride / 2) > FP_THREADS) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
     if (p->cut_front_window < 1 || p->cut_tail_window < 1 || p->cut_right_window < 1) return set_err(FP_E_INVAL, "cut window must be >= 1");
@@ -277,7 +277,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     d.n_fasta = (int)c->fasta.size();
     d.fasta_match_req = d.n_fasta > 256 ? 6 : d.n_fasta > 16 ? 5 : 4;                                /* adaptertrimmer.cpp:49-53 */
     d.dimer_max_len = p->dimer_max_len;
-    d.correction = p->correction_enabled; d.ov_require = p->overlap_require;
+    d.correction = p->correction_enabled; d.ov_require = p->overlap_require; d.allow_gap = p->allow_gap_overlap_trimming;
     d.qual_filter = p->qual_filter_enabled; d.qualified_qual = p->qualified_qual & 0xFF; d.n_base_limit = p->n_base_limit; d.avg_qual_req = p->avg_qual_req;
     d.length_filter = p->length_filter_enabled; d.length_required = p->length_required; d.length_limit = p->length_limit;
     d.complexity_filter = p->complexity_filter_enabled;

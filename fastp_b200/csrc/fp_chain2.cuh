@@ -329,6 +329,57 @@ __device__ __noinline__ fp_ov_result t_analyze_bytes(const TRead r1, const TRead
     return ov;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * The one-gap passes of OverlapAnalysis::analyze (overlapanalysis.cpp:91-139, --allow_gap_overlap_trimming) with
+ * Matcher::diffWithOneInsertion (matcher.cpp:56-100) in closed form: with D1[j] = ins[j]!=norm[j], D2[j] = ins[j+1]!=norm[j]
+ * and prefix sums P1/P2 it returns -1 when P1[c-1] + D2[c-1] > limit, else min_{1<=i<=c-1}(P1[i]-P2[i]) + P2[c]
+ * (the early breaks / sentinel never change an accepted value, cf. tests/test_closed_forms.py).  Byte-level, one
+ * sequential scan per (offset, orientation) with an early reject on the lower bound sum(D1 & D2); rare option, kept simple.
+ * ------------------------------------------------------------------------------------------------ */
+template <class FI, class FN>
+__device__ __forceinline__ int t_diff_one_insertion(FI ins, FN norm, int c, int limit) {
+    int p1 = 0, p2 = 0, runmin = 1 << 20, lb = 0, p1cm1 = 0, d2last = 0;
+    for (int j = 0; j < c; j++) {
+        const uint8_t nj = norm(j);
+        const int d1 = ins(j) != nj, d2 = ins(j + 1) != nj;
+        lb += d1 & d2;
+        if (lb > limit) return 1 << 20;                                   /* every split costs at least lb */
+        p1 += d1; p2 += d2;
+        if (j + 1 <= c - 1) runmin = min(runmin, p1 - p2);
+        if (j == c - 2) p1cm1 = p1;
+        if (j == c - 1) d2last = d2;
+    }
+    if (c >= 2 && p1cm1 + d2last > limit) return -1;
+    return runmin + p2;
+}
+
+__device__ __noinline__ fp_ov_result t_analyze_gap(const TRead r1, const TRead r2, const int16_t* lut, int sub, int g) {
+    const uint8_t* s1 = r1.seq + r1.front; const uint8_t* s2 = r2.seq + r2.front;
+    const int len1 = r1.len, len2 = r2.len, req = c_p.ov_require;
+    fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+    for (int dir = 0; dir < 2; dir++) {
+        const int ncand = dir == 0 ? len1 - req : len2 - req;
+        int my_o = 1 << 20, my_d = 0, my_ol = 0;
+        for (int o = sub; o < ncand; o += g) {
+            const int ol = dir == 0 ? min(len1 - o, len2) : min(len1, len2 - o);
+            const int limit = lut[ol], c = ol - 1;
+            const int ao = dir == 0 ? o : 0, bo = dir == 0 ? 0 : o;       /* str1 + ao  vs  rc(r2) + bo */
+            auto A = [&](int j) -> uint8_t { return s1[ao + j]; };
+            auto B = [&](int j) -> uint8_t { return dev_complement(s2[len2 - 1 - bo - j]); };
+            int d = t_diff_one_insertion(A, B, c, limit);
+            if (d < 0 || d > limit) d = t_diff_one_insertion(B, A, c, limit);
+            if (d <= limit && d >= 0) { my_o = o; my_d = d; my_ol = ol; break; }
+        }
+        const int best = group_min(my_o, g);
+        if (best < (1 << 20)) {
+            ov.overlapped = 1; ov.has_gap = 1; ov.offset = (int16_t)(dir == 0 ? best : -best);
+            ov.diff = (int16_t)group_pick(my_d, my_o == best, g); ov.overlap_len = (int16_t)group_pick(my_ol, my_o == best, g);
+            return ov;
+        }
+    }
+    return ov;
+}
+
 /* Effect of ONE corrected base on the post-filter statistics, in full-read context (cycle = row position P, 5-mers of
  * the whole original row): -(old base, old quality) +(new base, new quality).  The dense pass credited the ORIGINAL row to
  * pre and post; with this delta the block-private (or, for unclean rows, global) post accumulators describe the CURRENT row,
@@ -918,6 +969,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 r2.seq = rs2; r2.qual = rq2; r2.pl = pl2; r2.front = 0; r2.len = l2; r2.null = false; r2.clean = clean2;
                 int flags1 = 0, flags2 = 0, apos1 = 0, apos2 = 0, ab1 = 0, ab2 = 0, pb1 = 255, pb2 = 255, pl1n = 0, pl2n = 0;
                 fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
+                fp_ov_result ovA = ov;                    /* ovForAdapter */
                 bool both = false, need_correct = false;
                 if (active) {
                     r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len);   /* :425-426 */
@@ -940,7 +992,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             else red_add64(&G[L.off_isize + isize], 1ull);
                         }
                     }
-                    need_correct = both && c_p.correction && ov.overlapped && ov.diff != 0;       /* :443,:453-456 */
+                    /* :445-447 gap-aware adapter trimming: analyze(..., allowGap) repeats the no-gap passes, then tries one gap */
+                    if (both && c_p.allow_gap && (c_p.adapter_enabled || c_p.correction) && !ov.overlapped) ovA = t_analyze_gap(r1, r2, s_lut, sub, GL);
+                    else ovA = ov;
+                    need_correct = both && c_p.correction && !ovA.has_gap && ovA.overlapped && ovA.diff != 0;       /* :443,:453-456 */
                 }
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
@@ -950,7 +1005,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                         int cf = 0;
                         if (lead) {
                             bool c1, c2;
-                            t_correct(r1, r2, pl1, pl2, PW, ov, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
+                            t_correct(r1, r2, pl1, pl2, PW, ovA, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
                                       a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, D, G, l1, l2, c1, c2);
                             cf = (c1 ? 1 : 0) | (c2 ? 2 : 0);
                         }
@@ -961,8 +1016,8 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                     }
                     if (both && c_p.adapter_enabled) {                                            /* :457-485 */
                         bool trimmed = false;
-                        if (ov.overlapped && ov.offset < 0) {                                     /* trimByOverlapAnalysis adaptertrimmer.cpp:17-46 */
-                            const int ol = ov.overlap_len;
+                        if (ovA.overlapped && ovA.offset < 0) {                                   /* trimByOverlapAnalysis adaptertrimmer.cpp:17-46 */
+                            const int ol = ovA.overlap_len;
                             const int nl1 = min(r1.len, ol + r2.front), nl2 = min(r2.len, ol + r1.front);
                             const int a1 = r1.len - nl1, a2 = r2.len - nl2;
                             r1.len = nl1; r2.len = nl2;

@@ -14,6 +14,7 @@
  *            read-through (src/knownadapters.h:14-15) then poly-G fill; per-base substitution errors
  *            with p = 10^(-q/10); N bases; polyG / polyA tails; low-quality 3' tails; planted
  *            correctable mismatches (Q>=30 vs Q<=14); short / empty reads; adapter dimers.
+ * profile 2  profile 1 plus single-base deletions (8 % of R2) / insertions (4 % of R1).
  */
 #ifndef FP_SYNTH_H
 #define FP_SYNTH_H
@@ -84,7 +85,7 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
                          uint8_t* seq1, uint8_t* qual1, uint16_t* len1,
                          uint8_t* seq2, uint8_t* qual2, uint16_t* len2) {
     fp_rng r; fp_rng_seed(&r, seed, index, 0);
-    int n1 = L, n2 = L;
+    int n1 = L, n2 = L, ins = L;
     if (profile == 0) {
         uint32_t t1 = fp_rng_below(&r, 512), t2 = fp_rng_below(&r, 512);
         for (int j = 0; j < L; j++) { seq1[j] = fp_synth_base(fp_rng_u32(&r) >> 13); qual1[j] = fp_synth_pool_qual(seed, t1, j, L); }
@@ -96,10 +97,14 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
         int64_t z = 0;
         for (int k = 0; k < 12; k++) z += (int64_t)(fp_rng_u32(&r) >> 16);
         z -= 6 * 65536;
-        int ins = mean + (int)((z * sd) / 65536);
+        ins = mean + (int)((z * sd) / 65536);
         if (ins < 35) ins = 35;
         if (fp_rng_permille(&r, 3)) ins = (int)fp_rng_below(&r, 3);          /* adapter dimer: insert 0..2 */
         else if (fp_rng_permille(&r, 50)) ins = 20 + (int)fp_rng_below(&r, (uint32_t)L);   /* extra short inserts */
+        if (profile >= 2) {   /* many short inserts: only there can a gap near the overlap's end decide the outcome */
+            fp_rng rj; fp_rng_seed(&rj, seed, index, 2);
+            if (fp_rng_permille(&rj, 150)) ins = 30 + (int)fp_rng_below(&rj, 40);
+        }
         if (ins > FP_SYNTH_MAXFRAG) ins = FP_SYNTH_MAXFRAG;
         int lowcomplex = fp_rng_permille(&r, 5);
         for (int j = 0; j < ins; j++) {
@@ -168,6 +173,23 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
                     if (flip1) { qual1[p1] = badq; qual2[p2] = goodq; } else { qual2[p2] = badq; qual1[p1] = goodq; }
                 }
             }
+        }
+    }
+    if (profile >= 2 && seq2) {
+        /* profile 2 = enriched + single-base indels, so the one-gap overlap passes (--allow_gap_overlap_trimming) have work */
+        fp_rng ri; fp_rng_seed(&ri, seed, index, 1);
+        if (fp_rng_permille(&ri, 80) && n2 > 20) {                       /* deletion in R2 */
+            /* half of them within the first 8 bases: the reference only accepts a gap whose shifted remainder stays
+               within the mismatch limit (Matcher::diffWithOneInsertion's early return), i.e. gaps near the overlap's end */
+            const int q = fp_rng_permille(&ri, 500) ? 1 + (int)fp_rng_below(&ri, 7) : 5 + (int)fp_rng_below(&ri, (uint32_t)(n2 - 10));
+            for (int j = q; j + 1 < n2; j++) { seq2[j] = seq2[j + 1]; qual2[j] = qual2[j + 1]; }
+            seq2[n2 - 1] = fp_synth_base(fp_rng_u32(&ri) >> 13);
+        }
+        if (fp_rng_permille(&ri, 40) && n1 > 20) {                       /* insertion in R1 */
+            const int e1 = ins < n1 ? ins : n1;
+            const int q = (e1 > 12 && fp_rng_permille(&ri, 500)) ? e1 - 2 - (int)fp_rng_below(&ri, 7) : 5 + (int)fp_rng_below(&ri, (uint32_t)(n1 - 10));
+            for (int j = n1 - 1; j > q; j--) { seq1[j] = seq1[j - 1]; qual1[j] = qual1[j - 1]; }
+            seq1[q] = fp_synth_base(fp_rng_u32(&ri) >> 13);
         }
     }
     for (int j = n1; j < stride; j++) { seq1[j] = 0; qual1[j] = 0; }

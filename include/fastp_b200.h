@@ -88,7 +88,7 @@ typedef struct fp_params {
     const char* adapter_seq_r2;             /* adapter.sequenceR2                               */
     int32_t n_fasta_adapters;               /* adapter.hasFasta <=> n_fasta_adapters > 0        */
     const char* const* fasta_adapters;      /* adapter.seqsInFasta                              */
-    int32_t allow_gap_overlap_trimming;     /* must be 0 (FP_E_UNSUPPORTED otherwise)           */
+    int32_t allow_gap_overlap_trimming;     /* --allow_gap_overlap_trimming (overlapanalysis.cpp:91) */
     int32_t dimer_max_len;                  /* adapter.dimerMaxLen (default 2)                  */
     /* CorrectionOptions + overlap thresholds options.h:123-130,376-379 (defaults 30/5/20 options.cpp:24-26) */
     int32_t correction_enabled;

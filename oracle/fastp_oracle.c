@@ -289,7 +289,9 @@ static int count_mismatches(const uint8_t* a, const uint8_t* b, int len) {    /*
 /* ------------------------------------------------------------------------------------------
  * OverlapAnalysis::analyze  src/overlapanalysis.cpp:17-146 (allowGap=false passes only)
  * ------------------------------------------------------------------------------------------ */
-static fp_ov_result analyze(const oread* r1, const oread* r2, int diffLimit, int overlapRequire, double diffPercentLimit) {
+static int diff_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit);
+
+static fp_ov_result analyze(const oread* r1, const oread* r2, int diffLimit, int overlapRequire, double diffPercentLimit, int allowGap) {
     uint8_t rcr2[FP_MAX_STRIDE + 8];
     int len2 = r2->len;
     reverse_complement(r2->seq, rcr2, len2);
@@ -327,6 +329,34 @@ static fp_ov_result analyze(const oread* r1, const oread* r2, int diffLimit, int
             return ov;
         }
         offset -= 1;
+    }
+    if (allowGap) {
+        /* forward with one gap: overlapanalysis.cpp:91-114 */
+        offset = 0;
+        while (offset < len1 - overlapRequire) {
+            overlap_len = imin(len1 - offset, len2);
+            int overlapDiffLimit = imin(diffLimit, (int)(overlap_len * diffPercentLimit));
+            int d = diff_with_one_insertion(str1 + offset, str2, overlap_len - 1, overlapDiffLimit);
+            if (d < 0 || d > overlapDiffLimit) d = diff_with_one_insertion(str2, str1 + offset, overlap_len - 1, overlapDiffLimit);
+            if (d <= overlapDiffLimit && d >= 0) {
+                ov.overlapped = 1; ov.offset = (int16_t)offset; ov.overlap_len = (int16_t)overlap_len; ov.diff = (int16_t)d; ov.has_gap = 1;
+                return ov;
+            }
+            offset += 1;
+        }
+        /* reverse with one gap: overlapanalysis.cpp:116-138 */
+        offset = 0;
+        while (offset > -(len2 - overlapRequire)) {
+            overlap_len = imin(len1, len2 - abs(offset));
+            int overlapDiffLimit = imin(diffLimit, (int)(overlap_len * diffPercentLimit));
+            int d = diff_with_one_insertion(str1, str2 - offset, overlap_len - 1, overlapDiffLimit);
+            if (d < 0 || d > overlapDiffLimit) d = diff_with_one_insertion(str2 - offset, str1, overlap_len - 1, overlapDiffLimit);
+            if (d <= overlapDiffLimit && d >= 0) {
+                ov.overlapped = 1; ov.offset = (int16_t)offset; ov.overlap_len = (int16_t)overlap_len; ov.diff = (int16_t)d; ov.has_gap = 1;
+                return ov;
+            }
+            offset -= 1;
+        }
     }
     return ov;                                                          /* :141-145 all zero */
 }
@@ -398,6 +428,37 @@ static int match_with_one_insertion(const uint8_t* insData, const uint8_t* norma
         if (diff <= diffLimit) return 1;
     }
     return 0;
+}
+
+/* Matcher::diffWithOneInsertion  src/matcher.cpp:56-100 (literal restatement, arrays zero-filled) */
+static int diff_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit) {
+    int accL[FP_MAX_STRIDE + 8];
+    int accR[FP_MAX_STRIDE + 8];
+    if (cmplen <= 0) return 100000000;
+    memset(accL, 0, sizeof(int) * cmplen);
+    memset(accR, 0, sizeof(int) * cmplen);
+    accL[0] = insData[0] == normalData[0] ? 0 : 1;
+    accR[cmplen - 1] = insData[cmplen] == normalData[cmplen - 1] ? 0 : 1;
+    for (int i = 1; i < cmplen; i++) {
+        if (insData[i] != normalData[i]) accL[i] = accL[i - 1] + 1;
+        else accL[i] = accL[i - 1];
+        if (accL[i] + accR[cmplen - 1] > diffLimit) break;
+    }
+    for (int i = cmplen - 2; i >= 0; i--) {
+        if (insData[i + 1] != normalData[i]) accR[i] = accR[i + 1] + 1;
+        else accR[i] = accR[i + 1];
+        if (accR[i] + accL[0] > diffLimit) {
+            for (int q = 0; q < i; q++) accR[q] = diffLimit + 1;
+            break;
+        }
+    }
+    int minDiff = 100000000;
+    for (int i = 1; i < cmplen; i++) {
+        if (accL[i - 1] + accR[cmplen - 1] > diffLimit) return -1;
+        int diff = accL[i - 1] + accR[i];
+        if (diff <= minDiff) minDiff = diff;
+    }
+    return minDiff;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -574,10 +635,13 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
     fp_ov_result ov; memset(&ov, 0, sizeof(ov));
     int ovComputed = 0;
     if (both && (p->adapter_enabled || p->correction_enabled || p->thread0_semantics)) {   /* :438-441 */
-        ov = analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0);
+        ov = analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0, 0);
         ovComputed = 1;
     }
     if (both && (p->adapter_enabled || p->correction_enabled)) {        /* :443 */
+        /* :445-447 gap-aware adapter trimming computes a separate overlap */
+        fp_ov_result ovForAdapter = p->allow_gap_overlap_trimming
+            ? analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0, 1) : ov;
         if (p->thread0_semantics) {                                     /* :449-452 statInsertSize */
             int isize = p->insert_size_max;
             if (ov.overlapped) {
@@ -588,17 +652,17 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
             ISZ[isize]++;
             isizeEvaluated = 1;
         }
-        if (p->correction_enabled) {                                    /* :453-456 */
+        if (p->correction_enabled && !ovForAdapter.has_gap) {             /* :453-456 */
             int c1, c2;
-            correct_by_overlap(&r1, &r2, FR, ov, &c1, &c2);
+            correct_by_overlap(&r1, &r2, FR, ovForAdapter, &c1, &c2);
             if (c1) flags1 |= FP_F_CORRECTED;
             if (c2) flags2 |= FP_F_CORRECTED;
         }
         if (p->adapter_enabled) {                                       /* :457-485 */
             int trimmed = 0;
             /* AdapterTrimmer::trimByOverlapAnalysis adaptertrimmer.cpp:17-46 */
-            if (ov.overlapped && ov.offset < 0) {
-                int ol = ov.overlap_len;
+            if (ovForAdapter.overlapped && ovForAdapter.offset < 0) {
+                int ol = ovForAdapter.overlap_len;
                 int nl1 = imin(r1.len, ol + ft2);
                 int nl2 = imin(r2.len, ol + ft1);
                 int a1 = r1.len - nl1, a2 = r2.len - nl2;
@@ -625,7 +689,7 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
     }
     if (p->thread0_semantics && !isizeEvaluated && both) {              /* :497-504 */
         if (!ovComputed) {
-            ov = analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0);
+            ov = analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0, 0);
             ovComputed = 1;
         }
         int isize = p->insert_size_max;
@@ -670,7 +734,6 @@ int fp_oracle_process(const fp_params* p, const fp_counter_layout* L, const fp_b
                       fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov, int64_t* counters) {
     if (!p || !L || !b || !out1 || !counters) return FP_E_INVAL;
     if (b->stride > FP_MAX_STRIDE) return FP_E_INVAL;
-    if (p->allow_gap_overlap_trimming) return FP_E_UNSUPPORTED;
     if (p->paired) {
         if (!out2) return FP_E_INVAL;
         for (int64_t i = 0; i < b->n; i++)
@@ -705,7 +768,7 @@ int fp_oracle_trim_by_sequence(uint8_t* seq, int len, const char* adapter, int* 
 }
 fp_ov_result fp_oracle_analyze(uint8_t* seq1, int len1, uint8_t* seq2, int len2, int diffLimit, int overlapRequire, double diffPercentLimit) {
     oread r1 = {seq1, seq1, len1, 0}, r2 = {seq2, seq2, len2, 0};
-    return analyze(&r1, &r2, diffLimit, overlapRequire, diffPercentLimit);
+    return analyze(&r1, &r2, diffLimit, overlapRequire, diffPercentLimit, 0);
 }
 int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int len) {
     oread r = {seq, qual, len, 0};

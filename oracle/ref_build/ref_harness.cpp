@@ -192,7 +192,8 @@ void pe_one(Worker& w, const fp_params* p, uint8_t* seq1, uint8_t* qual1, int le
         ovComputed = true;
     }
     if (r1 != NULL && r2 != NULL && (mOptions->adapter.enabled || mOptions->correction.enabled)) {   // :443
-        OverlapResult ovForAdapter = ov;                                      // allowGapOverlapTrimming unsupported here
+        OverlapResult ovForAdapter = mOptions->adapter.allowGapOverlapTrimming                                             // :445-447
+            ? OverlapAnalysis::analyze(r1, r2, mOptions->overlapDiffLimit, mOptions->overlapRequire, mOptions->overlapDiffPercentLimit / 100.0, true) : ov;
         if (tid0) { stat_isize(w, r1, r2, ov, frontTrimmed1, frontTrimmed2); isizeEvaluated = true; }   // :449-452
         if (mOptions->correction.enabled && !ovForAdapter.hasGap) {           // :453-456
             std::string s1 = *r1->mSeq, s2 = *r2->mSeq;
@@ -341,7 +342,6 @@ extern "C" {
 // Same contract as fp_oracle_process (oracle/fastp_oracle.h). Counters are ADDED into `counters`.
 int fp_ref_process(const fp_params* p, const fp_counter_layout* L, const fp_batch* b,
                    fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov, int64_t* counters) {
-    if (p->allow_gap_overlap_trimming) return FP_E_UNSUPPORTED;
     run_range(p, L, b, 0, b->n, out1, out2, ov, counters);
     return FP_OK;
 }
@@ -351,7 +351,6 @@ int fp_ref_process(const fp_params* p, const fp_counter_layout* L, const fp_batc
 // out1/out2/ov may be NULL (baseline timing).
 int fp_ref_process_mt(const fp_params* p, const fp_counter_layout* L, const fp_batch* b,
                       fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov, int64_t* counters, int nthreads) {
-    if (p->allow_gap_overlap_trimming) return FP_E_UNSUPPORTED;
     if (nthreads < 1) nthreads = 1;
     std::vector<std::vector<int64_t>> part(nthreads, std::vector<int64_t>(L->total, 0));
     std::vector<std::thread> th;

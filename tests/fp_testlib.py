@@ -184,6 +184,13 @@ def assert_counters_equal(cx, cy, what=""):
 def config_params(name, paired, lib=None):
     lib = lib or oracle()
     P = lambda **kw: capi.default_params(paired, lib=lib, **kw)  # noqa: E731
+    if name.startswith("gap_"):               # --allow_gap_overlap_trimming on top of a base option set
+        p = config_params(name[4:], paired, lib)
+        capi.set_params(p, allow_gap_overlap_trimming=1)
+        return p
+    if name == "tight_overlap":               # stricter overlap thresholds + correction + gap passes
+        return P(correction_enabled=1, allow_gap_overlap_trimming=1, overlap_require=20, overlap_diff_limit=3,
+                 overlap_diff_percent_limit=10, adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
     if name == "default":
         return P()
     if name == "cfg2_cut_right_polyg":        # BASELINE config 2: --cut_right --trim_poly_g -A
@@ -243,3 +250,5 @@ def overrep_params(name, paired, arrs, L, sampling=20, lib=None):
 
 CONFIG_NAMES = ["default", "cfg2_cut_right_polyg", "cfg3_overlap_correction", "cfg4_full", "cut_front_tail", "trim_fixed",
                 "all_cuts", "filters", "no_filters", "fasta_adapters", "tid_nonzero", "short_adapter"]
+# option sets for the one-gap overlap passes; run on synthetic profile 2 (reads with single-base indels)
+GAP_CONFIG_NAMES = ["gap_default", "gap_cfg3_overlap_correction", "gap_cfg4_full", "gap_all_cuts", "tight_overlap"]

@@ -38,7 +38,7 @@ def load_fixture(path):
 
 
 def test_fixture_count():
-    assert len(GOLDEN) >= 31
+    assert len(GOLDEN) >= 36
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

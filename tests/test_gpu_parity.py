@@ -38,6 +38,20 @@ def test_enriched_host_mode(gpu, name, paired):
     T.assert_results_equal(got, want, paired, what=f"host {name}")
 
 
+@pytest.mark.parametrize("mode", ["device", "host"])
+@pytest.mark.parametrize("L,stride", [(150, 160), (100, 112), (250, 256)])
+@pytest.mark.parametrize("name", T.GAP_CONFIG_NAMES)
+def test_gap_overlap_passes(gpu, name, L, stride, mode):
+    """--allow_gap_overlap_trimming (analyze allowGap passes + diffWithOneInsertion) on reads with single-base indels."""
+    if mode == "host" and L != 150:
+        pytest.skip("host mode covered at L=150")
+    p = T.config_params(name, 1)
+    _, arrs = T.synth_host(6000, stride, 1, 300, 31, 2, L)
+    want = T.run_cpu("oracle", p, arrs, stride)
+    got = gpu.run_gpu(p, arrs, stride, mode=mode)
+    T.assert_results_equal(got, want, 1, what=f"{name}/L{L}/{mode}")
+
+
 @pytest.mark.parametrize("paired", [1, 0])
 def test_ref_style_profile(gpu, paired):
     p = T.config_params("cfg4_full", paired)

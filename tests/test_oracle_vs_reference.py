@@ -23,6 +23,19 @@ def test_port_equals_reference_objects(name, paired):
 
 
 @needs_ref
+@pytest.mark.parametrize("L,stride", [(150, 160), (100, 112), (250, 256)])
+@pytest.mark.parametrize("name", T.GAP_CONFIG_NAMES)
+def test_port_equals_reference_gap_overlap(name, L, stride):
+    """--allow_gap_overlap_trimming: OverlapAnalysis::analyze(..., allowGap=true) + Matcher::diffWithOneInsertion
+    (src/overlapanalysis.cpp:106-160, src/matcher.cpp:40-91) on reads that carry single-base indels."""
+    p = T.config_params(name, 1)
+    _, arrs = T.synth_host(8000, stride, 1, 300, 31, 2, L)
+    x = T.run_cpu("oracle", p, arrs, stride)
+    y = T.run_cpu("ref", p, arrs, stride)
+    T.assert_results_equal(x, y, 1, skip=("adapter_pos",), what=name)
+
+
+@needs_ref
 @pytest.mark.parametrize("L,stride", [(250, 256), (100, 112), (36, 48)])
 def test_port_equals_reference_other_lengths(L, stride):
     p = T.config_params("cfg4_full", 1)
