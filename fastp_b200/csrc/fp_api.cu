@@ -124,7 +124,7 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     sl.off_clean = (int)off; off += (size_t)sides * T;
     off = align_up(off, 16);
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
-    sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
+    sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * FP_QH_REP * 4;
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
     off = align_up(off, 16);
     sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);

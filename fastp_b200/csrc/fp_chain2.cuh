@@ -674,6 +674,21 @@ __device__ __forceinline__ void warp_serve_delta(bool want, bool clean, const De
 /* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
 struct ColAcc2 { unsigned int v[2][NB][4]; };
 
+/* 2-bit codes ((base>>1)&3: A0 C1 T2 G3) of a word's 4 bases gathered into one byte: code_mul4 leaves it in byte 3 */
+__device__ __forceinline__ uint32_t code_mul4(uint32_t w) { return ((w >> 1) & 0x03030303u) * 0x01041040u; }
+__device__ __forceinline__ uint32_t pack_codes4(uint32_t w) { return code_mul4(w) >> 24; }
+/* table index used while counting (oldest base in the low digit, codes A0 C1 T2 G3) -> reference 5-mer index
+   (oldest base in the high digit, base2val A0 T1 C2 G3; stats.cpp:248-266) */
+__device__ __forceinline__ int kmer_ref_index(int f) {
+    int r = 0;
+    #pragma unroll
+    for (int d = 0; d < 5; d++) {
+        const int c = (f >> (2 * d)) & 3;
+        r |= (((c & 1) << 1) | (c >> 1)) << (2 * (4 - d));
+    }
+    return r;
+}
+
 /* exact "byte is one of A,C,G,T" per byte (0/1 bytes): class by base&7 plus the upper-bit pattern */
 __device__ __forceinline__ uint32_t exact_acgt(uint32_t w) {
     const uint32_t K = 0x01010101u;
@@ -719,7 +734,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     uint16_t* s_len = reinterpret_cast<uint16_t*>(smem + sl.off_len);       /* [SIDES][T] */
     uint8_t* s_clean = smem + sl.off_clean;                                 /* [SIDES][T] */
     unsigned int* s_kmer = reinterpret_cast<unsigned int*>(smem + sl.off_kmer);    /* [SIDES][1024] */
-    unsigned int* s_qhist = reinterpret_cast<unsigned int*>(smem + sl.off_qhist);  /* [SIDES][128]  */
+    unsigned int* s_qhist = reinterpret_cast<unsigned int*>(smem + sl.off_qhist);  /* [SIDES][128][FP_QH_REP] */
     BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem + sl.off_bc);
     DeltaAcc D;
     D.cycles = S;
@@ -733,7 +748,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
 
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) s_qhist[i] = 0;
+    for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_THREADS) s_qhist[i] = 0;
     for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
     for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
     for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
@@ -753,7 +768,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         for (int b = 0; b < NB; b++)
             #pragma unroll
             for (int k = 0; k < 4; k++) acc.v[c][b][k] = 0;
-    unsigned long long rl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* per-thread reads / lengthSum of pre1 post1 pre2 post2 */
+    unsigned int rl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* per-thread reads / lengthSum of pre1 post1 pre2 post2 (a thread sees < 2^32 bases per launch) */
 
     constexpr int GL = PAIRED ? 4 : 2;            /* lanes per unit */
     constexpr int UPW = 32 / GL;                  /* units per warp step */
@@ -862,42 +877,48 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
                             const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                             const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                            if (!plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq)) s_clean[sd * T + rr2] = 0;
-                            /* pre-filter quality histogram (stats.cpp:213) and 5-mer counts (stats.cpp:228-266) of these bases */
-                            unsigned int* kh = s_kmer + sd * FP_KMER_BINS; unsigned int* qh = s_qhist + sd * FP_QUAL_BINS;
+                            uint32_t okm;
+                            const bool pok = plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq, okm);
+                            if (!pok) s_clean[sd * T + rr2] = 0;
+                            /* pre-filter quality histogram (stats.cpp:213): FP_QH_REP copies per bin, copy = lane & (REP-1) */
+                            unsigned int* qh = s_qhist + sd * (FP_QUAL_BINS * FP_QH_REP) + (lane & (FP_QH_REP - 1));
                             const int nv = min(n, 32);
-                            int kmer = 0, run = 0;
-                            if (j > 0) {                                   /* context: the 4 bases before this chunk */
+                            if (pok) {                                      /* every valid quality < 128 */
+                                #pragma unroll
+                                for (int k8 = 0; k8 < 8; k8++)
+                                    #pragma unroll
+                                    for (int b4 = 0; b4 < 4; b4++)
+                                        if (4 * k8 + b4 < nv) atomicAdd(&qh[((q[k8] >> (8 * b4)) & 0xFFu) * FP_QH_REP], 1u);
+                            } else {
+                                #pragma unroll 1
+                                for (int i = 0; i < nv; i++) {
+                                    const uint32_t qb = tile_qual[sd][rr2 * S + 32 * j + i];
+                                    if (qb < FP_QUAL_BINS) atomicAdd(&qh[qb * FP_QH_REP], 1u);
+                                }
+                            }
+                            /* pre-filter 5-mer counts (stats.cpp:228-266): a 5-mer counts iff its five bases are exact A/C/G/T.
+                               Z = 2-bit codes of the 4 bases before this chunk and its 32 bases, 2 bits per base; the 5-mer ending
+                               at chunk position p is the 10-bit field at bit 2p.  The table is indexed by that field (oldest base
+                               in the LOW digit, code A0 C1 T2 G3); the flush maps it to the reference's index. */
+                            unsigned int* kh = s_kmer + sd * FP_KMER_BINS;
+                            uint32_t cz = 0, cok = 0;
+                            if (j > 0) {
                                 const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tile_seq[sd] + rr2 * S + 32 * j - 4);
-                                const uint32_t okp = exact_acgt(pw_);
-                                #pragma unroll
-                                for (int b4 = 0; b4 < 4; b4++) {
-                                    const uint32_t xx = (pw_ >> (8 * b4 + 1)) & 3u;
-                                    kmer = ((kmer << 2) | ((0xD8u >> (2 * xx)) & 3u)) & 0x3FF;
-                                    run = ((okp >> (8 * b4)) & 1u) ? run + 1 : 0;
-                                }
+                                cz = pack_codes4(pw_); cok = pack_nibble(exact_acgt(pw_));
                             }
-                            int curq = -1, cnt = 0;
-                            #pragma unroll 1
-                            for (int k8 = 0; k8 < 8; k8++) {
-                                if (4 * k8 >= nv) break;
-                                const uint32_t w = *reinterpret_cast<const uint32_t*>(tile_seq[sd] + rr2 * S + 32 * j + 4 * k8);
-                                const uint32_t qw = *reinterpret_cast<const uint32_t*>(tile_qual[sd] + rr2 * S + 32 * j + 4 * k8);
-                                const uint32_t okw = exact_acgt(w);
-                                #pragma unroll
-                                for (int b4 = 0; b4 < 4; b4++) {
-                                    if (4 * k8 + b4 < nv) {
-                                        const uint32_t xx = (w >> (8 * b4 + 1)) & 3u;
-                                        kmer = ((kmer << 2) | ((0xD8u >> (2 * xx)) & 3u)) & 0x3FF;      /* A0 T1 C2 G3 */
-                                        run = ((okw >> (8 * b4)) & 1u) ? run + 1 : 0;
-                                        if (run >= 5) atomicAdd(&kh[kmer], 1u);
-                                        const int qb = (int)((qw >> (8 * b4)) & 0xFFu);
-                                        if (qb == curq) cnt++;
-                                        else { if (cnt && curq < FP_QUAL_BINS) atomicAdd(&qh[curq], (unsigned)cnt); curq = qb; cnt = 1; }
-                                    }
-                                }
+                            const uint32_t m0 = code_mul4(x[0]), m1 = code_mul4(x[1]), m2 = code_mul4(x[2]), m3 = code_mul4(x[3]);
+                            const uint32_t m4 = code_mul4(x[4]), m5 = code_mul4(x[5]), m6 = code_mul4(x[6]), m7 = code_mul4(x[7]);
+                            const uint32_t clo = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
+                            const uint32_t chi = __byte_perm(__byte_perm(m4, m5, 0x0073), __byte_perm(m6, m7, 0x0073), 0x5410);
+                            const uint32_t Z0 = cz | (clo << 8), Z1 = __funnelshift_r(clo, chi, 24), Z2 = chi >> 24;
+                            const uint32_t O0 = cok | (okm << 4), O1 = okm >> 28;
+                            const uint32_t vwin = O0 & __funnelshift_r(O0, O1, 1) & __funnelshift_r(O0, O1, 2) & __funnelshift_r(O0, O1, 3) & __funnelshift_r(O0, O1, 4);
+                            #pragma unroll
+                            for (int pp = 0; pp < 32; pp++) {
+                                const int wz = (2 * pp) >> 5, sh = (2 * pp) & 31;
+                                const uint32_t f = wz == 0 ? __funnelshift_r(Z0, Z1, sh) : wz == 1 ? __funnelshift_r(Z1, Z2, sh) : 0u;
+                                if ((vwin >> pp) & 1u) atomicAdd(&kh[f & 0x3FFu], 1u);
                             }
-                            if (cnt && curq < FP_QUAL_BINS) atomicAdd(&qh[curq], (unsigned)cnt);
                         }
                     }
                     uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;
@@ -1122,11 +1143,13 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     #pragma unroll 1
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) {
         const unsigned int v = s_kmer[i];
-        if (v) { const int sd = i / FP_KMER_BINS, k = i % FP_KMER_BINS; red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
+        if (v) { const int sd = i / FP_KMER_BINS, k = kmer_ref_index(i % FP_KMER_BINS); red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
     for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) {
-        const unsigned int v = s_qhist[i];
+        unsigned int v = 0;
+        #pragma unroll
+        for (int c = 0; c < FP_QH_REP; c++) v += s_qhist[i * FP_QH_REP + c];
         if (v) { const int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
@@ -1150,7 +1173,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     }
     #pragma unroll
     for (int k = 0; k < 8; k++) {
-        unsigned long long v = rl[k];
+        unsigned long long v = (unsigned long long)rl[k];
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
         if (lane == 0 && k < 2 * L.n_stats && v) red_add64(&G[(k & 1) ? fp_off_length_sum(&L, k >> 1) : fp_off_reads(&L, k >> 1)], v);

@@ -118,9 +118,9 @@ __device__ __forceinline__ uint32_t pack_nibble(uint32_t v01) { return ((v01 * 0
 /* One plane word (32 bases = 8 seq words + 8 qual words) of one row: returns false if a valid byte is outside
  * {A,C,G,T,N} or a quality has bit 7 set.  x/q: the 8 words; n = number of valid bases in this word (0..32). */
 __device__ __forceinline__ bool plane_word_from_bytes(const uint32_t (&x)[8], const uint32_t (&q)[8], int n, uint32_t qq4,
-                                                      uint32_t& lo, uint32_t& hi, uint32_t& nn, uint32_t& lq) {
+                                                      uint32_t& lo, uint32_t& hi, uint32_t& nn, uint32_t& lq, uint32_t& ok) {
     const uint32_t K = 0x01010101u;
-    lo = hi = nn = lq = 0;
+    lo = hi = nn = lq = ok = 0;
     uint32_t bad = 0;
     #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -141,6 +141,7 @@ __device__ __forceinline__ bool plane_word_from_bytes(const uint32_t (&x)[8], co
         hi |= pack_nibble(c2 & acgt) << (4 * k);
         nn |= pack_nibble(isN) << (4 * k);
         lq |= pack_nibble(ql) << (4 * k);
+        ok |= pack_nibble(acgt) << (4 * k);                         /* exact: byte is one of 'A','C','G','T' */
     }
     return bad == 0;
 }
@@ -157,6 +158,7 @@ struct PatchSink { fp_patch* patches; unsigned int cap; unsigned int* count; };
  * 3 = sum of raw quality chars (qualsum = kind3 - 33*kind0).  Bins: A C T N G (base&7 = 1 3 4 6 7);
  * any other byte goes through a slow global-atomic path.
  * ------------------------------------------------------------------------------------------------ */
+#define FP_QH_REP 4           /* copies of the block-private quality histogram (spreads same-value shared-memory atomics) */
 #define NB 5
 struct ColAcc { unsigned int v[4][NB][4]; };
 
