@@ -277,7 +277,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     d.n_fasta = (int)c->fasta.size();
     d.fasta_match_req = d.n_fasta > 256 ? 6 : d.n_fasta > 16 ? 5 : 4;                                /* adaptertrimmer.cpp:49-53 */
     d.dimer_max_len = p->dimer_max_len;
-    d.correction = p->correction_enabled; d.ov_require = p->overlap_require; d.allow_gap = p->allow_gap_overlap_trimming;
+    d.correction = p->correction_enabled; d.ov_require = p->overlap_require; d.allow_gap = p->allow_gap_overlap_trimming; d.ov_diff_limit = p->overlap_diff_limit;
     d.qual_filter = p->qual_filter_enabled; d.qualified_qual = p->qualified_qual & 0xFF; d.n_base_limit = p->n_base_limit; d.avg_qual_req = p->avg_qual_req;
     d.length_filter = p->length_filter_enabled; d.length_required = p->length_required; d.length_limit = p->length_limit;
     d.complexity_filter = p->complexity_filter_enabled;

@@ -16,6 +16,9 @@
 #include "fp_device.cuh"
 
 /* thread-level view of one read: row pointers (smem), plane pointers, current window */
+/* tell the compiler a pointer is a shared-memory address, so loads become LDS / atomics ATOMS instead of generic LD / ATOM */
+#define FP_SMEM(p) __builtin_assume(__isShared(p))
+
 struct TRead {
     uint8_t* seq;          /* row start in the shared-memory tile */
     uint8_t* qual;
@@ -51,6 +54,7 @@ __device__ __forceinline__ int group_pick(int v, bool mine, int g) {
  * Filter::trimAndCut  (filter.cpp:68-207), scalar per thread.  Returns false for NULL.
  * ------------------------------------------------------------------------------------------------ */
 __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut) {
+    FP_SMEM(seq);    FP_SMEM(qualu);
     frontOut = 0; lenOut = l0;
     const bool anycut = c_p.cut_front || c_p.cut_tail || c_p.cut_right;
     if (front == 0 && tail == 0 && !anycut) return true;                  /* :71-72 */
@@ -114,6 +118,7 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
 
 /* PolyX::trimPolyG  (polyx.cpp:16-42): returns the new length */
 __device__ __noinline__ int t_trim_polyg(const uint8_t* data, int rlen, int minLen) {
+    FP_SMEM(data);
     int mismatch = 0, i = 0, firstGPos = rlen - 1;
     for (i = 0; i < rlen; i++) {
         if (data[rlen - i - 1] != 'G') mismatch++; else firstGPos = rlen - i - 1;
@@ -126,6 +131,7 @@ __device__ __noinline__ int t_trim_polyg(const uint8_t* data, int rlen, int minL
 
 /* PolyX::trimPolyX  (polyx.cpp:49-116): returns true if addPolyXTrimmed is called */
 __device__ __noinline__ bool t_trim_polyx(const uint8_t* data, int rlen, int minLen, int& newLen, int& polyOut, int& nOut) {
+    FP_SMEM(data);
     int a = 0, t = 0, c = 0, g = 0, pos = 0;
     for (pos = 0; pos < rlen; pos++) {
         const uint8_t ch = data[rlen - pos - 1];
@@ -177,6 +183,7 @@ __device__ __forceinline__ unsigned long long tp_bits64(const uint32_t* P, int b
 __device__ __forceinline__ unsigned long long mask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
 
 __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRead r2, int PW, const int16_t* lut, int sub, int g) {
+    FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(lut);
     const uint32_t *alo = r1.pl, *ahi = r1.pl + PW, *ann = r1.pl + 2 * PW;
     const uint32_t *plo = r2.pl, *phi = r2.pl + PW, *pnn = r2.pl + 2 * PW;
     const int len1 = r1.len, len2 = r2.len, f1 = r1.front;
@@ -188,6 +195,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
     for (int k = 0; k * 32 < len1; k++) anyN |= tp_bits(ann, f1 + 32 * k) & low_mask(len1 - 32 * k);
     for (int k = 0; k * 32 < len2; k++) anyN |= tp_bits(pnn, r2.front + 32 * k) & low_mask(len2 - 32 * k);
     int found_dir = -1, found_o = 0, found_mm = 0, found_ol = 0;
+    const int dmax = c_p.ov_diff_limit;          /* every lut entry is min(diffLimit, ...) <= diffLimit */
     /* ---- forward: offset 0 .. len1-req-1 (:48-65) ---- */
     {
         const unsigned long long bnn = ((unsigned long long)__brev(tp_bits_z(pnn, e - 63)) << 32) | __brev(tp_bits_z(pnn, e - 31));
@@ -210,10 +218,13 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                 do {
                     const int sh = c & 31;
                     const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
-                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
-                    const int mm = __popc(x0) + __popc(x1);
-                    const int ol = min(len1 - o, len2);
-                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    const int mm0 = __popc(x0);
+                    if (mm0 <= dmax) {       /* rare: the first 32 bases alone are within the largest limit -> finish the 50-base count */
+                        const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
+                        const int mm = mm0 + __popc(x1);
+                        const int ol = min(len1 - o, len2);
+                        if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    }
                     o += g; c += g;
                 } while (o < nfast && (c >> 5) == w);
             }
@@ -253,10 +264,13 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                 do {
                     const int sh = c & 31;
                     const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
-                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
-                    const int mm = __popc(x0) + __popc(x1);
-                    const int ol = min(len1, len2 - o);
-                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    const int mm0 = __popc(x0);
+                    if (mm0 <= dmax) {
+                        const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
+                        const int mm = mm0 + __popc(x1);
+                        const int ol = min(len1, len2 - o);
+                        if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    }
                     o += g; c -= g;
                 } while (o < nfast && c >= 0 && (c >> 5) == w);
             }
@@ -297,6 +311,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
 
 /* byte-exact twin for rows with bytes outside {A,C,G,T,N} */
 __device__ __noinline__ fp_ov_result t_analyze_bytes(const TRead r1, const TRead r2, const int16_t* lut) {
+    FP_SMEM(r1.seq);    FP_SMEM(r2.seq);    FP_SMEM(lut);
     const uint8_t* s1 = r1.seq + r1.front; const uint8_t* s2 = r2.seq + r2.front;
     const int len1 = r1.len, len2 = r2.len, req = c_p.ov_require;
     fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
@@ -354,6 +369,7 @@ __device__ __forceinline__ int t_diff_one_insertion(FI ins, FN norm, int c, int 
 }
 
 __device__ __noinline__ fp_ov_result t_analyze_gap(const TRead r1, const TRead r2, const int16_t* lut, int sub, int g) {
+    FP_SMEM(r1.seq);    FP_SMEM(r2.seq);    FP_SMEM(lut);
     const uint8_t* s1 = r1.seq + r1.front; const uint8_t* s2 = r2.seq + r2.front;
     const int len1 = r1.len, len2 = r2.len, req = c_p.ov_require;
     fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
@@ -387,6 +403,7 @@ __device__ __noinline__ fp_ov_result t_analyze_gap(const TRead r1, const TRead r
  * Called by one thread while seq[P] still holds the old base. */
 __device__ __noinline__ void t_patch_delta(const DeltaAcc D, unsigned long long* G, bool clean, int side, const uint8_t* seq, int l0, int P,
                                            uint8_t ob, uint8_t oq, uint8_t nb, uint8_t nq) {
+    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);    FP_SMEM(seq);
     const fp_counter_layout& L = c_p.L;
     #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -446,6 +463,7 @@ __device__ __forceinline__ void t_plane_set_base(uint32_t* pl, int PW, int pos, 
 __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t* pl1, uint32_t* pl2, int PW, const fp_ov_result ov,
                                        uint8_t* g1s, uint8_t* g1q, uint8_t* g2s, uint8_t* g2q, unsigned int pair_index, const PatchSink& sink,
                                        BlockCounters* bc, const DeltaAcc D, unsigned long long* G, int l1, int l2, bool& c1, bool& c2) {
+    FP_SMEM(r1.seq);    FP_SMEM(r1.qual);    FP_SMEM(r2.seq);    FP_SMEM(r2.qual);    FP_SMEM(pl1);    FP_SMEM(pl2);    FP_SMEM(bc);    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);
     c1 = c2 = false;
     if (ov.diff == 0 || !ov.overlapped) return;                           /* :23-24 */
     const int ol = ov.overlap_len;
@@ -526,6 +544,7 @@ __device__ __forceinline__ int t_gap_scan(const uint8_t* ins, const uint8_t* nor
 
 __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, int alen, int matchReq, int aidx, int PW,
                                                 int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
+    FP_SMEM(r.seq);    FP_SMEM(r.pl);    FP_SMEM(bc);
     const int rlen = r.len;
     const uint8_t* rdata = r.seq + r.front;
     if (alen < matchReq) return false;                                    /* :73-74 */
@@ -601,6 +620,7 @@ __device__ __forceinline__ bool t_trim_by_multi(TRead& r, int PW, int& posOut, i
  * Filter::passFilter  (filter.cpp:15-57), one thread per read: planes for clean rows, bytes otherwise.
  * ------------------------------------------------------------------------------------------------ */
 __device__ __noinline__ int t_pass_filter(const TRead r, int PW, const int16_t* lut) {
+    FP_SMEM(r.pl);    FP_SMEM(r.seq);    FP_SMEM(r.qual);    FP_SMEM(lut);
     if (r.null || r.len == 0) return FP_FAIL_LENGTH;
     const int rlen = r.len;
     int lowq = 0, nb = 0, adj = 0;
@@ -813,6 +833,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         /* ---------------- dense column pass: pre-filter stats of every row, two cycles per thread, exact for any byte ---------------- */
             if (col_active) {
                 const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
+                FP_SMEM(ts); FP_SMEM(tq);
                 const uint16_t* lens = s_len + my_side * T;
                 const int w4 = my_w * 4;
                 const int j0 = my_half * 2;
@@ -872,8 +893,9 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                     if (j < nwords && rr2 < rows) {
                         const int n = (int)s_len[sd * T + rr2] - 32 * j;
                         if (n > 0) {
-                            const uint4* s4 = reinterpret_cast<const uint4*>(tile_seq[sd] + rr2 * S + 32 * j);
-                            const uint4* q4 = reinterpret_cast<const uint4*>(tile_qual[sd] + rr2 * S + 32 * j);
+                            const uint8_t* tseq_sd = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes; const uint8_t* tqual_sd = tseq_sd + sl.tile_array_bytes;
+                            const uint4* s4 = reinterpret_cast<const uint4*>(tseq_sd + rr2 * S + 32 * j);
+                            const uint4* q4 = reinterpret_cast<const uint4*>(tqual_sd + rr2 * S + 32 * j);
                             const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
                             const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                             const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -892,7 +914,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             } else {
                                 #pragma unroll 1
                                 for (int i = 0; i < nv; i++) {
-                                    const uint32_t qb = tile_qual[sd][rr2 * S + 32 * j + i];
+                                    const uint32_t qb = tqual_sd[rr2 * S + 32 * j + i];
                                     if (qb < FP_QUAL_BINS) atomicAdd(&qh[qb * FP_QH_REP], 1u);
                                 }
                             }
@@ -903,7 +925,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             unsigned int* kh = s_kmer + sd * FP_KMER_BINS;
                             uint32_t cz = 0, cok = 0;
                             if (j > 0) {
-                                const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tile_seq[sd] + rr2 * S + 32 * j - 4);
+                                const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tseq_sd + rr2 * S + 32 * j - 4);
                                 cz = pack_codes4(pw_); cok = pack_nibble(exact_acgt(pw_));
                             }
                             const uint32_t m0 = code_mul4(x[0]), m1 = code_mul4(x[1]), m2 = code_mul4(x[2]), m3 = code_mul4(x[3]);
@@ -1109,7 +1131,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 if (qi >= nreq) break;
                 const DeltaReq rq = s_queue[qi];
                 const int row = rq.row_side & 0xFFFF, side = (rq.row_side >> 16) & 1, sign = ((rq.row_side >> 18) & 1) ? -1 : +1;
-                const uint8_t* sq = tile_seq[side] + row * S; const uint8_t* ql = tile_qual[side] + row * S;
+                const uint8_t* sq = smem + sl.off_tile + side * 2 * sl.tile_array_bytes + row * S; const uint8_t* ql = sq + sl.tile_array_bytes;
                 if ((rq.row_side >> 17) & 1) dev_stat_positions_smem(D, side, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
                 else dev_stat_positions(G, side * 2 + 1, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
             }

@@ -26,7 +26,7 @@ struct fp_dev_params {
     int cf_w, cf_thr, ct_w, ct_thr, cr_w, cr_thr, cr_q;      /* thr = w*(33+Q); cr_q = 33+Q */
     int polyg, polyg_min, polyx, polyx_min;
     int adapter_enabled, has_r1, has_r2, n_fasta, fasta_match_req, dimer_max_len;
-    int correction, ov_require, allow_gap;
+    int correction, ov_require, allow_gap, ov_diff_limit;   /* ov_diff_limit: upper bound of every lut_ovlimit entry */
     int qual_filter, qualified_qual, n_base_limit, avg_qual_req;
     int length_filter, length_required, length_limit;
     int complexity_filter;
