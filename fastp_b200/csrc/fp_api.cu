@@ -46,6 +46,7 @@ struct fp_ctx {
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
     fp_smem_layout sl{};
+    uint32_t smem_base = 1024;        /* shared-window address of dynamic shared memory (probed) */
     cudaStream_t stream[2] = {nullptr, nullptr};
     /* device tables */
     int16_t *d_ovlimit = nullptr, *d_lowq = nullptr, *d_mindiff = nullptr;
@@ -108,6 +109,8 @@ static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov,
     }
 }
 
+__global__ void fp_probe_smem_base(uint32_t* out) { extern __shared__ uint8_t probe_sm[]; *out = smem_u32(probe_sm); }
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
@@ -118,16 +121,22 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     sl.off_mbar = (int)off; off += 16;
     sl.off_next = (int)off; off += 16;                                     /* delta queue length + pop cursor */
     off = align_up(off, 128);
-    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
-    off = align_up(off, 16);
+    sl.off_dummy = (int)off; off += 128;
     sl.off_len = (int)off; off += (size_t)sides * T * 2;
     sl.off_clean = (int)off; off += (size_t)sides * T;
     off = align_up(off, 16);
+    sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
+    /* the two histograms are addressed as (field | table address): the 5-mer table (4 KB per side) must start on a 4 KB
+       boundary of the SHARED WINDOW (c->smem_base = window address of dynamic shared memory, probed at fp_ctx_create),
+       the quality histogram (2 KB per side) follows it */
+    off = align_up(off + c->smem_base, 4096) - c->smem_base;
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
     sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * FP_QH_REP * 4;
+    off = align_up(off, 128);
+    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
+    off = align_up(off, 16);
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
     off = align_up(off, 16);
-    sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
     sl.off_delta = (int)off; off += (size_t)sides * ((size_t)S * 20 + FP_KMER_BINS + FP_QUAL_BINS) * 4;
     sl.plane_words = (S + 31) / 32 + 2;
     sl.plane_stride = (4 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
@@ -182,6 +191,14 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     c->p.overrep_seqs1 = nullptr; c->p.overrep_seqs2 = nullptr;
     fp_counter_layout_make_overrep(&c->L, p->paired, cycles, p->insert_size_max, (int)c->overrep[0].size(), p->seq_len1,
                                    (int)c->overrep[1].size(), p->seq_len2);
+    {   /* window address of dynamic shared memory (for the aligned histogram tables, see smem_layout_for_tile) */
+        uint32_t* d_base = nullptr; uint32_t h_base = 0;
+        CK(cudaMalloc(&d_base, 4));
+        fp_probe_smem_base<<<1, 1, 16>>>(d_base);
+        CK(cudaMemcpy(&h_base, d_base, 4, cudaMemcpyDeviceToHost));
+        CK(cudaFree(d_base));
+        c->smem_base = h_base;
+    }
     make_smem_layout(c);
 
     cudaDeviceProp prop;

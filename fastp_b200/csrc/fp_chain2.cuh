@@ -19,6 +19,12 @@
 /* tell the compiler a pointer is a shared-memory address, so loads become LDS / atomics ATOMS instead of generic LD / ATOM */
 #define FP_SMEM(p) __builtin_assume(__isShared(p))
 
+/* shared-memory counter += 1 at a 32-bit shared-window address, optionally predicated (no branch, no return value) */
+__device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
+__device__ __forceinline__ void smem_inc_if(uint32_t addr, uint32_t cond) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" :: "r"(addr), "r"(cond) : "memory");
+}
+
 struct TRead {
     uint8_t* seq;          /* row start in the shared-memory tile */
     uint8_t* qual;
@@ -765,8 +771,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free lane-group-per-row access */
     uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
     DeltaReq* s_queue = reinterpret_cast<DeltaReq*>(smem + sl.off_queue);    /* [SIDES * T * 2] */
+    unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
     int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
 
+    if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
     for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_THREADS) s_qhist[i] = 0;
     for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
@@ -902,44 +910,57 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             uint32_t okm;
                             const bool pok = plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq, okm);
                             if (!pok) s_clean[sd * T + rr2] = 0;
-                            /* pre-filter quality histogram (stats.cpp:213): FP_QH_REP copies per bin, copy = lane & (REP-1) */
-                            unsigned int* qh = s_qhist + sd * (FP_QUAL_BINS * FP_QH_REP) + (lane & (FP_QH_REP - 1));
+                            /* pre-filter quality histogram (stats.cpp:213): FP_QH_REP copies per bin, copy = lane & (REP-1);
+                               byte offset of a bin = q*16 | copy*4 | side*2048 -- one shift + one LOP3 per base */
+                            uint8_t* qhb = smem + sl.off_qhist;
+                            const uint32_t qsel = ((uint32_t)(lane & (FP_QH_REP - 1)) << 2) | ((uint32_t)sd * (FP_QUAL_BINS * FP_QH_REP * 4));
+                            const uint32_t qaddr = smem_u32(qhb) + qsel;          /* tables 2 KB-aligned: the bin offset (bits 4..10) ORs in */
                             const int nv = min(n, 32);
-                            if (pok) {                                      /* every valid quality < 128 */
+                            if (pok && n >= 32) {                           /* full chunk, every quality < 128: no predicates */
                                 #pragma unroll
                                 for (int k8 = 0; k8 < 8; k8++)
                                     #pragma unroll
-                                    for (int b4 = 0; b4 < 4; b4++)
-                                        if (4 * k8 + b4 < nv) atomicAdd(&qh[((q[k8] >> (8 * b4)) & 0xFFu) * FP_QH_REP], 1u);
+                                    for (int b4 = 0; b4 < 4; b4++) {
+                                        const uint32_t sh = b4 == 0 ? (q[k8] << 4) : (q[k8] >> (8 * b4 - 4));
+                                        smem_inc(qaddr | (sh & 0xFF0u));
+                                    }
+                            } else if (pok) {                               /* every valid quality < 128 */
+                                #pragma unroll
+                                for (int k8 = 0; k8 < 8; k8++)
+                                    #pragma unroll
+                                    for (int b4 = 0; b4 < 4; b4++) {
+                                        const uint32_t sh = b4 == 0 ? (q[k8] << 4) : (q[k8] >> (8 * b4 - 4));
+                                        smem_inc_if(qaddr | (sh & 0xFF0u), (uint32_t)(4 * k8 + b4 < nv));
+                                    }
                             } else {
                                 #pragma unroll 1
                                 for (int i = 0; i < nv; i++) {
                                     const uint32_t qb = tqual_sd[rr2 * S + 32 * j + i];
-                                    if (qb < FP_QUAL_BINS) atomicAdd(&qh[qb * FP_QH_REP], 1u);
+                                    if (qb < FP_QUAL_BINS) atomicAdd(reinterpret_cast<unsigned int*>(qhb + ((qb << 4) | qsel)), 1u);
                                 }
                             }
                             /* pre-filter 5-mer counts (stats.cpp:228-266): a 5-mer counts iff its five bases are exact A/C/G/T.
                                Z = 2-bit codes of the 4 bases before this chunk and its 32 bases, 2 bits per base; the 5-mer ending
                                at chunk position p is the 10-bit field at bit 2p.  The table is indexed by that field (oldest base
                                in the LOW digit, code A0 C1 T2 G3); the flush maps it to the reference's index. */
-                            unsigned int* kh = s_kmer + sd * FP_KMER_BINS;
                             uint32_t cz = 0, cok = 0;
                             if (j > 0) {
                                 const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tseq_sd + rr2 * S + 32 * j - 4);
                                 cz = pack_codes4(pw_); cok = pack_nibble(exact_acgt(pw_));
                             }
-                            const uint32_t m0 = code_mul4(x[0]), m1 = code_mul4(x[1]), m2 = code_mul4(x[2]), m3 = code_mul4(x[3]);
-                            const uint32_t m4 = code_mul4(x[4]), m5 = code_mul4(x[5]), m6 = code_mul4(x[6]), m7 = code_mul4(x[7]);
-                            const uint32_t clo = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
-                            const uint32_t chi = __byte_perm(__byte_perm(m4, m5, 0x0073), __byte_perm(m6, m7, 0x0073), 0x5410);
+                            const uint32_t clo = gather_top4(code_mul4(x[0]), code_mul4(x[1]), code_mul4(x[2]), code_mul4(x[3]));
+                            const uint32_t chi = gather_top4(code_mul4(x[4]), code_mul4(x[5]), code_mul4(x[6]), code_mul4(x[7]));
                             const uint32_t Z0 = cz | (clo << 8), Z1 = __funnelshift_r(clo, chi, 24), Z2 = chi >> 24;
                             const uint32_t O0 = cok | (okm << 4), O1 = okm >> 28;
                             const uint32_t vwin = O0 & __funnelshift_r(O0, O1, 1) & __funnelshift_r(O0, O1, 2) & __funnelshift_r(O0, O1, 3) & __funnelshift_r(O0, O1, 4);
+                            uint8_t* khb = smem + sl.off_kmer;
+                            const uint32_t kaddr = smem_u32(khb) + (uint32_t)sd * (FP_KMER_BINS * 4);     /* 4 KB-aligned: the field (bits 2..11) ORs in */
+                            const uint32_t kdummy = smem_u32(s_dummy) + 4u * (uint32_t)lane;                /* windows that do not count land here */
                             #pragma unroll
-                            for (int pp = 0; pp < 32; pp++) {
-                                const int wz = (2 * pp) >> 5, sh = (2 * pp) & 31;
-                                const uint32_t f = wz == 0 ? __funnelshift_r(Z0, Z1, sh) : wz == 1 ? __funnelshift_r(Z1, Z2, sh) : 0u;
-                                if ((vwin >> pp) & 1u) atomicAdd(&kh[f & 0x3FFu], 1u);
+                            for (int pp = 0; pp < 32; pp++) {              /* byte offset of the bin = field*4 | side*4096 */
+                                const int bit = 2 * pp - 2;
+                                const uint32_t f4 = pp == 0 ? (Z0 << 2) : (bit < 32 ? __funnelshift_r(Z0, Z1, bit) : __funnelshift_r(Z1, Z2, bit - 32));
+                                smem_inc((vwin & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy);
                             }
                         }
                     }

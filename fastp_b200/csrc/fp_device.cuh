@@ -116,34 +116,46 @@ __device__ __forceinline__ uint32_t low_mask(int nbits) {     /* mask of min(max
 __device__ __forceinline__ uint32_t pack_nibble(uint32_t v01) { return ((v01 * 0x01020408u) >> 24) & 0xFu; }
 
 /* One plane word (32 bases = 8 seq words + 8 qual words) of one row: returns false if a valid byte is outside
- * {A,C,G,T,N} or a quality has bit 7 set.  x/q: the 8 words; n = number of valid bases in this word (0..32). */
+ * {A,C,G,T,N} or a quality has bit 7 set.  x/q: the 8 words; n = number of valid bases in this word (1..32+).
+ * Words are handled in PAIRS: per-byte flags of the even word sit in bit 0 of each byte, those of the odd word in
+ * bit 4, so ONE multiply gathers the 8 flags of 8 bases into the product's top byte; PRMT assembles the 32-bit word. */
+__device__ __forceinline__ uint32_t gather_top4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    return __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
+}
 __device__ __forceinline__ bool plane_word_from_bytes(const uint32_t (&x)[8], const uint32_t (&q)[8], int n, uint32_t qq4,
                                                       uint32_t& lo, uint32_t& hi, uint32_t& nn, uint32_t& lq, uint32_t& ok) {
-    const uint32_t K = 0x01010101u;
-    lo = hi = nn = lq = ok = 0;
-    uint32_t bad = 0;
+    const uint32_t K = 0x01010101u, K4 = 0x10101010u, M = 0x01020408u;
+    uint32_t plo[4], phi[4], pnn[4], plq[4], pok[4], pbad[4];
     #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int nv = n - 4 * k;                                   /* valid bytes of this word */
-        const uint32_t vm = nv >= 4 ? K : (nv <= 0 ? 0u : (K & ((1u << (8 * nv)) - 1u)));
-        const uint32_t w = x[k];
-        const uint32_t c0 = w & K, c1 = (w >> 1) & K, c2 = (w >> 2) & K, b3 = (w >> 3) & K, b4 = (w >> 4) & K;
-        const uint32_t up = (~(w >> 5)) & (w >> 6) & (~(w >> 7)) & K;         /* bits 7..5 == 010 */
-        const uint32_t isACG = c0 & (~c2 | c1) & ~b3 & ~b4;                     /* 0x41 0x43 0x47 */
-        const uint32_t isT = ~c0 & ~c1 & c2 & ~b3 & b4;                          /* 0x54 */
-        const uint32_t isN = ~c0 & c1 & c2 & b3 & ~b4 & up & vm;                 /* 0x4E */
-        const uint32_t acgt = (isACG | isT) & up & vm;
-        bad |= vm & ~(acgt | isN);
-        bad |= (q[k] >> 7) & vm;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = x[2 * k], b = x[2 * k + 1], qa = q[2 * k], qb = q[2 * k + 1];
+        /* even word: bit j of every byte moved to bit 0 */
+        const uint32_t a1 = a >> 1, a2 = a >> 2, a3 = a >> 3, a4 = a >> 4;
+        const uint32_t upA = ~(a >> 5) & (a >> 6) & ~(a >> 7);                           /* bits 7..5 == 010 */
+        const uint32_t okA = ((a & (~a2 | a1) & ~a3 & ~a4) | (~a & ~a1 & a2 & ~a3 & a4)) & upA & K;   /* 0x41 0x43 0x47 | 0x54 */
+        const uint32_t nA = ~a & a1 & a2 & a3 & ~a4 & upA & K;                           /* 0x4E */
+        /* odd word: bit j of every byte moved to bit 4 */
+        const uint32_t b0 = b << 4, b1 = b << 3, b2 = b << 2, b3 = b << 1;
+        const uint32_t upB = ~(b >> 1) & (b >> 2) & ~(b >> 3);
+        const uint32_t okB = ((b0 & (~b2 | b1) & ~b3 & ~b) | (~b0 & ~b1 & b2 & ~b3 & b)) & upB & K4;
+        const uint32_t nB = ~b0 & b1 & b2 & b3 & ~b & upB & K4;
+        const uint32_t okp = okA | okB, np = nA | nB;
         /* q < qualified_qual  <=>  bit7 of (q | 0x80) - qq is clear (q, qq < 128) */
-        const uint32_t ql = (~(((q[k] | 0x80808080u) - qq4) >> 7)) & vm;
-        lo |= pack_nibble(c1 & acgt) << (4 * k);
-        hi |= pack_nibble(c2 & acgt) << (4 * k);
-        nn |= pack_nibble(isN) << (4 * k);
-        lq |= pack_nibble(ql) << (4 * k);
-        ok |= pack_nibble(acgt) << (4 * k);                         /* exact: byte is one of 'A','C','G','T' */
+        const uint32_t ta = ~((qa | 0x80808080u) - qq4), tb = ~((qb | 0x80808080u) - qq4);
+        plo[k] = (((a1 & K) | (b1 & K4)) & okp) * M;
+        phi[k] = (((a2 & K) | (b2 & K4)) & okp) * M;
+        pnn[k] = np * M;
+        pok[k] = okp * M;
+        plq[k] = (((ta >> 7) & K) | ((tb >> 3) & K4)) * M;
+        pbad[k] = ((~(okp | np) & (K | K4)) | ((qa >> 7) & K) | ((qb >> 3) & K4)) * M;
     }
-    return bad == 0;
+    const uint32_t vm = low_mask(n);
+    lo = gather_top4(plo[0], plo[1], plo[2], plo[3]) & vm;
+    hi = gather_top4(phi[0], phi[1], phi[2], phi[3]) & vm;
+    nn = gather_top4(pnn[0], pnn[1], pnn[2], pnn[3]) & vm;
+    lq = gather_top4(plq[0], plq[1], plq[2], plq[3]) & vm;
+    ok = gather_top4(pok[0], pok[1], pok[2], pok[3]) & vm;                                /* exact: byte is one of 'A','C','G','T' */
+    return (gather_top4(pbad[0], pbad[1], pbad[2], pbad[3]) & vm) == 0;
 }
 
 /* ballot-based rebuild of one row's planes (used after base correction rewrote the row; rare) */
@@ -308,7 +320,7 @@ __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side,
  * Shared-memory layout of one CTA (offsets computed on the host, fp_api.cu)
  * ------------------------------------------------------------------------------------------------ */
 struct fp_smem_layout {
-    int off_mbar, off_next, off_tile, tile_array_bytes, off_len, off_clean, off_kmer, off_qhist, off_bc, off_lut, off_delta,
+    int off_dummy, off_mbar, off_next, off_tile, tile_array_bytes, off_len, off_clean, off_kmer, off_qhist, off_bc, off_lut, off_delta,
         off_planes, off_queue, plane_words, plane_stride, total;
 };
 
