@@ -201,6 +201,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
     for (int k = 0; k * 32 < len1; k++) anyN |= tp_bits(ann, f1 + 32 * k) & low_mask(len1 - 32 * k);
     for (int k = 0; k * 32 < len2; k++) anyN |= tp_bits(pnn, r2.front + 32 * k) & low_mask(len2 - 32 * k);
     int found_dir = -1, found_o = 0, found_mm = 0, found_ol = 0;
+    const int lg = g == 4 ? 2 : (g == 2 ? 1 : 0);   /* g lanes per pair, a power of two */
     const int dmax = c_p.ov_diff_limit;          /* every lut entry is min(diffLimit, ...) <= diffLimit */
     /* ---- forward: offset 0 .. len1-req-1 (:48-65) ---- */
     {
@@ -217,12 +218,15 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
             const uint32_t b_lo0 = (uint32_t)blo, b_lo1 = (uint32_t)(blo >> 32), b_hi0 = (uint32_t)bhi, b_hi1 = (uint32_t)(bhi >> 32),
                            b_nn0 = (uint32_t)bnn, b_nn1 = (uint32_t)(bnn >> 32);
             while (o < nfast && my_o == (1 << 20)) {
-                int c = f1 + o;
+                const int c = f1 + o;
                 const int w = c >> 5;
                 const uint32_t L0 = alo[w], L1 = alo[w + 1], L2 = alo[w + 2], H0 = ahi[w], H1 = ahi[w + 1], H2 = ahi[w + 2],
                                N0 = ann[w], N1 = ann[w + 1], N2 = ann[w + 2];
-                do {
-                    const int sh = c & 31;
+                /* candidates of this lane whose 50-bit field starts in word w: a counted loop, the shift just advances */
+                int sh = c & 31;
+                int cnt = min((nfast - o + g - 1) >> lg, (32 - sh + g - 1) >> lg);
+                #pragma unroll 2
+                for (; cnt > 0; cnt--, sh += g, o += g) {
                     const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
                     const int mm0 = __popc(x0);
                     if (mm0 <= dmax) {       /* rare: the first 32 bases alone are within the largest limit -> finish the 50-base count */
@@ -231,8 +235,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                         const int ol = min(len1 - o, len2);
                         if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
                     }
-                    o += g; c += g;
-                } while (o < nfast && (c >> 5) == w);
+                }
             }
         }
         for (; o < nfwd && my_o == (1 << 20); o += g) {
@@ -263,12 +266,14 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
             const uint32_t y_lo0 = (uint32_t)ylo, y_lo1 = (uint32_t)(ylo >> 32), y_hi0 = (uint32_t)yhi, y_hi1 = (uint32_t)(yhi >> 32),
                            y_nn0 = (uint32_t)ynn, y_nn1 = (uint32_t)(ynn >> 32);
             while (o < nfast && my_o == (1 << 20)) {
-                int c = e - 49 - o;                                        /* >= front2 >= 0 */
+                const int c = e - 49 - o;                                  /* >= front2 >= 0 */
                 const int w = c >> 5;
                 const uint32_t L0 = plo[w], L1 = plo[w + 1], L2 = plo[w + 2], H0 = phi[w], H1 = phi[w + 1], H2 = phi[w + 2],
                                N0 = pnn[w], N1 = pnn[w + 1], N2 = pnn[w + 2];
-                do {
-                    const int sh = c & 31;
+                int sh = c & 31;
+                int cnt = min((nfast - o + g - 1) >> lg, (sh >> lg) + 1);   /* the field start moves DOWN by g per candidate */
+                #pragma unroll 2
+                for (; cnt > 0; cnt--, sh -= g, o += g) {
                     const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
                     const int mm0 = __popc(x0);
                     if (mm0 <= dmax) {
@@ -277,8 +282,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                         const int ol = min(len1, len2 - o);
                         if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
                     }
-                    o += g; c -= g;
-                } while (o < nfast && c >= 0 && (c >> 5) == w);
+                }
             }
         }
         for (; o < nbwd && my_o == (1 << 20); o += g) {
@@ -775,6 +779,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
+    for (int i = tid; i < SIDES * T * PSTR; i += FP_THREADS) tile_planes[i] = 0;
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
     for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_THREADS) s_qhist[i] = 0;
     for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
@@ -848,6 +853,23 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 #pragma unroll 1
                 for (int r0 = 0; r0 < rows; r0 += 4) {
                     uint32_t xs[4], xq[4];
+                    const unsigned sel = my_half ? 0x7362u : 0x5140u;
+                    /* rows beyond the tile have length 0, so the minimum also covers a partial tile */
+                    const uint2 l4 = *reinterpret_cast<const uint2*>(lens + r0);
+                    const uint32_t minl = min(min(l4.x & 0xFFFFu, l4.x >> 16), min(l4.y & 0xFFFFu, l4.y >> 16));
+                    if ((uint32_t)(w4 + 4) <= minl) {            /* all four rows cover this word: no masks */
+                        #pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            xs[kk] = *reinterpret_cast<const uint32_t*>(ts + (r0 + kk) * S + w4);
+                            xq[kk] = *reinterpret_cast<const uint32_t*>(tq + (r0 + kk) * S + w4);
+                        }
+                        const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+                        const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+                        acc_cycle_full(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410), G, my_side, w4 + j0);
+                        acc_cycle_full(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632), G, my_side, w4 + j0 + 1);
+                        continue;
+                    }
+                    if ((uint32_t)w4 >= max(max(l4.x & 0xFFFFu, l4.x >> 16), max(l4.y & 0xFFFFu, l4.y >> 16))) continue;   /* nothing here */
                     #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {
                         const int r = r0 + kk;
@@ -875,7 +897,6 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                         }
                         xs[kk] = x; xq[kk] = q;
                     }
-                    const unsigned sel = my_half ? 0x7362u : 0x5140u;
                     const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
                     const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
                     acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
@@ -887,7 +908,8 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         {   /* bit planes + validation: 32-item batches claimed dynamically -- warps without columns start at once, the dense warps join */
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
-            const int total = SIDES * T * PW;
+            const int total = SIDES * T * nwords;              /* pad words of the planes stay zero (cleared once at kernel start) */
+            const uint32_t nw_magic = 0xFFFFFFFFu / (uint32_t)nwords + 1u;   /* it / nwords == umulhi(it, magic) for it < 2^16 */
             #pragma unroll 1
             for (;;) {
                 int base = 0;
@@ -896,9 +918,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                 if (base >= total) break;
                 const int it = base + lane;
                 if (it < total) {
-                    const int j = it % PW, rr2 = (it / PW) % T, sd = it / (PW * T);
+                    const int rowi = (int)__umulhi((uint32_t)it, nw_magic), j = it - rowi * nwords;
+                    const int sd = rowi >= T ? 1 : 0, rr2 = rowi - sd * T;
                     uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
-                    if (j < nwords && rr2 < rows) {
+                    if (rr2 < rows) {
                         const int n = (int)s_len[sd * T + rr2] - 32 * j;
                         if (n > 0) {
                             const uint8_t* tseq_sd = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes; const uint8_t* tqual_sd = tseq_sd + sl.tile_array_bytes;
@@ -916,15 +939,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
                             const uint32_t qsel = ((uint32_t)(lane & (FP_QH_REP - 1)) << 2) | ((uint32_t)sd * (FP_QUAL_BINS * FP_QH_REP * 4));
                             const uint32_t qaddr = smem_u32(qhb) + qsel;          /* tables 2 KB-aligned: the bin offset (bits 4..10) ORs in */
                             const int nv = min(n, 32);
-                            if (pok && n >= 32) {                           /* full chunk, every quality < 128: no predicates */
-                                #pragma unroll
-                                for (int k8 = 0; k8 < 8; k8++)
-                                    #pragma unroll
-                                    for (int b4 = 0; b4 < 4; b4++) {
-                                        const uint32_t sh = b4 == 0 ? (q[k8] << 4) : (q[k8] >> (8 * b4 - 4));
-                                        smem_inc(qaddr | (sh & 0xFF0u));
-                                    }
-                            } else if (pok) {                               /* every valid quality < 128 */
+                            if (pok) {                                      /* every valid quality < 128 */
                                 #pragma unroll
                                 for (int k8 = 0; k8 < 8; k8++)
                                     #pragma unroll

@@ -218,6 +218,38 @@ __device__ __forceinline__ void acc_cycle(unsigned int (&a)[NB][4], uint32_t s, 
     }
 }
 
+__device__ __noinline__ void slow_cycle_byte(unsigned long long* G, int stats, int cycle, uint8_t base, uint8_t q);
+
+/* acc_cycle for 4 rows that ALL reach this cycle (no window masks): bytes the register path cannot represent
+ * (base&7 in {0,2,5} or quality >= 128) are found on the transposed word and take the exact global path. */
+__device__ __forceinline__ void acc_cycle_full(unsigned int (&a)[NB][4], uint32_t s, uint32_t q, unsigned long long* G, int side, int cycle) {
+    const uint32_t K = 0x01010101u;
+    uint32_t p0 = s & K, p1 = (s >> 1) & K, p2 = (s >> 2) & K;
+    const uint32_t bad = ((~p0 & ~p2) | (p0 & ~p1 & p2) | (q >> 7)) & K;
+    if (bad) {
+        #pragma unroll 1
+        for (int k = 0; k < 4; k++)
+            if ((bad >> (8 * k)) & 1u) {
+                const uint8_t bb = (uint8_t)(s >> (8 * k)), qb = (uint8_t)(q >> (8 * k));
+                slow_cycle_byte(G, side * 2, cycle, bb, qb);               /* dense feeds pre AND post */
+                slow_cycle_byte(G, side * 2 + 1, cycle, bb, qb);
+            }
+        p0 &= ~bad; p1 &= ~bad; p2 &= ~bad;                                 /* 000 matches no bin */
+    }
+    uint32_t mA = p0 & ~p1 & ~p2, mC = p0 & p1 & ~p2, mT = ~p0 & ~p1 & p2, mN = ~p0 & p1 & p2, mG = p0 & p1 & p2;
+    uint32_t q7 = q & 0x7F7F7F7Fu;
+    uint32_t t20 = ((q7 + 0x4B4B4B4Bu) >> 7) & K;
+    uint32_t t30 = ((q7 + 0x41414141u) >> 7) & K;
+    uint32_t m[NB] = {mA, mC, mT, mN, mG};
+    #pragma unroll
+    for (int b = 0; b < NB; b++) {
+        a[b][0] = __dp4a(m[b], K, a[b][0]);
+        a[b][1] = __dp4a(m[b], t20, a[b][1]);
+        a[b][2] = __dp4a(m[b], t30, a[b][2]);
+        a[b][3] = __dp4a(m[b], q, a[b][3]);
+    }
+}
+
 /* slow path for one byte that is not A/C/G/T/N (or a quality >= 128): global atomics */
 __device__ __noinline__ void slow_cycle_byte(unsigned long long* G, int stats, int cycle, uint8_t base, uint8_t q) {
     const fp_counter_layout& L = c_p.L;
