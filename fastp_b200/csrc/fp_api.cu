@@ -164,7 +164,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     if (cycles <= 0) cycles = stride;
     if (p->allow_gap_overlap_trimming && p->overlap_require < 2) return set_err(FP_E_INVAL, "allow_gap_overlap_trimming needs overlap_require >= 2");
     if (p->insert_size_max < 0 || p->insert_size_max > (1 << 20)) return set_err(FP_E_INVAL, "insert_size_max out of range");
-    if ((p->paired ? 2 : 1) * (stride / 2) > FP_THREADS) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
+    if ((p->paired ? 2 : 1) * (stride / 2) > FP_CT) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
     if (p->cut_front_window < 1 || p->cut_tail_window < 1 || p->cut_right_window < 1) return set_err(FP_E_INVAL, "cut window must be >= 1");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -309,10 +309,10 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     int occ = 0;
     if (p->paired) {
         CK(cudaFuncSetAttribute(fp_chain2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<true>, FP_THREADS, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<true>, FP_CT, c->sl.total));
     } else {
         CK(cudaFuncSetAttribute(fp_chain2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<false>, FP_THREADS, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<false>, FP_CT, c->sl.total));
     }
     if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
     c->grid_max = occ * c->num_sms;
@@ -410,8 +410,8 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
     if (c->evs.size() > 4096) { int rc = drain_events(c); if (rc) return rc; }
     CK(cudaEventRecord(ev.a, st));
-    if (c->p.paired) fp_chain2_kernel<true><<<grid, FP_THREADS, c->sl.total, st>>>(a);
-    else fp_chain2_kernel<false><<<grid, FP_THREADS, c->sl.total, st>>>(a);
+    if (c->p.paired) fp_chain2_kernel<true><<<grid, FP_CT, c->sl.total, st>>>(a);
+    else fp_chain2_kernel<false><<<grid, FP_CT, c->sl.total, st>>>(a);
     CK(cudaEventRecord(ev.b, st));
     c->evs.push_back(ev);
     CK(cudaGetLastError());

@@ -727,6 +727,107 @@ __device__ __forceinline__ uint32_t exact_acgt(uint32_t w) {
     return ((c0 & (~c2 | c1) & ~b3 & ~b4) | (~c0 & ~c1 & c2 & ~b3 & b4)) & up;
 }
 
+/* dense pass, one step of 4 rows for a word that some of the rows do not fully cover (the read ends inside or before it).
+ * Out of line on purpose: it is rare, and keeping it out of the hot loop keeps the 40 accumulators in registers there. */
+__device__ __noinline__ void dense_masked_step(ColAcc2& acc, const uint8_t* ts, const uint8_t* tq, const uint16_t* lens, int r0, int S, int w4, int j0,
+                                               unsigned sel, unsigned long long* G, int my_side) {
+    FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(lens);
+    uint32_t xs[4], xq[4];
+    #pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        const int r = r0 + kk;
+        const uint32_t m = window_mask(w4, 0, lens[r]);          /* rows beyond the tile have length 0 */
+        uint32_t x = 0, q = 0;
+        if (m) {
+            const uint32_t K = 0x01010101u;
+            x = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;
+            q = *reinterpret_cast<const uint32_t*>(tq + r * S + w4) & m;
+            /* bytes the register fast path cannot represent: base&7 in {0,2,5} or quality >= 128 -> exact global path */
+            const uint32_t c0 = x & K, c1 = (x >> 1) & K, c2 = (x >> 2) & K;
+            const uint32_t present = (m & K);
+            uint32_t bad = present & (((~c0) & (~c2)) | (c0 & (~c1) & c2) | (q >> 7));
+            if (bad) {
+                #pragma unroll 1
+                for (int j = j0; j < j0 + 2; j++)
+                    if ((bad >> (8 * j)) & 1) {
+                        const uint8_t bb = (uint8_t)(x >> (8 * j)), qb = (uint8_t)(q >> (8 * j));
+                        slow_cycle_byte(G, my_side * 2, w4 + j, bb, qb);           /* dense feeds pre AND post */
+                        slow_cycle_byte(G, my_side * 2 + 1, w4 + j, bb, qb);
+                    }
+                x &= ~(bad * 0xFFu);                                              /* drop them from the fast path */
+            }
+        }
+        xs[kk] = x; xq[kk] = q;
+    }
+    const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+    const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+    acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
+    acc_cycle(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
+}
+
+/* Dense column pass over one tile for one thread's two cycles (w4 + 2*my_half, +1) of one side: Stats::statRead's per-cycle
+ * counters (stats.cpp:204-227), exact for any byte.  A function of its own (accumulators in and out BY VALUE, once per tile) so
+ * that the 40 accumulators get registers of their own inside the hot loop whatever the rest of the kernel keeps live. */
+__device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* ts, const uint8_t* tq, const uint16_t* lens, int rows, int S, int w4, int my_half,
+                                           int rfirst, int rstep, unsigned long long* G, int my_side) {
+    FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(lens);
+    unsigned int acc[2][NB][4];                      /* element-wise copies: the accumulators must live in registers in the loop */
+    #pragma unroll
+    for (int c = 0; c < 2; c++)
+        #pragma unroll
+        for (int b = 0; b < NB; b++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) acc[c][b][k] = acc_in.v[c][b][k];
+    const int j0 = my_half * 2;
+    const unsigned sel = my_half ? 0x7362u : 0x5140u;
+    #pragma unroll 1
+    for (int r0 = rfirst; r0 < rows; r0 += rstep) {
+        /* rows beyond the tile have length 0, so the minimum also covers a partial tile */
+        const uint2 l4 = *reinterpret_cast<const uint2*>(lens + r0);
+        const uint32_t minl = min(min(l4.x & 0xFFFFu, l4.x >> 16), min(l4.y & 0xFFFFu, l4.y >> 16));
+        const uint32_t maxl = max(max(l4.x & 0xFFFFu, l4.x >> 16), max(l4.y & 0xFFFFu, l4.y >> 16));
+        const uint32_t cov = min(minl, (uint32_t)(w4 + 4));
+        if ((uint32_t)w4 >= maxl) continue;           /* no row reaches this word */
+        if (cov == min(maxl, (uint32_t)(w4 + 4))) {   /* the four rows cover the SAME bytes of this word: no masks, whole cycles in or out */
+            uint32_t xs[4], xq[4];
+            #pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                xs[kk] = *reinterpret_cast<const uint32_t*>(ts + (r0 + kk) * S + w4);
+                xq[kk] = *reinterpret_cast<const uint32_t*>(tq + (r0 + kk) * S + w4);
+            }
+            const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+            const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+            if ((uint32_t)(w4 + j0) < cov) acc_cycle_full(acc[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410), G, my_side, w4 + j0);
+            if ((uint32_t)(w4 + j0 + 1) < cov) acc_cycle_full(acc[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632), G, my_side, w4 + j0 + 1);
+            continue;
+        }
+        {   /* boundary words: rare, out of line; the accumulators travel through a copy so they stay in registers here */
+            ColAcc2 tmp;
+            #pragma unroll
+            for (int c = 0; c < 2; c++)
+                #pragma unroll
+                for (int b = 0; b < NB; b++)
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) tmp.v[c][b][k] = acc[c][b][k];
+            dense_masked_step(tmp, ts, tq, lens, r0, S, w4, j0, sel, G, my_side);
+            #pragma unroll
+            for (int c = 0; c < 2; c++)
+                #pragma unroll
+                for (int b = 0; b < NB; b++)
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) acc[c][b][k] = tmp.v[c][b][k];
+        }
+    }
+    ColAcc2 out;
+    #pragma unroll
+    for (int c = 0; c < 2; c++)
+        #pragma unroll
+        for (int b = 0; b < NB; b++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) out.v[c][b][k] = acc[c][b][k];
+    return out;
+}
+
 /* deferred post-filter statistics request (phase C): contribution of positions [lo,hi) of one tile row */
 struct DeltaReq { int row_side; int ctx0, lo, hi; };        /* row_side = row | side<<16 | clean<<17 | (sign<0)<<18 */
 
@@ -746,7 +847,7 @@ __device__ __forceinline__ void push_delta(DeltaReq* q, int* qn, bool want, bool
  *   C  the queue is drained by all warps (balanced), then the tile buffer is free for the next TMA load
  * ------------------------------------------------------------------------------------------------ */
 template <bool PAIRED>
-__global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launch_args a) {
+__global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int SIDES = PAIRED ? 2 : 1;
     const fp_smem_layout& sl = a.sl;
@@ -779,20 +880,22 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
     int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
-    for (int i = tid; i < SIDES * T * PSTR; i += FP_THREADS) tile_planes[i] = 0;
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) s_kmer[i] = 0;
-    for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_THREADS) s_qhist[i] = 0;
-    for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_THREADS) D.cyc[i] = 0;
-    for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_THREADS) reinterpret_cast<unsigned int*>(bc)[i] = 0;
-    for (int i = tid; i < S + 2; i += FP_THREADS) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
+    for (int i = tid; i < SIDES * T * PSTR; i += FP_CT) tile_planes[i] = 0;
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) s_kmer[i] = 0;
+    for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_CT) s_qhist[i] = 0;
+    for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_CT) D.cyc[i] = 0;
+    for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_CT) reinterpret_cast<unsigned int*>(bc)[i] = 0;
+    for (int i = tid; i < S + 2; i += FP_CT) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
     const int HPR = S >> 1;
-    const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_THREADS */
-    const bool col_active = tid < ncols;
-    const int ndense_warps = (ncols + 31) >> 5;
-    const int my_side = col_active ? tid / HPR : 0, my_hc = col_active ? tid % HPR : 0;
+    const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_CT */
+    const int nsplit = FP_CT / ncols;             /* row groups are dealt round-robin to nsplit threads per column */
+    const bool col_active = tid < ncols * nsplit;
+    const int ndense_warps = (ncols * nsplit + 31) >> 5;
+    const int my_part = col_active ? tid / ncols : 0, my_col = col_active ? tid % ncols : 0;
+    const int my_side = my_col / HPR, my_hc = my_col % HPR;
     const int my_w = my_hc >> 1, my_half = my_hc & 1;
     ColAcc2 acc;
     #pragma unroll
@@ -830,7 +933,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
             }
             s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0;
         }
-        for (int i = tid; i < SIDES * T; i += FP_THREADS) {
+        for (int i = tid; i < SIDES * T; i += FP_CT) {
             const int sd = i / T, r = i % T;
             uint16_t ln = 0;
             if (r < rows) { ln = (sd == 0 ? a.b.len1 : a.b.len2)[row0 + r]; if (ln > S) ln = (uint16_t)S; }
@@ -842,69 +945,8 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         __syncthreads();
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
-        if (warp < ndense_warps) {
-        /* ---------------- dense column pass: pre-filter stats of every row, two cycles per thread, exact for any byte ---------------- */
-            if (col_active) {
-                const uint8_t* ts = tile_seq[my_side]; const uint8_t* tq = tile_qual[my_side];
-                FP_SMEM(ts); FP_SMEM(tq);
-                const uint16_t* lens = s_len + my_side * T;
-                const int w4 = my_w * 4;
-                const int j0 = my_half * 2;
-                #pragma unroll 1
-                for (int r0 = 0; r0 < rows; r0 += 4) {
-                    uint32_t xs[4], xq[4];
-                    const unsigned sel = my_half ? 0x7362u : 0x5140u;
-                    /* rows beyond the tile have length 0, so the minimum also covers a partial tile */
-                    const uint2 l4 = *reinterpret_cast<const uint2*>(lens + r0);
-                    const uint32_t minl = min(min(l4.x & 0xFFFFu, l4.x >> 16), min(l4.y & 0xFFFFu, l4.y >> 16));
-                    if ((uint32_t)(w4 + 4) <= minl) {            /* all four rows cover this word: no masks */
-                        #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            xs[kk] = *reinterpret_cast<const uint32_t*>(ts + (r0 + kk) * S + w4);
-                            xq[kk] = *reinterpret_cast<const uint32_t*>(tq + (r0 + kk) * S + w4);
-                        }
-                        const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
-                        const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
-                        acc_cycle_full(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410), G, my_side, w4 + j0);
-                        acc_cycle_full(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632), G, my_side, w4 + j0 + 1);
-                        continue;
-                    }
-                    if ((uint32_t)w4 >= max(max(l4.x & 0xFFFFu, l4.x >> 16), max(l4.y & 0xFFFFu, l4.y >> 16))) continue;   /* nothing here */
-                    #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const int r = r0 + kk;
-                        const int hi = (r < rows) ? lens[r] : 0;
-                        const uint32_t m = window_mask(w4, 0, hi);
-                        uint32_t x = 0, q = 0;
-                        if (m) {
-                            const uint32_t K = 0x01010101u;
-                            x = *reinterpret_cast<const uint32_t*>(ts + r * S + w4) & m;
-                            q = *reinterpret_cast<const uint32_t*>(tq + r * S + w4) & m;
-                            /* bytes the register fast path cannot represent: base&7 in {0,2,5} or quality >= 128 -> exact global path */
-                            const uint32_t c0 = x & K, c1 = (x >> 1) & K, c2 = (x >> 2) & K;
-                            const uint32_t present = (m & K);
-                            uint32_t bad = present & (((~c0) & (~c2)) | (c0 & (~c1) & c2) | (q >> 7));
-                            if (bad) {
-                                #pragma unroll 1
-                                for (int j = j0; j < j0 + 2; j++)
-                                    if ((bad >> (8 * j)) & 1) {
-                                        const uint8_t bb = (uint8_t)(x >> (8 * j)), qb = (uint8_t)(q >> (8 * j));
-                                        slow_cycle_byte(G, my_side * 2, w4 + j, bb, qb);           /* dense feeds pre AND post */
-                                        slow_cycle_byte(G, my_side * 2 + 1, w4 + j, bb, qb);
-                                    }
-                                x &= ~(bad * 0xFFu);                                              /* drop them from the fast path */
-                            }
-                        }
-                        xs[kk] = x; xq[kk] = q;
-                    }
-                    const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
-                    const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
-                    acc_cycle(acc.v[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
-                    acc_cycle(acc.v[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
-                }
-            }
-
-        }
+        if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
+            acc = dense_tile(acc, tile_seq[my_side], tile_qual[my_side], s_len + my_side * T, rows, S, my_w * 4, my_half, 4 * my_part, 4 * nsplit, G, my_side);
         {   /* bit planes + validation: 32-item batches claimed dynamically -- warps without columns start at once, the dense warps join */
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
@@ -988,7 +1030,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
 
         /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
-        for (int rbase = warp * UPW; rbase < rows; rbase += FP_WARPS * UPW) {
+        for (int rbase = warp * UPW; rbase < rows; rbase += FP_CW * UPW) {
             const int r = rbase + lane / GL;
             const bool active = r < rows;
             const int rr = active ? r : 0;
@@ -1199,19 +1241,19 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) {
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) {
         const unsigned int v = s_kmer[i];
         if (v) { const int sd = i / FP_KMER_BINS, k = kmer_ref_index(i % FP_KMER_BINS); red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) {
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) {
         unsigned int v = 0;
         #pragma unroll
         for (int c = 0; c < FP_QH_REP; c++) v += s_qhist[i * FP_QH_REP + c];
         if (v) { const int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * S * 20; i += FP_THREADS) {
+    for (int i = tid; i < SIDES * S * 20; i += FP_CT) {
         const int v = D.cyc[i];
         if (v == 0) continue;
         const int sd = i / (S * 20), rem = i % (S * 20), cyc = rem / 20, bin = (rem % 20) / 4, kind = rem & 3;
@@ -1220,14 +1262,14 @@ __global__ void __launch_bounds__(FP_THREADS, 2) fp_chain2_kernel(const fp_launc
         red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_THREADS) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, i % FP_KMER_BINS)], (unsigned long long)(long long)v); }
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, i % FP_KMER_BINS)], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_THREADS) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = tid; i < FP_FR_WORDS; i += FP_THREADS) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
+    for (int i = tid; i < FP_FR_WORDS; i += FP_CT) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
     if (c_p.isize_max < FP_MAX_ISIZE_SMEM) {
         #pragma unroll 1
-        for (int i = tid; i <= c_p.isize_max; i += FP_THREADS) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
+        for (int i = tid; i <= c_p.isize_max; i += FP_CT) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
     }
     #pragma unroll
     for (int k = 0; k < 8; k++) {
