@@ -21,6 +21,8 @@
 
 /* shared-memory counter += 1 at a 32-bit shared-window address, optionally predicated (no branch, no return value) */
 __device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
+/* += 1 iff a > B */
+#define smem_inc_gt(addr, a, B) asm volatile("{ .reg .pred p; setp.gt.s32 p, %1, %2; @p red.shared.add.u32 [%0], 1; }" :: "r"(addr), "r"(a), "r"(B) : "memory")
 __device__ __forceinline__ void smem_inc_if(uint32_t addr, uint32_t cond) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" :: "r"(addr), "r"(cond) : "memory");
 }
@@ -967,57 +969,69 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                         const int n = (int)s_len[sd * T + rr2] - 32 * j;
                         if (n > 0) {
                             const uint8_t* tseq_sd = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes; const uint8_t* tqual_sd = tseq_sd + sl.tile_array_bytes;
-                            const uint4* s4 = reinterpret_cast<const uint4*>(tseq_sd + rr2 * S + 32 * j);
-                            const uint4* q4 = reinterpret_cast<const uint4*>(tqual_sd + rr2 * S + 32 * j);
-                            const uint4 s0 = s4[0], s1 = s4[1], q0 = q4[0], q1 = q4[1];
-                            const uint32_t x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                            const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                            uint32_t okm;
-                            const bool pok = plane_word_from_bytes(x, q, n, qq4, lo, hi, nn, lq, okm);
-                            if (!pok) s_clean[sd * T + rr2] = 0;
-                            /* pre-filter quality histogram (stats.cpp:213): FP_QH_REP copies per bin, copy = lane & (REP-1);
-                               byte offset of a bin = q*16 | copy*4 | side*2048 -- one shift + one LOP3 per base */
+                            /* One pass over the chunk in four steps of 8 bases (two words): per-byte class flags of the even word in bit 0,
+                               of the odd word in bit 4, so one multiply gathers 8 flags into the product's top byte (see plane_pair) and
+                               PRMT shifts it into the plane word.  The same step packs the 2-bit base codes for the 5-mer windows and
+                               counts the 8 qualities.  Rolled on purpose: straight-line code this size does not stay in the I-cache. */
+                            const uint8_t* sp = tseq_sd + rr2 * S + 32 * j; const uint8_t* qp = tqual_sd + rr2 * S + 32 * j;
                             uint8_t* qhb = smem + sl.off_qhist;
+                            /* quality histogram (stats.cpp:213): FP_QH_REP copies per bin (copy = lane & 3); bin address = q*16 | copy*4 | side*2048 */
                             const uint32_t qsel = ((uint32_t)(lane & (FP_QH_REP - 1)) << 2) | ((uint32_t)sd * (FP_QUAL_BINS * FP_QH_REP * 4));
                             const uint32_t qaddr = smem_u32(qhb) + qsel;          /* tables 2 KB-aligned: the bin offset (bits 4..10) ORs in */
-                            const int nv = min(n, 32);
-                            if (pok) {                                      /* every valid quality < 128 */
-                                #pragma unroll
-                                for (int k8 = 0; k8 < 8; k8++)
+                            uint32_t okm = 0, bad = 0, clo = 0, chi = 0;
+                            #pragma unroll 1
+                            for (int k = 0; k < 4; k++) {
+                                const uint2 sw = *reinterpret_cast<const uint2*>(sp + 8 * k), qw = *reinterpret_cast<const uint2*>(qp + 8 * k);
+                                uint32_t f_lo, f_hi, f_nn, f_lq, f_ok, f_bad;
+                                plane_pair(sw.x, sw.y, qw.x, qw.y, qq4, f_lo, f_hi, f_nn, f_lq, f_ok, f_bad);
+                                lo = __byte_perm(lo, f_lo, 0x7321); hi = __byte_perm(hi, f_hi, 0x7321); nn = __byte_perm(nn, f_nn, 0x7321);
+                                lq = __byte_perm(lq, f_lq, 0x7321); okm = __byte_perm(okm, f_ok, 0x7321); bad = __byte_perm(bad, f_bad, 0x7321);
+                                const uint32_t cc = __byte_perm(code_mul4(sw.x), code_mul4(sw.y), 0x7310);   /* bytes 2,3 = codes of the two words */
+                                clo = __byte_perm(clo, chi, 0x5432); chi = __byte_perm(chi, cc, 0x7632);
+                                const int rem = n - 8 * k;                   /* valid bases from this step on */
+                                if (!((qw.x | qw.y) & 0x80808080u)) {        /* every quality < 128 (else the exact loop below) */
                                     #pragma unroll
-                                    for (int b4 = 0; b4 < 4; b4++) {
-                                        const uint32_t sh = b4 == 0 ? (q[k8] << 4) : (q[k8] >> (8 * b4 - 4));
-                                        smem_inc_if(qaddr | (sh & 0xFF0u), (uint32_t)(4 * k8 + b4 < nv));
+                                    for (int b8 = 0; b8 < 8; b8++) {
+                                        const uint32_t w = b8 < 4 ? qw.x : qw.y;
+                                        const int bb = b8 & 3;
+                                        const uint32_t sh = bb == 0 ? (w << 4) : (w >> (8 * bb - 4));
+                                        smem_inc_gt(qaddr | (sh & 0xFF0u), rem, b8);
                                     }
-                            } else {
-                                #pragma unroll 1
-                                for (int i = 0; i < nv; i++) {
-                                    const uint32_t qb = tqual_sd[rr2 * S + 32 * j + i];
-                                    if (qb < FP_QUAL_BINS) atomicAdd(reinterpret_cast<unsigned int*>(qhb + ((qb << 4) | qsel)), 1u);
+                                } else {
+                                    #pragma unroll 1
+                                    for (int i = 0; i < min(rem, 8); i++) {
+                                        const uint32_t qb = qp[8 * k + i];
+                                        if (qb < FP_QUAL_BINS) atomicAdd(reinterpret_cast<unsigned int*>(qhb + ((qb << 4) | qsel)), 1u);
+                                    }
                                 }
                             }
+                            const uint32_t vm = low_mask(n);
+                            lo &= vm; hi &= vm; nn &= vm; lq &= vm; okm &= vm;
+                            if (bad & vm) s_clean[sd * T + rr2] = 0;
                             /* pre-filter 5-mer counts (stats.cpp:228-266): a 5-mer counts iff its five bases are exact A/C/G/T.
                                Z = 2-bit codes of the 4 bases before this chunk and its 32 bases, 2 bits per base; the 5-mer ending
                                at chunk position p is the 10-bit field at bit 2p.  The table is indexed by that field (oldest base
                                in the LOW digit, code A0 C1 T2 G3); the flush maps it to the reference's index. */
                             uint32_t cz = 0, cok = 0;
                             if (j > 0) {
-                                const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(tseq_sd + rr2 * S + 32 * j - 4);
+                                const uint32_t pw_ = *reinterpret_cast<const uint32_t*>(sp - 4);
                                 cz = pack_codes4(pw_); cok = pack_nibble(exact_acgt(pw_));
                             }
-                            const uint32_t clo = gather_top4(code_mul4(x[0]), code_mul4(x[1]), code_mul4(x[2]), code_mul4(x[3]));
-                            const uint32_t chi = gather_top4(code_mul4(x[4]), code_mul4(x[5]), code_mul4(x[6]), code_mul4(x[7]));
                             const uint32_t Z0 = cz | (clo << 8), Z1 = __funnelshift_r(clo, chi, 24), Z2 = chi >> 24;
                             const uint32_t O0 = cok | (okm << 4), O1 = okm >> 28;
                             const uint32_t vwin = O0 & __funnelshift_r(O0, O1, 1) & __funnelshift_r(O0, O1, 2) & __funnelshift_r(O0, O1, 3) & __funnelshift_r(O0, O1, 4);
                             uint8_t* khb = smem + sl.off_kmer;
                             const uint32_t kaddr = smem_u32(khb) + (uint32_t)sd * (FP_KMER_BINS * 4);     /* 4 KB-aligned: the field (bits 2..11) ORs in */
                             const uint32_t kdummy = smem_u32(s_dummy) + 4u * (uint32_t)lane;                /* windows that do not count land here */
-                            #pragma unroll
-                            for (int pp = 0; pp < 32; pp++) {              /* byte offset of the bin = field*4 | side*4096 */
-                                const int bit = 2 * pp - 2;
-                                const uint32_t f4 = pp == 0 ? (Z0 << 2) : (bit < 32 ? __funnelshift_r(Z0, Z1, bit) : __funnelshift_r(Z1, Z2, bit - 32));
-                                smem_inc((vwin & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy);
+                            #pragma unroll 1
+                            for (int g8 = 0; g8 < 4; g8++) {               /* 8 windows per step: W = Z bits [16*g8, 16*g8 + 32) */
+                                const uint32_t W = __funnelshift_r(g8 < 2 ? Z0 : Z1, g8 < 2 ? Z1 : Z2, (g8 & 1) * 16);
+                                const uint32_t v8 = vwin >> (8 * g8);
+                                #pragma unroll
+                                for (int pp = 0; pp < 8; pp++) {           /* byte offset of the bin = field*4 | side*4096 */
+                                    const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
+                                    smem_inc((v8 & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy);
+                                }
                             }
                         }
                     }

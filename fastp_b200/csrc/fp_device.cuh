@@ -124,40 +124,30 @@ __device__ __forceinline__ uint32_t pack_nibble(uint32_t v01) { return ((v01 * 0
 __device__ __forceinline__ uint32_t gather_top4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
     return __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
 }
-__device__ __forceinline__ bool plane_word_from_bytes(const uint32_t (&x)[8], const uint32_t (&q)[8], int n, uint32_t qq4,
-                                                      uint32_t& lo, uint32_t& hi, uint32_t& nn, uint32_t& lq, uint32_t& ok) {
+/* flags of 8 bases (even word a, odd word b; qualities qa, qb): each f_* holds the 8 flags in its TOP byte
+ * (bit 24+i = base i of a, bit 28+i = base i of b).  f_bad: byte outside {A,C,G,T,N} or quality bit 7 set. */
+__device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, uint32_t qb, uint32_t qq4,
+                                           uint32_t& f_lo, uint32_t& f_hi, uint32_t& f_nn, uint32_t& f_lq, uint32_t& f_ok, uint32_t& f_bad) {
     const uint32_t K = 0x01010101u, K4 = 0x10101010u, M = 0x01020408u;
-    uint32_t plo[4], phi[4], pnn[4], plq[4], pok[4], pbad[4];
-    #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t a = x[2 * k], b = x[2 * k + 1], qa = q[2 * k], qb = q[2 * k + 1];
-        /* even word: bit j of every byte moved to bit 0 */
-        const uint32_t a1 = a >> 1, a2 = a >> 2, a3 = a >> 3, a4 = a >> 4;
-        const uint32_t upA = ~(a >> 5) & (a >> 6) & ~(a >> 7);                           /* bits 7..5 == 010 */
-        const uint32_t okA = ((a & (~a2 | a1) & ~a3 & ~a4) | (~a & ~a1 & a2 & ~a3 & a4)) & upA & K;   /* 0x41 0x43 0x47 | 0x54 */
-        const uint32_t nA = ~a & a1 & a2 & a3 & ~a4 & upA & K;                           /* 0x4E */
-        /* odd word: bit j of every byte moved to bit 4 */
-        const uint32_t b0 = b << 4, b1 = b << 3, b2 = b << 2, b3 = b << 1;
-        const uint32_t upB = ~(b >> 1) & (b >> 2) & ~(b >> 3);
-        const uint32_t okB = ((b0 & (~b2 | b1) & ~b3 & ~b) | (~b0 & ~b1 & b2 & ~b3 & b)) & upB & K4;
-        const uint32_t nB = ~b0 & b1 & b2 & b3 & ~b & upB & K4;
-        const uint32_t okp = okA | okB, np = nA | nB;
-        /* q < qualified_qual  <=>  bit7 of (q | 0x80) - qq is clear (q, qq < 128) */
-        const uint32_t ta = ~((qa | 0x80808080u) - qq4), tb = ~((qb | 0x80808080u) - qq4);
-        plo[k] = (((a1 & K) | (b1 & K4)) & okp) * M;
-        phi[k] = (((a2 & K) | (b2 & K4)) & okp) * M;
-        pnn[k] = np * M;
-        pok[k] = okp * M;
-        plq[k] = (((ta >> 7) & K) | ((tb >> 3) & K4)) * M;
-        pbad[k] = ((~(okp | np) & (K | K4)) | ((qa >> 7) & K) | ((qb >> 3) & K4)) * M;
-    }
-    const uint32_t vm = low_mask(n);
-    lo = gather_top4(plo[0], plo[1], plo[2], plo[3]) & vm;
-    hi = gather_top4(phi[0], phi[1], phi[2], phi[3]) & vm;
-    nn = gather_top4(pnn[0], pnn[1], pnn[2], pnn[3]) & vm;
-    lq = gather_top4(plq[0], plq[1], plq[2], plq[3]) & vm;
-    ok = gather_top4(pok[0], pok[1], pok[2], pok[3]) & vm;                                /* exact: byte is one of 'A','C','G','T' */
-    return (gather_top4(pbad[0], pbad[1], pbad[2], pbad[3]) & vm) == 0;
+    /* even word: bit j of every byte moved to bit 0 */
+    const uint32_t a1 = a >> 1, a2 = a >> 2, a3 = a >> 3, a4 = a >> 4;
+    const uint32_t upA = ~(a >> 5) & (a >> 6) & ~(a >> 7);                           /* bits 7..5 == 010 */
+    const uint32_t okA = ((a & (~a2 | a1) & ~a3 & ~a4) | (~a & ~a1 & a2 & ~a3 & a4)) & upA & K;   /* 0x41 0x43 0x47 | 0x54 */
+    const uint32_t nA = ~a & a1 & a2 & a3 & ~a4 & upA & K;                           /* 0x4E */
+    /* odd word: bit j of every byte moved to bit 4 */
+    const uint32_t b0 = b << 4, b1 = b << 3, b2 = b << 2, b3 = b << 1;
+    const uint32_t upB = ~(b >> 1) & (b >> 2) & ~(b >> 3);
+    const uint32_t okB = ((b0 & (~b2 | b1) & ~b3 & ~b) | (~b0 & ~b1 & b2 & ~b3 & b)) & upB & K4;
+    const uint32_t nB = ~b0 & b1 & b2 & b3 & ~b & upB & K4;
+    const uint32_t okp = okA | okB, np = nA | nB;
+    /* q < qualified_qual  <=>  bit7 of (q | 0x80) - qq is clear (q, qq < 128) */
+    const uint32_t ta = ~((qa | 0x80808080u) - qq4), tb = ~((qb | 0x80808080u) - qq4);
+    f_lo = (((a1 & K) | (b1 & K4)) & okp) * M;
+    f_hi = (((a2 & K) | (b2 & K4)) & okp) * M;
+    f_nn = np * M;
+    f_ok = okp * M;                                                                   /* exact: byte is one of 'A','C','G','T' */
+    f_lq = (((ta >> 7) & K) | ((tb >> 3) & K4)) * M;
+    f_bad = ((~(okp | np) & (K | K4)) | ((qa >> 7) & K) | ((qb >> 3) & K4)) * M;
 }
 
 /* ballot-based rebuild of one row's planes (used after base correction rewrote the row; rare) */
