@@ -16,9 +16,6 @@
 #include "fp_device.cuh"
 
 /* thread-level view of one read: row pointers (smem), plane pointers, current window */
-/* tell the compiler a pointer is a shared-memory address, so loads become LDS / atomics ATOMS instead of generic LD / ATOM */
-#define FP_SMEM(p) __builtin_assume(__isShared(p))
-
 /* shared-memory counter += 1 at a 32-bit shared-window address, optionally predicated (no branch, no return value) */
 __device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
 /* += 1 iff a > B */
@@ -224,19 +221,24 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                 const int w = c >> 5;
                 const uint32_t L0 = alo[w], L1 = alo[w + 1], L2 = alo[w + 2], H0 = ahi[w], H1 = ahi[w + 1], H2 = ahi[w + 2],
                                N0 = ann[w], N1 = ann[w + 1], N2 = ann[w + 2];
-                /* candidates of this lane whose 50-bit field starts in word w: a counted loop, the shift just advances */
+                /* candidates of this lane whose 50-bit field starts in word w.  Tight loop: only the first 32 bases against the
+                   largest limit; the rare survivor is finished (50 bases, lut) outside it and the scan resumes after it. */
                 int sh = c & 31;
                 int cnt = min((nfast - o + g - 1) >> lg, (32 - sh + g - 1) >> lg);
-                #pragma unroll 2
-                for (; cnt > 0; cnt--, sh += g, o += g) {
-                    const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
-                    const int mm0 = __popc(x0);
-                    if (mm0 <= dmax) {       /* rare: the first 32 bases alone are within the largest limit -> finish the 50-base count */
-                        const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
-                        const int mm = mm0 + __popc(x1);
-                        const int ol = min(len1 - o, len2);
-                        if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                while (cnt > 0) {
+                    int mm0 = 0;
+                    #pragma unroll 2
+                    for (; cnt > 0; cnt--, sh += g, o += g) {
+                        const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
+                        mm0 = __popc(x0);
+                        if (mm0 <= dmax) break;
                     }
+                    if (cnt <= 0) break;
+                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
+                    const int mm = mm0 + __popc(x1);
+                    const int ol = min(len1 - o, len2);
+                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    cnt--; sh += g; o += g;
                 }
             }
         }
@@ -274,16 +276,20 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                                N0 = pnn[w], N1 = pnn[w + 1], N2 = pnn[w + 2];
                 int sh = c & 31;
                 int cnt = min((nfast - o + g - 1) >> lg, (sh >> lg) + 1);   /* the field start moves DOWN by g per candidate */
-                #pragma unroll 2
-                for (; cnt > 0; cnt--, sh -= g, o += g) {
-                    const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
-                    const int mm0 = __popc(x0);
-                    if (mm0 <= dmax) {
-                        const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
-                        const int mm = mm0 + __popc(x1);
-                        const int ol = min(len1, len2 - o);
-                        if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                while (cnt > 0) {
+                    int mm0 = 0;
+                    #pragma unroll 2
+                    for (; cnt > 0; cnt--, sh -= g, o += g) {
+                        const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
+                        mm0 = __popc(x0);
+                        if (mm0 <= dmax) break;
                     }
+                    if (cnt <= 0) break;
+                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
+                    const int mm = mm0 + __popc(x1);
+                    const int ol = min(len1, len2 - o);
+                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
+                    cnt--; sh -= g; o += g;
                 }
             }
         }

@@ -11,6 +11,9 @@
 #include <stdint.h>
 #include "fastp_b200.h"
 
+/* tell the compiler a pointer is a shared-memory address, so loads become LDS / atomics ATOMS instead of generic LD / ATOM */
+#define FP_SMEM(p) __builtin_assume(__isShared(p))
+
 #define FP_THREADS 256
 #define FP_WARPS (FP_THREADS / 32)
 #define FP_CT 256              /* threads of the chain kernel: 2 CTAs x 8 warps per SM (<= 128 registers) */
@@ -302,6 +305,7 @@ struct DeltaAcc { int* cyc; int* kmer; int* qh; int cycles; };
 
 __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side, const uint8_t* seq, const uint8_t* qual,
                                                     int ctx0, int lo, int hi, int sign) {
+    FP_SMEM(D.cyc); FP_SMEM(D.kmer); FP_SMEM(D.qh); FP_SMEM(seq); FP_SMEM(qual);
     const int lane = lane_id();
     int* cy = D.cyc + side * D.cycles * 20;
     int* km = D.kmer + side * FP_KMER_BINS;
