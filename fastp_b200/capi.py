@@ -86,6 +86,14 @@ PATCH_DTYPE = np.dtype([
 ])
 assert READ_RESULT_DTYPE.itemsize == 16 and OV_RESULT_DTYPE.itemsize == 8 and PATCH_DTYPE.itemsize == 12
 
+FASTQ_REC_DTYPE = np.dtype([("name_off", "<u4"), ("name_len", "<u4"), ("strand_off", "<u4"), ("strand_len", "<u4")])
+
+
+class FastqInfo(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("consumed", C.c_int64), ("n_lines", C.c_int64), ("error", C.c_int32), ("more", C.c_int32),
+                ("error_record", C.c_int64)]
+
+
 # name -> (restype, argtypes): every symbol include/fastp_b200.h declares
 SYMBOLS = {
     "fp_params_default": (None, [C.POINTER(Params), C.c_int]),
@@ -110,6 +118,14 @@ SYMBOLS = {
     "fp_synth_fill": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "fp_kernel_time_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "fp_version": (C.c_int, []),
+    "fp_fastq_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.POINTER(FastqInfo)]),
+    "fp_fastq_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.POINTER(C.c_int64)]),
+    "fp_fastq_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(FastqInfo), C.POINTER(FastqInfo)]),
 }
 
 

@@ -19,6 +19,7 @@
 #include "fastp_b200.h"
 #include "fp_device.cuh"
 #include "fp_chain2.cuh"
+#include "fp_fastq.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
@@ -77,6 +78,10 @@ struct fp_ctx {
     fp_patch* h_patch[2] = {nullptr, nullptr};
     unsigned int* h_npatch[2] = {nullptr, nullptr};
     uint32_t patch_cap = 0;
+    /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
+    Buf fqh_text[2], fqh_seq[2], fqh_qual[2], fqh_len[2], fqh_recs[2], fqh_res[2], fqh_ov, fqh_out[2];
     /* kernel timing */
     std::vector<EvPair> evs;
     std::vector<EvPair> ev_pool;
@@ -320,6 +325,8 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     return FP_OK;
 }
 
+static void fq_free(fp_ctx::Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
 static void free_staging(fp_ctx* c) {
     for (int i = 0; i < 2; i++) {
         for (int k = 0; k < 4; k++) { cudaFree(c->d_stage[i][k]); c->d_stage[i][k] = nullptr; }
@@ -338,6 +345,12 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_staging(c);
+    {
+        fp_ctx::Buf* all[] = {&c->fq_term, &c->fq_bcnt, &c->fq_agg, &c->fq_bstate, &c->fq_brec, &c->fq_recline, &c->fq_recend, &c->fq_info, &c->fq_bsum,
+                              &c->fqh_text[0], &c->fqh_text[1], &c->fqh_seq[0], &c->fqh_seq[1], &c->fqh_qual[0], &c->fqh_qual[1], &c->fqh_len[0], &c->fqh_len[1],
+                              &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1]};
+        for (auto* b : all) fq_free(*b);
+    }
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
     cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
@@ -559,6 +572,185 @@ extern "C" int fp_process_pe_host(fp_ctx* c, const fp_batch* b, fp_read_result* 
     if (!c || !b || !out1 || !out2) return set_err(FP_E_INVAL, "null argument");
     if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
     return process_host(c, b, out1, out2, ov);
+}
+
+/* ---------------- FASTQ text <-> rows (fp_fastq.cuh) ---------------- */
+static int fq_ensure(fp_ctx::Buf& b, size_t need) {
+    if (need <= b.cap) return FP_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t cap = need + need / 4 + 256;
+    CK(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return FP_OK;
+}
+
+static_assert(sizeof(fp_fastq_rec) == sizeof(fq_rec), "fp_fastq_rec layout");
+
+/* rec_end_out (optional, host): consumed bytes if only the first k records are kept is read later through fq_recend */
+extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, int32_t final_chunk, int32_t phred64,
+                               uint8_t* d_seq, uint8_t* d_qual, uint16_t* d_len, int64_t capacity, fp_fastq_rec* d_recs,
+                               fp_fastq_info* info) {
+    if (!c || !info || (nbytes > 0 && !d_text)) return set_err(FP_E_INVAL, "null argument");
+    if (nbytes < 0 || nbytes >= ((int64_t)1 << 32) - 16) return set_err(FP_E_TOOLARGE, "FASTQ chunk must be smaller than 4 GiB");
+    if (capacity < 0 || (capacity > 0 && (!d_seq || !d_qual || !d_len || !d_recs))) return set_err(FP_E_INVAL, "null row buffers");
+    memset(info, 0, sizeof(*info));
+    info->error_record = -1;
+    if (nbytes == 0 || capacity == 0) return FP_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream[0];
+    const int nbb = (int)((nbytes + FQ_BB - 1) / FQ_BB);
+    int rc;
+    if ((rc = fq_ensure(c->fq_bcnt, (size_t)(nbb + 1) * 4))) return rc;
+    if ((rc = fq_ensure(c->fq_info, 64))) return rc;
+    unsigned int* d_info = (unsigned int*)c->fq_info.p;
+    CK(cudaMemsetAsync(d_info, 0, 64, st));
+    fq_term_count_kernel<<<nbb, FQ_T, 0, st>>>(d_text, nbytes, (unsigned int*)c->fq_bcnt.p);
+    fq_term_scan_kernel<<<1, 32, 0, st>>>((unsigned int*)c->fq_bcnt.p, nbb, d_text, nbytes, final_chunk, nullptr, 0, d_info);
+    unsigned int h_info[16];
+    CK(cudaMemcpyAsync(h_info, d_info, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned int nlines = h_info[0], nterm = h_info[1];
+    info->n_lines = nlines;
+    if (nlines == 0) return FP_OK;
+    if ((rc = fq_ensure(c->fq_term, (size_t)(nlines + 2) * 4))) return rc;
+    unsigned int* d_term = (unsigned int*)c->fq_term.p;
+    fq_term_fill_kernel<<<nbb, FQ_T, 0, st>>>(d_text, nbytes, (unsigned int*)c->fq_bcnt.p, d_term, nlines + 1);
+    if (nlines > nterm) { const unsigned int v = (unsigned int)nbytes; CK(cudaMemcpyAsync(d_term + nterm, &v, 4, cudaMemcpyHostToDevice, st)); }
+    /* record automaton over the lines */
+    const int nlb = (int)((nlines + FQ_LB - 1) / FQ_LB);
+    if ((rc = fq_ensure(c->fq_agg, (size_t)nlb * sizeof(fq_elem)))) return rc;
+    if ((rc = fq_ensure(c->fq_bstate, (size_t)nlb * 4))) return rc;
+    if ((rc = fq_ensure(c->fq_brec, (size_t)nlb * 4))) return rc;
+    fq_fsm_kernel<0><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, (fq_elem*)c->fq_agg.p, nullptr, nullptr, nullptr, 0);
+    fq_fsm_scan_kernel<<<1, 32, 0, st>>>((const fq_elem*)c->fq_agg.p, nlb, (unsigned int*)c->fq_bstate.p, (unsigned int*)c->fq_brec.p, d_info);
+    CK(cudaMemcpyAsync(h_info, d_info, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned int nstarted = h_info[2], ncomplete = h_info[3];
+    if (ncomplete == 0) return FP_OK;
+    if ((rc = fq_ensure(c->fq_recline, (size_t)(nstarted + 1) * 4))) return rc;
+    fq_fsm_kernel<1><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, nullptr, (const unsigned int*)c->fq_bstate.p, (const unsigned int*)c->fq_brec.p,
+                                           (unsigned int*)c->fq_recline.p, nstarted);
+    const unsigned int nrec = (unsigned int)std::min<int64_t>(ncomplete, capacity);
+    if (c->stride > 0xFFFF) return set_err(FP_E_INVAL, "stride");
+    if ((rc = fq_ensure(c->fq_recend, (size_t)nrec * 4))) return rc;
+    unsigned int first_bad = 0xFFFFFFFFu;
+    CK(cudaMemcpyAsync(d_info + 8, &first_bad, 4, cudaMemcpyHostToDevice, st));
+    fq_scatter_kernel<<<(nrec + FQ_T / 32 - 1) / (FQ_T / 32), FQ_T, 0, st>>>(d_text, nbytes, d_term, (const unsigned int*)c->fq_recline.p, nrec, c->stride, phred64,
+                                                                               d_seq, d_qual, d_len, reinterpret_cast<fq_rec*>(d_recs),
+                                                                               (unsigned int*)c->fq_recend.p, d_info + 8, d_info + 9);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&first_bad, d_info + 8, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    unsigned int keep = nrec;
+    if (first_bad != 0xFFFFFFFFu) {
+        fp_fastq_rec br;
+        CK(cudaMemcpy(&br, d_recs + first_bad, sizeof(br), cudaMemcpyDeviceToHost));
+        info->error = (int32_t)((br.name_len >> 28) & 7u);
+        info->error_record = first_bad;
+        keep = first_bad;                                         /* the reference reader stops here: fastqreader.cpp:349-364 */
+    }
+    info->n_records = keep;
+    info->more = (first_bad == 0xFFFFFFFFu && ncomplete > nrec) ? 1 : 0;
+    if (first_bad != 0xFFFFFFFFu) info->consumed = nbytes;         /* nothing after a bad record is read */
+    else if (keep > 0) { unsigned int e; CK(cudaMemcpy(&e, (unsigned int*)c->fq_recend.p + (keep - 1), 4, cudaMemcpyDeviceToHost)); info->consumed = e; }
+    return FP_OK;
+}
+
+extern "C" int fp_fastq_encode(fp_ctx* c, const uint8_t* d_text, const fp_fastq_rec* d_recs, const fp_read_result* d_res,
+                               const uint8_t* d_seq, const uint8_t* d_qual, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* out_bytes) {
+    if (!c || !out_bytes) return set_err(FP_E_INVAL, "null argument");
+    *out_bytes = 0;
+    if (n <= 0) return FP_OK;
+    if (!d_text || !d_recs || !d_res || !d_seq || !d_qual || (out_cap > 0 && !d_out)) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream[0];
+    const int nblk = (int)((n + FQ_SCAN_ITEMS - 1) / FQ_SCAN_ITEMS);
+    int rc;
+    if ((rc = fq_ensure(c->fq_bsum, (size_t)(nblk + 1) * 8))) return rc;
+    unsigned long long* d_bs = (unsigned long long*)c->fq_bsum.p;
+    fq_size_blocksum_kernel<<<nblk, FQ_T, 0, st>>>(reinterpret_cast<const fq_rec*>(d_recs), d_res, n, d_bs);
+    fq_size_scan_kernel<<<1, 32, 0, st>>>(d_bs, nblk, d_bs + nblk);
+    fq_encode_kernel<<<nblk, FQ_T, 0, st>>>(d_text, reinterpret_cast<const fq_rec*>(d_recs), d_res, d_seq, d_qual, c->stride, n, d_bs, d_out,
+                                            (unsigned long long)std::max<int64_t>(out_cap, 0));
+    CK(cudaGetLastError());
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, d_bs + nblk, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out_bytes = (int64_t)total;
+    return FP_OK;
+}
+
+extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2, int64_t nbytes2,
+                                     int32_t final_chunk, int32_t phred64,
+                                     uint8_t* out1, int64_t out_cap1, int64_t* out_bytes1,
+                                     uint8_t* out2, int64_t out_cap2, int64_t* out_bytes2,
+                                     int64_t* n_units, int64_t* consumed1, int64_t* consumed2, fp_fastq_info* info1, fp_fastq_info* info2) {
+    if (!c || !n_units || !consumed1 || !out_bytes1) return set_err(FP_E_INVAL, "null argument");
+    const int sides = c->p.paired ? 2 : 1;
+    if (sides == 2 && (!consumed2 || !out_bytes2)) return set_err(FP_E_INVAL, "paired ctx needs the second side");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream[0];
+    const uint8_t* text[2] = {text1, text2};
+    const int64_t nb[2] = {nbytes1, nbytes2};
+    fp_fastq_info inf[2];
+    const int64_t cap = c->max_batch;
+    int rc;
+    for (int s = 0; s < sides; s++) {
+        if ((rc = fq_ensure(c->fqh_text[s], (size_t)nb[s] + 64))) return rc;
+        if ((rc = fq_ensure(c->fqh_seq[s], (size_t)cap * c->stride + 64))) return rc;
+        if ((rc = fq_ensure(c->fqh_qual[s], (size_t)cap * c->stride + 64))) return rc;
+        if ((rc = fq_ensure(c->fqh_len[s], (size_t)cap * 2))) return rc;
+        if ((rc = fq_ensure(c->fqh_recs[s], (size_t)cap * sizeof(fp_fastq_rec)))) return rc;
+        if ((rc = fq_ensure(c->fqh_res[s], (size_t)cap * sizeof(fp_read_result)))) return rc;
+        if (nb[s] > 0) CK(cudaMemcpyAsync(c->fqh_text[s].p, text[s], (size_t)nb[s], cudaMemcpyHostToDevice, st));
+        rc = fp_fastq_decode(c, (const uint8_t*)c->fqh_text[s].p, nb[s], final_chunk, phred64, (uint8_t*)c->fqh_seq[s].p, (uint8_t*)c->fqh_qual[s].p,
+                             (uint16_t*)c->fqh_len[s].p, cap, (fp_fastq_rec*)c->fqh_recs[s].p, &inf[s]);
+        if (rc) return rc;
+    }
+    int64_t n = inf[0].n_records;
+    if (sides == 2) n = std::min(n, inf[1].n_records);            /* pairs end with the shorter input (FastqReaderPair::read) */
+    /* bytes covered by the first n records of each side */
+    int64_t cons[2] = {0, 0};
+    for (int s = 0; s < sides; s++) {
+        if (n == inf[s].n_records) cons[s] = inf[s].consumed;
+        else if (n > 0) {
+            /* this side decoded more records than the pair count: re-derive the end of record n-1 from the workspace of the LAST decode only
+               when it is this side's; otherwise decode again restricted to n records */
+            fp_fastq_info tmp;
+            rc = fp_fastq_decode(c, (const uint8_t*)c->fqh_text[s].p, nb[s], final_chunk, phred64, (uint8_t*)c->fqh_seq[s].p, (uint8_t*)c->fqh_qual[s].p,
+                                 (uint16_t*)c->fqh_len[s].p, n, (fp_fastq_rec*)c->fqh_recs[s].p, &tmp);
+            if (rc) return rc;
+            cons[s] = tmp.consumed;
+        }
+    }
+    *n_units = n; *consumed1 = cons[0]; if (consumed2) *consumed2 = cons[1];
+    if (info1) *info1 = inf[0];
+    if (info2 && sides == 2) *info2 = inf[1];
+    *out_bytes1 = 0; if (out_bytes2) *out_bytes2 = 0;
+    if (n == 0) return FP_OK;
+    fp_batch b; memset(&b, 0, sizeof(b));
+    b.n = n; b.stride = c->stride;
+    b.seq1 = (uint8_t*)c->fqh_seq[0].p; b.qual1 = (uint8_t*)c->fqh_qual[0].p; b.len1 = (uint16_t*)c->fqh_len[0].p;
+    if (sides == 2) {
+        b.seq2 = (uint8_t*)c->fqh_seq[1].p; b.qual2 = (uint8_t*)c->fqh_qual[1].p; b.len2 = (uint16_t*)c->fqh_len[1].p;
+        rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, (fp_read_result*)c->fqh_res[1].p, nullptr, nullptr, 0, nullptr, st);
+    } else rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, nullptr, nullptr, nullptr, 0, nullptr, st);
+    if (rc) return rc;
+    uint8_t* outs[2] = {out1, out2}; const int64_t ocap[2] = {out_cap1, out_cap2}; int64_t* ob[2] = {out_bytes1, out_bytes2};
+    for (int s = 0; s < sides; s++) {
+        if (!outs[s]) continue;                                   /* caller does not want this side's text */
+        if ((rc = fq_ensure(c->fqh_out[s], (size_t)ocap[s] + 64))) return rc;
+        int64_t total = 0;
+        rc = fp_fastq_encode(c, (const uint8_t*)c->fqh_text[s].p, (const fp_fastq_rec*)c->fqh_recs[s].p, (const fp_read_result*)c->fqh_res[s].p,
+                             (const uint8_t*)c->fqh_seq[s].p, (const uint8_t*)c->fqh_qual[s].p, n, (uint8_t*)c->fqh_out[s].p, ocap[s], &total);
+        if (rc) return rc;
+        *ob[s] = total;
+        if (total > ocap[s]) return set_err(FP_E_TOOLARGE, "output buffer too small for the encoded FASTQ text");
+        if (total > 0) CK(cudaMemcpyAsync(outs[s], c->fqh_out[s].p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return FP_OK;
 }
 
 /* ---------------- counters ---------------- */

@@ -73,6 +73,8 @@ size_t fp_abi_sizeof(int which) {
         case 3: return sizeof(fp_ov_result);
         case 4: return sizeof(fp_patch);
         case 5: return sizeof(fp_counter_layout);
+        case 6: return sizeof(fp_fastq_rec);
+        case 7: return sizeof(fp_fastq_info);
         default: return 0;
     }
 }

@@ -285,6 +285,47 @@ int  fp_counters_device_ptr(fp_ctx* ctx, int64_t** dev_ptr, int64_t* n_words);
 /* Collective form: `comm` is an ncclComm_t (void*); no-op when comm == NULL. */
 int  fp_counters_allreduce(fp_ctx* ctx, void* comm, void* stream);
 
+/* ---------------- FASTQ text <-> rows on the device ----------------
+ * fp_fastq_decode  replaces FastqReader::read / getLine (src/fastqreader.cpp:240-368) for a chunk of plain FASTQ text that
+ *                  is already in DEVICE memory: it finds the records, checks them like the reference ('+' line, equal
+ *                  lengths) and scatters bases / qualities into rows of `stride` bytes (zero-filled behind the read).
+ * fp_fastq_encode  replaces Read::appendToString (src/read.cpp:119-134) for the reads / pairs that pass
+ *                  (src/peprocessor.cpp:583-584, src/seprocessor.cpp:268): name, trimmed (and corrected) bases, strand line,
+ *                  trimmed qualities, in input order.
+ * Line rules are the reference's: '\n', or a '\r' not followed by '\n', ends a line; "\r\n" is one terminator; a record starts
+ * at the first non-empty line beginning with '@'; the next three lines are taken as they come.  Where the reference reader
+ * gives up (strand line not '+', lengths differ) it stops reading: info->error / error_record say so and n_records counts
+ * the records before it.  Chunks must be smaller than 4 GiB.                                                             */
+#define FP_FQ_OK            0
+#define FP_FQ_ERR_STRAND    1   /* "Expected '+'"  fastqreader.cpp:349  */
+#define FP_FQ_ERR_LENGTH    2   /* sequence and quality have different length  fastqreader.cpp:356 */
+#define FP_FQ_ERR_STRIDE    3   /* a read is longer than the row stride (not a reference error) */
+typedef struct fp_fastq_rec { uint32_t name_off, name_len, strand_off, strand_len; } fp_fastq_rec;   /* offsets into the chunk */
+typedef struct fp_fastq_info {
+    int64_t n_records;      /* records decoded into the rows (<= capacity)                              */
+    int64_t consumed;       /* bytes of the chunk they cover (the caller carries the rest to the next chunk) */
+    int64_t n_lines;        /* lines seen in the chunk                                                  */
+    int32_t error;          /* FP_FQ_* of the first bad record, FP_FQ_OK if none                        */
+    int32_t more;           /* 1 if complete records were left because capacity was reached             */
+    int64_t error_record;   /* its index, -1 if none                                                    */
+} fp_fastq_info;
+/* d_text .. d_recs are DEVICE pointers; final_chunk: the text ends here (an unterminated last line counts).  Synchronous. */
+int  fp_fastq_decode(fp_ctx* ctx, const uint8_t* d_text, int64_t nbytes, int32_t final_chunk, int32_t phred64,
+                     uint8_t* d_seq, uint8_t* d_qual, uint16_t* d_len, int64_t capacity, fp_fastq_rec* d_recs,
+                     fp_fastq_info* info);
+/* Output text of side `d_res` (its pair_verdict decides, so for pairs both sides keep the same records).
+ * *out_bytes = size of the full output; if it exceeds out_cap nothing beyond out_cap is written.  Synchronous. */
+int  fp_fastq_encode(fp_ctx* ctx, const uint8_t* d_text, const fp_fastq_rec* d_recs, const fp_read_result* d_res,
+                     const uint8_t* d_seq, const uint8_t* d_qual, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* out_bytes);
+/* Whole path on HOST buffers: text chunk(s) in, filtered text out (text2/out2 NULL for single-end).
+ * Decodes up to the ctx's max_batch records per side, runs the operator chain, encodes the passing reads.
+ * n_units = reads / pairs processed; consumed1/2 = bytes of each input they cover.  Synchronous.      */
+int  fp_fastq_process_host(fp_ctx* ctx, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2, int64_t nbytes2,
+                           int32_t final_chunk, int32_t phred64,
+                           uint8_t* out1, int64_t out_cap1, int64_t* out_bytes1,
+                           uint8_t* out2, int64_t out_cap2, int64_t* out_bytes2,
+                           int64_t* n_units, int64_t* consumed1, int64_t* consumed2, fp_fastq_info* info1, fp_fastq_info* info2);
+
 /* Pinned host memory helpers for the staging shim. */
 int  fp_host_alloc(void** p, size_t bytes);
 int  fp_host_free(void* p);

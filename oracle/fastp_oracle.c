@@ -777,3 +777,85 @@ int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int l
 int fp_oracle_match_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit) {
     return match_with_one_insertion(insData, normalData, cmplen, diffLimit);
 }
+
+
+/* ==========================================================================================
+ * FASTQ text <-> rows
+ * ========================================================================================== */
+/* FastqReader::getLine  src/fastqreader.cpp:240-266 over one in-memory chunk: the line starting at *pos.
+ * Returns 0 when no (complete) line is left.  '\n', or '\r' not followed by '\n', ends a line; "\r\n" is one terminator.
+ * (The reference's `end < mBufDataLen-1` test leaves the '\n' of a "\r\n" that ends its I/O buffer for the next call, where it
+ *  is an empty line that the name search skips -- unobservable, so not restated.) */
+static int fq_get_line(const uint8_t* t, int64_t n, int final_chunk, int64_t* pos, int64_t* ls, int64_t* le) {
+    int64_t start = *pos, end = start;
+    if (start >= n) return 0;
+    while (end < n && t[end] != '\r' && t[end] != '\n') end++;                 /* :248-253 */
+    if (end >= n && !final_chunk) return 0;                                       /* line not complete in this chunk */
+    *ls = start; *le = end;
+    if (end < n) {
+        end++;                                                                    /* :260 skip \n or \r */
+        if (t[end - 1] == '\r' && end < n && t[end] == '\n') end++;               /* :262 handle \r\n */
+    }
+    *pos = end;
+    return 1;
+}
+
+int fp_oracle_fastq_decode(const uint8_t* text, int64_t nbytes, int final_chunk, int phred64, int stride,
+                           uint8_t* seq, uint8_t* qual, uint16_t* len, int64_t capacity, fp_fastq_rec* recs, fp_fastq_info* info) {
+    memset(info, 0, sizeof(*info));
+    info->error_record = -1;
+    int64_t pos = 0, nrec = 0, nlines = 0;
+    /* count lines the way the device reports them (complete lines of the chunk) */
+    { int64_t p2 = 0, a, b; while (fq_get_line(text, nbytes, final_chunk, &p2, &a, &b)) nlines++; }
+    info->n_lines = nlines;
+    for (;;) {
+        int64_t save = pos, ns, ne, ss, se, ps, pe, qs, qe;
+        /* FastqReader::read :336-343: skip lines until one is non-empty and starts with '@' */
+        int got;
+        while ((got = fq_get_line(text, nbytes, final_chunk, &pos, &ns, &ne)) && !(ne > ns && text[ns] == '@')) save = pos;
+        if (!got) { pos = save; break; }
+        if (!fq_get_line(text, nbytes, final_chunk, &pos, &ss, &se) || !fq_get_line(text, nbytes, final_chunk, &pos, &ps, &pe) ||
+            !fq_get_line(text, nbytes, final_chunk, &pos, &qs, &qe)) { pos = save; break; }      /* record not complete in this chunk */
+        if (nrec >= capacity) { info->more = 1; pos = save; break; }
+        int code = FP_FQ_OK;
+        if (pe == ps || text[ps] != '+') code = FP_FQ_ERR_STRAND;                 /* :349 */
+        else if (qe - qs != se - ss) code = FP_FQ_ERR_LENGTH;                     /* :356 */
+        else if (se - ss > stride) code = FP_FQ_ERR_STRIDE;
+        if (code != FP_FQ_OK) { info->error = code; info->error_record = nrec; pos = nbytes; break; }   /* the reader returns NULL: input ends */
+        const int L = (int)(se - ss);
+        uint8_t* srow = seq + (size_t)nrec * stride; uint8_t* qrow = qual + (size_t)nrec * stride;
+        memset(srow, 0, stride); memset(qrow, 0, stride);
+        memcpy(srow, text + ss, L);
+        for (int i = 0; i < L; i++) {
+            uint8_t q = text[qs + i];
+            if (phred64) { int v = (int)(signed char)q - (64 - 33); q = (uint8_t)(v < 33 ? 33 : v); }   /* read.cpp:35-39 */
+            qrow[i] = q;
+        }
+        len[nrec] = (uint16_t)L;
+        recs[nrec].name_off = (uint32_t)ns; recs[nrec].name_len = (uint32_t)(ne - ns);
+        recs[nrec].strand_off = (uint32_t)ps; recs[nrec].strand_len = (uint32_t)(pe - ps);
+        nrec++;
+    }
+    info->n_records = nrec;
+    info->consumed = pos;
+    return 0;
+}
+
+/* Read::appendToString  src/read.cpp:119-134 for every read whose pair verdict is PASS (peprocessor.cpp:583-584) */
+int64_t fp_oracle_fastq_encode(const uint8_t* text, const fp_fastq_rec* recs, const fp_read_result* res, const uint8_t* seq, const uint8_t* qual,
+                               int stride, int64_t n, uint8_t* out, int64_t out_cap) {
+    int64_t o = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (res[i].pair_verdict != FP_PASS_FILTER) continue;
+        const int64_t need = (int64_t)recs[i].name_len + recs[i].strand_len + 2 * (int64_t)res[i].len + 4;
+        if (o + need <= out_cap) {
+            uint8_t* d = out + o;
+            memcpy(d, text + recs[i].name_off, recs[i].name_len); d += recs[i].name_len; *d++ = '\n';
+            memcpy(d, seq + (size_t)i * stride + res[i].front, res[i].len); d += res[i].len; *d++ = '\n';
+            memcpy(d, text + recs[i].strand_off, recs[i].strand_len); d += recs[i].strand_len; *d++ = '\n';
+            memcpy(d, qual + (size_t)i * stride + res[i].front, res[i].len); d += res[i].len; *d++ = '\n';
+        }
+        o += need;
+    }
+    return o;
+}

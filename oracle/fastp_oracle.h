@@ -21,6 +21,13 @@ int fp_oracle_trim_by_sequence(uint8_t* seq, int len, const char* adapter, int* 
 fp_ov_result fp_oracle_analyze(uint8_t* seq1, int len1, uint8_t* seq2, int len2, int diffLimit, int overlapRequire, double diffPercentLimit);
 int fp_oracle_pass_filter(const fp_params* p, uint8_t* seq, uint8_t* qual, int len);
 int fp_oracle_match_with_one_insertion(const uint8_t* insData, const uint8_t* normalData, int cmplen, int diffLimit);
+
+/* FASTQ text <-> rows: FastqReader::getLine / read (src/fastqreader.cpp:240-368) and Read::appendToString (src/read.cpp:119-134)
+ * restated over an in-memory chunk; same arguments and results as fp_fastq_decode / fp_fastq_encode, HOST pointers. */
+int fp_oracle_fastq_decode(const uint8_t* text, int64_t nbytes, int final_chunk, int phred64, int stride,
+                           uint8_t* seq, uint8_t* qual, uint16_t* len, int64_t capacity, fp_fastq_rec* recs, fp_fastq_info* info);
+int64_t fp_oracle_fastq_encode(const uint8_t* text, const fp_fastq_rec* recs, const fp_read_result* res, const uint8_t* seq, const uint8_t* qual,
+                               int stride, int64_t n, uint8_t* out, int64_t out_cap);
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@
 #include "options.h"
 #include "read.h"
 #include "stats.h"
+#include "fastqreader.h"
 #include "filter.h"
 #include "filterresult.h"
 #include "polyx.h"
@@ -362,6 +363,32 @@ int fp_ref_process_mt(const fp_params* p, const fp_counter_layout* L, const fp_b
     for (int t = 0; t < nthreads; t++)
         for (int64_t i = 0; i < L->total; i++) counters[i] += part[t][i];
     return FP_OK;
+}
+
+// FastqReader itself (src/fastqreader.cpp) over a plain FASTQ file: every record it returns, flattened as
+// [name_len, seq_len, strand_len, qual_len] (4 x int32) followed by the four byte strings.  Returns the record count,
+// *used = bytes written (nothing is written past cap, the count still runs on).
+int64_t fp_ref_fastq_read_file(const char* path, int phred64, uint8_t* out, int64_t cap, int64_t* used) {
+    FastqReader reader(path, true, phred64 != 0);
+    int64_t n = 0, o = 0;
+    for (;;) {
+        Read* r = reader.read();
+        if (!r) break;
+        const std::string* f[4] = {r->mName, r->mSeq, r->mStrand, r->mQuality};
+        int64_t need = 16;
+        for (int k = 0; k < 4; k++) need += (int64_t)f[k]->size();
+        if (o + need <= cap) {
+            int32_t* h = reinterpret_cast<int32_t*>(out + o);
+            for (int k = 0; k < 4; k++) h[k] = (int32_t)f[k]->size();
+            uint8_t* d = out + o + 16;
+            for (int k = 0; k < 4; k++) { memcpy(d, f[k]->data(), f[k]->size()); d += f[k]->size(); }
+        }
+        o += need;
+        n++;
+        delete r;
+    }
+    *used = o;
+    return n;
 }
 
 }  // extern "C"

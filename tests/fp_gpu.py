@@ -120,3 +120,61 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
     if own:
         ctx.close()
     return res
+
+
+# ---------------- FASTQ text <-> rows ----------------
+def gpu_fastq_decode(ctx, text, final=1, phred64=0, capacity=None):
+    """fp_fastq_decode on cuda:0; same return shape as fp_testlib.oracle_fastq_decode (+ the device tensors)."""
+    torch = _torch()
+    lib = ctx.lib
+    cap = capacity if capacity is not None else text.count(b"@") + 2
+    cap1 = max(cap, 1)
+    d_text = torch.from_numpy(np.frombuffer(text, np.uint8).copy() if len(text) else np.zeros(1, np.uint8)).cuda()
+    d_seq = torch.full((cap1 * ctx.stride + 64,), 0xEE, dtype=torch.uint8, device="cuda:0")
+    d_qual = torch.full((cap1 * ctx.stride + 64,), 0xEE, dtype=torch.uint8, device="cuda:0")
+    d_len = torch.zeros(cap1, dtype=torch.int16, device="cuda:0")
+    d_recs = torch.zeros(cap1 * 16, dtype=torch.uint8, device="cuda:0")
+    info = capi.FastqInfo()
+    capi.check(lib.fp_fastq_decode(ctx.h, d_text.data_ptr(), len(text), final, phred64, d_seq.data_ptr(), d_qual.data_ptr(), d_len.data_ptr(), cap,
+                                   d_recs.data_ptr(), C.byref(info)), lib)
+    n = int(info.n_records)
+    S = ctx.stride
+    out = {"seq": d_seq.cpu().numpy()[:cap1 * S].reshape(cap1, S)[:n], "qual": d_qual.cpu().numpy()[:cap1 * S].reshape(cap1, S)[:n],
+           "len": d_len.cpu().numpy().view(np.uint16)[:n], "recs": d_recs.cpu().numpy().view(capi.FASTQ_REC_DTYPE)[:n].copy(),
+           "info": {k: int(getattr(info, k)) for k, _ in capi.FastqInfo._fields_},
+           "dev": (d_text, d_seq, d_qual, d_len, d_recs)}
+    return out
+
+
+def gpu_fastq_encode(ctx, dev, res, n):
+    torch = _torch()
+    lib = ctx.lib
+    d_text, d_seq, d_qual, d_len, d_recs = dev
+    d_res = torch.from_numpy(np.ascontiguousarray(res).view(np.uint8).copy() if n else np.zeros(16, np.uint8)).cuda()
+    total = C.c_int64()
+    capi.check(lib.fp_fastq_encode(ctx.h, d_text.data_ptr(), d_recs.data_ptr(), d_res.data_ptr(), d_seq.data_ptr(), d_qual.data_ptr(), n, None, 0, C.byref(total)), lib)
+    d_out = torch.zeros(max(total.value, 1), dtype=torch.uint8, device="cuda:0")
+    t2 = C.c_int64()
+    capi.check(lib.fp_fastq_encode(ctx.h, d_text.data_ptr(), d_recs.data_ptr(), d_res.data_ptr(), d_seq.data_ptr(), d_qual.data_ptr(), n, d_out.data_ptr(), total.value,
+                                   C.byref(t2)), lib)
+    assert t2.value == total.value
+    return d_out.cpu().numpy()[:total.value].tobytes()
+
+
+def gpu_fastq_process_host(ctx, text1, text2=None, final=1, phred64=0):
+    """fp_fastq_process_host: text in, filtered text out (host buffers)."""
+    lib = ctx.lib
+    b1 = np.frombuffer(text1, np.uint8).copy() if len(text1) else np.zeros(1, np.uint8)
+    o1 = np.zeros(len(text1) + 64, np.uint8); n1 = C.c_int64(); c1 = C.c_int64(); c2 = C.c_int64(); nu = C.c_int64()
+    i1, i2 = capi.FastqInfo(), capi.FastqInfo()
+    if text2 is not None:
+        b2 = np.frombuffer(text2, np.uint8).copy() if len(text2) else np.zeros(1, np.uint8)
+        o2 = np.zeros(len(text2) + 64, np.uint8); n2 = C.c_int64()
+        capi.check(lib.fp_fastq_process_host(ctx.h, b1.ctypes.data, len(text1), b2.ctypes.data, len(text2), final, phred64,
+                                             o1.ctypes.data, o1.size, C.byref(n1), o2.ctypes.data, o2.size, C.byref(n2),
+                                             C.byref(nu), C.byref(c1), C.byref(c2), C.byref(i1), C.byref(i2)), lib)
+        return {"out1": o1[:n1.value].tobytes(), "out2": o2[:n2.value].tobytes(), "n": nu.value, "consumed": (c1.value, c2.value)}
+    capi.check(lib.fp_fastq_process_host(ctx.h, b1.ctypes.data, len(text1), None, 0, final, phred64,
+                                         o1.ctypes.data, o1.size, C.byref(n1), None, 0, None,
+                                         C.byref(nu), C.byref(c1), None, C.byref(i1), None), lib)
+    return {"out1": o1[:n1.value].tobytes(), "n": nu.value, "consumed": (c1.value,)}

@@ -252,3 +252,110 @@ CONFIG_NAMES = ["default", "cfg2_cut_right_polyg", "cfg3_overlap_correction", "c
                 "all_cuts", "filters", "no_filters", "fasta_adapters", "tid_nonzero", "short_adapter"]
 # option sets for the one-gap overlap passes; run on synthetic profile 2 (reads with single-base indels)
 GAP_CONFIG_NAMES = ["gap_default", "gap_cfg3_overlap_correction", "gap_cfg4_full", "gap_all_cuts", "tight_overlap"]
+
+
+# ---------------- FASTQ text <-> rows ----------------
+def fastq_text(seq, qual, lens, tag, eol="\n", strand="+"):
+    """FASTQ text of one side of a batch (names as the reference's benchmark generator writes them)."""
+    out = []
+    for i in range(seq.shape[0]):
+        n = int(lens[i])
+        out.append(f"@SIM:1:{i} {tag}{eol}{bytes(seq[i, :n]).decode()}{eol}{strand}{eol}{bytes(qual[i, :n]).decode()}{eol}")
+    return "".join(out).encode()
+
+
+def _bind_fastq(lib):
+    if getattr(lib, "_fq_bound", False):
+        return
+    lib.fp_oracle_fastq_decode.restype = C.c_int
+    lib.fp_oracle_fastq_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.POINTER(capi.FastqInfo)]
+    lib.fp_oracle_fastq_encode.restype = C.c_int64
+    lib.fp_oracle_fastq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64]
+    lib._fq_bound = True
+
+
+def info_dict(info):
+    return {k: int(getattr(info, k)) for k, _ in capi.FastqInfo._fields_}
+
+
+def oracle_fastq_decode(text, final=1, phred64=0, stride=160, capacity=None):
+    """CPU oracle (FastqReader::read restated): rows, lens, records, info of one chunk."""
+    lib = oracle(); _bind_fastq(lib)
+    cap = capacity if capacity is not None else text.count(b"@") + 2
+    buf = np.frombuffer(text, np.uint8).copy() if len(text) else np.zeros(1, np.uint8)
+    seq = np.zeros((max(cap, 1), stride), np.uint8); qual = np.zeros((max(cap, 1), stride), np.uint8)
+    ln = np.zeros(max(cap, 1), np.uint16); recs = np.zeros(max(cap, 1), capi.FASTQ_REC_DTYPE)
+    info = capi.FastqInfo()
+    rc = lib.fp_oracle_fastq_decode(buf.ctypes.data, len(text), final, phred64, stride, seq.ctypes.data, qual.ctypes.data, ln.ctypes.data, cap,
+                                    recs.ctypes.data, C.byref(info))
+    assert rc == 0
+    n = int(info.n_records)
+    return {"seq": seq[:n], "qual": qual[:n], "len": ln[:n], "recs": recs[:n], "info": info_dict(info)}
+
+
+def oracle_fastq_encode(text, recs, res, seq, qual, stride):
+    lib = oracle(); _bind_fastq(lib)
+    n = len(recs)
+    buf = np.frombuffer(text, np.uint8).copy() if len(text) else np.zeros(1, np.uint8)
+    recs = np.ascontiguousarray(recs); res = np.ascontiguousarray(res); seq = np.ascontiguousarray(seq); qual = np.ascontiguousarray(qual)
+    total = lib.fp_oracle_fastq_encode(buf.ctypes.data, recs.ctypes.data, res.ctypes.data, seq.ctypes.data, qual.ctypes.data, stride, n, None, 0)
+    out = np.zeros(max(int(total), 1), np.uint8)
+    got = lib.fp_oracle_fastq_encode(buf.ctypes.data, recs.ctypes.data, res.ctypes.data, seq.ctypes.data, qual.ctypes.data, stride, n, out.ctypes.data, int(total))
+    assert got == total
+    return out[:total].tobytes()
+
+
+def ref_fastq_read(path, phred64=0):
+    """The reference's FastqReader over a file: list of (name, seq, strand, qual) byte strings."""
+    lib = ref()
+    lib.fp_ref_fastq_read_file.restype = C.c_int64
+    lib.fp_ref_fastq_read_file.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    cap = os.path.getsize(path) * 2 + 4096
+    out = np.zeros(cap, np.uint8); used = C.c_int64()
+    n = lib.fp_ref_fastq_read_file(str(path).encode(), phred64, out.ctypes.data, cap, C.byref(used))
+    assert used.value <= cap
+    recs, o = [], 0
+    for _ in range(n):
+        h = out[o:o + 16].view(np.int32); o += 16
+        f = []
+        for k in range(4):
+            f.append(out[o:o + int(h[k])].tobytes()); o += int(h[k])
+        recs.append(tuple(f))
+    return recs
+
+
+def decoded_fields(text, d):
+    """(name, seq, strand, qual) tuples of a decode result, for comparison with ref_fastq_read."""
+    out = []
+    for i in range(len(d["recs"])):
+        r = d["recs"][i]; n = int(d["len"][i])
+        out.append((text[int(r["name_off"]):int(r["name_off"]) + int(r["name_len"])], d["seq"][i, :n].tobytes(),
+                    text[int(r["strand_off"]):int(r["strand_off"]) + int(r["strand_len"])], d["qual"][i, :n].tobytes()))
+    return out
+
+
+def fastq_edge_cases():
+    """name -> text: the line / record rules of FastqReader::getLine and ::read, one quirk each."""
+    rec = lambda i, s, q, nm="r", st="+": f"@{nm}{i}\n{s}\n{st}\n{q}\n"        # noqa: E731
+    good = "".join(rec(i, "ACGTN" * (i % 7 + 1), "IIII#" * (i % 7 + 1)) for i in range(40))
+    return {
+        "plain": good.encode(),
+        "crlf": good.replace("\n", "\r\n").encode(),
+        "lone_cr": good.replace("\n", "\r").encode(),
+        "mixed_eol": (rec(0, "ACGT", "IIII") + rec(1, "ACG", "III").replace("\n", "\r\n") + rec(2, "AC", "II").replace("\n", "\r") + rec(3, "A", "I")).encode(),
+        "no_final_newline": good.rstrip("\n").encode(),
+        "blank_lines_between": ("\n\n" + rec(0, "ACGT", "IIII") + "\n" + rec(1, "GG", "##") + "\n\n\n" + rec(2, "TTT", "ABC")).encode(),
+        "junk_before_name": ("garbage line\nmore junk\n" + rec(0, "ACGT", "IIII") + "not a name\n" + rec(1, "GG", "##")).encode(),
+        "quality_starts_with_at": (rec(0, "ACGT", "@III") + rec(1, "GGTT", "@@@@") + rec(2, "AC", "+I")).encode(),
+        "plus_with_name": "".join(rec(i, "ACGTAC", "IIIIII", st=f"+r{i}") for i in range(5)).encode(),
+        "empty_reads": (rec(0, "", "") + rec(1, "ACGT", "IIII") + rec(2, "", "")).encode(),
+        "bad_strand": (rec(0, "ACGT", "IIII") + rec(1, "ACGT", "IIII") + "@r2\nACGT\n-\nIIII\n" + rec(3, "ACGT", "IIII")).encode(),
+        "empty_strand": (rec(0, "ACGT", "IIII") + "@r1\nACGT\n\nIIII\n" + rec(2, "ACGT", "IIII")).encode(),
+        "length_mismatch": (rec(0, "ACGT", "IIII") + "@r1\nACGT\n+\nIII\n" + rec(2, "ACGT", "IIII")).encode(),
+        "truncated_record": (good + "@last\nACGT\n+\n").encode(),
+        "only_newlines": b"\n\n\n",
+        "empty": b"",
+        "long_names": "".join(rec(i, "ACGTACGTAC", "IIIIIIIIII", nm="instrument:run:flowcell:lane:tile:" + "x" * 300 + ":") for i in range(9)).encode(),
+        "name_only_at": "@\nAC\n+\nII\n".encode(),
+    }
