@@ -596,7 +596,7 @@ extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes,
     if (capacity < 0 || (capacity > 0 && (!d_seq || !d_qual || !d_len || !d_recs))) return set_err(FP_E_INVAL, "null row buffers");
     memset(info, 0, sizeof(*info));
     info->error_record = -1;
-    if (nbytes == 0 || capacity == 0) return FP_OK;
+    if (nbytes == 0) return FP_OK;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream[0];
     const int nbb = (int)((nbytes + FQ_BB - 1) / FQ_BB);
@@ -627,20 +627,31 @@ extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes,
     CK(cudaMemcpyAsync(h_info, d_info, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const unsigned int nstarted = h_info[2], ncomplete = h_info[3];
-    if (ncomplete == 0) return FP_OK;
+    /* first byte of line l / first byte after the last complete line (what the sequential reader has consumed by then) */
+    auto line_start = [&](unsigned int l, int64_t* out) -> int {
+        if (l == 0) { *out = 0; return FP_OK; }
+        unsigned int t; CK(cudaMemcpy(&t, d_term + (l - 1), 4, cudaMemcpyDeviceToHost)); *out = (int64_t)t + 1; return FP_OK;
+    };
+    auto lines_end = [&](int64_t* out) -> int {
+        if (nlines > nterm) { *out = nbytes; return FP_OK; }
+        unsigned int t; CK(cudaMemcpy(&t, d_term + (nlines - 1), 4, cudaMemcpyDeviceToHost)); *out = (int64_t)t + 1; return FP_OK;
+    };
     if ((rc = fq_ensure(c->fq_recline, (size_t)(nstarted + 1) * 4))) return rc;
-    fq_fsm_kernel<1><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, nullptr, (const unsigned int*)c->fq_bstate.p, (const unsigned int*)c->fq_brec.p,
-                                           (unsigned int*)c->fq_recline.p, nstarted);
+    unsigned int* d_recline = (unsigned int*)c->fq_recline.p;
+    if (nstarted > 0)
+        fq_fsm_kernel<1><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, nullptr, (const unsigned int*)c->fq_bstate.p, (const unsigned int*)c->fq_brec.p,
+                                               d_recline, nstarted);
     const unsigned int nrec = (unsigned int)std::min<int64_t>(ncomplete, capacity);
-    if (c->stride > 0xFFFF) return set_err(FP_E_INVAL, "stride");
-    if ((rc = fq_ensure(c->fq_recend, (size_t)nrec * 4))) return rc;
     unsigned int first_bad = 0xFFFFFFFFu;
-    CK(cudaMemcpyAsync(d_info + 8, &first_bad, 4, cudaMemcpyHostToDevice, st));
-    fq_scatter_kernel<<<(nrec + FQ_T / 32 - 1) / (FQ_T / 32), FQ_T, 0, st>>>(d_text, nbytes, d_term, (const unsigned int*)c->fq_recline.p, nrec, c->stride, phred64,
-                                                                               d_seq, d_qual, d_len, reinterpret_cast<fq_rec*>(d_recs),
-                                                                               (unsigned int*)c->fq_recend.p, d_info + 8, d_info + 9);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&first_bad, d_info + 8, 4, cudaMemcpyDeviceToHost, st));
+    if (nrec > 0) {
+        if ((rc = fq_ensure(c->fq_recend, (size_t)nrec * 4))) return rc;
+        CK(cudaMemcpyAsync(d_info + 8, &first_bad, 4, cudaMemcpyHostToDevice, st));
+        fq_scatter_kernel<<<(nrec + FQ_T / 32 - 1) / (FQ_T / 32), FQ_T, 0, st>>>(d_text, nbytes, d_term, d_recline, nrec, c->stride, phred64,
+                                                                                   d_seq, d_qual, d_len, reinterpret_cast<fq_rec*>(d_recs),
+                                                                                   (unsigned int*)c->fq_recend.p, d_info + 8, d_info + 9);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&first_bad, d_info + 8, 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     unsigned int keep = nrec;
     if (first_bad != 0xFFFFFFFFu) {
@@ -649,11 +660,16 @@ extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes,
         info->error = (int32_t)((br.name_len >> 28) & 7u);
         info->error_record = first_bad;
         keep = first_bad;                                         /* the reference reader stops here: fastqreader.cpp:349-364 */
-    }
+        info->consumed = nbytes;                                  /* nothing after a bad record is read */
+    } else if (ncomplete > nrec) {                                /* capacity reached: the next record's name line is where to resume */
+        info->more = 1;
+        unsigned int l; CK(cudaMemcpy(&l, d_recline + nrec, 4, cudaMemcpyDeviceToHost));
+        if ((rc = line_start(l, &info->consumed))) return rc;
+    } else if (nstarted > ncomplete) {                            /* the last record is not complete in this chunk: resume at its name line */
+        unsigned int l; CK(cudaMemcpy(&l, d_recline + ncomplete, 4, cudaMemcpyDeviceToHost));
+        if ((rc = line_start(l, &info->consumed))) return rc;
+    } else if ((rc = lines_end(&info->consumed))) return rc;      /* every complete line was a record line or skipped */
     info->n_records = keep;
-    info->more = (first_bad == 0xFFFFFFFFu && ncomplete > nrec) ? 1 : 0;
-    if (first_bad != 0xFFFFFFFFu) info->consumed = nbytes;         /* nothing after a bad record is read */
-    else if (keep > 0) { unsigned int e; CK(cudaMemcpy(&e, (unsigned int*)c->fq_recend.p + (keep - 1), 4, cudaMemcpyDeviceToHost)); info->consumed = e; }
     return FP_OK;
 }
 
