@@ -216,6 +216,139 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+
+def fastq_text_np(np, seq, qual, lens, tag):
+    """FASTQ text of one side as a uint8 array, vectorised (names @SIM:1:<9 digits> <tag>, '+' strand lines)."""
+    n, S = seq.shape
+    lens = lens.astype(np.int64)
+    name = np.frombuffer(("@SIM:1:000000000 " + tag + "\n").encode(), np.uint8)
+    nl = name.size
+    rec = nl + 2 * lens + 4                                   # name\n seq\n +\n qual\n  (name already holds its \n)
+    off = np.concatenate([[0], np.cumsum(rec)[:-1]])
+    out = np.zeros(int(rec.sum()), np.uint8)
+    idx = np.arange(n)
+    for k in range(nl):
+        out[off + k] = name[k]
+    for d in range(9):                                        # decimal digits of the index, most significant first
+        out[off + 7 + d] = 48 + (idx // 10 ** (8 - d)) % 10
+    col = np.arange(S)[None, :]
+    m = col < lens[:, None]
+    rows = np.nonzero(m)
+    out[(off + nl)[rows[0]] + rows[1]] = seq[m]
+    out[off + nl + lens] = 10
+    out[off + nl + lens + 1] = 43
+    out[off + nl + lens + 2] = 10
+    out[(off + nl + lens + 3)[rows[0]] + rows[1]] = qual[m]
+    out[off + nl + 2 * lens + 3] = 10
+    return out
+
+
+def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
+    """Text in -> text out through fp_fastq_process_host (pinned host buffers; H2D of the raw text, device parse, operator chain,
+    device encode, D2H of the output text inside the timed region), the two codec kernels' own throughput on HBM-resident text,
+    and the unmodified reference CLI on the same files with all host threads."""
+    import numpy as np
+    nf = args.fastq_units
+    gen = min(nf, 250_000)                                    # the text of `gen` units is tiled up to nf
+    hctx = C.c_void_p()
+    capi.check(lib.fp_ctx_create(C.byref(params), torch.cuda.current_device(), nf, STRIDE, STRIDE, C.byref(hctx)), lib)
+    t = {k: torch.empty(gen * (2 if k.startswith("len") else STRIDE), dtype=torch.uint8, device=dev)
+         for k in (["seq1", "qual1", "len1"] + (["seq2", "qual2", "len2"] if paired else []))}
+    b = capi.Batch(); b.n, b.stride = gen, STRIDE
+    for k, v in t.items():
+        setattr(b, k, v.data_ptr())
+    capi.check(lib.fp_synth_fill(hctx, C.byref(b), 0, SEED, args.profile, READ_LEN, None), lib)
+    torch.cuda.synchronize()
+    reps = max(1, nf // gen)
+    nf = gen * reps
+    texts = []
+    for side in ("1", "2")[: 2 if paired else 1]:
+        seq = t["seq" + side].cpu().numpy().reshape(gen, STRIDE); qual = t["qual" + side].cpu().numpy().reshape(gen, STRIDE)
+        lens = t["len" + side].cpu().numpy().view(np.uint16)
+        one = fastq_text_np(np, seq, qual, lens, side + ":N:0")
+        texts.append(np.tile(one, reps))
+    del t
+    pin = [torch.from_numpy(x).pin_memory() for x in texts]
+    outs = [torch.empty(x.numel() + 64, dtype=torch.uint8).pin_memory() for x in pin]
+    ob = [C.c_int64(), C.c_int64()]; nu = C.c_int64(); c1 = C.c_int64(); c2 = C.c_int64()
+    i1, i2 = capi.FastqInfo(), capi.FastqInfo()
+
+    def call():
+        capi.check(lib.fp_fastq_process_host(hctx, pin[0].data_ptr(), pin[0].numel(), pin[1].data_ptr() if paired else None, pin[1].numel() if paired else 0, 1, 0,
+                                             outs[0].data_ptr(), outs[0].numel(), C.byref(ob[0]),
+                                             outs[1].data_ptr() if paired else None, outs[1].numel() if paired else 0, C.byref(ob[1]) if paired else None,
+                                             C.byref(nu), C.byref(c1), C.byref(c2) if paired else None, C.byref(i1), C.byref(i2) if paired else None), lib)
+    for _ in range(2):
+        call()
+    assert nu.value == nf, (nu.value, nf)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call()
+    dt = (time.perf_counter() - t0) / args.steps
+    in_bytes = sum(int(x.numel()) for x in pin); out_bytes = ob[0].value + (ob[1].value if paired else 0)
+    res = {"value": nf / dt, "unit": unit, "units_per_step": nf, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+           "text_GBps_in": in_bytes / dt / 1e9, "api": "fp_fastq_process_host",
+           "note": "plain FASTQ text in pinned host memory -> H2D -> device decode (FastqReader::read) -> operator chain -> device encode "
+                   "(Read::appendToString) -> D2H of the output text"}
+    # codec kernels alone, text and rows resident in HBM
+    d_text = pin[0].to(dev)
+    d_seq = torch.empty(nf * STRIDE + 64, dtype=torch.uint8, device=dev); d_qual = torch.empty_like(d_seq)
+    d_len = torch.empty(nf * 2, dtype=torch.uint8, device=dev); d_recs = torch.empty(nf * 16, dtype=torch.uint8, device=dev)
+    info = capi.FastqInfo()
+
+    def dec():
+        capi.check(lib.fp_fastq_decode(hctx, d_text.data_ptr(), d_text.numel(), 1, 0, d_seq.data_ptr(), d_qual.data_ptr(), d_len.data_ptr(), nf,
+                                       d_recs.data_ptr(), C.byref(info)), lib)
+    dec(); dec()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec()
+    torch.cuda.synchronize(); td = (time.perf_counter() - t0) / args.steps
+    d_res = torch.zeros(nf * 16, dtype=torch.uint8, device=dev)
+    d_res.view(torch.int16).view(nf, 8)[:, 1] = d_len.view(torch.int16)          # front 0, len = read length, verdicts PASS
+    d_out = torch.empty(d_text.numel() + 64, dtype=torch.uint8, device=dev); tot = C.c_int64()
+
+    def enc():
+        capi.check(lib.fp_fastq_encode(hctx, d_text.data_ptr(), d_recs.data_ptr(), d_res.data_ptr(), d_seq.data_ptr(), d_qual.data_ptr(), nf,
+                                       d_out.data_ptr(), d_out.numel(), C.byref(tot)), lib)
+    enc(); enc()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc()
+    torch.cuda.synchronize(); te = (time.perf_counter() - t0) / args.steps
+    assert tot.value == d_text.numel(), (tot.value, d_text.numel())        # untouched reads re-encode to the input text
+    tb = int(d_text.numel())
+    res["decode"] = {"ms": td * 1e3, "text_GBps": tb / td / 1e9, "algorithmic_bytes": tb + 2 * nf * READ_LEN,
+                     "achieved_GBps": (tb + 2 * nf * READ_LEN) / td / 1e9, "note": "one side; synchronous call incl. its host round trips"}
+    res["encode"] = {"ms": te * 1e3, "text_GBps": tb / te / 1e9, "achieved_GBps": (tb + 2 * nf * READ_LEN) / te / 1e9}
+    lib.fp_ctx_destroy(hctx)
+    # the unmodified reference CLI on the same text (plain files in a temp dir), all host threads, no output files
+    cli = os.path.join(ROOT, "oracle", "_ref", "fastp_ref")
+    if os.path.exists(cli) and not args.no_cpu_baseline:
+        import subprocess
+        import tempfile
+        try:
+            with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+                names = []
+                for k, x in enumerate(texts):
+                    fn = os.path.join(d, f"r{k + 1}.fq"); x.tofile(fn); names.append(fn)
+                flags = {"pe150_overlap_correction": ["-c"], "pe150_full": ["--cut_right", "-g", "-x", "-c", "-a", "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA",
+                                                                           "--adapter_sequence_r2", "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"],
+                         "se150_cut_right_polyg": ["--cut_right", "-g", "-A"]}[args.workload]
+                thr = min(os.cpu_count() or 1, 16)
+                cmd = [cli, "-i", names[0], "-w", str(thr), "--dont_eval_duplication", "-j", os.path.join(d, "x.json"), "-h", os.path.join(d, "x.html")] + flags
+                if paired:
+                    cmd += ["-I", names[1]]
+                t0 = time.perf_counter()
+                subprocess.run(cmd, check=True, capture_output=True, cwd=d, timeout=600)
+                tc = time.perf_counter() - t0
+            res["cpu_cli"] = {"value": nf / tc, "unit": unit, "threads": thr, "seconds": tc,
+                              "sample": f"{nf} units, unmodified reference CLI (oracle/_ref/fastp_ref, plain FASTQ in a RAM-backed dir, no output files, -w {thr})"}
+        except Exception as e:
+            res["cpu_cli"] = {"value": None, "sample": repr(e)}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,6 +362,8 @@ def main():
     ap.add_argument("--profile", type=int, default=1, help="synthetic profile: 1 = enriched fragment model, 0 = ref-style")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fastq-units", type=int, default=1_000_000,
+                    help="units of the text-in/text-out measurement (device FASTQ decode + chain + encode); 0 = skip")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -419,6 +554,11 @@ def main():
     lib.fp_ctx_destroy(h)
     del t, out1, out2, ov
     torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and args.fastq_units > 0:
+        try:
+            line["fastq_path"] = fastq_path(args, torch, capi, lib, params, paired, dev, unit)
+        except Exception as e:   # an extra object: never a reason to lose the main line
+            line["fastq_path"] = {"value": None, "error": repr(e)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -27,6 +27,8 @@ int main(int argc, char** argv) {
     Options opt;
     std::string in1, in2, out1, out2, json;
     int packSize = 1 << 16, maxLen = 0;
+    bool deviceFastq = false, phred64 = false;
+    size_t chunkBytes = 0;                 /* text path: bytes read per side per step (default: about one device batch) */
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -56,6 +58,8 @@ int main(int argc, char** argv) {
         else if (a == "-c" || a == "--correction") opt.correction.enabled = true;
         else if (a == "--overlap_len_require") opt.overlapRequire = atoi(next()); else if (a == "--overlap_diff_limit") opt.overlapDiffLimit = atoi(next());
         else if (a == "--overlap_diff_percent_limit") opt.overlapDiffPercentLimit = atoi(next());
+        else if (a == "--device_fastq") deviceFastq = true; else if (a == "-6" || a == "--phred64") phred64 = true;
+        else if (a == "--chunk_bytes") chunkBytes = (size_t)atoll(next());
         else if (a == "--max_read_len") maxLen = atoi(next()); else if (a == "--pack_size") packSize = atoi(next());
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -69,11 +73,41 @@ int main(int argc, char** argv) {
         while (n < 4000 && std::getline(peek, l)) { if (n % 4 == 1) maxLen = std::max(maxLen, (int)l.size()); n++; }
         maxLen += 64;
     }
+    if (chunkBytes == 0) chunkBytes = (size_t)packSize * (size_t)(2 * maxLen + 64);
     GpuChainWorker worker(&opt, maxLen, 0, packSize);
     if (!worker.ok()) { fprintf(stderr, "fastp_gpu_cli: %s\n", worker.error().c_str()); return 1; }
     std::ofstream o1, o2;
     if (!out1.empty()) o1.open(out1);
     if (!out2.empty()) o2.open(out2);
+    if (deviceFastq) {
+        /* text path: raw file chunks go to the device, which parses, filters and re-encodes them (fp_fastq_process_host);
+           whatever a chunk's last, incomplete record (or the longer side of a pair) leaves over is carried into the next chunk */
+        std::string buf1, buf2;
+        bool eof1 = false, eof2 = !opt.paired;
+        auto fill = [&](std::ifstream& f, std::string& buf, bool& eof) {
+            if (eof) return;
+            const size_t old = buf.size();
+            buf.resize(old + chunkBytes);
+            f.read(&buf[old], (std::streamsize)chunkBytes);
+            const size_t got = (size_t)f.gcount();
+            buf.resize(old + got);
+            if (got < chunkBytes) eof = true;
+        };
+        for (;;) {
+            fill(f1, buf1, eof1);
+            if (opt.paired) fill(f2, buf2, eof2);
+            const bool final = eof1 && eof2;
+            std::string s1, s2; size_t c1 = 0, c2 = 0; long units = 0;
+            if (!worker.processFastqText(buf1.data(), buf1.size(), buf2.data(), buf2.size(), final, phred64, &s1, &s2, &c1, &c2, &units)) {
+                fprintf(stderr, "fastp_gpu_cli: %s\n", worker.error().c_str()); return 1;
+            }
+            if (o1.is_open()) o1 << s1;
+            if (o2.is_open()) o2 << s2;
+            buf1.erase(0, c1); if (opt.paired) buf2.erase(0, c2);
+            if (final && (units == 0 || (buf1.empty() && buf2.empty()))) break;
+            if (final && c1 == 0 && c2 == 0) break;
+        }
+    } else
     for (;;) {
         ReadPack* lp = new ReadPack{new Read*[packSize], 0};
         ReadPack* rp = opt.paired ? new ReadPack{new Read*[packSize], 0} : nullptr;

@@ -90,6 +90,12 @@ public:
     bool processSingleEnd(ReadPack* pack, std::string* outstr, std::string* failedOut = nullptr);
     bool processPairEnd(ReadPack* leftPack, ReadPack* rightPack, std::string* outstr1, std::string* outstr2, std::string* failedOut = nullptr);
 
+    /* Text path (device FASTQ codec): one chunk of plain FASTQ text per side in, the passing reads' text out.
+     * Replaces the reader's parse (FastqReader::read), the body above and Read::appendToString in one call; `consumed*` says how many
+     * bytes of each chunk were used -- the caller prepends the rest to its next chunk.  `final`: no more input follows.        */
+    bool processFastqText(const char* text1, size_t n1, const char* text2, size_t n2, bool final, bool phred64,
+                          std::string* outstr1, std::string* outstr2, size_t* consumed1, size_t* consumed2, long* units);
+
     /* end of run: what Stats::merge / FilterResult::merge hand to the reporters (src/peprocessor.cpp:217-234) */
     bool finish(Stats* pre1, Stats* post1, Stats* pre2, Stats* post2, FilterResult* fr, std::vector<long>* insertSizeHist);
 
@@ -106,6 +112,7 @@ private:
     uint16_t* mLen[2] = {nullptr, nullptr};
     fp_read_result* mRes[2] = {nullptr, nullptr};
     fp_ov_result* mOv = nullptr;
+    std::vector<uint8_t> mTextOut[2];
     std::string mError;
 };
 

@@ -161,6 +161,28 @@ bool GpuChainWorker::processPairEnd(ReadPack* leftPack, ReadPack* rightPack, std
     return true;
 }
 
+bool GpuChainWorker::processFastqText(const char* text1, size_t n1, const char* text2, size_t n2, bool final, bool phred64,
+                                      std::string* outstr1, std::string* outstr2, size_t* consumed1, size_t* consumed2, long* units) {
+    const bool paired = mParams.paired != 0;
+    int64_t ob1 = 0, ob2 = 0, nu = 0, c1 = 0, c2 = 0;
+    fp_fastq_info i1, i2;
+    mTextOut[0].resize(n1 + 64);
+    if (paired) mTextOut[1].resize(n2 + 64);
+    const int rc = fp_fastq_process_host(mCtx, reinterpret_cast<const uint8_t*>(text1), (int64_t)n1, paired ? reinterpret_cast<const uint8_t*>(text2) : nullptr,
+                                         paired ? (int64_t)n2 : 0, final ? 1 : 0, phred64 ? 1 : 0,
+                                         mTextOut[0].data(), (int64_t)mTextOut[0].size(), &ob1,
+                                         paired ? mTextOut[1].data() : nullptr, paired ? (int64_t)mTextOut[1].size() : 0, paired ? &ob2 : nullptr,
+                                         &nu, &c1, paired ? &c2 : nullptr, &i1, paired ? &i2 : nullptr);
+    if (rc != FP_OK) { mError = fp_last_error(); return false; }
+    if (i1.error == FP_FQ_ERR_STRIDE || (paired && i2.error == FP_FQ_ERR_STRIDE)) { mError = "a read is longer than the row stride (raise --max_read_len)"; return false; }
+    if (outstr1) outstr1->append(reinterpret_cast<const char*>(mTextOut[0].data()), (size_t)ob1);
+    if (paired && outstr2) outstr2->append(reinterpret_cast<const char*>(mTextOut[1].data()), (size_t)ob2);
+    if (consumed1) *consumed1 = (size_t)c1;
+    if (consumed2) *consumed2 = (size_t)c2;
+    if (units) *units = (long)nu;
+    return true;
+}
+
 bool GpuChainWorker::finish(Stats* pre1, Stats* post1, Stats* pre2, Stats* post2, FilterResult* fr, std::vector<long>* isize) {
     if (!mCtx) return false;
     fp_counter_layout L;

@@ -8,7 +8,7 @@ U=${U:-8000000}
 python bench.py --units $U --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err
 python -c "
 import json;d=json.load(open('gpurun_out/bench_iter.json'))
-print('VALUE %.1f M/s  kernel_ms %.2f  frac %.4f  e2e %.1f M/s' % (d['value']/1e6, d['roofline']['kernel_ms'], d['roofline']['frac'], d.get('e2e',{}).get('value',0)/1e6), d['checks'], d['clocks'])"
+print('VALUE %.1f M/s  kernel_ms %.2f  frac %.4f  e2e %.1f M/s' % (d['value']/1e6, d['roofline']['kernel_ms'], d['roofline']['frac'], d.get('e2e',{}).get('value',0)/1e6), d['checks'], d['clocks']); print('FASTQ', json.dumps(d.get('fastq_path')))"
 tail -3 gpurun_out/bench_iter.err
 if [ -n "$NCU" ]; then
   ncu --set full --clock-control none --import-source on -k regex:fp_chain -s 1 -c 1 -o gpurun_out/prof_iter \

@@ -86,3 +86,29 @@ def test_synthetic_full_chain_output_reads(cli, tmp_path, paired):
     assert js["adapter_cutting"]["adapter_trimmed_bases"] == c.filter[capi.FR_ADAPTER_BASES]
     posts = (capi.STATS_POST1, capi.STATS_POST2) if paired else (capi.STATS_POST1,)
     assert js["after_filtering"]["total_bases"] == sum(c.summary(s)["bases"] for s in posts)
+
+
+@pytest.mark.parametrize("chunk", [0, 70001])
+@pytest.mark.parametrize("paired", [1, 0])
+def test_device_fastq_text_path_equals_object_path(cli, tmp_path, paired, chunk):
+    """--device_fastq (raw file chunks -> device parse / filter / encode) writes the same files and summary as the object path;
+    a small odd chunk size puts chunk borders inside records, names and between the sides of a pair."""
+    n = 20000
+    _, arrs = T.synth_host(n, 160, paired, 0, 78, 1, 150)
+    write_fastq(tmp_path / "r1.fq", arrs["seq1"], arrs["qual1"], arrs["len1"])
+    base = ["-i", str(tmp_path / "r1.fq"), "--cut_right", "-g", "-x", "-a", T.TRUSEQ_R1, "--pack_size", "4096", "--max_read_len", "150"]
+    if paired:
+        write_fastq(tmp_path / "r2.fq", arrs["seq2"], arrs["qual2"], arrs["len2"])
+        base += ["-I", str(tmp_path / "r2.fq"), "-c", "--adapter_sequence_r2", T.TRUSEQ_R2]
+    outs = {}
+    for mode in ("obj", "text"):
+        cmd = [cli] + base + ["-o", str(tmp_path / f"{mode}1.fq"), "-j", str(tmp_path / f"{mode}.json")]
+        if paired:
+            cmd += ["-O", str(tmp_path / f"{mode}2.fq")]
+        if mode == "text":
+            cmd += ["--device_fastq"] + (["--chunk_bytes", str(chunk)] if chunk else [])
+        subprocess.run(cmd, check=True, timeout=600)
+        outs[mode] = [(tmp_path / f"{mode}{k}.fq").read_bytes() for k in ((1, 2) if paired else (1,))]
+    assert outs["text"] == outs["obj"]
+    assert len(outs["text"][0]) > 1000000
+    assert json.load(open(tmp_path / "text.json")) == json.load(open(tmp_path / "obj.json"))
