@@ -58,7 +58,7 @@ __device__ __forceinline__ int group_pick(int v, bool mine, int g) {
 /* ------------------------------------------------------------------------------------------------
  * Filter::trimAndCut  (filter.cpp:68-207), scalar per thread.  Returns false for NULL.
  * ------------------------------------------------------------------------------------------------ */
-__device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut) {
+__device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut, int sub, int g) {
     FP_SMEM(seq);    FP_SMEM(qualu);
     frontOut = 0; lenOut = l0;
     const bool anycut = c_p.cut_front || c_p.cut_tail || c_p.cut_right;
@@ -91,6 +91,27 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
         int total = 0;
         for (int i = 0; i < w - 1; i++) total += q[s + i];
         bool found = false;
+        if (w == 4) {
+            /* window of 4 = one 32-bit field: the group's lanes take consecutive aligned words (4 window starts each), the window sum is
+               one dp4a; rounds advance together so the group-min picks the first start in the reference's order */
+            const int smax = l - tail - w;                                /* window starts s in [front, smax) */
+            int best = 1 << 20;
+            for (int wb = (front >> 2) + sub; (wb - sub) * 4 < smax && best == (1 << 20); wb += g) {
+                const int b0 = wb * 4;
+                int mine = 1 << 20;
+                if (b0 < smax) {
+                    const uint32_t W0 = *reinterpret_cast<const uint32_t*>(qualu + b0), W1 = *reinterpret_cast<const uint32_t*>(qualu + b0 + 4);
+                    #pragma unroll
+                    for (int k = 3; k >= 0; k--) {
+                        const int sk = b0 + k;
+                        const int tot = __dp4a((int)__funnelshift_r(W0, W1, 8 * k), 0x01010101, 0);       /* signed chars, like the reference's char sum */
+                        if (sk >= front && sk < smax && tot < c_p.cr_thr) mine = sk;
+                    }
+                }
+                best = group_min(mine, g);
+            }
+            if (best < (1 << 20)) { found = true; s = best; }
+        } else
         for (s = front; s + w < l - tail; s++) {
             total += q[s + w - 1];
             if (s > front) total -= q[s - 1];
@@ -585,7 +606,7 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
             const uint32_t* alo = c_p.adapter_planes + aidx * 24; const uint32_t* ahi = alo + 8; const uint32_t* ann = alo + 16;
             const uint32_t *plo = r.pl, *phi = r.pl + PW, *pnn = r.pl + 2 * PW;
             const int nw = (alen + 31) >> 5;
-            for (int p = sub; p < npos; p += g) {
+            auto full_check = [&](int p) -> bool {                         /* exact count over the whole compared length */
                 const int cmplen = min(rlen - p, alen);
                 int mm = 0;
                 for (int k = 0; k < nw && 32 * k < cmplen; k++) {
@@ -593,8 +614,35 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
                     const uint32_t x = (tp_bits(plo, bit) ^ __ldg(alo + k)) | (tp_bits(phi, bit) ^ __ldg(ahi + k)) | (tp_bits(pnn, bit) ^ __ldg(ann + k));
                     mm += __popc(x & low_mask(cmplen - 32 * k));
                 }
-                if (mm <= cmplen / 8) { my_p = p; break; }
+                return mm <= cmplen / 8;
+            };
+            /* main range: the first min(alen,32) adapter bases lie inside the read, so their mismatch count alone (one sliding 32-bit
+               field per plane, constant mask) already exceeds the largest allowance alen/8 for almost every position */
+            const int a0 = min(alen, 32);
+            const int pmain = min(npos, rlen - a0 + 1);
+            const uint32_t M0 = low_mask(a0), A_lo = __ldg(alo), A_hi = __ldg(ahi), A_nn = __ldg(ann);
+            const int amax = alen / 8;
+            const int lg = g == 4 ? 2 : (g == 2 ? 1 : 0);
+            int p = sub;
+            while (p < pmain && my_p == (1 << 20)) {
+                const int c = r.front + p;
+                const int w = c >> 5;
+                const uint32_t L0 = plo[w], L1 = plo[w + 1], H0 = phi[w], H1 = phi[w + 1], N0 = pnn[w], N1 = pnn[w + 1];
+                int sh = c & 31;
+                int cnt = min((pmain - p + g - 1) >> lg, (32 - sh + g - 1) >> lg);
+                while (cnt > 0) {
+                    #pragma unroll 2
+                    for (; cnt > 0; cnt--, sh += g, p += g) {
+                        const uint32_t x0 = ((__funnelshift_r(L0, L1, sh) ^ A_lo) | (__funnelshift_r(H0, H1, sh) ^ A_hi) | (__funnelshift_r(N0, N1, sh) ^ A_nn)) & M0;
+                        if (__popc(x0) <= amax) break;
+                    }
+                    if (cnt <= 0) break;
+                    if (full_check(p)) { my_p = p; break; }
+                    cnt--; sh += g; p += g;
+                }
             }
+            for (; p < npos && my_p == (1 << 20); p += g)                  /* tail: the adapter runs past the read end */
+                if (full_check(p)) { my_p = p; break; }
         } else {
             for (int p = sub; p < npos; p += g) {
                 const int cmplen = min(rlen - p, alen), allowed = cmplen / 8;
@@ -1065,7 +1113,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 int flags = 0, apos = 0, abases = 0, pbase = 255, plen = 0, result = FP_FAIL_LENGTH;
                 bool counted = false;
                 if (active) {
-                    r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len);   /* :235 */
+                    r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :235 */
                     if (!r1.null && c_p.polyg) { const int nl = t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
                     bool dimer = false;
                     if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
@@ -1113,8 +1161,8 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 fp_ov_result ovA = ov;                    /* ovForAdapter */
                 bool both = false, need_correct = false;
                 if (active) {
-                    r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len);   /* :425-426 */
-                    r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len);
+                    r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :425-426 */
+                    r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len, sub, GL);
                     both = !r1.null && !r2.null;
                     if (both && c_p.polyg) {                                                      /* :428-431 */
                         int nl = t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; }
