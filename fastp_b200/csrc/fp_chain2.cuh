@@ -581,6 +581,16 @@ __device__ __forceinline__ int t_gap_scan(const uint8_t* ins, const uint8_t* nor
     return best;
 }
 
+/* can the one-gap scan over lengths <= cmax accept anything?  D1 / D2: aligned / shifted mismatch bits (bit j = position j) */
+__device__ __forceinline__ bool gap_may_hit(unsigned long long D1, unsigned long long D2, int cmax) {
+    if (cmax < 8) return false;                                           /* c/8 - 1 < 0 for every c < 8 */
+    const uint32_t d1 = (uint32_t)D1 & 0xFFu, d2 = (uint32_t)D2 & 0xFFu;
+    int v = 8;
+    #pragma unroll
+    for (int i = 0; i <= 8; i++) v = min(v, __popc(d1 & ((1u << i) - 1u)) + __popc(d2 & ~((1u << i) - 1u)));
+    return v <= cmax / 8 - 1;
+}
+
 __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, int alen, int matchReq, int aidx, int PW,
                                                 int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
     FP_SMEM(r.seq);    FP_SMEM(r.pl);    FP_SMEM(bc);
@@ -592,11 +602,24 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
     bool found = false;
     int pos = 0;
     const bool planes = r.clean && c_p.adapter_clean[aidx];
+    /* 64-bit plane fields of the read start and of the adapter (adapters up to 64 bases): the negative starts of scan 1 and the
+       quick rejects of scans 2 / 3 are popcounts on them */
+    const bool planes64 = planes && alen <= 64;
+    unsigned long long R_lo = 0, R_hi = 0, R_nn = 0, A_lo = 0, A_hi = 0, A_nn = 0;
+    if (planes64) {
+        const uint32_t* ap = c_p.adapter_planes + aidx * 24;
+        A_lo = (unsigned long long)__ldg(ap) | ((unsigned long long)__ldg(ap + 1) << 32);
+        A_hi = (unsigned long long)__ldg(ap + 8) | ((unsigned long long)__ldg(ap + 9) << 32);
+        A_nn = (unsigned long long)__ldg(ap + 16) | ((unsigned long long)__ldg(ap + 17) << 32);
+        const unsigned long long live = mask64(rlen);
+        R_lo = tp_bits64(r.pl, r.front) & live; R_hi = tp_bits64(r.pl + PW, r.front) & live; R_nn = tp_bits64(r.pl + 2 * PW, r.front) & live;
+    }
     /* scan 1 (:87-100) */
     for (int p = start; p < 0 && p < rlen - matchReq && !found; p++) {
         const int cmplen = min(rlen - p, alen), so = -p, n = cmplen - so;
         int mm = 0;
-        for (int k = 0; k < n; k++) mm += (adata[so + k] != rdata[k]);
+        if (planes64) mm = __popcll(((R_lo ^ (A_lo >> so)) | (R_hi ^ (A_hi >> so)) | (R_nn ^ (A_nn >> so))) & mask64(n));
+        else for (int k = 0; k < n; k++) mm += (adata[so + k] != rdata[k]);
         if (mm <= cmplen / 8) { found = true; pos = p; }
     }
     if (!found) {
@@ -654,14 +677,22 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
         const int best = group_min(my_p, g);
         if (best < (1 << 20)) { found = true; pos = best; }
     }
+    /* Scans 2 / 3 accept a length c only if some split i has (aligned mismatches before i) + (shifted mismatches from i to c)
+       <= c/8 - 1, which is negative below c = 8 and at most cmax/8 - 1 overall; the same quantity restricted to the first 8
+       positions is a lower bound for every c >= 8, so when even that exceeds the largest allowance the scan cannot hit. */
+    const unsigned long long D1 = (R_lo ^ A_lo) | (R_hi ^ A_hi) | (R_nn ^ A_nn);                                  /* read[j] != adapter[j] */
     if (!found && rlen - matchReq - 1 > 0) {                              /* scan 2 (:105-118) */
         const int cmax = min(rlen - 1, alen);
-        const int c = t_gap_scan(rdata, adata, cmax, matchReq + 1);
+        bool may = true;
+        if (planes64) may = gap_may_hit(D1, ((R_lo >> 1) ^ A_lo) | ((R_hi >> 1) ^ A_hi) | ((R_nn >> 1) ^ A_nn), cmax);   /* read[j+1] != adapter[j] */
+        const int c = may ? t_gap_scan(rdata, adata, cmax, matchReq + 1) : -1;
         if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - 1 - c; }
     }
     if (!found && rlen - matchReq > 0) {                                  /* scan 3 (:122-135) */
         const int cmax = min(rlen, alen - 1);
-        const int c = t_gap_scan(adata, rdata, cmax, matchReq + 1);
+        bool may = true;
+        if (planes64) may = gap_may_hit(D1, ((A_lo >> 1) ^ R_lo) | ((A_hi >> 1) ^ R_hi) | ((A_nn >> 1) ^ R_nn), cmax);   /* adapter[j+1] != read[j] */
+        const int c = may ? t_gap_scan(adata, rdata, cmax, matchReq + 1) : -1;
         if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - c; }
     }
     if (found) {                                                          /* :137-154 */
