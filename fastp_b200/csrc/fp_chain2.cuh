@@ -20,9 +20,6 @@
 __device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
 /* += 1 iff a > B */
 #define smem_inc_gt(addr, a, B) asm volatile("{ .reg .pred p; setp.gt.s32 p, %1, %2; @p red.shared.add.u32 [%0], 1; }" :: "r"(addr), "r"(a), "r"(B) : "memory")
-__device__ __forceinline__ void smem_inc_if(uint32_t addr, uint32_t cond) {
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" :: "r"(addr), "r"(cond) : "memory");
-}
 
 struct TRead {
     uint8_t* seq;          /* row start in the shared-memory tile */
@@ -772,22 +769,6 @@ __device__ __forceinline__ fp_read_result t_make_result(const TRead& r, int verd
     return o;
 }
 
-/* warp-cooperative execution of per-lane statistics requests: every lane may ask for the contribution of positions
- * [lo,hi) of one row (context start ctx0, sign +-1); the warp serves the requests one lane at a time. */
-__device__ __forceinline__ void warp_serve_delta(bool want, bool clean, const DeltaAcc& D, unsigned long long* G, int side,
-                                                 const uint8_t* seq, const uint8_t* qual, int ctx0, int lo, int hi, int sign) {
-    unsigned m = __ballot_sync(FULL_MASK, want && hi > lo);
-    while (m) {
-        const int l = __ffs(m) - 1;
-        m &= m - 1;
-        const bool cl = __shfl_sync(FULL_MASK, (int)clean, l) != 0;
-        const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)seq, l));
-        const uint8_t* ql = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)qual, l));
-        const int c0 = __shfl_sync(FULL_MASK, ctx0, l), a = __shfl_sync(FULL_MASK, lo, l), b = __shfl_sync(FULL_MASK, hi, l), sg = __shfl_sync(FULL_MASK, sign, l);
-        if (cl) dev_stat_positions_smem(D, side, sq, ql, c0, a, b, sg);
-        else dev_stat_positions(G, side * 2 + 1, sq, ql, c0, a, b, sg);
-    }
-}
 /* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
 struct ColAcc2 { unsigned int v[2][NB][4]; };
 
@@ -980,7 +961,6 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
     const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_CT */
     const int nsplit = FP_CT / ncols;             /* row groups are dealt round-robin to nsplit threads per column */
     const bool col_active = tid < ncols * nsplit;
-    const int ndense_warps = (ncols * nsplit + 31) >> 5;
     const int my_part = col_active ? tid / ncols : 0, my_col = col_active ? tid % ncols : 0;
     const int my_side = my_col / HPR, my_hc = my_col % HPR;
     const int my_w = my_hc >> 1, my_half = my_hc & 1;
