@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -81,7 +83,9 @@ struct fp_ctx {
     /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
-    Buf fqh_text[2], fqh_seq[2], fqh_qual[2], fqh_len[2], fqh_recs[2], fqh_res[2], fqh_ov, fqh_out[2];
+    Buf fqh_text[2], fqh_seq[2], fqh_qual[2], fqh_len[2], fqh_recs[2], fqh_res[2], fqh_ov, fqh_out[2], fqh_outbuf[2][2], fqh_recend[2];
+    cudaStream_t fq_stream_out = nullptr;
+    cudaEvent_t fq_ev_up = nullptr, fq_ev_out[2] = {nullptr, nullptr};
     /* kernel timing */
     std::vector<EvPair> evs;
     std::vector<EvPair> ev_pool;
@@ -348,7 +352,9 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     {
         fp_ctx::Buf* all[] = {&c->fq_term, &c->fq_bcnt, &c->fq_agg, &c->fq_bstate, &c->fq_brec, &c->fq_recline, &c->fq_recend, &c->fq_info, &c->fq_bsum,
                               &c->fqh_text[0], &c->fqh_text[1], &c->fqh_seq[0], &c->fqh_seq[1], &c->fqh_qual[0], &c->fqh_qual[1], &c->fqh_len[0], &c->fqh_len[1],
-                              &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1]};
+                              &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1],
+                              &c->fqh_outbuf[0][0], &c->fqh_outbuf[0][1], &c->fqh_outbuf[1][0], &c->fqh_outbuf[1][1], &c->fqh_recend[0], &c->fqh_recend[1]};
+        if (c->fq_stream_out) { cudaStreamDestroy(c->fq_stream_out); cudaEventDestroy(c->fq_ev_up); cudaEventDestroy(c->fq_ev_out[0]); cudaEventDestroy(c->fq_ev_out[1]); }
         for (auto* b : all) fq_free(*b);
     }
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
@@ -588,9 +594,9 @@ static int fq_ensure(fp_ctx::Buf& b, size_t need) {
 static_assert(sizeof(fp_fastq_rec) == sizeof(fq_rec), "fp_fastq_rec layout");
 
 /* rec_end_out (optional, host): consumed bytes if only the first k records are kept is read later through fq_recend */
-extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, int32_t final_chunk, int32_t phred64,
-                               uint8_t* d_seq, uint8_t* d_qual, uint16_t* d_len, int64_t capacity, fp_fastq_rec* d_recs,
-                               fp_fastq_info* info) {
+static int fastq_decode_impl(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, int32_t final_chunk, int32_t phred64,
+                             uint8_t* d_seq, uint8_t* d_qual, uint16_t* d_len, int64_t capacity, fp_fastq_rec* d_recs,
+                             fp_fastq_info* info, fp_ctx::Buf& recend) {
     if (!c || !info || (nbytes > 0 && !d_text)) return set_err(FP_E_INVAL, "null argument");
     if (nbytes < 0 || nbytes >= ((int64_t)1 << 32) - 16) return set_err(FP_E_TOOLARGE, "FASTQ chunk must be smaller than 4 GiB");
     if (capacity < 0 || (capacity > 0 && (!d_seq || !d_qual || !d_len || !d_recs))) return set_err(FP_E_INVAL, "null row buffers");
@@ -644,11 +650,11 @@ extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes,
     const unsigned int nrec = (unsigned int)std::min<int64_t>(ncomplete, capacity);
     unsigned int first_bad = 0xFFFFFFFFu;
     if (nrec > 0) {
-        if ((rc = fq_ensure(c->fq_recend, (size_t)nrec * 4))) return rc;
+        if ((rc = fq_ensure(recend, (size_t)nrec * 4))) return rc;
         CK(cudaMemcpyAsync(d_info + 8, &first_bad, 4, cudaMemcpyHostToDevice, st));
         fq_scatter_kernel<<<(nrec + FQ_T / 32 - 1) / (FQ_T / 32), FQ_T, 0, st>>>(d_text, nbytes, d_term, d_recline, nrec, c->stride, phred64,
                                                                                    d_seq, d_qual, d_len, reinterpret_cast<fq_rec*>(d_recs),
-                                                                                   (unsigned int*)c->fq_recend.p, d_info + 8, d_info + 9);
+                                                                                   (unsigned int*)recend.p, d_info + 8, d_info + 9);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&first_bad, d_info + 8, 4, cudaMemcpyDeviceToHost, st));
     }
@@ -671,6 +677,13 @@ extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes,
     } else if ((rc = lines_end(&info->consumed))) return rc;      /* every complete line was a record line or skipped */
     info->n_records = keep;
     return FP_OK;
+}
+
+extern "C" int fp_fastq_decode(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, int32_t final_chunk, int32_t phred64,
+                               uint8_t* d_seq, uint8_t* d_qual, uint16_t* d_len, int64_t capacity, fp_fastq_rec* d_recs,
+                               fp_fastq_info* info) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    return fastq_decode_impl(c, d_text, nbytes, final_chunk, phred64, d_seq, d_qual, d_len, capacity, d_recs, info, c->fq_recend);
 }
 
 extern "C" int fp_fastq_encode(fp_ctx* c, const uint8_t* d_text, const fp_fastq_rec* d_recs, const fp_read_result* d_res,
@@ -706,11 +719,22 @@ extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nb
     const int sides = c->p.paired ? 2 : 1;
     if (sides == 2 && (!consumed2 || !out_bytes2)) return set_err(FP_E_INVAL, "paired ctx needs the second side");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream[0];
+    cudaStream_t st = c->stream[0], up = c->stream[1];
+    if (!c->fq_stream_out) {
+        CK(cudaStreamCreateWithFlags(&c->fq_stream_out, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->fq_ev_up, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->fq_ev_out[k], cudaEventDisableTiming));
+    }
+    cudaStream_t outst = c->fq_stream_out;
     const uint8_t* text[2] = {text1, text2};
-    const int64_t nb[2] = {nbytes1, nbytes2};
-    fp_fastq_info inf[2];
+    const int64_t nb[2] = {nbytes1, sides == 2 ? nbytes2 : 0};
+    uint8_t* outs[2] = {out1, out2}; const int64_t ocap[2] = {out_cap1, out_cap2};
     const int64_t cap = c->max_batch;
+    /* The text goes up in pieces on its own stream while the pieces already on the device are decoded, run through the chain and
+       encoded, and the previous round's output text goes down on a third stream: H2D, kernels and D2H overlap inside ONE call
+       (pinned host buffers assumed; pageable ones still work, serialised).  A piece is a fraction of a device batch of text; the
+       host never has to find record borders -- the decode of a prefix reports what it consumed and the next round starts there. */
+    const int64_t piece = std::max<int64_t>((int64_t)4 << 20, std::min<int64_t>((int64_t)64 << 20, cap * (int64_t)(2 * c->stride + 64) / 4));
     int rc;
     for (int s = 0; s < sides; s++) {
         if ((rc = fq_ensure(c->fqh_text[s], (size_t)nb[s] + 64))) return rc;
@@ -719,53 +743,99 @@ extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nb
         if ((rc = fq_ensure(c->fqh_len[s], (size_t)cap * 2))) return rc;
         if ((rc = fq_ensure(c->fqh_recs[s], (size_t)cap * sizeof(fp_fastq_rec)))) return rc;
         if ((rc = fq_ensure(c->fqh_res[s], (size_t)cap * sizeof(fp_read_result)))) return rc;
-        if (nb[s] > 0) CK(cudaMemcpyAsync(c->fqh_text[s].p, text[s], (size_t)nb[s], cudaMemcpyHostToDevice, st));
-        rc = fp_fastq_decode(c, (const uint8_t*)c->fqh_text[s].p, nb[s], final_chunk, phred64, (uint8_t*)c->fqh_seq[s].p, (uint8_t*)c->fqh_qual[s].p,
-                             (uint16_t*)c->fqh_len[s].p, cap, (fp_fastq_rec*)c->fqh_recs[s].p, &inf[s]);
-        if (rc) return rc;
     }
-    int64_t n = inf[0].n_records;
-    if (sides == 2) n = std::min(n, inf[1].n_records);            /* pairs end with the shorter input (FastqReaderPair::read) */
-    /* bytes covered by the first n records of each side */
-    int64_t cons[2] = {0, 0};
-    for (int s = 0; s < sides; s++) {
-        if (n == inf[s].n_records) cons[s] = inf[s].consumed;
-        else if (n > 0) {
-            /* this side decoded more records than the pair count: re-derive the end of record n-1 from the workspace of the LAST decode only
-               when it is this side's; otherwise decode again restricted to n records */
-            fp_fastq_info tmp;
-            rc = fp_fastq_decode(c, (const uint8_t*)c->fqh_text[s].p, nb[s], final_chunk, phred64, (uint8_t*)c->fqh_seq[s].p, (uint8_t*)c->fqh_qual[s].p,
-                                 (uint16_t*)c->fqh_len[s].p, n, (fp_fastq_rec*)c->fqh_recs[s].p, &tmp);
-            if (rc) return rc;
-            cons[s] = tmp.consumed;
+    int64_t upl[2] = {0, 0}, start[2] = {0, 0}, obytes[2] = {0, 0}, units = 0;
+    fp_fastq_info agg[2]; memset(agg, 0, sizeof(agg)); agg[0].error_record = agg[1].error_record = -1;
+    int flip = 0;
+    auto upload_more = [&]() -> int {
+        bool any = false;
+        for (int s = 0; s < sides; s++) {
+            const int64_t n = std::min(piece, nb[s] - upl[s]);
+            if (n > 0) { CK(cudaMemcpyAsync((uint8_t*)c->fqh_text[s].p + upl[s], text[s] + upl[s], (size_t)n, cudaMemcpyHostToDevice, up)); upl[s] += n; any = true; }
         }
+        if (any) CK(cudaEventRecord(c->fq_ev_up, up));
+        return FP_OK;
+    };
+    if ((rc = upload_more())) return rc;
+    const bool trace = getenv("FP_FQ_TRACE") != nullptr;
+    auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double t_begin = now();
+    for (;;) {
+        const double t0 = now();
+        CK(cudaStreamWaitEvent(st, c->fq_ev_up, 0));             /* this round reads what has been issued so far ... */
+        const int64_t have[2] = {upl[0], upl[1]}, rstart[2] = {start[0], start[1]};
+        const bool saw_all = have[0] >= nb[0] && have[1] >= nb[1];
+        if ((rc = upload_more())) return rc;                      /* ... while the next piece flies */
+        fp_fastq_info inf[2]; memset(inf, 0, sizeof(inf));
+        int fin[2];
+        for (int s = 0; s < sides; s++) {
+            fin[s] = (final_chunk && have[s] >= nb[s]) ? 1 : 0;
+            rc = fastq_decode_impl(c, (const uint8_t*)c->fqh_text[s].p + rstart[s], have[s] - rstart[s], fin[s], phred64, (uint8_t*)c->fqh_seq[s].p,
+                                   (uint8_t*)c->fqh_qual[s].p, (uint16_t*)c->fqh_len[s].p, cap, (fp_fastq_rec*)c->fqh_recs[s].p, &inf[s], c->fqh_recend[s]);
+            if (rc) return rc;
+        }
+        const double t1 = now();
+        int64_t n = inf[0].n_records;
+        if (sides == 2) n = std::min(n, inf[1].n_records);        /* pairs end with the shorter input (FastqReaderPair::read) */
+        bool reader_ended = false;                                /* a reader hit a record it rejects: it returns NULL, the stream ends */
+        for (int s = 0; s < sides; s++) {
+            int64_t used = inf[s].consumed;
+            if (n != inf[s].n_records) {                          /* this side decoded more records than the pair count: keep only n */
+                used = 0;                                         /* resume right after record n-1 (end offsets were kept per side) */
+                if (n > 0) { unsigned int e; CK(cudaMemcpy(&e, (unsigned int*)c->fqh_recend[s].p + (n - 1), 4, cudaMemcpyDeviceToHost)); used = e; }
+            } else if (inf[s].error != FP_FQ_OK) {
+                reader_ended = true;
+                agg[s].error = inf[s].error; agg[s].error_record = agg[s].n_records + inf[s].error_record;
+            }
+            agg[s].n_records += n; agg[s].n_lines += inf[s].n_lines;
+            start[s] = rstart[s] + used;
+        }
+        if (n > 0) {
+            fp_batch b; memset(&b, 0, sizeof(b));
+            b.n = n; b.stride = c->stride;
+            b.seq1 = (uint8_t*)c->fqh_seq[0].p; b.qual1 = (uint8_t*)c->fqh_qual[0].p; b.len1 = (uint16_t*)c->fqh_len[0].p;
+            if (sides == 2) {
+                b.seq2 = (uint8_t*)c->fqh_seq[1].p; b.qual2 = (uint8_t*)c->fqh_qual[1].p; b.len2 = (uint16_t*)c->fqh_len[1].p;
+                rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, (fp_read_result*)c->fqh_res[1].p, nullptr, nullptr, 0, nullptr, st);
+            } else rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, nullptr, nullptr, nullptr, 0, nullptr, st);
+            if (rc) return rc;
+            CK(cudaEventSynchronize(c->fq_ev_out[flip]));        /* the output buffers of two rounds ago have gone down */
+            for (int s = 0; s < sides; s++) {
+                if (!outs[s]) continue;                           /* caller does not want this side's text */
+                fp_ctx::Buf& ob = c->fqh_outbuf[flip][s];
+                const int64_t room = std::max<int64_t>(ocap[s] - obytes[s], 0);
+                int64_t want = std::min<int64_t>(room, n * (int64_t)(2 * c->stride + 256));
+                int64_t total = 0;
+                for (int attempt = 0; attempt < 2; attempt++) {   /* names longer than the estimate: encode again into a buffer of the exact size */
+                    if ((rc = fq_ensure(ob, (size_t)want + 64))) return rc;
+                    rc = fp_fastq_encode(c, (const uint8_t*)c->fqh_text[s].p + rstart[s], (const fp_fastq_rec*)c->fqh_recs[s].p, (const fp_read_result*)c->fqh_res[s].p,
+                                         (const uint8_t*)c->fqh_seq[s].p, (const uint8_t*)c->fqh_qual[s].p, n, (uint8_t*)ob.p, want, &total);
+                    if (rc) return rc;
+                    if (total <= want) break;
+                    if (total > room) return set_err(FP_E_TOOLARGE, "output buffer too small for the encoded FASTQ text");
+                    want = total;
+                }
+                if (total > 0) CK(cudaMemcpyAsync(outs[s] + obytes[s], ob.p, (size_t)total, cudaMemcpyDeviceToHost, outst));
+                obytes[s] += total;
+            }
+            CK(cudaEventRecord(c->fq_ev_out[flip], outst));
+            flip ^= 1;
+            units += n;
+        }
+        if (trace) fprintf(stderr, "[fq] round t=%.2f ms: decode %.2f, rest %.2f, n=%lld have=%lld/%lld\n", t0 - t_begin, t1 - t0, now() - t1, (long long)n, (long long)have[0], (long long)nb[0]);
+        if (reader_ended) break;
+        if (n == 0 && saw_all) break;                             /* nothing more can become complete in this call */
     }
-    *n_units = n; *consumed1 = cons[0]; if (consumed2) *consumed2 = cons[1];
-    if (info1) *info1 = inf[0];
-    if (info2 && sides == 2) *info2 = inf[1];
-    *out_bytes1 = 0; if (out_bytes2) *out_bytes2 = 0;
-    if (n == 0) return FP_OK;
-    fp_batch b; memset(&b, 0, sizeof(b));
-    b.n = n; b.stride = c->stride;
-    b.seq1 = (uint8_t*)c->fqh_seq[0].p; b.qual1 = (uint8_t*)c->fqh_qual[0].p; b.len1 = (uint16_t*)c->fqh_len[0].p;
-    if (sides == 2) {
-        b.seq2 = (uint8_t*)c->fqh_seq[1].p; b.qual2 = (uint8_t*)c->fqh_qual[1].p; b.len2 = (uint16_t*)c->fqh_len[1].p;
-        rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, (fp_read_result*)c->fqh_res[1].p, nullptr, nullptr, 0, nullptr, st);
-    } else rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, nullptr, nullptr, nullptr, 0, nullptr, st);
-    if (rc) return rc;
-    uint8_t* outs[2] = {out1, out2}; const int64_t ocap[2] = {out_cap1, out_cap2}; int64_t* ob[2] = {out_bytes1, out_bytes2};
-    for (int s = 0; s < sides; s++) {
-        if (!outs[s]) continue;                                   /* caller does not want this side's text */
-        if ((rc = fq_ensure(c->fqh_out[s], (size_t)ocap[s] + 64))) return rc;
-        int64_t total = 0;
-        rc = fp_fastq_encode(c, (const uint8_t*)c->fqh_text[s].p, (const fp_fastq_rec*)c->fqh_recs[s].p, (const fp_read_result*)c->fqh_res[s].p,
-                             (const uint8_t*)c->fqh_seq[s].p, (const uint8_t*)c->fqh_qual[s].p, n, (uint8_t*)c->fqh_out[s].p, ocap[s], &total);
-        if (rc) return rc;
-        *ob[s] = total;
-        if (total > ocap[s]) return set_err(FP_E_TOOLARGE, "output buffer too small for the encoded FASTQ text");
-        if (total > 0) CK(cudaMemcpyAsync(outs[s], c->fqh_out[s].p, (size_t)total, cudaMemcpyDeviceToHost, st));
-    }
+    const double t_loop = now();
+    CK(cudaStreamSynchronize(up));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(outst));
+    if (trace) fprintf(stderr, "[fq] loop %.2f ms, drain %.2f ms\n", t_loop - t_begin, now() - t_loop);
+    agg[0].consumed = start[0]; agg[1].consumed = start[1];
+    *n_units = units; *consumed1 = start[0]; if (consumed2) *consumed2 = start[1];
+    *out_bytes1 = obytes[0]; if (out_bytes2) *out_bytes2 = obytes[1];
+    if (info1) *info1 = agg[0];
+    if (info2 && sides == 2) *info2 = agg[1];
     return FP_OK;
 }
 

@@ -16,7 +16,7 @@
 
 #define FP_THREADS 256
 #define FP_WARPS (FP_THREADS / 32)
-#define FP_CT 256              /* threads of the chain kernel: 2 CTAs x 8 warps per SM (<= 128 registers) */
+#define FP_CT 256              /* threads of the chain kernel: 2 CTAs x 8 warps per SM (128 registers); 320 x 96 registers was measured and lost to spills */
 #define FP_CW (FP_CT / 32)
 #define FULL_MASK 0xffffffffu
 #define FP_MAX_ISIZE_SMEM 1025
