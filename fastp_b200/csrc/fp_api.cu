@@ -45,6 +45,8 @@ struct fp_ctx {
     std::string ad1, ad2;
     std::vector<std::string> fasta;
     fp_dev_params dp{};
+    fp_dev_params* d_dp = nullptr;      /* device copy of dp, source of the per-launch constant refresh */
+    void* d_cp_sym = nullptr;           /* global address of the __constant__ block */
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
@@ -84,6 +86,7 @@ struct fp_ctx {
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
     Buf fqh_text[2], fqh_seq[2], fqh_qual[2], fqh_len[2], fqh_recs[2], fqh_res[2], fqh_ov, fqh_out[2], fqh_outbuf[2][2], fqh_recend[2];
+    unsigned int *fq_hinfo = nullptr, *fq_hinfo_dev = nullptr;      /* mapped pinned control words */
     cudaStream_t fq_stream_out = nullptr;
     cudaEvent_t fq_ev_up = nullptr, fq_ev_out[2] = {nullptr, nullptr};
     /* kernel timing */
@@ -116,6 +119,10 @@ static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov,
         }
         mind[len] = (int16_t)d;
     }
+}
+
+__global__ void fp_set_params_kernel(uint32_t* dst, const uint32_t* src, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void fp_probe_smem_base(uint32_t* out) { extern __shared__ uint8_t probe_sm[]; *out = smem_u32(probe_sm); }
@@ -354,9 +361,11 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
                               &c->fqh_text[0], &c->fqh_text[1], &c->fqh_seq[0], &c->fqh_seq[1], &c->fqh_qual[0], &c->fqh_qual[1], &c->fqh_len[0], &c->fqh_len[1],
                               &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1],
                               &c->fqh_outbuf[0][0], &c->fqh_outbuf[0][1], &c->fqh_outbuf[1][0], &c->fqh_outbuf[1][1], &c->fqh_recend[0], &c->fqh_recend[1]};
+        if (c->fq_hinfo) cudaFreeHost(c->fq_hinfo);
         if (c->fq_stream_out) { cudaStreamDestroy(c->fq_stream_out); cudaEventDestroy(c->fq_ev_up); cudaEventDestroy(c->fq_ev_out[0]); cudaEventDestroy(c->fq_ev_out[1]); }
         for (auto* b : all) fq_free(*b);
     }
+    cudaFree(c->d_dp);
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
     cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
@@ -401,7 +410,15 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     a.n_tiles = (b->n + c->tile - 1) / c->tile;
     a.sl = c->sl;
     int grid = (int)std::min<long long>(a.n_tiles, c->grid_max);
-    CK(cudaMemcpyToSymbolAsync(c_p, &c->dp, sizeof(fp_dev_params), 0, cudaMemcpyHostToDevice, st));
+    /* The operator parameters live in one __constant__ block per device; it is refreshed before every launch BY A KERNEL from the
+       context's device copy (stream-ordered, no copy engine: a cudaMemcpyToSymbolAsync would queue behind bulk text / batch
+       transfers).  Contexts running concurrently on one device must therefore share the same fp_params. */
+    if (!c->d_dp) {
+        CK(cudaMalloc(&c->d_dp, sizeof(fp_dev_params)));
+        CK(cudaMemcpy(c->d_dp, &c->dp, sizeof(fp_dev_params), cudaMemcpyHostToDevice));
+        CK(cudaGetSymbolAddress((void**)&c->d_cp_sym, c_p));
+    }
+    fp_set_params_kernel<<<1, 128, 0, st>>>(reinterpret_cast<uint32_t*>(c->d_cp_sym), reinterpret_cast<const uint32_t*>(c->d_dp), (int)(sizeof(fp_dev_params) / 4));
     fp_overrep_args oa;
     const bool ovr = c->p.overrep_enabled && (c->ovr_side[0].K > 0 || c->ovr_side[1].K > 0);
     if (ovr) {
@@ -609,12 +626,14 @@ static int fastq_decode_impl(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, i
     int rc;
     if ((rc = fq_ensure(c->fq_bcnt, (size_t)(nbb + 1) * 4))) return rc;
     if ((rc = fq_ensure(c->fq_info, 64))) return rc;
+    /* control words come back through MAPPED pinned host memory written by the kernels themselves: a small cudaMemcpy would queue
+       behind the bulk text transfers on the copy engines (milliseconds when the text path is streaming) */
+    if (!c->fq_hinfo) { CK(cudaHostAlloc((void**)&c->fq_hinfo, 256, cudaHostAllocMapped)); CK(cudaHostGetDevicePointer((void**)&c->fq_hinfo_dev, c->fq_hinfo, 0)); }
+    volatile unsigned int* h_info = c->fq_hinfo;
+    unsigned int* m_info = c->fq_hinfo_dev;
     unsigned int* d_info = (unsigned int*)c->fq_info.p;
-    CK(cudaMemsetAsync(d_info, 0, 64, st));
     fq_term_count_kernel<<<nbb, FQ_T, 0, st>>>(d_text, nbytes, (unsigned int*)c->fq_bcnt.p);
-    fq_term_scan_kernel<<<1, 32, 0, st>>>((unsigned int*)c->fq_bcnt.p, nbb, d_text, nbytes, final_chunk, nullptr, 0, d_info);
-    unsigned int h_info[16];
-    CK(cudaMemcpyAsync(h_info, d_info, 64, cudaMemcpyDeviceToHost, st));
+    fq_term_scan_kernel<<<1, 32, 0, st>>>((unsigned int*)c->fq_bcnt.p, nbb, d_text, nbytes, final_chunk, nullptr, 0, m_info);
     CK(cudaStreamSynchronize(st));
     const unsigned int nlines = h_info[0], nterm = h_info[1];
     info->n_lines = nlines;
@@ -622,60 +641,37 @@ static int fastq_decode_impl(fp_ctx* c, const uint8_t* d_text, int64_t nbytes, i
     if ((rc = fq_ensure(c->fq_term, (size_t)(nlines + 2) * 4))) return rc;
     unsigned int* d_term = (unsigned int*)c->fq_term.p;
     fq_term_fill_kernel<<<nbb, FQ_T, 0, st>>>(d_text, nbytes, (unsigned int*)c->fq_bcnt.p, d_term, nlines + 1);
-    if (nlines > nterm) { const unsigned int v = (unsigned int)nbytes; CK(cudaMemcpyAsync(d_term + nterm, &v, 4, cudaMemcpyHostToDevice, st)); }
+    if (nlines > nterm) fq_set_u32_kernel<<<1, 1, 0, st>>>(d_term + nterm, (unsigned int)nbytes);     /* virtual terminator after the last byte */
     /* record automaton over the lines */
     const int nlb = (int)((nlines + FQ_LB - 1) / FQ_LB);
     if ((rc = fq_ensure(c->fq_agg, (size_t)nlb * sizeof(fq_elem)))) return rc;
     if ((rc = fq_ensure(c->fq_bstate, (size_t)nlb * 4))) return rc;
     if ((rc = fq_ensure(c->fq_brec, (size_t)nlb * 4))) return rc;
     fq_fsm_kernel<0><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, (fq_elem*)c->fq_agg.p, nullptr, nullptr, nullptr, 0);
-    fq_fsm_scan_kernel<<<1, 32, 0, st>>>((const fq_elem*)c->fq_agg.p, nlb, (unsigned int*)c->fq_bstate.p, (unsigned int*)c->fq_brec.p, d_info);
-    CK(cudaMemcpyAsync(h_info, d_info, 64, cudaMemcpyDeviceToHost, st));
+    fq_fsm_scan_kernel<<<1, 32, 0, st>>>((const fq_elem*)c->fq_agg.p, nlb, (unsigned int*)c->fq_bstate.p, (unsigned int*)c->fq_brec.p, m_info);
     CK(cudaStreamSynchronize(st));
     const unsigned int nstarted = h_info[2], ncomplete = h_info[3];
-    /* first byte of line l / first byte after the last complete line (what the sequential reader has consumed by then) */
-    auto line_start = [&](unsigned int l, int64_t* out) -> int {
-        if (l == 0) { *out = 0; return FP_OK; }
-        unsigned int t; CK(cudaMemcpy(&t, d_term + (l - 1), 4, cudaMemcpyDeviceToHost)); *out = (int64_t)t + 1; return FP_OK;
-    };
-    auto lines_end = [&](int64_t* out) -> int {
-        if (nlines > nterm) { *out = nbytes; return FP_OK; }
-        unsigned int t; CK(cudaMemcpy(&t, d_term + (nlines - 1), 4, cudaMemcpyDeviceToHost)); *out = (int64_t)t + 1; return FP_OK;
-    };
     if ((rc = fq_ensure(c->fq_recline, (size_t)(nstarted + 1) * 4))) return rc;
     unsigned int* d_recline = (unsigned int*)c->fq_recline.p;
     if (nstarted > 0)
         fq_fsm_kernel<1><<<nlb, FQ_T, 0, st>>>(d_text, nbytes, d_term, nlines, nullptr, (const unsigned int*)c->fq_bstate.p, (const unsigned int*)c->fq_brec.p,
                                                d_recline, nstarted);
     const unsigned int nrec = (unsigned int)std::min<int64_t>(ncomplete, capacity);
-    unsigned int first_bad = 0xFFFFFFFFu;
     if (nrec > 0) {
         if ((rc = fq_ensure(recend, (size_t)nrec * 4))) return rc;
-        CK(cudaMemcpyAsync(d_info + 8, &first_bad, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(d_info + 8, 0xFF, 4, st));             /* first bad record = none */
         fq_scatter_kernel<<<(nrec + FQ_T / 32 - 1) / (FQ_T / 32), FQ_T, 0, st>>>(d_text, nbytes, d_term, d_recline, nrec, c->stride, phred64,
                                                                                    d_seq, d_qual, d_len, reinterpret_cast<fq_rec*>(d_recs),
                                                                                    (unsigned int*)recend.p, d_info + 8, d_info + 9);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&first_bad, d_info + 8, 4, cudaMemcpyDeviceToHost, st));
     }
+    fq_finish_kernel<<<1, 1, 0, st>>>(d_term, nlines, nterm, nbytes, d_recline, nstarted, ncomplete, nrec, reinterpret_cast<const fq_rec*>(d_recs), d_info + 8, m_info + 8);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    unsigned int keep = nrec;
-    if (first_bad != 0xFFFFFFFFu) {
-        fp_fastq_rec br;
-        CK(cudaMemcpy(&br, d_recs + first_bad, sizeof(br), cudaMemcpyDeviceToHost));
-        info->error = (int32_t)((br.name_len >> 28) & 7u);
-        info->error_record = first_bad;
-        keep = first_bad;                                         /* the reference reader stops here: fastqreader.cpp:349-364 */
-        info->consumed = nbytes;                                  /* nothing after a bad record is read */
-    } else if (ncomplete > nrec) {                                /* capacity reached: the next record's name line is where to resume */
-        info->more = 1;
-        unsigned int l; CK(cudaMemcpy(&l, d_recline + nrec, 4, cudaMemcpyDeviceToHost));
-        if ((rc = line_start(l, &info->consumed))) return rc;
-    } else if (nstarted > ncomplete) {                            /* the last record is not complete in this chunk: resume at its name line */
-        unsigned int l; CK(cudaMemcpy(&l, d_recline + ncomplete, 4, cudaMemcpyDeviceToHost));
-        if ((rc = line_start(l, &info->consumed))) return rc;
-    } else if ((rc = lines_end(&info->consumed))) return rc;      /* every complete line was a record line or skipped */
-    info->n_records = keep;
+    info->n_records = h_info[8];
+    info->error = (int32_t)h_info[9];
+    info->error_record = h_info[10] == 0xFFFFFFFFu ? -1 : (int64_t)h_info[10];
+    info->more = (int32_t)h_info[11];
+    info->consumed = (int64_t)h_info[12] | ((int64_t)h_info[13] << 32);
     return FP_OK;
 }
 
@@ -699,14 +695,13 @@ extern "C" int fp_fastq_encode(fp_ctx* c, const uint8_t* d_text, const fp_fastq_
     if ((rc = fq_ensure(c->fq_bsum, (size_t)(nblk + 1) * 8))) return rc;
     unsigned long long* d_bs = (unsigned long long*)c->fq_bsum.p;
     fq_size_blocksum_kernel<<<nblk, FQ_T, 0, st>>>(reinterpret_cast<const fq_rec*>(d_recs), d_res, n, d_bs);
-    fq_size_scan_kernel<<<1, 32, 0, st>>>(d_bs, nblk, d_bs + nblk);
+    if (!c->fq_hinfo) { CK(cudaHostAlloc((void**)&c->fq_hinfo, 256, cudaHostAllocMapped)); CK(cudaHostGetDevicePointer((void**)&c->fq_hinfo_dev, c->fq_hinfo, 0)); }
+    fq_size_scan_kernel<<<1, 32, 0, st>>>(d_bs, nblk, reinterpret_cast<unsigned long long*>(c->fq_hinfo_dev + 32));
     fq_encode_kernel<<<nblk, FQ_T, 0, st>>>(d_text, reinterpret_cast<const fq_rec*>(d_recs), d_res, d_seq, d_qual, c->stride, n, d_bs, d_out,
                                             (unsigned long long)std::max<int64_t>(out_cap, 0));
     CK(cudaGetLastError());
-    unsigned long long total = 0;
-    CK(cudaMemcpyAsync(&total, d_bs + nblk, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    *out_bytes = (int64_t)total;
+    *out_bytes = (int64_t)*reinterpret_cast<volatile unsigned long long*>(c->fq_hinfo + 32);
     return FP_OK;
 }
 
@@ -782,7 +777,11 @@ extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nb
             int64_t used = inf[s].consumed;
             if (n != inf[s].n_records) {                          /* this side decoded more records than the pair count: keep only n */
                 used = 0;                                         /* resume right after record n-1 (end offsets were kept per side) */
-                if (n > 0) { unsigned int e; CK(cudaMemcpy(&e, (unsigned int*)c->fqh_recend[s].p + (n - 1), 4, cudaMemcpyDeviceToHost)); used = e; }
+                if (n > 0) {
+                    fq_copy_u32_kernel<<<1, 1, 0, st>>>((const unsigned int*)c->fqh_recend[s].p + (n - 1), c->fq_hinfo_dev + 48);
+                    CK(cudaStreamSynchronize(st));
+                    used = *reinterpret_cast<volatile unsigned int*>(c->fq_hinfo + 48);
+                }
             } else if (inf[s].error != FP_FQ_OK) {
                 reader_ended = true;
                 agg[s].error = inf[s].error; agg[s].error_record = agg[s].n_records + inf[s].error_record;

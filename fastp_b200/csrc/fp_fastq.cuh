@@ -280,6 +280,31 @@ __global__ void __launch_bounds__(FQ_T) fq_scatter_kernel(const uint8_t* text, l
     }
 }
 
+/* ---- finish: everything the host needs from a decode, written to (mapped) host memory by one thread ----
+ * out[0] records kept, out[1] error code, out[2] error record (0xFFFFFFFF none), out[3] more, out[4] consumed bytes */
+__global__ void fq_finish_kernel(const unsigned int* term, unsigned int nlines, unsigned int nterm, long long nbytes,
+                                 const unsigned int* rec_line, unsigned int nstarted, unsigned int ncomplete, unsigned int nrec,
+                                 const fq_rec* recs, const unsigned int* first_bad, unsigned int* out) {
+    if (blockIdx.x || threadIdx.x) return;
+    const unsigned int fb = nrec > 0 ? *first_bad : 0xFFFFFFFFu;
+    unsigned int keep = nrec, err = FQ_ERR_NONE, more = 0;
+    long long consumed;
+    auto line_start = [&](unsigned int l) -> long long { return l == 0 ? 0ll : (long long)term[l - 1] + 1; };
+    if (fb != 0xFFFFFFFFu) {                                   /* the reference reader stops here: fastqreader.cpp:349-364 */
+        err = (recs[fb].name_len >> 28) & 7u; keep = fb; consumed = nbytes;
+    } else if (ncomplete > nrec) {                             /* capacity reached: resume at the next record's name line */
+        more = 1; consumed = line_start(rec_line[nrec]);
+    } else if (nstarted > ncomplete) {                         /* the last record is not complete in this chunk: resume at its name line */
+        consumed = line_start(rec_line[ncomplete]);
+    } else {                                                   /* every complete line was a record line or skipped */
+        consumed = nlines > nterm ? nbytes : (long long)term[nlines - 1] + 1;
+    }
+    out[0] = keep; out[1] = err; out[2] = fb; out[3] = more;
+    out[4] = (unsigned int)(consumed & 0xFFFFFFFFll); out[5] = (unsigned int)(consumed >> 32);
+}
+__global__ void fq_set_u32_kernel(unsigned int* p, unsigned int v) { if (!blockIdx.x && !threadIdx.x) *p = v; }
+__global__ void fq_copy_u32_kernel(const unsigned int* src, unsigned int* dst) { if (!blockIdx.x && !threadIdx.x) *dst = *src; }
+
 /* ---- encode ---- */
 #define FQ_SCAN_ITEMS 2048
 __global__ void __launch_bounds__(FQ_T) fq_size_blocksum_kernel(const fq_rec* recs, const fp_read_result* res, long long n, unsigned long long* blocksum) {
