@@ -245,6 +245,11 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                 int cnt = min((nfast - o + g - 1) >> lg, (32 - sh + g - 1) >> lg);
                 while (cnt > 0) {
                     int mm0 = 0;
+                    for (; cnt >= 2; cnt -= 2, sh += 2 * g, o += 2 * g) {          /* two independent candidates per step (ILP); a hit is re-examined below */
+                        const uint32_t xa = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
+                        const uint32_t xb = (__funnelshift_r(L0, L1, sh + g) ^ b_lo0) | (__funnelshift_r(H0, H1, sh + g) ^ b_hi0) | (__funnelshift_r(N0, N1, sh + g) ^ b_nn0);
+                        if (min(__popc(xa), __popc(xb)) <= dmax) break;
+                    }
                     #pragma unroll 2
                     for (; cnt > 0; cnt--, sh += g, o += g) {
                         const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
@@ -296,6 +301,11 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                 int cnt = min((nfast - o + g - 1) >> lg, (sh >> lg) + 1);   /* the field start moves DOWN by g per candidate */
                 while (cnt > 0) {
                     int mm0 = 0;
+                    for (; cnt >= 2; cnt -= 2, sh -= 2 * g, o += 2 * g) {
+                        const uint32_t xa = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
+                        const uint32_t xb = (__funnelshift_r(L0, L1, sh - g) ^ y_lo0) | (__funnelshift_r(H0, H1, sh - g) ^ y_hi0) | (__funnelshift_r(N0, N1, sh - g) ^ y_nn0);
+                        if (min(__popc(xa), __popc(xb)) <= dmax) break;
+                    }
                     #pragma unroll 2
                     for (; cnt > 0; cnt--, sh -= g, o += g) {
                         const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
@@ -980,6 +990,21 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
     const unsigned gmask = group_mask(GL);
     const int glead = lane & ~(GL - 1);
 
+    /* stage the read lengths / clean flags of tile t (neither is read between the phase-B barrier and the end of the tile, so the
+       NEXT tile's values are written during phase C and become visible with the barrier that ends it) */
+    auto fill_lens = [&](long long t) {
+        if (t >= a.n_tiles) return;
+        const long long r0 = t * T;
+        const int nr = (int)min((long long)T, a.b.n - r0);
+        for (int i = tid; i < SIDES * T; i += FP_CT) {
+            const int sd = i / T, r = i % T;
+            uint16_t ln = 0;
+            if (r < nr) { ln = (sd == 0 ? a.b.len1 : a.b.len2)[r0 + r]; if (ln > S) ln = (uint16_t)S; }
+            s_len[i] = ln;
+            s_clean[i] = 1;
+        }
+    };
+    fill_lens(blockIdx.x);
     __syncthreads();
     uint32_t parity = 0;
 
@@ -998,18 +1023,12 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
-            s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0;
+            s_qn[0] = 0; s_qn[1] = 0;                  /* request queue: next used after the phase-A barrier */
         }
-        for (int i = tid; i < SIDES * T; i += FP_CT) {
-            const int sd = i / T, r = i % T;
-            uint16_t ln = 0;
-            if (r < rows) { ln = (sd == 0 ? a.b.len1 : a.b.len2)[row0 + r]; if (ln > S) ln = (uint16_t)S; }
-            s_len[i] = ln;
-            s_clean[i] = 1;
-        }
+        /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
+           mbarrier every thread waits on itself: no CTA barrier here */
         mbar_wait(mbar, parity);
         parity ^= 1;
-        __syncthreads();
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
         if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
@@ -1293,6 +1312,8 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 else dev_stat_positions(G, side * 2 + 1, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
             }
         }
+        fill_lens(tix + gridDim.x);
+        if (tid == 0) s_qn[2] = 0;                     /* item counter of phase A: idle since the phase-A barrier */
         __syncthreads();
     }
 
