@@ -359,3 +359,30 @@ def fastq_edge_cases():
         "long_names": "".join(rec(i, "ACGTACGTAC", "IIIIIIIIII", nm="instrument:run:flowcell:lane:tile:" + "x" * 300 + ":") for i in range(9)).encode(),
         "name_only_at": "@\nAC\n+\nII\n".encode(),
     }
+
+
+def fastq_fuzz_text(rng, nrec=30):
+    """Random FASTQ-ish text: mixed line ends, blank / junk lines between records, odd strand lines, empty reads,
+    occasional broken records, optional missing final terminator."""
+    eols = ["\n", "\r\n", "\r"]
+    out = []
+    for i in range(nrec):
+        e = eols[int(rng.integers(0, 3))] if rng.random() < 0.3 else "\n"
+        if rng.random() < 0.15:
+            out.append(["", "junk", "+", "#comment", "\t"][int(rng.integers(0, 5))] + e)
+        n = int(rng.integers(0, 40))
+        s = "".join(rng.choice(list("ACGTN"), n)) if n else ""
+        q = "".join(chr(int(x)) for x in rng.integers(33, 75, n)) if n else ""
+        if n and rng.random() < 0.1:
+            q = "@" + q[1:]
+        strand = "+" if rng.random() < 0.8 else "+" + "x" * int(rng.integers(1, 9))
+        r = rng.random()
+        if r < 0.02:
+            strand = "-"                               # reader stops here
+        elif r < 0.04:
+            q = q + "I"                                # length mismatch: reader stops here
+        out.append(f"@r{i} {'y' * int(rng.integers(0, 20))}{e}{s}{e}{strand}{e}{q}{e}")
+    text = "".join(out)
+    if rng.random() < 0.3 and text:
+        text = text.rstrip("\r\n")
+    return text.encode()

@@ -86,3 +86,16 @@ def test_capacity_limit_reports_more():
     rest = text[d["info"]["consumed"]:]
     d2 = T.oracle_fastq_decode(rest, final=1, stride=64)
     assert d["info"]["n_records"] + d2["info"]["n_records"] == 40
+
+
+@needs_ref
+@pytest.mark.reference
+def test_oracle_decode_fuzz_matches_fastqreader(tmp_path):
+    """300 random texts (mixed line ends, junk, broken records): same records as the reference's FastqReader."""
+    rng = np.random.default_rng(2026)
+    for k in range(300):
+        text = T.fastq_fuzz_text(rng)
+        path = tmp_path / "f.fq"; path.write_bytes(text)
+        want = T.ref_fastq_read(path)
+        got = T.decoded_fields(text, T.oracle_fastq_decode(text, final=1, stride=64))
+        assert got == want, (k, text)

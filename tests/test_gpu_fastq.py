@@ -61,6 +61,16 @@ def test_decode_every_prefix_length(gpu, ctx512, cut):
             same_decode(gpu.gpu_fastq_decode(ctx512, chunk, final=final), T.oracle_fastq_decode(chunk, final=final, stride=512), f"prefix {end} final {final}")
 
 
+def test_decode_fuzz(gpu, ctx512):
+    """Random texts (mixed line ends, junk, broken records), whole and as non-final prefixes: device == oracle."""
+    rng = np.random.default_rng(77)
+    for k in range(150):
+        text = T.fastq_fuzz_text(rng)
+        cut = int(rng.integers(0, len(text) + 1))
+        for chunk, final in ((text, 1), (text[:cut], 0)):
+            same_decode(gpu.gpu_fastq_decode(ctx512, chunk, final=final), T.oracle_fastq_decode(chunk, final=final, stride=512), f"fuzz {k} final {final}")
+
+
 def test_decode_capacity_and_phred64(gpu, ctx512):
     text = CASES["plain"]
     same_decode(gpu.gpu_fastq_decode(ctx512, text, capacity=7), T.oracle_fastq_decode(text, stride=512, capacity=7), "capacity")
