@@ -386,3 +386,34 @@ def fastq_fuzz_text(rng, nrec=30):
     if rng.random() < 0.3 and text:
         text = text.rstrip("\r\n")
     return text.encode()
+
+
+def random_params(rng, paired, lib=None):
+    """A random but valid option set: every knob the chain reads gets exercised in combinations no fixed config has."""
+    R = lambda a, b: int(rng.integers(a, b + 1))          # noqa: E731
+    coin = lambda p=0.5: bool(rng.random() < p)           # noqa: E731
+    kw = dict(
+        thread0_semantics=1 if coin(0.8) else 0,
+        trim_front1=R(0, 8) if coin(0.4) else 0, trim_tail1=R(0, 8) if coin(0.4) else 0,
+        max_len1=R(60, 140) if coin(0.3) else 0,
+        cut_front=int(coin(0.4)), cut_tail=int(coin(0.4)), cut_right=int(coin(0.5)),
+        cut_front_window=R(1, 8), cut_front_quality=R(5, 30), cut_tail_window=R(1, 8), cut_tail_quality=R(5, 30),
+        cut_right_window=4 if coin(0.5) else R(1, 10), cut_right_quality=R(10, 30),
+        polyg_enabled=int(coin()), polyg_min_len=R(5, 20), polyx_enabled=int(coin()), polyx_min_len=R(5, 20),
+        adapter_enabled=int(coin(0.85)), dimer_max_len=R(0, 12),
+        qual_filter_enabled=int(coin(0.85)), qualified_qual=33 + R(5, 30), unqualified_percent_limit=R(5, 80),
+        n_base_limit=R(0, 10), avg_qual_req=R(0, 30) if coin(0.4) else 0,
+        length_filter_enabled=int(coin(0.85)), length_required=R(0, 80), length_limit=R(100, 150) if coin(0.3) else 0,
+        complexity_filter_enabled=int(coin(0.4)), complexity_threshold=R(5, 60) / 100.0,
+    )
+    if coin(0.5):
+        kw["adapter_seq_r1"] = TRUSEQ_R1[: R(6, len(TRUSEQ_R1))]
+    if coin(0.3):
+        kw["fasta_adapters"] = [TRUSEQ_R1[: R(8, 33)], "CTGTCTCTTATACACATCT", "G" * R(8, 14)][: R(1, 3)]
+    if paired:
+        kw.update(trim_front2=R(0, 8) if coin(0.4) else 0, trim_tail2=R(0, 8) if coin(0.4) else 0, max_len2=R(60, 140) if coin(0.3) else 0,
+                  correction_enabled=int(coin()), overlap_require=R(10, 40), overlap_diff_limit=R(1, 8), overlap_diff_percent_limit=R(5, 40),
+                  allow_gap_overlap_trimming=int(coin(0.3)), insert_size_max=R(300, 600) if coin(0.3) else 512)
+        if coin(0.5):
+            kw["adapter_seq_r2"] = TRUSEQ_R2[: R(6, len(TRUSEQ_R2))]
+    return capi.default_params(paired, lib=lib or oracle(), **kw), kw

@@ -106,3 +106,15 @@ def test_overrepresentation_with_correction_host_mode(gpu):
     want = T.run_cpu("oracle", p, arrs, 160)
     got = gpu.run_gpu(p, arrs, 160, mode="host")
     T.assert_results_equal(got, want, 1, what="overrep-host")
+
+
+@pytest.mark.parametrize("paired", [1, 0])
+def test_random_option_sets(gpu, paired):
+    """30 random option sets (the same generator the port is pinned to the reference with): CUDA == oracle."""
+    rng = np.random.default_rng(4321 + paired)
+    for k in range(30):
+        p, kw = T.random_params(rng, paired)
+        _, arrs = T.synth_host(2500, 160, paired, 100 * k, 700 + k, 2 if paired else 1, 150)
+        want = T.run_cpu("oracle", p, arrs, 160)
+        got = gpu.run_gpu(p, arrs, 160, mode="device")
+        T.assert_results_equal(got, want, paired, what=f"random set {k}: {kw}")

@@ -64,3 +64,17 @@ def test_port_equals_reference_overrepresentation(paired, L, stride, sampling):
     y = T.run_cpu("ref", p, arrs, stride)
     T.assert_results_equal(x, y, paired, skip=("adapter_pos",), what="overrep")
     assert sum(int(x["counters"].overrep(s)[0].sum()) for s in range(4 if paired else 2)) > 10
+
+
+@needs_ref
+@pytest.mark.parametrize("paired", [1, 0])
+def test_port_equals_reference_random_option_sets(paired):
+    """30 random option sets (windows, thresholds, trims, adapter lists, overlap limits ...) on reads with indels."""
+    import numpy as np
+    rng = np.random.default_rng(1234 + paired)
+    for k in range(30):
+        p, kw = T.random_params(rng, paired)
+        _, arrs = T.synth_host(1500, 160, paired, 100 * k, 900 + k, 2 if paired else 1, 150)
+        x = T.run_cpu("oracle", p, arrs, 160)
+        y = T.run_cpu("ref", p, arrs, 160)
+        T.assert_results_equal(x, y, paired, skip=("adapter_pos",), what=f"random set {k}: {kw}")
