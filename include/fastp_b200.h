@@ -318,8 +318,13 @@ int  fp_fastq_decode(fp_ctx* ctx, const uint8_t* d_text, int64_t nbytes, int32_t
 int  fp_fastq_encode(fp_ctx* ctx, const uint8_t* d_text, const fp_fastq_rec* d_recs, const fp_read_result* d_res,
                      const uint8_t* d_seq, const uint8_t* d_qual, int64_t n, uint8_t* d_out, int64_t out_cap, int64_t* out_bytes);
 /* Whole path on HOST buffers: text chunk(s) in, filtered text out (text2/out2 NULL for single-end).
- * Decodes up to the ctx's max_batch records per side, runs the operator chain, encodes the passing reads.
- * n_units = reads / pairs processed; consumed1/2 = bytes of each input they cover.  Synchronous.      */
+ * The chunk is worked through in rounds of at most the ctx's max_batch records: the text goes up in pieces on its own
+ * stream while earlier pieces are decoded, run through the operator chain and encoded, and their output text goes down
+ * on a third stream (pinned host buffers overlap; pageable ones work, serialised).  n_units = reads / pairs processed
+ * (pairs end with the shorter side); consumed1/2 = bytes of each input they cover -- the caller prepends the rest
+ * (an incomplete last record, the longer side's surplus) to its next chunk; final_chunk: no more input follows.
+ * info1/2 (optional): records, lines, first reader error (the stream ends there, like FastqReader returning NULL).
+ * Counters accumulate in the ctx as with fp_process_*.  Synchronous.                                            */
 int  fp_fastq_process_host(fp_ctx* ctx, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2, int64_t nbytes2,
                            int32_t final_chunk, int32_t phred64,
                            uint8_t* out1, int64_t out_cap1, int64_t* out_bytes1,
