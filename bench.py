@@ -357,7 +357,7 @@ def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
                 flags = {"pe150_overlap_correction": ["-c"], "pe150_full": ["--cut_right", "-g", "-x", "-c", "-a", "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA",
                                                                            "--adapter_sequence_r2", "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"],
                          "se150_cut_right_polyg": ["--cut_right", "-g", "-A"]}[args.workload]
-                thr = min(os.cpu_count() or 1, 16)
+                thr = os.cpu_count() or 1                    # the reference clamps --thread to hardware_concurrency (src/options.cpp:294-300)
                 cmd = [cli, "-i", names[0], "-w", str(thr), "--dont_eval_duplication", "-j", os.path.join(d, "x.json"), "-h", os.path.join(d, "x.html")] + flags
                 if paired:
                     cmd += ["-I", names[1]]
@@ -365,7 +365,7 @@ def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
                 subprocess.run(cmd, check=True, capture_output=True, cwd=d, timeout=600)
                 tc = time.perf_counter() - t0
             res["cpu_cli"] = {"value": nf / tc, "unit": unit, "threads": thr, "seconds": tc,
-                              "sample": f"{nf} units, unmodified reference CLI (oracle/_ref/fastp_ref, plain FASTQ in a RAM-backed dir, no output files, -w {thr})"}
+                              "sample": f"{nf} units, unmodified reference CLI (oracle/_ref/fastp_ref, plain FASTQ in a RAM-backed dir, no output files, -w {thr}; wall clock of the whole process incl. start-up)"}
         except Exception as e:
             res["cpu_cli"] = {"value": None, "sample": repr(e)}
     return res
