@@ -357,12 +357,14 @@ def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
                 flags = {"pe150_overlap_correction": ["-c"], "pe150_full": ["--cut_right", "-g", "-x", "-c", "-a", "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA",
                                                                            "--adapter_sequence_r2", "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"],
                          "se150_cut_right_polyg": ["--cut_right", "-g", "-A"]}[args.workload]
-                thr = os.cpu_count() or 1                    # the reference clamps --thread to hardware_concurrency (src/options.cpp:294-300)
+                # 16 worker threads: with one thread per core of a 128-core box the unmodified CLI did not finish 1 M pairs in 5 minutes
+                # (its reader / writer hand-off spins), while 16 take about a second; the in-memory reference arm (cpu_baseline) uses every core
+                thr = min(os.cpu_count() or 1, 16)
                 cmd = [cli, "-i", names[0], "-w", str(thr), "--dont_eval_duplication", "-j", os.path.join(d, "x.json"), "-h", os.path.join(d, "x.html")] + flags
                 if paired:
                     cmd += ["-I", names[1]]
                 t0 = time.perf_counter()
-                subprocess.run(cmd, check=True, capture_output=True, cwd=d, timeout=600)
+                subprocess.run(cmd, check=True, capture_output=True, cwd=d, timeout=90)
                 tc = time.perf_counter() - t0
             res["cpu_cli"] = {"value": nf / tc, "unit": unit, "threads": thr, "seconds": tc,
                               "sample": f"{nf} units, unmodified reference CLI (oracle/_ref/fastp_ref, plain FASTQ in a RAM-backed dir, no output files, -w {thr}; wall clock of the whole process incl. start-up)"}
