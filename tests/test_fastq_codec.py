@@ -99,3 +99,28 @@ def test_oracle_decode_fuzz_matches_fastqreader(tmp_path):
         want = T.ref_fastq_read(path)
         got = T.decoded_fields(text, T.oracle_fastq_decode(text, final=1, stride=64))
         assert got == want, (k, text)
+
+
+@needs_ref
+@pytest.mark.reference
+@pytest.mark.parametrize("paired", [1, 0])
+@pytest.mark.parametrize("case", ["default", "full"])
+def test_oracle_text_pipeline_equals_reference_cli(tmp_path, case, paired):
+    """decode -> operator chain -> encode, all in the C port, against the UNMODIFIED reference CLI's output files: pins the whole
+    text-path oracle (the -m gpu twin holds fp_fastq_process_host to the same files)."""
+    import os
+    import test_gpu_fastq as G
+    if not os.path.exists(T.REF_CLI):
+        pytest.skip("oracle/_ref/fastp_ref not built")
+    flags, p, t1, t2 = G.cli_inputs(case, paired, n=2000)
+    want = G.run_cli(tmp_path, flags, t1, t2)
+    d1 = T.oracle_fastq_decode(t1, stride=160)
+    arrs = {"seq1": d1["seq"].copy(), "qual1": d1["qual"].copy(), "len1": d1["len"].copy()}
+    if paired:
+        d2 = T.oracle_fastq_decode(t2, stride=160)
+        arrs.update(seq2=d2["seq"].copy(), qual2=d2["qual"].copy(), len2=d2["len"].copy())
+    res = T.run_cpu("oracle", p, arrs, 160)
+    got = [T.oracle_fastq_encode(t1, d1["recs"], res["out1"], res["arrs"]["seq1"], res["arrs"]["qual1"], 160)]
+    if paired:
+        got.append(T.oracle_fastq_encode(t2, d2["recs"], res["out2"], res["arrs"]["seq2"], res["arrs"]["qual2"], 160))
+    assert got == want
