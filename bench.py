@@ -299,12 +299,14 @@ def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
                                                  ob_[1].data_ptr() if paired else None, ob_[1].numel() if paired else 0, C.byref(o[1]) if paired else None,
                                                  C.byref(n_), C.byref(a_), C.byref(b_) if paired else None, C.byref(j1), C.byref(j2) if paired else None), lib)
     worker(h2, outs2)
-    th = [threading.Thread(target=worker, args=(hctx, outs)), threading.Thread(target=worker, args=(h2, outs2))]
+    th = [threading.Thread(target=worker, args=(hctx, outs), daemon=True), threading.Thread(target=worker, args=(h2, outs2), daemon=True)]
     t0 = time.perf_counter()
     for x in th:
         x.start()
     for x in th:
-        x.join()
+        x.join(timeout=120)
+    if any(x.is_alive() for x in th):
+        raise RuntimeError("two-worker text path did not finish within 120 s")
     dt2 = (time.perf_counter() - t0) / (2 * args.steps)
     lib.fp_ctx_destroy(h2)
     in_bytes = sum(int(x.numel()) for x in pin); out_bytes = ob[0].value + (ob[1].value if paired else 0)
