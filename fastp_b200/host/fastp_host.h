@@ -63,6 +63,7 @@ struct FilterResult {                 /* src/filterresult.h:66-79 */
     long mTrimmedPolyXReads[4] = {0}, mTrimmedPolyXBases[4] = {0};
     long mCorrectionMatrix[64] = {0};
     long mCorrectedReads = 0, mMergedPairs = 0;
+    void fill(const int64_t* block, const fp_counter_layout& L);       /* FilterResult::merge of the device block (filterresult.cpp:38-89) */
 };
 struct Stats {                        /* src/stats.h:77-101, summarize() src/stats.cpp:102-182 */
     int mCycles = 0, mBufLen = 0;

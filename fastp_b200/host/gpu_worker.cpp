@@ -43,6 +43,15 @@ void Options::toParams(fp_params* p, std::vector<const char*>& fastaKeep, std::v
     p->n_overrep2 = (int)ovr2Keep.size(); p->overrep_seqs2 = ovr2Keep.empty() ? nullptr : ovr2Keep.data();
 }
 
+void FilterResult::fill(const int64_t* B, const fp_counter_layout& L) {
+    const int64_t* F = B + L.off_filter;
+    for (int i = 0; i < FP_FILTER_RESULT_TYPES; i++) mFilterReadStats[i] = F[FP_FR_READSTATS + i];
+    mTrimmedAdapterRead = F[FP_FR_ADAPTER_READS]; mTrimmedAdapterBases = F[FP_FR_ADAPTER_BASES];
+    for (int b = 0; b < 4; b++) { mTrimmedPolyXReads[b] = F[FP_FR_POLYX_READS + b]; mTrimmedPolyXBases[b] = F[FP_FR_POLYX_BASES + b]; }
+    for (int i = 0; i < 64; i++) mCorrectionMatrix[i] = F[FP_FR_CORRECTION + i];
+    mCorrectedReads = F[FP_FR_CORRECTED_READS]; mMergedPairs = F[FP_FR_MERGED_PAIRS];
+}
+
 void Stats::fillOverRep(const int64_t* B, const fp_counter_layout& L, int which, const std::vector<const char*>& keys) {
     const int side = which >> 1;
     for (int k = 0; k < L.n_overrep[side] && k < (int)keys.size(); k++) {
@@ -195,14 +204,7 @@ bool GpuChainWorker::finish(Stats* pre1, Stats* post1, Stats* pre2, Stats* post2
         if (pre2) { pre2->fill(B.data(), L, FP_STATS_PRE2); pre2->fillOverRep(B.data(), L, FP_STATS_PRE2, mOvr2Keep); }
         if (post2) { post2->fill(B.data(), L, FP_STATS_POST2); post2->fillOverRep(B.data(), L, FP_STATS_POST2, mOvr2Keep); }
     }
-    if (fr) {
-        const int64_t* F = B.data() + L.off_filter;
-        for (int i = 0; i < FP_FILTER_RESULT_TYPES; i++) fr->mFilterReadStats[i] = F[FP_FR_READSTATS + i];
-        fr->mTrimmedAdapterRead = F[FP_FR_ADAPTER_READS]; fr->mTrimmedAdapterBases = F[FP_FR_ADAPTER_BASES];
-        for (int b = 0; b < 4; b++) { fr->mTrimmedPolyXReads[b] = F[FP_FR_POLYX_READS + b]; fr->mTrimmedPolyXBases[b] = F[FP_FR_POLYX_BASES + b]; }
-        for (int i = 0; i < 64; i++) fr->mCorrectionMatrix[i] = F[FP_FR_CORRECTION + i];
-        fr->mCorrectedReads = F[FP_FR_CORRECTED_READS]; fr->mMergedPairs = F[FP_FR_MERGED_PAIRS];
-    }
+    if (fr) fr->fill(B.data(), L);
     if (isize) { isize->assign(L.isize_bins, 0); for (int i = 0; i < L.isize_bins; i++) (*isize)[i] = B[L.off_isize + i]; }
     return true;
 }

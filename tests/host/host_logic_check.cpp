@@ -63,6 +63,14 @@ static int doStats(const char* path) {
         printf("stats%d reads=%ld bases=%ld q20=%ld q30=%ld cycles=%d length_sum=%ld kmer=%ld qualhist=%ld tq0=%ld tb0=%ld A5=%ld\n", which, s.mReads, s.mBases,
                s.mQ20Total, s.mQ30Total, s.mCycles, s.mLengthSum, kmer, qh, s.mCycleTotalQual[0], s.mCycleTotalBase[0], s.mCycleBaseContents['A' & 7][5]);
     }
+    FilterResult fr; fr.fill(B.data(), L);
+    long corr = 0;
+    for (int i = 0; i < 64; i++) corr += fr.mCorrectionMatrix[i];
+    printf("filter pass=%ld lowq=%ld nbase=%ld tooshort=%ld adapter_reads=%ld adapter_bases=%ld corrected_reads=%ld corrections=%ld polyx_reads=%ld polyx_bases=%ld\n",
+           fr.mFilterReadStats[FP_PASS_FILTER], fr.mFilterReadStats[FP_FAIL_QUALITY], fr.mFilterReadStats[FP_FAIL_N_BASE], fr.mFilterReadStats[FP_FAIL_LENGTH],
+           fr.mTrimmedAdapterRead, fr.mTrimmedAdapterBases, fr.mCorrectedReads, corr,
+           fr.mTrimmedPolyXReads[0] + fr.mTrimmedPolyXReads[1] + fr.mTrimmedPolyXReads[2] + fr.mTrimmedPolyXReads[3],
+           fr.mTrimmedPolyXBases[0] + fr.mTrimmedPolyXBases[1] + fr.mTrimmedPolyXBases[2] + fr.mTrimmedPolyXBases[3]);
     return 0;
 }
 

@@ -53,8 +53,16 @@ def test_stats_fill_from_counter_block(exe, tmp_path, paired):
     with open(path, "wb") as f:
         f.write(bytes(cv.L)); f.write(np.ascontiguousarray(cv.data, np.int64).tobytes())
     out = subprocess.run([exe, "stats", str(path)], check=True, capture_output=True, text=True).stdout.strip().split("\n")
-    assert len(out) == (4 if paired else 2)
-    for line in out:
+    assert len(out) == (4 if paired else 2) + 1
+    fl = dict(x.split("=") for x in out[-1].split()[1:])
+    F = cv.filter
+    assert int(fl["pass"]) == F[capi.PASS_FILTER] and int(fl["lowq"]) == F[capi.FAIL_QUALITY] and int(fl["nbase"]) == F[capi.FAIL_N_BASE]
+    assert int(fl["tooshort"]) == F[capi.FAIL_LENGTH]
+    assert int(fl["adapter_reads"]) == F[capi.FR_ADAPTER_READS] and int(fl["adapter_bases"]) == F[capi.FR_ADAPTER_BASES]
+    assert int(fl["corrected_reads"]) == F[capi.FR_CORRECTED_READS] and int(fl["corrections"]) == int(F[capi.FR_CORRECTION:capi.FR_CORRECTION + 64].sum())
+    assert int(fl["polyx_reads"]) == int(F[capi.FR_POLYX_READS:capi.FR_POLYX_READS + 4].sum()) and int(fl["polyx_bases"]) == int(F[capi.FR_POLYX_BASES:capi.FR_POLYX_BASES + 4].sum())
+    assert int(fl["adapter_reads"]) > 0 and int(fl["polyx_reads"]) > 0
+    for line in out[:-1]:
         f = dict(x.split("=") for x in line.split()[1:])
         which = int(line.split()[0][5:])
         s, st = cv.summary(which), cv.stats(which)
