@@ -859,3 +859,81 @@ int64_t fp_oracle_fastq_encode(const uint8_t* text, const fp_fastq_rec* recs, co
     }
     return o;
 }
+
+
+/* ==========================================================================================
+ * Duplication bloom filter   src/duplicate.cpp
+ * ========================================================================================== */
+#include <math.h>
+#include <stdlib.h>
+#define DUP_PRIME_ARRAY_LEN (1 << 9)                                     /* duplicate.cpp:7 */
+struct fp_oracle_dup {
+    uint64_t bufLenInBytes, bufLenInBits, offsetMask;
+    int bufNum;
+    uint8_t* buf;
+    uint64_t* primes;
+    int64_t total, dups;
+};
+
+fp_oracle_dup* fp_oracle_dup_create(int accuracy_level) {                 /* Duplicate::Duplicate :9-66 */
+    fp_oracle_dup* d = (fp_oracle_dup*)calloc(1, sizeof(*d));
+    d->bufLenInBytes = 1ull << 29; d->bufNum = 2;
+    switch (accuracy_level) {
+        case 2: d->bufLenInBytes *= 2; break;
+        case 3: d->bufLenInBytes *= 2; d->bufNum *= 2; break;
+        case 4: d->bufLenInBytes *= 4; d->bufNum *= 2; break;
+        case 5: d->bufLenInBytes *= 8; d->bufNum *= 2; break;
+        case 6: d->bufLenInBytes *= 8; d->bufNum *= 4; break;
+        default: break;
+    }
+    d->offsetMask = (uint64_t)DUP_PRIME_ARRAY_LEN * d->bufNum - 1;
+    d->bufLenInBits = d->bufLenInBytes << 3;
+    d->buf = (uint8_t*)calloc(d->bufLenInBytes * d->bufNum, 1);
+    d->primes = (uint64_t*)calloc((size_t)d->bufNum * DUP_PRIME_ARRAY_LEN, 8);
+    if (!d->buf || !d->primes) { free(d->buf); free(d->primes); free(d); return NULL; }
+    uint64_t number = 10000, count = 0;                                   /* initPrimeArrays :68-86 */
+    while (count < (uint64_t)d->bufNum * DUP_PRIME_ARRAY_LEN) {
+        number++;
+        int isPrime = 1;
+        for (uint64_t i = 2; i <= sqrt((double)number); i++) if (number % i == 0) { isPrime = 0; break; }
+        if (isPrime) { d->primes[count++] = number; number += 10000; }
+    }
+    return d;
+}
+void fp_oracle_dup_destroy(fp_oracle_dup* d) { if (d) { free(d->buf); free(d->primes); free(d); } }
+
+static uint64_t dup_hash_val(uint8_t c) {                                 /* SEQ_HASH_VAL :94-112 */
+    switch (c) { case 'A': return 7; case 'T': return 222; case 'C': return 74; case 'G': return 31; default: return 13; }
+}
+static void dup_seq2intvector(const fp_oracle_dup* d, const uint8_t* data, int len, uint64_t* out, int posOffset) {   /* :114-124 */
+    for (int p = 0; p < len; p++) {
+        const uint64_t base = dup_hash_val(data[p]);
+        for (int i = 0; i < d->bufNum; i++) {
+            uint64_t offset = (uint64_t)((p + posOffset) * d->bufNum + i) & d->offsetMask;
+            out[i] += d->primes[offset] * (base + (uint64_t)(p + posOffset));
+        }
+    }
+}
+static int dup_apply(fp_oracle_dup* d, const uint64_t* positions) {       /* applyBloomFilter :156-169 */
+    int isDup = 1;
+    for (int i = 0; i < d->bufNum; i++) {
+        const uint64_t pos = positions[i] % d->bufLenInBits;
+        uint8_t* byte = d->buf + (uint64_t)i * d->bufLenInBytes + (pos >> 3);
+        const uint8_t bit = (uint8_t)(1u << (pos & 7));
+        isDup &= (*byte & bit) != 0;
+        *byte |= bit;
+    }
+    return isDup;
+}
+void fp_oracle_dup_check(fp_oracle_dup* d, const fp_batch* b, int paired, uint8_t* is_dup) {   /* checkRead :126-139, checkPair :141-154 */
+    for (int64_t i = 0; i < b->n; i++) {
+        uint64_t positions[8] = {0};
+        const int l1 = b->len1[i];
+        dup_seq2intvector(d, b->seq1 + (size_t)i * b->stride, l1, positions, 0);
+        if (paired) dup_seq2intvector(d, b->seq2 + (size_t)i * b->stride, b->len2[i], positions, l1);
+        const int dup = dup_apply(d, positions);
+        d->total++; d->dups += dup;
+        if (is_dup) is_dup[i] = (uint8_t)dup;
+    }
+}
+void fp_oracle_dup_totals(const fp_oracle_dup* d, int64_t* total, int64_t* dups) { *total = d->total; *dups = d->dups; }

@@ -28,6 +28,14 @@ int fp_oracle_fastq_decode(const uint8_t* text, int64_t nbytes, int final_chunk,
                            uint8_t* seq, uint8_t* qual, uint16_t* len, int64_t capacity, fp_fastq_rec* recs, fp_fastq_info* info);
 int64_t fp_oracle_fastq_encode(const uint8_t* text, const fp_fastq_rec* recs, const fp_read_result* res, const uint8_t* seq, const uint8_t* qual,
                                int stride, int64_t n, uint8_t* out, int64_t out_cap);
+
+/* Duplication bloom filter (src/duplicate.cpp) -- oracle first, the device path comes next round.
+ * is_dup[i] = what Duplicate::checkRead / checkPair returns for unit i when the units are fed in index order. */
+typedef struct fp_oracle_dup fp_oracle_dup;
+fp_oracle_dup* fp_oracle_dup_create(int accuracy_level);
+void fp_oracle_dup_destroy(fp_oracle_dup* d);
+void fp_oracle_dup_check(fp_oracle_dup* d, const fp_batch* b, int paired, uint8_t* is_dup);
+void fp_oracle_dup_totals(const fp_oracle_dup* d, int64_t* total, int64_t* dups);
 #ifdef __cplusplus
 }
 #endif

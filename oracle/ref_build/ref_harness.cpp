@@ -20,6 +20,7 @@
 #include "read.h"
 #include "stats.h"
 #include "fastqreader.h"
+#include "duplicate.h"
 #include "filter.h"
 #include "filterresult.h"
 #include "polyx.h"
@@ -389,6 +390,32 @@ int64_t fp_ref_fastq_read_file(const char* path, int phred64, uint8_t* out, int6
     }
     *used = o;
     return n;
+}
+
+// The reference's own Duplicate object (src/duplicate.cpp), units fed in index order.
+struct fp_ref_dup { Options opt; Duplicate* d; int64_t total = 0, dups = 0; };
+void* fp_ref_dup_create(int accuracy_level) {
+    fp_ref_dup* h = new fp_ref_dup();
+    h->opt.duplicate.enabled = true; h->opt.duplicate.accuracyLevel = accuracy_level;
+    h->d = new Duplicate(&h->opt);
+    return h;
+}
+void fp_ref_dup_destroy(void* hp) { fp_ref_dup* h = (fp_ref_dup*)hp; delete h->d; delete h; }
+void fp_ref_dup_check(void* hp, const fp_batch* b, int paired, uint8_t* is_dup) {
+    fp_ref_dup* h = (fp_ref_dup*)hp;
+    for (int64_t i = 0; i < b->n; i++) {
+        Read r1("@a", std::string((const char*)b->seq1 + (size_t)i * b->stride, b->len1[i]).c_str(), "+", std::string(b->len1[i], 'I').c_str());
+        bool dup;
+        if (paired) {
+            Read r2("@a", std::string((const char*)b->seq2 + (size_t)i * b->stride, b->len2[i]).c_str(), "+", std::string(b->len2[i], 'I').c_str());
+            dup = h->d->checkPair(&r1, &r2);
+        } else dup = h->d->checkRead(&r1);
+        h->total++; h->dups += dup ? 1 : 0;
+        if (is_dup) is_dup[i] = dup ? 1 : 0;
+    }
+}
+void fp_ref_dup_totals(void* hp, int64_t* total, int64_t* dups, double* rate) {
+    fp_ref_dup* h = (fp_ref_dup*)hp; *total = h->total; *dups = h->dups; *rate = h->d->getDupRate();
 }
 
 }  // extern "C"
