@@ -60,3 +60,62 @@ def test_port_equals_reference_duplicate(paired):
         assert do.value >= int(n / 1.4 * 0.4) - 80
     finally:
         olib.fp_oracle_dup_destroy(od); rlib.fp_ref_dup_destroy(rd)
+
+
+def _dup_positions(arrs, paired, buf_num=2, prime_len=512, buf_bits=(1 << 29) * 8):
+    """Bit position of every unit in every array, vectorised restatement of seq2intvector (uint64 wrap-around arithmetic)."""
+    primes = []
+    number = 10000
+    while len(primes) < buf_num * prime_len:
+        number += 1
+        if all(number % i for i in range(2, int(number ** 0.5) + 1)):
+            primes.append(number); number += 10000
+    primes = np.array(primes, np.uint64)
+    lut = np.full(256, 13, np.uint64); lut[ord("A")] = 7; lut[ord("T")] = 222; lut[ord("C")] = 74; lut[ord("G")] = 31
+    n = len(arrs["len1"])
+    pos = np.zeros((n, buf_num), np.uint64)
+    mask = buf_num * prime_len - 1
+    with np.errstate(over="ignore"):
+        for side, off in (("1", np.zeros(n, np.int64)), ("2", arrs["len1"].astype(np.int64)))[: 2 if paired else 1]:
+            S = arrs["seq" + side].shape[1]
+            p = np.arange(S)[None, :] + off[:, None]
+            valid = np.arange(S)[None, :] < arrs["len" + side][:, None]
+            base = lut[arrs["seq" + side]] + p.astype(np.uint64)
+            for i in range(buf_num):
+                w = primes[((p * buf_num + i) & mask)]
+                pos[:, i] += np.where(valid, w * base, np.uint64(0)).sum(axis=1, dtype=np.uint64)
+    return pos % np.uint64(buf_bits)
+
+
+def test_first_toucher_formulation_equals_sequential_filter():
+    """The device design: unit i is a duplicate iff, in every array, its bit is set from earlier batches or the smallest
+    index touching that bit in this batch is < i.  Emulated with numpy and compared with the sequential C port, batch by batch."""
+    olib = T.oracle()
+    olib.fp_oracle_dup_create.restype = C.c_void_p; olib.fp_oracle_dup_create.argtypes = [C.c_int]
+    olib.fp_oracle_dup_check.argtypes = [C.c_void_p, C.POINTER(capi.Batch), C.c_int, C.c_void_p]
+    olib.fp_oracle_dup_destroy.argtypes = [C.c_void_p]
+    for paired in (1, 0):
+        arrs = planted(paired, n=3000, seed=21 + paired)
+        n = len(arrs["len1"])
+        od = olib.fp_oracle_dup_create(1)
+        try:
+            persistent = [set(), set()]
+            for lo, hi in ((0, n // 2), (n // 2, n)):
+                sub = {k: np.ascontiguousarray(v[lo:hi]) for k, v in arrs.items()}
+                b = capi.batch_from_arrays(sub)
+                want = np.zeros(hi - lo, np.uint8)
+                olib.fp_oracle_dup_check(od, C.byref(b), paired, want.ctypes.data)
+                pos = _dup_positions(sub, paired)
+                m = hi - lo
+                got = np.ones(m, bool)
+                for a in range(2):
+                    first = {}
+                    for i in range(m):                                   # pass 1: first toucher of every bit (atomicMin on the device)
+                        first.setdefault(int(pos[i, a]), i)
+                    for i in range(m):                                   # pass 2
+                        k = int(pos[i, a])
+                        got[i] &= (k in persistent[a]) or first[k] < i
+                    persistent[a].update(first)                           # pass 3
+                assert np.array_equal(got.astype(np.uint8), want), (paired, lo)
+        finally:
+            olib.fp_oracle_dup_destroy(od)
