@@ -118,6 +118,9 @@ SYMBOLS = {
     "fp_synth_fill": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "fp_kernel_time_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "fp_version": (C.c_int, []),
+    "fp_dup_check": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p]),
+    "fp_dup_totals": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fp_dup_reset": (C.c_int, [C.c_void_p]),
     "fp_fastq_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.POINTER(FastqInfo)]),
     "fp_fastq_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

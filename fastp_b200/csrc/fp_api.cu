@@ -22,6 +22,7 @@
 #include "fp_device.cuh"
 #include "fp_chain2.cuh"
 #include "fp_fastq.cuh"
+#include "fp_dup.cuh"
 
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
@@ -89,6 +90,13 @@ struct fp_ctx {
     unsigned int *fq_hinfo = nullptr, *fq_hinfo_dev = nullptr;      /* mapped pinned control words */
     cudaStream_t fq_stream_out = nullptr;
     cudaEvent_t fq_ev_up = nullptr, fq_ev_out[2] = {nullptr, nullptr};
+    /* duplication bloom filter (fp_dup.h) */
+    fp_dup_state dup{};
+    int dup_level = 0;
+    uint64_t* d_dup_primes = nullptr;
+    unsigned long long* d_dup_count = nullptr;
+    int64_t dup_total = 0;
+    Buf dup_pos, dup_keys, dup_vals;
     /* kernel timing */
     std::vector<EvPair> evs;
     std::vector<EvPair> ev_pool;
@@ -361,6 +369,9 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
                               &c->fqh_text[0], &c->fqh_text[1], &c->fqh_seq[0], &c->fqh_seq[1], &c->fqh_qual[0], &c->fqh_qual[1], &c->fqh_len[0], &c->fqh_len[1],
                               &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1],
                               &c->fqh_outbuf[0][0], &c->fqh_outbuf[0][1], &c->fqh_outbuf[1][0], &c->fqh_outbuf[1][1], &c->fqh_recend[0], &c->fqh_recend[1]};
+        if (c->dup.bits) cudaFree(c->dup.bits);
+        cudaFree(c->d_dup_primes); cudaFree(c->d_dup_count);
+        fq_free(c->dup_pos); fq_free(c->dup_keys); fq_free(c->dup_vals);
         if (c->fq_hinfo) cudaFreeHost(c->fq_hinfo);
         if (c->fq_stream_out) { cudaStreamDestroy(c->fq_stream_out); cudaEventDestroy(c->fq_ev_up); cudaEventDestroy(c->fq_ev_out[0]); cudaEventDestroy(c->fq_ev_out[1]); }
         for (auto* b : all) fq_free(*b);
@@ -835,6 +846,75 @@ extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nb
     *out_bytes1 = obytes[0]; if (out_bytes2) *out_bytes2 = obytes[1];
     if (info1) *info1 = agg[0];
     if (info2 && sides == 2) *info2 = agg[1];
+    return FP_OK;
+}
+
+/* ---------------- duplication bloom filter (fp_dup.h / fp_dup.cuh) ---------------- */
+extern "C" int fp_dup_check(fp_ctx* c, const fp_batch* b, int32_t accuracy_level, uint8_t* d_is_dup, void* stream) {
+    if (!c || !b) return set_err(FP_E_INVAL, "null argument");
+    if (b->n < 0 || b->n >= ((int64_t)1 << 31)) return set_err(FP_E_TOOLARGE, "batch larger than 2^31 (split it)");
+    if (accuracy_level < 1 || accuracy_level > 6) return set_err(FP_E_INVAL, "dup accuracy level must be 1..6");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
+    const int paired = c->p.paired ? 1 : 0;
+    if (!c->dup.bits) {                                        /* Duplicate::Duplicate src/duplicate.cpp:9-66 */
+        uint64_t buf_bytes; int buf_num;
+        fp_dup_sizes(accuracy_level, &buf_bytes, &buf_num);
+        std::vector<uint64_t> primes((size_t)buf_num * FP_DUP_PRIME_LEN);
+        fp_dup_primes(primes.data(), (int)primes.size());
+        CK(cudaMalloc(&c->dup.bits, (size_t)buf_num * buf_bytes));
+        CK(cudaMemset(c->dup.bits, 0, (size_t)buf_num * buf_bytes));
+        CK(cudaMalloc(&c->d_dup_primes, primes.size() * 8));
+        CK(cudaMemcpy(c->d_dup_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_dup_count, 8));
+        CK(cudaMemset(c->d_dup_count, 0, 8));
+        c->dup.buf_num = buf_num; c->dup.buf_bits = buf_bytes << 3; c->dup.offset_mask = (uint64_t)FP_DUP_PRIME_LEN * buf_num - 1;
+        c->dup.primes = c->d_dup_primes;
+        c->dup_level = accuracy_level; c->dup_total = 0;
+    } else if (accuracy_level != c->dup_level) return set_err(FP_E_INVAL, "dup accuracy level differs from the first call's");
+    const int64_t n = b->n;
+    if (n == 0) return FP_OK;
+    if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    const int64_t total = n * c->dup.buf_num;
+    uint64_t cap = 1; while (cap < (uint64_t)(2 * total + 16)) cap <<= 1;
+    int rc;
+    if ((rc = fq_ensure(c->dup_pos, (size_t)total * 8))) return rc;
+    if ((rc = fq_ensure(c->dup_keys, (size_t)cap * 8))) return rc;
+    if ((rc = fq_ensure(c->dup_vals, (size_t)cap * 4))) return rc;
+    fp_dup_state S = c->dup;
+    S.pos = (uint64_t*)c->dup_pos.p; S.keys = (uint64_t*)c->dup_keys.p; S.vals = (uint32_t*)c->dup_vals.p; S.table_mask = cap - 1;
+    CK(cudaMemsetAsync(S.keys, 0xFF, (size_t)cap * 8, st));    /* FP_DUP_EMPTY */
+    CK(cudaMemsetAsync(S.vals, 0xFF, (size_t)cap * 4, st));
+    const unsigned gu = (unsigned)((n + 255) / 256), gt = (unsigned)((total + 255) / 256);
+    fp_dup_hash_kernel<<<gu, 256, 0, st>>>(S, n, b->seq1, b->len1, b->seq2, b->len2, b->stride, paired);
+    fp_dup_first_kernel<<<gt, 256, 0, st>>>(S, total);
+    fp_dup_decide_kernel<<<gu, 256, 0, st>>>(S, n, d_is_dup, c->d_dup_count);
+    fp_dup_commit_kernel<<<gt, 256, 0, st>>>(S, total);
+    CK(cudaGetLastError());
+    c->dup_total += n;
+    return FP_OK;
+}
+
+extern "C" int fp_dup_totals(fp_ctx* c, int64_t* total, int64_t* dups) {
+    if (!c || !total || !dups) return set_err(FP_E_INVAL, "null argument");
+    *total = c->dup_total; *dups = 0;
+    if (!c->d_dup_count) return FP_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, c->d_dup_count, 8, cudaMemcpyDeviceToHost));
+    *dups = (int64_t)v;
+    return FP_OK;
+}
+
+extern "C" int fp_dup_reset(fp_ctx* c) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    if (!c->dup.bits) return FP_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(c->dup.bits, 0, (size_t)c->dup.buf_num * (c->dup.buf_bits >> 3)));
+    CK(cudaMemset(c->d_dup_count, 0, 8));
+    c->dup_total = 0;
     return FP_OK;
 }
 

@@ -331,6 +331,16 @@ int  fp_fastq_process_host(fp_ctx* ctx, const uint8_t* text1, int64_t nbytes1, c
                            uint8_t* out2, int64_t out_cap2, int64_t* out_bytes2,
                            int64_t* n_units, int64_t* consumed1, int64_t* consumed2, fp_fastq_info* info1, fp_fastq_info* info2);
 
+/* ---------------- duplication bloom filter (src/duplicate.cpp) ----------------
+ * fp_dup_check replaces Duplicate::checkRead / checkPair (src/duplicate.cpp:126-154) for a batch in DEVICE memory: d_is_dup[i]
+ * (nullable) = what the reference returns for unit i when units are fed in index order, batch after batch -- deterministic, not
+ * the scheduling-dependent answer plain atomicOr would give.  The bit arrays live in the ctx (1 GiB at accuracy
+ * level 1, --dup_accuracy_level src/main.cpp) and are allocated by the first call; later calls must use the same level.
+ * fp_dup_totals: Duplicate::mTotalReads / mDupReads (getDupRate = dups / total).  Enqueued on `stream` (NULL = the ctx's). */
+int  fp_dup_check(fp_ctx* ctx, const fp_batch* b, int32_t accuracy_level, uint8_t* d_is_dup, void* stream);
+int  fp_dup_totals(fp_ctx* ctx, int64_t* total, int64_t* dups);
+int  fp_dup_reset(fp_ctx* ctx);
+
 /* Pinned host memory helpers for the staging shim. */
 int  fp_host_alloc(void** p, size_t bytes);
 int  fp_host_free(void* p);

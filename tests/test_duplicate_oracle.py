@@ -119,3 +119,44 @@ def test_first_toucher_formulation_equals_sequential_filter():
                 assert np.array_equal(got.astype(np.uint8), want), (paired, lo)
         finally:
             olib.fp_oracle_dup_destroy(od)
+
+
+def test_device_bodies_emulated_on_host_equal_the_oracle(tmp_path):
+    """fastp_b200/csrc/fp_dup.h holds the per-thread bodies of the device passes as host+device functions; here they run on the host,
+    one thread at a time in shuffled order, over three batches -- same flags as the sequential C port, whatever the order."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "dup_emulation"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "fastp_b200", "csrc"), os.path.join(root, "tests", "host", "dup_emulation.cpp"),
+                    "-o", str(exe)], check=True)
+    olib = T.oracle()
+    olib.fp_oracle_dup_create.restype = C.c_void_p; olib.fp_oracle_dup_create.argtypes = [C.c_int]
+    olib.fp_oracle_dup_check.argtypes = [C.c_void_p, C.POINTER(capi.Batch), C.c_int, C.c_void_p]
+    olib.fp_oracle_dup_destroy.argtypes = [C.c_void_p]
+    for paired in (1, 0):
+        arrs = planted(paired, n=3000, seed=33 + paired)
+        n = len(arrs["len1"])
+        cuts = [(0, n // 3), (n // 3, n // 2), (n // 2, n)]
+        path = tmp_path / f"b{paired}.bin"
+        od = olib.fp_oracle_dup_create(1)
+        want = []
+        try:
+            with open(path, "wb") as f:
+                f.write(np.int64(len(cuts)).tobytes())
+                for lo, hi in cuts:
+                    sub = {k: np.ascontiguousarray(v[lo:hi]) for k, v in arrs.items()}
+                    f.write(np.int64(hi - lo).tobytes()); f.write(np.int32(160).tobytes()); f.write(np.int32(paired).tobytes())
+                    f.write(sub["seq1"].tobytes()); f.write(sub["len1"].tobytes())
+                    if paired:
+                        f.write(sub["seq2"].tobytes()); f.write(sub["len2"].tobytes())
+                    b = capi.batch_from_arrays(sub)
+                    w = np.zeros(hi - lo, np.uint8)
+                    olib.fp_oracle_dup_check(od, C.byref(b), paired, w.ctypes.data)
+                    want.append("".join(map(str, w)))
+        finally:
+            olib.fp_oracle_dup_destroy(od)
+        for seed in (1, 2):
+            got = subprocess.run([str(exe), str(path), "1", str(seed)], check=True, capture_output=True, text=True).stdout.strip().split("\n")
+            assert got == want, (paired, seed)
+        assert sum(x.count("1") for x in want) > 500
