@@ -104,6 +104,7 @@ int main(int argc, char** argv) {
             if (o1.is_open()) o1 << s1;
             if (o2.is_open()) o2 << s2;
             buf1.erase(0, c1); if (opt.paired) buf2.erase(0, c2);
+            if (worker.inputEnded()) break;                    /* a reader gave up on a record: the reference stops reading there */
             if (final && (units == 0 || (buf1.empty() && buf2.empty()))) break;
             if (final && c1 == 0 && c2 == 0) break;
         }

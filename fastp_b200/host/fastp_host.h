@@ -94,6 +94,9 @@ public:
     /* Text path (device FASTQ codec): one chunk of plain FASTQ text per side in, the passing reads' text out.
      * Replaces the reader's parse (FastqReader::read), the body above and Read::appendToString in one call; `consumed*` says how many
      * bytes of each chunk were used -- the caller prepends the rest to its next chunk.  `final`: no more input follows.        */
+    /* true once a reader rejected a record (strand line not '+', |quality| != |sequence|): like FastqReader::read returning NULL the
+     * input ENDS there -- the caller stops feeding chunks (src/fastqreader.cpp:349-364) */
+    bool inputEnded() const { return mInputEnded; }
     bool processFastqText(const char* text1, size_t n1, const char* text2, size_t n2, bool final, bool phred64,
                           std::string* outstr1, std::string* outstr2, size_t* consumed1, size_t* consumed2, long* units);
 
@@ -114,6 +117,7 @@ private:
     fp_read_result* mRes[2] = {nullptr, nullptr};
     fp_ov_result* mOv = nullptr;
     std::vector<uint8_t> mTextOut[2];
+    bool mInputEnded = false;
     std::string mError;
 };
 

@@ -7,6 +7,7 @@
  * (output string building src/peprocessor.cpp:575-620) runs here on the verdicts.
  */
 #include "fastp_host.h"
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
 
@@ -184,6 +185,12 @@ bool GpuChainWorker::processFastqText(const char* text1, size_t n1, const char* 
                                          &nu, &c1, paired ? &c2 : nullptr, &i1, paired ? &i2 : nullptr);
     if (rc != FP_OK) { mError = fp_last_error(); return false; }
     if (i1.error == FP_FQ_ERR_STRIDE || (paired && i2.error == FP_FQ_ERR_STRIDE)) { mError = "a read is longer than the row stride (raise --max_read_len)"; return false; }
+    if (i1.error != FP_FQ_OK || (paired && i2.error != FP_FQ_OK)) {
+        const fp_fastq_info& bad = i1.error != FP_FQ_OK ? i1 : i2;
+        fprintf(stderr, "%s (record %lld of read%d)\nYour FASTQ may be invalid, please check the tail of your FASTQ file\n",
+                bad.error == FP_FQ_ERR_STRAND ? "Expected '+'" : "ERROR: sequence and quality have different length:", (long long)bad.error_record, i1.error != FP_FQ_OK ? 1 : 2);
+        mInputEnded = true;
+    }
     if (outstr1) outstr1->append(reinterpret_cast<const char*>(mTextOut[0].data()), (size_t)ob1);
     if (paired && outstr2) outstr2->append(reinterpret_cast<const char*>(mTextOut[1].data()), (size_t)ob2);
     if (consumed1) *consumed1 = (size_t)c1;
