@@ -88,7 +88,7 @@ FP_DUP_HD void fp_dup_first(const fp_dup_state& S, long long t) {
     const long long u = t / S.buf_num; const int a = (int)(t % S.buf_num);
     const uint64_t key = fp_dup_key(a, S.pos[t]);
     uint64_t slot = fp_dup_slot(key, S.table_mask);
-    for (;;) {
+    for (uint64_t probes = 0; probes <= S.table_mask; probes++) {          /* the table is at most half full: ends after a few probes */
         const uint64_t prev = FP_DUP_CAS64(&S.keys[slot], FP_DUP_EMPTY, key);
         if (prev == FP_DUP_EMPTY || prev == key) { FP_DUP_MIN32(&S.vals[slot], (uint32_t)u); return; }
         slot = (slot + 1) & S.table_mask;
@@ -104,8 +104,9 @@ FP_DUP_HD int fp_dup_decide(const fp_dup_state& S, long long u) {
         if ((word >> (pos & 31)) & 1u) continue;                          /* set by an earlier batch */
         const uint64_t key = fp_dup_key(a, pos);
         uint64_t slot = fp_dup_slot(key, S.table_mask);
-        while (S.keys[slot] != key) slot = (slot + 1) & S.table_mask;       /* present: pass 1 inserted it */
-        if (!(S.vals[slot] < (uint32_t)u)) dup = 0;                         /* nobody before me touched it */
+        uint64_t probes = 0;
+        while (S.keys[slot] != key && probes++ <= S.table_mask) slot = (slot + 1) & S.table_mask;     /* present: pass 1 inserted it */
+        if (S.keys[slot] != key || !(S.vals[slot] < (uint32_t)u)) dup = 0;  /* nobody before me touched it */
     }
     return dup;
 }

@@ -17,5 +17,5 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.parametrize("paired", [1, 0])
 def test_device_duplicate_filter_equals_oracle(paired):
-    r = subprocess.run([sys.executable, os.path.join(HERE, "_gpu_dup_worker.py"), str(paired)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "_gpu_dup_worker.py"), str(paired)], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
