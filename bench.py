@@ -32,8 +32,28 @@ BYTES_PER_PAIR = 4 * READ_LEN + 32          # 4*L in + two 16-by
 SEED = 42
 
 
-def workload_params(capi, lib, name):
-    """fp_params of the named BASELINE.json config."""
+# BASELINE.json configs -> bench workloads.  configs[0] (testdata, CPU plumbing) is a parity test, not a bench line.
+WORKLOADS = {
+    "pe150_overlap_correction": dict(cfg="configs[2]", paired=1, L=150, S=160, units=100_000_000, profile=1),
+    "pe150_full":               dict(cfg="configs[3]", paired=1, L=150, S=160, units=125_000_000, profile=1),
+    "se150_cut_right_polyg":    dict(cfg="configs[1]", paired=0, L=150, S=160, units=10_000_000, profile=1),
+    "pe250_overrep":            dict(cfg="configs[4]", paired=1, L=250, S=256, units=12_500_000, profile=3),
+}
+OVERREP_PRESCAN_UNITS = 8192        # > 151*10000 / 250 reads: what Evaluator::computeOverRepSeq looks at (evaluator.cpp:83)
+
+
+def metric_string(paired, L):
+    """ONE string for both arms (the driver divides the two lines only when `metric` matches)."""
+    return (f"{'pairs' if paired else 'reads'} per second, {L} bp {'PE' if paired else 'SE'} synthetic FASTQ"
+            + (" (1 pair = 2 reads: reads_per_s = 2 x value)" if paired else ""))
+
+
+def bytes_per_unit(paired, L):
+    return (4 * L + 32) if paired else (2 * L + 16)     # SURVEY.md 8(d)
+
+
+def workload_params(capi, lib, name, overrep=None):
+    """fp_params of the named BASELINE.json config.  overrep = (candidates1, candidates2) for pe250_overrep."""
     if name == "pe150_overlap_correction":      # configs[2]
         return capi.default_params(1, lib=lib, correction_enabled=1)
     if name == "pe150_full":                    # configs[3]
@@ -41,7 +61,22 @@ def workload_params(capi, lib, name):
                                    adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
     if name == "se150_cut_right_polyg":         # configs[1]
         return capi.default_params(0, lib=lib, cut_right=1, polyg_enabled=1, adapter_enabled=0)
+    if name == "pe250_overrep":                 # configs[4]: -p, sampling 20 (options.h:71-80), candidates from the host pre-scan
+        c1, c2 = overrep if overrep is not None else ([], [])
+        return capi.default_params(1, lib=lib, overrep_enabled=1, overrep_sampling=20, seq_len1=250, seq_len2=250,
+                                   overrep_seqs1=c1, overrep_seqs2=c2)
     raise KeyError(name)
+
+
+def host_overrep_candidates(lib, seq, lens, stride, seqlen):
+    """Evaluator::computeOverRepSeq equivalent of the product library (host pre-scan, control plane) on rows in host memory."""
+    from fastp_b200 import capi
+    n_out = C.c_int32(); used = C.c_int64()
+    cap = 1 << 22
+    buf = C.create_string_buffer(cap)
+    capi.check(lib.fp_host_overrep_candidates(seq.ctypes.data, lens.ctypes.data, seq.shape[0], stride, seqlen, buf, cap,
+                                              C.byref(n_out), C.byref(used)), lib)
+    return [x.decode() for x in buf.raw[:used.value].split(b"\0")[:-1]]
 
 
 def measured_peak():
@@ -52,6 +87,24 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_resources():
+    """Threads this process may use: affinity mask and the cgroup CPU quota (a 128-core box leased with a quota reports 128)."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        f = open("/sys/fs/cgroup/cpu.max").read().split()
+        if f[0] != "max":
+            quota = float(f[0]) / float(f[1])
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    return {"os_cpu_count": os.cpu_count(), "affinity": aff, "cgroup_quota_cpus": quota}
 
 
 class ClockSampler:
@@ -107,9 +160,9 @@ def load_cpu_checker():
     return T, "port"
 
 
-def synth_host_parallel(T, n, paired, first, profile, threads):
+def synth_host_parallel(T, n, W, first, profile, threads):
     from fastp_b200 import capi
-    b, arrs = capi.host_batch(n, STRIDE, paired)
+    b, arrs = capi.host_batch(n, W["S"], W["paired"])
     lib = T.oracle()
     bounds = [n * i // threads for i in range(threads + 1)]
 
@@ -119,24 +172,39 @@ def synth_host_parallel(T, n, paired, first, profile, threads):
             return
         sub = {k: v[lo:hi] for k, v in arrs.items()}
         sb = capi.batch_from_arrays(sub)
-        lib.fp_synth_fill_host(C.byref(sb), first + lo, SEED, profile, READ_LEN)
+        lib.fp_synth_fill_host(C.byref(sb), first + lo, SEED, profile, W["L"])
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     [t.start() for t in ts]
     [t.join() for t in ts]
     return b, arrs
 
 
-def cpu_run(T, kind, params, arrs, threads):
-    """One pass of the reference worker body over the sample on `threads` host threads; returns seconds."""
+def cpu_params(T, name, W, arrs):
+    """fp_params for the CPU leg (same option set; the over-representation candidates come from the same pre-scan rule, here
+    through the product's host function on the host-generated rows -- the checker for it is tests/test_overrep_prescan.py)."""
+    from fastp_b200 import capi
+    if name == "pe250_overrep":
+        lib = capi.load()
+        m = min(OVERREP_PRESCAN_UNITS, arrs["seq1"].shape[0])
+        c = [host_overrep_candidates(lib, np.ascontiguousarray(arrs["seq" + sd][:m]), np.ascontiguousarray(arrs["len" + sd][:m]), W["S"], W["L"]) for sd in "12"]
+        return workload_params(capi, T.oracle(), name, overrep=(c[0], c[1]))
+    return workload_params(capi, T.oracle(), name)
+
+
+def cpu_run(T, kind, params, W, arrs, threads):
+    """One pass of the reference worker body over the sample on `threads` host threads.
+    Returns (seconds inside the worker bodies, merged counter block).  The input copy (base correction rewrites rows in
+    place, so every pass needs pristine rows) and the allocation of the counter block are OUTSIDE the clock."""
     from fastp_b200 import capi
     paired = bool(params.paired)
     a = {k: v.copy() for k, v in arrs.items()}
     b = capi.batch_from_arrays(a)
-    L = capi.make_layout(T.oracle(), paired, STRIDE, params.insert_size_max)
+    L = capi.make_layout(T.oracle(), paired, W["S"], params.insert_size_max, params=params)
     cnt = np.zeros(L.total, np.int64)
-    t0 = time.perf_counter()
     if kind == "reference":
+        t0 = time.perf_counter()
         rc = T.ref().fp_ref_process_mt(C.byref(params), C.byref(L), C.byref(b), None, None, None, cnt.ctypes.data, threads)
+        dt = time.perf_counter() - t0
         assert rc == 0
     else:
         # the C port is single-threaded per call: shard over python threads (ctypes drops the GIL)
@@ -156,30 +224,41 @@ def cpu_run(T, kind, params, arrs, threads):
                                          None, c.ctypes.data)
             outs.append(c)
         ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
         [t.start() for t in ts]
         [t.join() for t in ts]
-    return time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        for c in outs:
+            cnt += c
+    return dt, (L, cnt)
 
 
-def cpu_baseline(workload, profile, target_seconds=12.0):
-    from fastp_b200 import capi
+def cpu_baseline(name, profile=None, target_seconds=10.0, max_units=6_000_000):
+    """The reference's worker body (oracle/_ref, else the C port) on a bounded sample of the workload's own stream."""
     T, kind = load_cpu_checker()
-    params = workload_params(capi, T.oracle(), workload)
-    paired = bool(params.paired)
-    cores = os.cpu_count() or 1
+    W = WORKLOADS[name]
+    profile = W["profile"] if profile is None else profile
+    res = cpu_resources()
+    cores = res["affinity"]
     probe_n = 20000 * max(1, min(cores, 16))
-    _, arrs = synth_host_parallel(T, probe_n, paired, 0, profile, min(cores, 32))
-    dt = cpu_run(T, kind, params, arrs, cores)
+    _, arrs = synth_host_parallel(T, probe_n, W, 0, profile, min(cores, 32))
+    params = cpu_params(T, name, W, arrs)
+    dt, blk = cpu_run(T, kind, params, W, arrs, cores)
     rate = probe_n / dt
-    n = int(min(max(rate * target_seconds, probe_n), 6_000_000))
+    n = int(min(max(rate * target_seconds, probe_n), max_units))
     if n > probe_n:
-        _, arrs = synth_host_parallel(T, n, paired, 0, profile, min(cores, 32))
-        dt = cpu_run(T, kind, params, arrs, cores)
+        _, arrs = synth_host_parallel(T, n, W, 0, profile, min(cores, 32))
+        dt, blk = cpu_run(T, kind, params, W, arrs, cores)
     else:
         n = probe_n
-    return {"value": n / dt, "unit": "pairs/s" if paired else "reads/s", "cores": cores, "kind": kind,
-            "sample": f"first {n} units of the same synthetic stream (seed {SEED}, profile {profile}), in-memory batches, "
-                      f"{cores} worker threads each with private Stats/FilterResult, {dt:.2f} s"}, (T, kind, params, arrs)
+    unit = "pairs/s" if W["paired"] else "reads/s"
+    note = ""
+    if name == "pe250_overrep":
+        note = "; over-representation counts of this multi-threaded run sample per worker thread (SURVEY App. C): timing only"
+    return ({"value": n / dt, "unit": unit, "cores": cores, "kind": kind, "cpu": res,
+             "sample": f"first {n} units of the same synthetic stream (seed {SEED}, profile {profile}), in-memory batches, "
+                       f"{cores} worker threads each with private Stats/FilterResult, {dt:.2f} s inside the worker bodies{note}"},
+            dict(T=T, kind=kind, params=params, arrs=arrs, n=n, block=blk, W=W))
 
 
 def run_reference_arm(args):
@@ -187,26 +266,28 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from fastp_b200 import capi  # noqa: F401  (ctypes structs only; no CUDA is touched on this arm)
-    profile = args.profile
-    base, (T, kind, params, arrs) = cpu_baseline(args.workload, profile, target_seconds=6.0)
+    from fastp_b200 import capi  # noqa: F401  (ctypes structs + the host pre-scan only; no CUDA is touched on this arm)
+    W = WORKLOADS[args.workload]
+    base, ctx = cpu_baseline(args.workload, args.profile, target_seconds=6.0)
+    T, kind, params, arrs, n = ctx["T"], ctx["kind"], ctx["params"], ctx["arrs"], ctx["n"]
     cores = base["cores"]
-    n = arrs["seq1"].shape[0]
     for _ in range(args.warmup):
-        cpu_run(T, kind, params, arrs, cores)
-    t0 = time.perf_counter()
+        cpu_run(T, kind, params, W, arrs, cores)
+    dt = 0.0
     for _ in range(args.steps):
-        cpu_run(T, kind, params, arrs, cores)
-    dt = time.perf_counter() - t0
+        dt += cpu_run(T, kind, params, W, arrs, cores)[0]      # seconds inside fp_ref_process_mt only
     value = n * args.steps / dt
-    unit = "pairs/s" if params.paired else "reads/s"
+    unit = "pairs/s" if W["paired"] else "reads/s"
     line = {
-        "impl": "reference", "metric": f"{unit.split('/')[0]} per second, 150 bp {'PE' if params.paired else 'SE'} synthetic, reference worker body on host CPUs" + (" (1 pair = 2 reads: reads_per_s = 2 x value)" if params.paired else ""),
-        "value": value, "unit": unit, "reads_per_s": value * (2 if params.paired else 1), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_string(W["paired"], W["L"]),
+        "value": value, "unit": unit, "reads_per_s": value * (2 if W["paired"] else 1), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "units_per_step": n, "read_len": READ_LEN, "profile": profile, "threads": cores},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind,
+        "config": {"workload": args.workload, "baseline_config": W["cfg"], "units_per_step": n, "read_len": W["L"],
+                   "profile": W["profile"] if args.profile is None else args.profile, "threads": cores,
+                   "note": "reference worker body (unmodified objects, scalar simd shim) on in-memory batches; the clock covers the worker "
+                           "bodies only (input copy / allocation outside)"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "cpu": base["cpu"],
                          "sample": f"{n} units per step x {args.steps} steps, in-memory batches, {cores} threads"},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -376,19 +457,291 @@ def fastq_path(args, torch, capi, lib, params, paired, dev, unit):
     return res
 
 
+class _Raw:
+    """Expose a raw device pointer to torch (zero-copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
+    """W warm-up + K timed passes of one BASELINE config over a batch resident in HBM; returns the result dict
+    (value, roofline, checks, ...).  env: torch, dist, capi, lib, world, rank, local_rank, dev, comm."""
+    torch, dist, capi, lib = env["torch"], env["dist"], env["capi"], env["lib"]
+    world, rank, local_rank, dev = env["world"], env["rank"], env["local_rank"], env["dev"]
+    W = WORKLOADS[name]
+    paired, L_, S = bool(W["paired"]), W["L"], W["S"]
+    profile = W["profile"] if args.profile is None else args.profile
+    unit = "pairs/s" if paired else "reads/s"
+    sides = 2 if paired else 1
+    torch.cuda.empty_cache()
+    free_b, _ = torch.cuda.mem_get_info()
+    per_unit = sides * (2 * S + 2 + 16) + (8 + 6 if paired else 0)
+    n = int(min(units, 0.85 * free_b / per_unit))
+    first = rank * n                                   # rank r owns global indices [r*n, (r+1)*n)
+
+    def alloc(nbytes):
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+
+    # ---- over-representation candidates: host pre-scan (Evaluator::computeOverRepSeq) of the START of the global stream ----
+    overrep = None
+    if name == "pe250_overrep":
+        m = OVERREP_PRESCAN_UNITS
+        p0 = capi.default_params(1, lib=lib)
+        h0 = C.c_void_p()
+        capi.check(lib.fp_ctx_create(C.byref(p0), local_rank, m, S, S, C.byref(h0)), lib)
+        tt = {k: alloc(m * (2 if k.startswith("len") else S)) for k in ("seq1", "qual1", "len1", "seq2", "qual2", "len2")}
+        b0 = capi.Batch(); b0.n, b0.stride = m, S
+        for k, v in tt.items():
+            setattr(b0, k, v.data_ptr())
+        capi.check(lib.fp_synth_fill(h0, C.byref(b0), 0, SEED, profile, L_, None), lib)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        overrep = tuple(host_overrep_candidates(lib, tt["seq" + sd].cpu().numpy().reshape(m, S), tt["len" + sd].cpu().numpy().view(np.uint16), S, L_)
+                        for sd in "12")
+        prescan_s = time.perf_counter() - t0
+        lib.fp_ctx_destroy(h0)
+        del tt
+    params = workload_params(capi, lib, name, overrep=overrep)
+    has_ovr = bool(params.overrep_enabled)
+
+    h = C.c_void_p()
+    capi.check(lib.fp_ctx_create(C.byref(params), local_rank, min(n, 1 << 18), S, S, C.byref(h)), lib)
+    Lc = capi.CounterLayout()
+    capi.check(lib.fp_ctx_layout(h, C.byref(Lc)), lib)
+    t = {"seq1": alloc(n * S), "qual1": alloc(n * S), "len1": alloc(n * 2)}
+    if paired:
+        t.update(seq2=alloc(n * S), qual2=alloc(n * S), len2=alloc(n * 2))
+    out1 = alloc(n * 16)
+    out2 = alloc(n * 16) if paired else None
+    ov = alloc(n * 8) if paired else None
+    corr = paired and bool(params.correction_enabled)
+    patch_cap = int(0.5 * n) + 4096 if corr else 0
+    patches = alloc(patch_cap * 12) if corr else None
+    npatch = torch.zeros(1, dtype=torch.int32, device=dev) if corr else None
+    b = capi.Batch()
+    b.n, b.stride = n, S
+    b.flags, b.first_read_index = 1, first              # FP_B_INDEXED: pre-filter over-representation sampling by GLOBAL index
+    for k, v in t.items():
+        setattr(b, k, v.data_ptr())
+    capi.check(lib.fp_synth_fill(h, C.byref(b), first, SEED, profile, L_, None), lib)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    if has_ovr and world > 1:
+        capi.check(lib.fp_overrep_defer_post(h, 1), lib)
+    from fastp_b200 import sharding
+
+    def run_pass(bb, o1, o2, ovp, undo=True):
+        """one pass of the hot path over batch bb (+ the cross-rank exchanges of a sharded run)"""
+        capi.check(lib.fp_counters_reset(h), lib)
+        if corr:
+            with torch.cuda.stream(stream):
+                npatch.zero_()
+        if paired:
+            capi.check(lib.fp_process_pe(h, C.byref(bb), o1, o2, ovp, patches.data_ptr() if corr else None, patch_cap,
+                                         npatch.data_ptr() if corr else None, sp), lib)
+        else:
+            capi.check(lib.fp_process_se(h, C.byref(bb), o1, sp), lib)
+        if has_ovr and world > 1:
+            # post-filter sampling counts PASSING reads of the whole stream: exclusive scan of the shards' pass counts (8e)
+            cnt = C.c_int64()
+            capi.check(lib.fp_pass_count(h, o1, bb.n, C.byref(cnt), sp), lib)
+            base, _ = sharding.exclusive_pass_base(cnt.value, device=dev)
+            capi.check(lib.fp_overrep_post(h, C.byref(bb), o1, o2, base, sp), lib)
+        if corr and undo:
+            # base correction rewrites rows in place: put the old bases back so the NEXT pass corrects again (inside the timed region)
+            capi.check(lib.fp_patches_undo(h, C.byref(bb), patches.data_ptr(), npatch.data_ptr(), patch_cap, sp), lib)
+        if world > 1:
+            capi.check(lib.fp_counters_allreduce(h, env["comm"].handle, sp), lib)     # Stats::merge / FilterResult::merge are plain sums
+
+    def step():
+        run_pass(b, out1.data_ptr(), out2.data_ptr() if paired else None, ov.data_ptr() if paired else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    ms_tmp = C.c_double(); nl = C.c_int64()
+    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)   # reset kernel timers
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt_ = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt_.item())
+    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)
+    kernel_ms = ms_tmp.value / max(nl.value, 1)
+
+    # ---- size-independent invariants of the last full-size pass (the block is the job's total after the all-reduce) ----
+    cnt = np.zeros(Lc.total, np.int64)
+    capi.check(lib.fp_counters_fetch(h, cnt.ctypes.data), lib)
+    cv = capi.CounterView(Lc, cnt)
+    total_units = n * world
+    checks = {
+        "pre_reads_eq_units": bool(cv.stats(capi.STATS_PRE1)["reads"] == total_units),
+        "verdicts_sum": bool(int(cv.filter[:32].sum()) == total_units * sides),
+        "post_le_pre": bool(cv.stats(capi.STATS_POST1)["reads"] <= cv.stats(capi.STATS_PRE1)["reads"]),
+        "qualhist_eq_bases": bool(int(cv.stats(capi.STATS_PRE1)["qualhist"].sum()) == cv.stats(capi.STATS_PRE1)["length_sum"]),
+    }
+    if corr:
+        checks["corrected_reads_gt0_in_timed_steps"] = bool(int(cv.filter[106]) > 0)     # FP_FR_CORRECTED_READS
+    if has_ovr:
+        checks["overrep_hits_gt0"] = bool(int(cv.overrep(capi.STATS_PRE1)[0].sum()) > 0)
+
+    # ---- parity at scale: the whole counter block of the first units of the stream == the reference's (cpu leg) ----
+    parity = None
+    cpu = env.get("cpu", {}).get(name)
+    if cpu is not None:
+        # every rank takes an equal share of the CPU sample's prefix [0, m*world), at its place in the global stream
+        m = min(cpu["n"] // world, n)
+        bb = capi.Batch(); bb.n, bb.stride, bb.flags, bb.first_read_index = m, S, 1, rank * m
+        for k, v in t.items():
+            setattr(bb, k, v.data_ptr())
+        if world > 1:     # ranks > 0 hold other indices: regenerate the prefix shard in place (the timed data is not needed any more)
+            capi.check(lib.fp_synth_fill(h, C.byref(bb), rank * m, SEED, profile, L_, None), lib)
+        torch.cuda.synchronize()
+        run_pass(bb, out1.data_ptr(), out2.data_ptr() if paired else None, ov.data_ptr() if paired else None, undo=False)
+        got = np.zeros(Lc.total, np.int64)
+        capi.check(lib.fp_counters_fetch(h, got.ctypes.data), lib)
+        parity = {"units": m * world, "got": got}
+    value = total_units * steps / (elapsed_ms / 1e3)
+    peak, peak_src = measured_peak()
+    bpu = bytes_per_unit(paired, L_)
+    achieved = n * bpu / (kernel_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(name)
+            if tj:
+                traffic = tj["dram_bytes_per_unit"] * n
+                traffic_src = "static: " + tj.get("source", "ncu --set full capture under profiles/") + ", scaled per launch (not measured in this run)"
+        except Exception:
+            pass
+    res = {
+        "metric": metric_string(paired, L_), "value": value, "unit": unit, "reads_per_s": value * sides,
+        "ms_per_step": elapsed_ms / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": name, "baseline_config": W["cfg"], "units_per_gpu": n, "read_len": L_, "stride": S,
+                   "profile": {0: "ref-style", 1: "enriched", 2: "enriched+indels", 3: "enriched+planted over-represented sequences"}[profile],
+                   "seed": SEED, "parallelism": f"shard{world}",
+                   "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n * sides * 2 * S / 1e9),
+                   "note": ("every timed step corrects bases again: the pass's own patch list (old base / quality) is played back by "
+                            "fp_patches_undo inside the timed region" if corr else "")
+                           + (f"; over-representation candidates: {len(overrep[0])}+{len(overrep[1])} from the host pre-scan of the first "
+                              f"{OVERREP_PRESCAN_UNITS} pairs ({prescan_s:.1f} s, outside the timed region)" if overrep else "")},
+        "gpu_launches": int(nl.value),
+        "checks": checks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "fp_chain2_kernel", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_unit": bpu, "peak_source": peak_src},
+        "clocks": clocks,
+    }
+
+    # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region) ----
+    if with_e2e:
+        ne = int(min(args.e2e_units, n))
+        hb = {}
+        keys = ["seq1", "qual1"] + (["seq2", "qual2"] if paired else [])
+        if world > 1:        # the parity pass above regenerated a prefix in place: refill this rank's own rows
+            capi.check(lib.fp_synth_fill(h, C.byref(b), first, SEED, profile, L_, None), lib)
+            torch.cuda.synchronize()
+        for k in keys:
+            hb[k] = torch.empty(ne * S, dtype=torch.uint8).pin_memory()
+            hb[k].copy_(t[k][: ne * S])
+        for k in (["len1", "len2"] if paired else ["len1"]):
+            hb[k] = torch.empty(ne * 2, dtype=torch.uint8).pin_memory()
+            hb[k].copy_(t[k][: ne * 2])
+        ho1 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory()
+        ho2 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory() if paired else None
+        hov = torch.empty(ne * 8, dtype=torch.uint8).pin_memory() if paired else None
+        hp_cap = int(0.5 * ne) + 4096
+        hpat = np.zeros(hp_cap, capi.PATCH_DTYPE) if corr else None
+        hnp = C.c_uint64()
+        hbt = capi.Batch()
+        hbt.n, hbt.stride, hbt.flags, hbt.first_read_index = ne, S, 1, first
+        for k, v in hb.items():
+            setattr(hbt, k, v.data_ptr())
+        views = {k: hb[k].numpy().reshape(ne, S) for k in keys}
+
+        def e2e_step():
+            capi.check(lib.fp_counters_reset(h), lib)
+            if paired:
+                capi.check(lib.fp_process_pe_host_patches(h, C.byref(hbt), ho1.data_ptr(), ho2.data_ptr(), hov.data_ptr(),
+                                                          hpat.ctypes.data if corr else None, hp_cap if corr else 0, C.byref(hnp)), lib)
+            else:
+                capi.check(lib.fp_process_se_host(h, C.byref(hbt), ho1.data_ptr()), lib)
+
+        def e2e_undo():       # harness only (outside the clock): put the corrected host bytes back so the next step corrects again
+            if not corr:
+                return
+            k = int(min(hnp.value, hp_cap))
+            pt = hpat[:k]
+            for which, (sk, qk) in enumerate((("seq1", "qual1"), ("seq2", "qual2"))):
+                sel = pt[pt["which"] == which]
+                views[sk][sel["pair"], sel["pos"]] = sel["old_base"]
+                views[qk][sel["pair"], sel["pos"]] = sel["old_qual"]
+        for _ in range(max(1, min(warmup, 2))):
+            e2e_step(); e2e_undo()
+        barrier()
+        dt = 0.0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            dt += time.perf_counter() - t0
+            e2e_undo()
+        barrier()
+        e2e_cnt = np.zeros(Lc.total, np.int64)
+        capi.check(lib.fp_counters_fetch(h, e2e_cnt.ctypes.data), lib)
+        if world > 1:
+            tt_ = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            dt = float(tt_.item())
+        h2d = ne * (sides * 2 * S + sides * 2)
+        d2h = ne * ((32 + 8) if paired else 16)
+        e2e_val = ne * world * steps / dt
+        res["e2e"] = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "units_per_step_per_gpu": ne, "api": "fp_process_pe_host_patches" if paired else "fp_process_se_host",
+                      "pcie": {"h2d_GBps": h2d * steps / dt / 1e9, "d2h_GBps": d2h * steps / dt / 1e9,
+                               "peak_GBps": 63.0, "peak_source": "PCIe Gen5 x16 nominal 63 GB/s per direction",
+                               "frac": h2d * steps / dt / 1e9 / 63.0},
+                      "corrected_reads_last_step": int(capi.CounterView(Lc, e2e_cnt).filter[106]) if corr else None,
+                      "note": "pinned host SoA buffers -> chunked H2D on two streams -> kernel -> D2H of per-read records + correction patches, "
+                              "patches applied to the host rows inside the call; the harness undoes them between steps outside the clock"}
+    lib.fp_ctx_destroy(h)
+    del t, out1, out2, ov, patches
+    torch.cuda.empty_cache()
+    return res, parity, params
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pe150_overlap_correction",
-                    choices=["pe150_overlap_correction", "pe150_full", "se150_cut_right_polyg"])
+    ap.add_argument("--workload", default="pe150_overlap_correction", choices=sorted(WORKLOADS))
     ap.add_argument("--units", type=int, default=0, help="reads/pairs per GPU per step (default: BASELINE config size)")
     ap.add_argument("--e2e-units", type=int, default=4_000_000, help="host-buffer batch for the e2e measurement")
-    ap.add_argument("--profile", type=int, default=1, help="synthetic profile: 1 = enriched fragment model, 0 = ref-style")
+    ap.add_argument("--profile", type=int, default=None, help="synthetic profile (default: the workload's): 1 = enriched fragment model, 0 = ref-style, 3 = enriched + planted over-represented sequences")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the other BASELINE configs (the `workloads` object)")
     ap.add_argument("--fastq-units", type=int, default=1_000_000,
                     help="units of the text-in/text-out measurement (device FASTQ decode + chain + encode); 0 = skip")
     args = ap.parse_args()
@@ -399,7 +752,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fastp_b200 import capi
+    from fastp_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -407,195 +760,89 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (fastp_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        comm = sharding.NcclComm(world, rank)       # raw ncclComm_t for the C-ABI collective fp_counters_allreduce
     dev = f"cuda:{local_rank}"
     lib = capi.load()
-    params = workload_params(capi, lib, args.workload)
-    paired = bool(params.paired)
-    unit = "pairs/s" if paired else "reads/s"
-    default_units = {"pe150_overlap_correction": 100_000_000, "pe150_full": 125_000_000, "se150_cut_right_polyg": 10_000_000}
-    n = args.units or default_units[args.workload]
-    free_b, _ = torch.cuda.mem_get_info()
-    per_unit = (4 if paired else 2) * STRIDE + (2 if paired else 1) * (2 + 16) + (8 if paired else 0)
-    n = int(min(n, 0.85 * free_b / per_unit))
-    bytes_per_unit = BYTES_PER_PAIR if paired else 2 * READ_LEN + 16
+    env = dict(torch=torch, dist=dist, capi=capi, lib=lib, world=world, rank=rank, local_rank=local_rank, dev=dev, comm=comm, cpu={})
 
-    h = C.c_void_p()
-    capi.check(lib.fp_ctx_create(C.byref(params), local_rank, min(n, 1 << 18), STRIDE, STRIDE, C.byref(h)), lib)
-    L = capi.CounterLayout()
-    capi.check(lib.fp_ctx_layout(h, C.byref(L)), lib)
-
-    def alloc(nbytes):
-        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    t = {"seq1": alloc(n * STRIDE), "qual1": alloc(n * STRIDE), "len1": alloc(n * 2)}
-    if paired:
-        t.update(seq2=alloc(n * STRIDE), qual2=alloc(n * STRIDE), len2=alloc(n * 2))
-    out1 = alloc(n * 16)
-    out2 = alloc(n * 16) if paired else None
-    ov = alloc(n * 8) if paired else None
-    b = capi.Batch()
-    b.n, b.stride = n, STRIDE
-    for k, v in t.items():
-        setattr(b, k, v.data_ptr())
-    # inputs are generated ON the device: each rank owns global indices [rank*n, (rank+1)*n)
-    first = rank * n
-    capi.check(lib.fp_synth_fill(h, C.byref(b), first, SEED, args.profile, READ_LEN, None), lib)
-    torch.cuda.synchronize()
-
-    stream = torch.cuda.Stream(device=dev)
-    cnt_ptr = C.c_void_p(); cnt_words = C.c_int64()
-
-    class _Raw:  # expose the raw device counter block to torch (for the NCCL all-reduce)
-        def __init__(self, ptr, nwords):
-            self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-    def step():
-        capi.check(lib.fp_counters_reset(h), lib)
-        if paired:
-            capi.check(lib.fp_process_pe(h, C.byref(b), out1.data_ptr(), out2.data_ptr(), ov.data_ptr(), None, 0, None,
-                                         C.c_void_p(stream.cuda_stream)), lib)
-        else:
-            capi.check(lib.fp_process_se(h, C.byref(b), out1.data_ptr(), C.c_void_p(stream.cuda_stream)), lib)
-        if world > 1:
-            stream.synchronize()
-            capi.check(lib.fp_counters_device_ptr(h, C.byref(cnt_ptr), C.byref(cnt_words)), lib)
-            raw = torch.as_tensor(_Raw(cnt_ptr.value, cnt_words.value), device=dev)
-            dist.all_reduce(raw, op=dist.ReduceOp.SUM)      # Stats::merge / FilterResult::merge are plain sums
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    ms_tmp = C.c_double(); nl = C.c_int64()
-    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)   # reset kernel timers
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = ev0.elapsed_time(ev1)
+    names = [args.workload] + ([] if args.no_workloads else [w for w in ("se150_cut_right_polyg", "pe150_full", "pe250_overrep") if w != args.workload])
+    # ---- CPU legs first (rank 0): the reference's worker body on a bounded sample of each workload's stream; the same
+    #      sample's counter block is the parity target of the GPU pass below ----
+    cpu_lines = {}
+    if rank == 0 and not args.no_cpu_baseline:
+        for nm in names:
+            try:
+                tsec = 10.0 if nm == args.workload else 5.0
+                cpu_lines[nm], ctx = cpu_baseline(nm, args.profile if nm == args.workload else None, target_seconds=tsec,
+                                                  max_units=6_000_000 if nm == args.workload else 2_000_000)
+                if nm == "pe250_overrep":
+                    # over-representation counts depend on the worker-thread split: the parity target is ONE worker over a shorter prefix
+                    T = ctx["T"]; m = min(ctx["n"], 60_000)
+                    sub = {k: v[:m] for k, v in ctx["arrs"].items()}
+                    _, blk = cpu_run(T, ctx["kind"], ctx["params"], ctx["W"], sub, 1)
+                    ctx = dict(ctx, n=m, block=blk)
+                env["cpu"][nm] = ctx
+            except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
+                cpu_lines[nm] = {"value": None, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
     if world > 1:
-        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tt.item())
-    capi.check(lib.fp_kernel_time_ms(h, C.byref(ms_tmp), C.byref(nl), 1), lib)
-    kernel_ms = ms_tmp.value / max(nl.value, 1)
+        # every rank must take the parity pass with the same sample size
+        nn = torch.tensor([env["cpu"].get(nm, {}).get("n", 0) for nm in names], device=dev, dtype=torch.int64)
+        dist.broadcast(nn, src=0)
+        if rank != 0:
+            for nm, v in zip(names, nn.tolist()):
+                if v:
+                    env["cpu"][nm] = {"n": int(v)}
 
-    # sanity invariants on the full-size run (size-independent properties; the parity tests proper live in tests/)
-    cnt = np.zeros(L.total, np.int64)
-    capi.check(lib.fp_counters_fetch(h, cnt.ctypes.data), lib)
-    cv = capi.CounterView(L, cnt)
-    total_units = n * world
-    checks = {
-        "pre_reads_eq_units": cv.stats(capi.STATS_PRE1)["reads"] == total_units,
-        "verdicts_sum": int(cv.filter[:32].sum()) == total_units * (2 if paired else 1),
-        "post_le_pre": cv.stats(capi.STATS_POST1)["reads"] <= cv.stats(capi.STATS_PRE1)["reads"],
-        "qualhist_eq_bases": int(cv.stats(capi.STATS_PRE1)["qualhist"].sum()) == cv.stats(capi.STATS_PRE1)["length_sum"],
-    }
-
-    value = total_units * args.steps / (elapsed_ms / 1e3)
-    peak, peak_src = measured_peak()
-    achieved = n * bytes_per_unit / (kernel_ms / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    results = {}
+    for nm in names:
+        main_wl = nm == args.workload
+        units = (args.units or WORKLOADS[nm]["units"]) if main_wl else min(args.units or WORKLOADS[nm]["units"], WORKLOADS[nm]["units"])
         try:
-            tj = json.load(open(tp)).get(args.workload)
-            if tj:
-                traffic = tj["dram_bytes_per_unit"] * n     # ncu --set full capture, scaled per launch
-        except Exception:
-            pass
+            res, parity, _ = gpu_workload(nm, args, env, units, args.steps if main_wl else max(2, min(args.steps, 3)),
+                                          args.warmup if main_wl else 3, with_e2e=main_wl and not args.no_e2e)
+        except Exception as e:
+            if main_wl:
+                raise
+            results[nm] = {"value": None, "error": repr(e)}
+            continue
+        if rank == 0 and parity is not None and "block" in env["cpu"].get(nm, {}):
+            Lc_, want = env["cpu"][nm]["block"]
+            m = parity["units"]
+            key = f"counters_eq_reference_{m}_units"
+            if m == env["cpu"][nm]["n"]:
+                res["checks"][key] = bool(np.array_equal(parity["got"], want))
+            else:   # the sample did not divide evenly over the ranks: compare against a fresh CPU pass over exactly m units
+                ctx = env["cpu"][nm]
+                sub = {k: v[:m] for k, v in ctx["arrs"].items()}
+                _, blk = cpu_run(ctx["T"], ctx["kind"], ctx["params"], ctx["W"], sub, 1 if nm == "pe250_overrep" else cpu_resources()["affinity"])
+                res["checks"][key] = bool(np.array_equal(parity["got"], blk[1]))
+        if nm in cpu_lines:
+            res["cpu_baseline"] = cpu_lines[nm]
+        results[nm] = res
 
-    line = {
-        "metric": f"{unit.split('/')[0]} per second, 150 bp {'PE' if paired else 'SE'} synthetic FASTQ resident in HBM" + (" (1 pair = 2 reads: reads_per_s = 2 x value)" if paired else ""),
-        "value": value, "unit": unit, "reads_per_s": value * (2 if paired else 1), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "baseline_config": "configs[2]" if args.workload == "pe150_overlap_correction" else args.workload,
-                   "units_per_gpu": n, "read_len": READ_LEN, "stride": STRIDE, "profile": "enriched" if args.profile == 1 else "ref-style",
-                   "seed": SEED, "parallelism": f"shard{world}", "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n * (4 if paired else 2) * STRIDE / 1e9),
-                   "note": "base correction rewrites <1% of bases in place during warm-up; timed steps see the corrected rows"},
-        "gpu_launches": int(nl.value),
-        "checks": checks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fp_chain2_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_unit": bytes_per_unit,
-                     "peak_source": peak_src},
-    }
-    if rank == 0:
-        line["clocks"] = clocks
-
-    # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region) ----
-    if not args.no_e2e:
-        ne = int(min(args.e2e_units, n))
-        hb = {}
-        keys = ["seq1", "qual1"] + (["seq2", "qual2"] if paired else [])
-        for k in keys:
-            hb[k] = torch.empty(ne * STRIDE, dtype=torch.uint8).pin_memory()
-            hb[k].copy_(t[k][: ne * STRIDE])
-        for k in (["len1", "len2"] if paired else ["len1"]):
-            hb[k] = torch.empty(ne * 2, dtype=torch.uint8).pin_memory()
-            hb[k].copy_(t[k][: ne * 2])
-        ho1 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory()
-        ho2 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory() if paired else None
-        hov = torch.empty(ne * 8, dtype=torch.uint8).pin_memory() if paired else None
-        hbt = capi.Batch()
-        hbt.n, hbt.stride = ne, STRIDE
-        for k, v in hb.items():
-            setattr(hbt, k, v.data_ptr())
-
-        def e2e_step():
-            if paired:
-                capi.check(lib.fp_process_pe_host(h, C.byref(hbt), ho1.data_ptr(), ho2.data_ptr(), hov.data_ptr()), lib)
-            else:
-                capi.check(lib.fp_process_se_host(h, C.byref(hbt), ho1.data_ptr()), lib)
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        h2d = ne * ((4 if paired else 2) * STRIDE + (4 if paired else 2))
-        d2h = ne * ((32 + 8) if paired else 16)
-        line["e2e"] = {"value": ne * world * args.steps / dt, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "units_per_step_per_gpu": ne, "api": "fp_process_pe_host" if paired else "fp_process_se_host",
-                       "note": "pinned host SoA buffers -> chunked H2D on two streams -> kernel -> D2H of per-read records (+ correction patches)"}
-
-    lib.fp_ctx_destroy(h)
-    del t, out1, out2, ov
-    torch.cuda.empty_cache()
+    line = dict(results[args.workload])
+    line.update({"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic"})
+    if rank != 0:
+        line.pop("clocks", None)
+    others = {k: v for k, v in results.items() if k != args.workload}
+    if others:
+        line["workloads"] = {k: ({kk: vv for kk, vv in v.items() if kk not in ("metric",)} if isinstance(v, dict) else v) for k, v in others.items()}
     if rank == 0 and world == 1 and args.fastq_units > 0:
         try:
-            line["fastq_path"] = fastq_path(args, torch, capi, lib, params, paired, dev, unit)
+            params = workload_params(capi, lib, args.workload) if args.workload != "pe250_overrep" else None
+            if params is not None and WORKLOADS[args.workload]["S"] == STRIDE:
+                paired = bool(params.paired)
+                line["fastq_path"] = fastq_path(args, torch, capi, lib, params, paired, dev, "pairs/s" if paired else "reads/s")
         except Exception as e:   # an extra object: never a reason to lose the main line
             line["fastq_path"] = {"value": None, "error": repr(e)}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            line["cpu_baseline"], _ = cpu_baseline(args.workload, args.profile)
-        except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
-            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        comm.destroy()
         dist.destroy_process_group()
 
 

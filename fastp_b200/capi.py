@@ -56,9 +56,10 @@ class Params(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [
-        ("n", C.c_int64), ("stride", C.c_int32), ("_pad", C.c_int32),
+        ("n", C.c_int64), ("stride", C.c_int32), ("flags", C.c_int32),
         ("seq1", C.c_void_p), ("qual1", C.c_void_p), ("len1", C.c_void_p),
         ("seq2", C.c_void_p), ("qual2", C.c_void_p), ("len2", C.c_void_p),
+        ("first_read_index", C.c_int64),
     ]
 
 
@@ -82,7 +83,7 @@ OV_RESULT_DTYPE = np.dtype([
     ("overlapped", "u1"), ("has_gap", "u1"), ("offset", "<i2"), ("overlap_len", "<i2"), ("diff", "<i2"),
 ])
 PATCH_DTYPE = np.dtype([
-    ("pair", "<u4"), ("pos", "<u2"), ("which", "u1"), ("base", "u1"), ("qual", "u1"), ("_pad", "u1", (3,)),
+    ("pair", "<u4"), ("pos", "<u2"), ("which", "u1"), ("base", "u1"), ("qual", "u1"), ("old_base", "u1"), ("old_qual", "u1"), ("_pad", "u1"),
 ])
 assert READ_RESULT_DTYPE.itemsize == 16 and OV_RESULT_DTYPE.itemsize == 8 and PATCH_DTYPE.itemsize == 12
 
@@ -109,10 +110,18 @@ SYMBOLS = {
                                 C.c_uint32, C.c_void_p, C.c_void_p]),
     "fp_process_se_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "fp_process_pe_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fp_process_pe_host_patches": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                             C.POINTER(C.c_uint64)]),
     "fp_counters_reset": (C.c_int, [C.c_void_p]),
     "fp_counters_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fp_counters_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "fp_counters_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fp_patches_undo": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "fp_overrep_defer_post": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fp_pass_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "fp_overrep_post": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fp_host_overrep_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fp_host_free": (C.c_int, [C.c_void_p]),
     "fp_synth_fill": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),

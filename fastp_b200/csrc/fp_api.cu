@@ -71,6 +71,9 @@ struct fp_ctx {
     int ovr_base_cur = 0;
     int64_t ovr_scratch_n = 0;
     int64_t reads_seen = 0;
+    int ovr_defer_post = 0;             /* fp_overrep_defer_post: the caller runs fp_overrep_post itself (sharded runs) */
+    unsigned long long* d_pass_count = nullptr;
+    cudaEvent_t ovr_ev = nullptr;       /* host pipeline: orders the post-filter sampling state between the two chunk streams */
     long long *d_raw = nullptr, *d_fin = nullptr;
     /* host-mode staging (allocated lazily) */
     int64_t chunk = 0;
@@ -155,19 +158,23 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
        the quality histogram (2 KB per side) follows it */
     off = align_up(off + c->smem_base, 4096) - c->smem_base;
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
+    sl.off_dkmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;       /* signed post-filter deltas, same indexing, same alignment */
     sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * FP_QH_REP * 4;
+    sl.off_dqh = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
     off = align_up(off, 128);
     sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
     off = align_up(off, 16);
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
     off = align_up(off, 16);
-    sl.off_delta = (int)off; off += (size_t)sides * ((size_t)S * 20 + FP_KMER_BINS + FP_QUAL_BINS) * 4;
+    sl.off_delta = (int)off; off += (size_t)sides * (size_t)S * 20 * 4;
+    off = align_up(off, 16);
+    sl.off_rm = (int)off; off += (size_t)sides * (T + 4) * 4 + 16;          /* removal lists (one per side, padded to 4 entries) + their lengths */
     sl.plane_words = (S + 31) / 32 + 2;
     sl.plane_stride = (4 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
     off = align_up(off, 16);
     sl.off_planes = (int)off; off += (size_t)sides * T * sl.plane_stride * 4;
     off = align_up(off, 16);
-    sl.off_queue = (int)off; off += (size_t)sides * T * 2 * 16;
+    sl.off_queue = (int)off; off += (size_t)sides * T * 2 * 8;
     sl.total = (int)align_up(off, 128);
     return (size_t)sl.total;
 }
@@ -381,7 +388,8 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
     cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
     for (int sd = 0; sd < 2; sd++) { cudaFree(c->d_ovr_blob[sd]); cudaFree(c->d_ovr_off[sd]); cudaFree(c->d_ovr_len[sd]); cudaFree(c->d_ovr_thash[sd]); cudaFree(c->d_ovr_tidx[sd]); }
-    cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list); cudaFree(c->d_ovr_list_n); cudaFree(c->d_ovr_base);
+    cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list); cudaFree(c->d_ovr_list_n); cudaFree(c->d_ovr_base); cudaFree(c->d_pass_count);
+    if (c->ovr_ev) cudaEventDestroy(c->ovr_ev);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -403,6 +411,40 @@ static int drain_events(fp_ctx* c) {
         c->ev_pool.push_back(e);
     }
     c->evs.clear();
+    return FP_OK;
+}
+
+/* post-filter over-representation scan of one processed batch (stats.cpp:270-290): rank the counted reads (verdict records),
+ * emit the ones whose running count is a multiple of the sampling step, scan their trimmed windows.  host_base == nullptr:
+ * continue the ctx's own running count (and advance it); else start from *host_base (sharded runs, fp_overrep_post). */
+static int overrep_post_launch(fp_ctx* c, const fp_batch* b, const fp_read_result* out1, const fp_read_result* out2, const int64_t* host_base, cudaStream_t st) {
+    const int64_t nblk = (b->n + FP_RANK_ITEMS - 1) / FP_RANK_ITEMS;
+    const unsigned int cap = (unsigned int)(b->n / c->p.overrep_sampling + 64);
+    if (b->n > c->ovr_scratch_n) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list);
+        CK(cudaMalloc(&c->d_ovr_blocksum, (size_t)(nblk + 1) * 4)); CK(cudaMalloc(&c->d_ovr_list, (size_t)cap * 4));
+        c->ovr_scratch_n = b->n;
+    }
+    unsigned long long* base_cur = c->d_ovr_base + c->ovr_base_cur; unsigned long long* base_next = c->d_ovr_base + (c->ovr_base_cur ^ 1);
+    if (host_base) {
+        const unsigned long long v = (unsigned long long)*host_base;
+        CK(cudaMemcpyAsync(base_cur, &v, 8, cudaMemcpyHostToDevice, st));   /* pageable source: staged by the runtime before the call returns */
+    }
+    fp_overrep_args oa;
+    memset(&oa, 0, sizeof(oa));
+    oa.b = *b; oa.side[0] = c->ovr_side[0]; oa.side[1] = c->ovr_side[1];
+    oa.counters = reinterpret_cast<unsigned long long*>(c->d_raw); oa.L = c->L;
+    oa.sides = c->p.paired ? 2 : 1; oa.sampling = c->p.overrep_sampling;
+    CK(cudaMemsetAsync(c->d_ovr_list_n, 0, 4, st));
+    fp_overrep_blocksum_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum);
+    fp_overrep_scan_kernel<<<1, 32, 0, st>>>(c->d_ovr_blocksum, (int)nblk, base_cur, base_next);
+    fp_overrep_emit_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum, base_cur, c->p.overrep_sampling, c->d_ovr_list, c->d_ovr_list_n, cap);
+    oa.post = 1; oa.res[0] = out1; oa.res[1] = out2; oa.list = c->d_ovr_list; oa.list_n = c->d_ovr_list_n;
+    const long long warps = (long long)cap * oa.sides;
+    fp_overrep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(oa);
+    CK(cudaGetLastError());
+    c->ovr_base_cur ^= 1;
     return FP_OK;
 }
 
@@ -433,20 +475,12 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     fp_overrep_args oa;
     const bool ovr = c->p.overrep_enabled && (c->ovr_side[0].K > 0 || c->ovr_side[1].K > 0);
     if (ovr) {
-        const int64_t nblk = (b->n + FP_RANK_ITEMS - 1) / FP_RANK_ITEMS;
-        const int64_t cap = b->n / c->p.overrep_sampling + 64;
-        if (b->n > c->ovr_scratch_n) {
-            CK(cudaStreamSynchronize(st));
-            cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list);
-            CK(cudaMalloc(&c->d_ovr_blocksum, (size_t)(nblk + 1) * 4)); CK(cudaMalloc(&c->d_ovr_list, (size_t)cap * 4));
-            c->ovr_scratch_n = b->n;
-        }
         memset(&oa, 0, sizeof(oa));
         oa.b = *b; oa.side[0] = c->ovr_side[0]; oa.side[1] = c->ovr_side[1];
         oa.counters = reinterpret_cast<unsigned long long*>(c->d_raw); oa.L = c->L;
         oa.sides = c->p.paired ? 2 : 1; oa.sampling = c->p.overrep_sampling;
         /* pre-filter stats: the ORIGINAL rows, i.e. before the chain kernel may correct bases in place */
-        oa.post = 0; oa.first_index = c->reads_seen;
+        oa.post = 0; oa.first_index = (b->flags & FP_B_INDEXED) ? b->first_read_index : c->reads_seen;
         const long long units = (b->n + oa.sampling - 1) / oa.sampling + 1;
         const long long warps = units * oa.sides;
         fp_overrep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(oa);
@@ -463,20 +497,11 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     c->evs.push_back(ev);
     CK(cudaGetLastError());
     if (ovr) {
-        /* post-filter stats: rank the counted reads (verdict records), emit the sampled ones, scan their trimmed windows */
-        const int64_t nblk = (b->n + FP_RANK_ITEMS - 1) / FP_RANK_ITEMS;
-        const unsigned int cap = (unsigned int)(b->n / c->p.overrep_sampling + 64);
-        unsigned long long* base_cur = c->d_ovr_base + c->ovr_base_cur; unsigned long long* base_next = c->d_ovr_base + (c->ovr_base_cur ^ 1);
-        CK(cudaMemsetAsync(c->d_ovr_list_n, 0, 4, st));
-        fp_overrep_blocksum_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum);
-        fp_overrep_scan_kernel<<<1, 32, 0, st>>>(c->d_ovr_blocksum, (int)nblk, base_cur, base_next);
-        fp_overrep_emit_kernel<<<(unsigned)nblk, 256, 0, st>>>(out1, b->n, c->d_ovr_blocksum, base_cur, c->p.overrep_sampling, c->d_ovr_list, c->d_ovr_list_n, cap);
-        oa.post = 1; oa.res[0] = out1; oa.res[1] = out2; oa.list = c->d_ovr_list; oa.list_n = c->d_ovr_list_n;
-        const long long warps = (long long)cap * oa.sides;
-        fp_overrep_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(oa);
-        CK(cudaGetLastError());
-        c->ovr_base_cur ^= 1;
-        c->reads_seen += b->n;
+        if (!c->ovr_defer_post) {
+            int rc = overrep_post_launch(c, b, out1, out2, nullptr, st);
+            if (rc) return rc;
+        }
+        c->reads_seen = ((b->flags & FP_B_INDEXED) ? b->first_read_index : c->reads_seen) + b->n;
     }
     return FP_OK;
 }
@@ -494,6 +519,71 @@ extern "C" int fp_process_pe(fp_ctx* c, const fp_batch* b, fp_read_result* out1,
     if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
     CK(cudaSetDevice(c->device));
     return launch_chain(c, b, out1, out2, ov, patches, patch_cap, n_patches, stream ? (cudaStream_t)stream : c->stream[0]);
+}
+
+/* ---------------- undo of a pass's base corrections / sharded over-representation sampling ---------------- */
+__global__ void fp_patch_undo_kernel(fp_batch b, const fp_patch* __restrict__ patches, const uint32_t* __restrict__ n_patches, uint32_t cap) {
+    const uint32_t n = min(*n_patches, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const fp_patch pt = patches[i];
+        const size_t o = (size_t)pt.pair * (size_t)b.stride + pt.pos;
+        (pt.which ? b.seq2 : b.seq1)[o] = pt.old_base;
+        (pt.which ? b.qual2 : b.qual1)[o] = pt.old_qual;
+    }
+}
+
+extern "C" int fp_patches_undo(fp_ctx* c, const fp_batch* b, const fp_patch* patches, const uint32_t* n_patches, uint32_t patch_cap, void* stream) {
+    if (!c || !b || !patches || !n_patches) return set_err(FP_E_INVAL, "null argument");
+    if (!c->p.paired) return set_err(FP_E_INVAL, "base correction is a paired-end operator");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
+    if (patch_cap == 0) return FP_OK;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)patch_cap + 255) / 256, (uint64_t)c->num_sms * 8);
+    fp_patch_undo_kernel<<<blocks, 256, 0, st>>>(*b, patches, n_patches, patch_cap);
+    CK(cudaGetLastError());
+    return FP_OK;
+}
+
+__global__ void fp_pass_count_kernel(const fp_read_result* __restrict__ res, long long n, unsigned long long* out) {
+    unsigned int c = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += (res[i].pair_verdict == FP_PASS_FILTER);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+extern "C" int fp_overrep_defer_post(fp_ctx* c, int32_t defer) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    c->ovr_defer_post = defer ? 1 : 0;
+    return FP_OK;
+}
+
+extern "C" int fp_pass_count(fp_ctx* c, const fp_read_result* out1, int64_t n, int64_t* count, void* stream) {
+    if (!c || !count || (n > 0 && !out1)) return set_err(FP_E_INVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
+    if (!c->d_pass_count) CK(cudaMalloc(&c->d_pass_count, 8));
+    CK(cudaMemsetAsync(c->d_pass_count, 0, 8, st));
+    if (n > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
+        fp_pass_count_kernel<<<blocks, 256, 0, st>>>(out1, n, c->d_pass_count);
+        CK(cudaGetLastError());
+    }
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, c->d_pass_count, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *count = (int64_t)v;
+    return FP_OK;
+}
+
+extern "C" int fp_overrep_post(fp_ctx* c, const fp_batch* b, const fp_read_result* out1, const fp_read_result* out2, int64_t pass_base, void* stream) {
+    if (!c || !b || !out1) return set_err(FP_E_INVAL, "null argument");
+    if (c->p.paired && !out2) return set_err(FP_E_INVAL, "paired ctx needs the second side's records");
+    if (pass_base < 0) return set_err(FP_E_INVAL, "pass_base must be >= 0");
+    CK(cudaSetDevice(c->device));
+    if (!(c->p.overrep_enabled && (c->ovr_side[0].K > 0 || c->ovr_side[1].K > 0)) || b->n == 0) return FP_OK;
+    if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    return overrep_post_launch(c, b, out1, out2, &pass_base, stream ? (cudaStream_t)stream : c->stream[0]);
 }
 
 /* ---------------- host-buffer pipeline ---------------- */
@@ -520,7 +610,9 @@ static int ensure_staging(fp_ctx* c) {
 
 static const uint32_t PFAST = 16384;   /* patches copied back without waiting for their count */
 
-static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov) {
+static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                        fp_patch* hp_out = nullptr, uint64_t hp_cap = 0, uint64_t* hp_n = nullptr) {
+    if (hp_n) *hp_n = 0;
     CK(cudaSetDevice(c->device));
     int rc = ensure_staging(c);
     if (rc) return rc;
@@ -544,8 +636,13 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                     uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * S;
                     uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * S;
                     sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
+                    if (hp_n) {                                  /* caller's list: pair index relative to the whole host batch */
+                        if (*hp_n < hp_cap) { hp_out[*hp_n] = pt; hp_out[*hp_n].pair = (uint32_t)(lo + pt.pair); }
+                        (*hp_n)++;
+                    }
                 }
             } else {   /* patch list overflow: take the corrected rows wholesale */
+                if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
                 const size_t bytes = (size_t)pend[slot].cnt * S;
                 CK(cudaMemcpy(b->seq1 + lo * S, c->d_stage[slot][0], bytes, cudaMemcpyDeviceToHost));
                 CK(cudaMemcpy(b->qual1 + lo * S, c->d_stage[slot][1], bytes, cudaMemcpyDeviceToHost));
@@ -577,9 +674,16 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         db.n = cnt; db.stride = S;
         db.seq1 = c->d_stage[slot][0]; db.qual1 = c->d_stage[slot][1]; db.len1 = c->d_stage_len[slot][0];
         if (pe) { db.seq2 = c->d_stage[slot][2]; db.qual2 = c->d_stage[slot][3]; db.len2 = c->d_stage_len[slot][1]; }
+        /* the over-representation sampling state (running counts, rank scratch) is one per ctx: chunk k+1's kernels wait for chunk
+           k's (its H2D copies, issued above, still overlap them) */
+        if (c->p.overrep_enabled) {
+            if (!c->ovr_ev) CK(cudaEventCreateWithFlags(&c->ovr_ev, cudaEventDisableTiming));
+            else CK(cudaStreamWaitEvent(st, c->ovr_ev, 0));
+        }
         rc = launch_chain(c, &db, c->d_out[slot][0], pe ? c->d_out[slot][1] : nullptr, pe ? c->d_ov[slot] : nullptr,
                           pe ? c->d_patch[slot] : nullptr, c->patch_cap, pe ? c->d_npatch[slot] : nullptr, st);
         if (rc) return rc;
+        if (c->p.overrep_enabled) CK(cudaEventRecord(c->ovr_ev, st));
         CK(cudaMemcpyAsync(out1 + lo, c->d_out[slot][0], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
         if (pe) {
             CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
@@ -606,6 +710,13 @@ extern "C" int fp_process_pe_host(fp_ctx* c, const fp_batch* b, fp_read_result* 
     if (!c || !b || !out1 || !out2) return set_err(FP_E_INVAL, "null argument");
     if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
     return process_host(c, b, out1, out2, ov);
+}
+
+extern "C" int fp_process_pe_host_patches(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                                          fp_patch* patches, uint64_t patch_cap, uint64_t* n_patches) {
+    if (!c || !b || !out1 || !out2 || !n_patches || (patch_cap > 0 && !patches)) return set_err(FP_E_INVAL, "null argument");
+    if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
+    return process_host(c, b, out1, out2, ov, patches, patch_cap, n_patches);
 }
 
 /* ---------------- FASTQ text <-> rows (fp_fastq.cuh) ---------------- */
@@ -973,11 +1084,10 @@ extern "C" int fp_counters_allreduce(fp_ctx* c, void* comm, void* stream) {
     }
     CK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream[0];
-    CK(cudaDeviceSynchronize());
+    /* stream-ordered: the caller enqueues it behind its fp_process_* calls on the same stream; fp_counters_fetch waits for the device */
     /* ncclInt64 = 4, ncclSum = 0 (nccl.h) */
     int rc = fn(c->d_raw, c->d_raw, (size_t)c->L.total, 4, 0, comm, st);
     if (rc != 0) return set_err(FP_E_CUDA, "ncclAllReduce failed");
-    CK(cudaStreamSynchronize(st));
     return FP_OK;
 }
 
@@ -1012,5 +1122,74 @@ extern "C" int fp_kernel_time_ms(fp_ctx* c, double* total_ms, int64_t* n_launche
     if (total_ms) *total_ms = c->ev_ms;
     if (n_launches) *n_launches = c->ev_n;
     if (reset) { c->ev_ms = 0; c->ev_n = 0; }
+    return FP_OK;
+}
+
+/* ---------------- host-side pre-scan: over-representation candidates ----------------
+ * Evaluator::computeOverRepSeq (src/evaluator.cpp:78-169) over the first reads of one side, given as rows: count every
+ * substring of length 10 / 20 / 40 / 100 / min(150, seqlen-2) of the reads until 151*10000 bases have been seen, keep those at
+ * or above the per-length count thresholds, then drop a kept sequence that is a substring of another kept one unless it is at
+ * least ten times as frequent (integer division, in the reference's map order).  Control plane, runs once per input on the
+ * host like the reference's Evaluator; the result is what fp_params.overrep_seqs1/2 take.
+ * The reference counts in a std::map<string,long> (about 5 M entries for 2x250 bp); here a first pass counts 64-bit substring
+ * hashes in a flat table and only substrings whose HASH reaches the smallest threshold are counted exactly -- same set, same
+ * counts (a colliding hash can only nominate a string whose exact count then fails the threshold). */
+#include <map>
+#include <unordered_map>
+extern "C" int fp_host_overrep_candidates(const uint8_t* seq, const uint16_t* len, int64_t n, int32_t stride, int32_t seqlen,
+                                          char* out, int64_t out_cap, int32_t* n_out, int64_t* bytes_out) {
+    if (!seq || !len || !n_out || !bytes_out || n < 0 || stride <= 0) return set_err(FP_E_INVAL, "null argument");
+    const long BASE_LIMIT = 151 * 10000;                                    /* evaluator.cpp:83 */
+    const int steps[5] = {10, 20, 40, 100, std::min(150, seqlen - 2)};     /* :99 */
+    auto threshold = [&](int L) -> long {                                   /* :116-140 */
+        if (L >= seqlen - 1) return 3;
+        if (L >= 100) return 5;
+        if (L >= 40) return 20;
+        if (L >= 20) return 100;
+        if (L >= 10) return 500;
+        return -1;
+    };
+    int64_t nreads = 0; long bases = 0;
+    while (nreads < n && bases < BASE_LIMIT) { bases += len[nreads]; nreads++; }   /* :88-96: a read is taken whole once bases < limit */
+    const unsigned long long B = 0x9E3779B97F4A7C15ull;
+    std::unordered_map<unsigned long long, uint32_t> hcount;
+    hcount.reserve((size_t)nreads * 1024);
+    std::vector<unsigned long long> pref;
+    for (int pass = 0; pass < 2; pass++) {
+        std::map<std::string, long> exact;
+        for (int64_t r = 0; r < nreads; r++) {
+            const uint8_t* s = seq + (size_t)r * stride; const int rlen = len[r];
+            pref.assign(rlen + 1, 0);
+            for (int i = 0; i < rlen; i++) pref[i + 1] = pref[i] * B + (unsigned long long)(s[i] + 1);
+            for (int k = 0; k < 5; k++) {
+                const int step = steps[k];
+                if (step <= 0) continue;
+                unsigned long long bp = 1; for (int e = 0; e < step; e++) bp *= B;
+                const long thr = threshold(step);
+                for (int i = 0; i < rlen - step; i++) {                     /* :102 */
+                    const unsigned long long h = (pref[i + step] - pref[i] * bp) ^ ((unsigned long long)step << 56);
+                    if (pass == 0) hcount[h]++;
+                    else if (thr >= 0 && (long)hcount[h] >= thr) exact[std::string((const char*)s + i, step)]++;
+                }
+            }
+        }
+        if (pass == 0) continue;
+        std::map<std::string, long> hot;
+        for (auto& kv : exact) { const long thr = threshold((int)kv.first.size()); if (thr >= 0 && kv.second >= thr) hot[kv.first] = kv.second; }
+        for (auto it = hot.begin(); it != hot.end();) {                     /* :143-161 remove substrings, erasing while iterating */
+            bool sub = false;
+            for (auto it2 = hot.begin(); it2 != hot.end(); ++it2)
+                if (it->first != it2->first && it2->first.find(it->first) != std::string::npos && it->second / it2->second < 10) { sub = true; break; }
+            if (sub) it = hot.erase(it); else ++it;
+        }
+        int64_t used = 0; int32_t cnt = 0;
+        for (auto& kv : hot) {
+            const int64_t need = (int64_t)kv.first.size() + 1;
+            if (out && used + need <= out_cap) memcpy(out + used, kv.first.c_str(), (size_t)need);
+            used += need; cnt++;
+        }
+        *n_out = cnt; *bytes_out = used;
+        if (used > out_cap) return set_err(FP_E_TOOLARGE, "candidate buffer too small (bytes_out holds the size needed)");
+    }
     return FP_OK;
 }

@@ -205,135 +205,113 @@ __device__ __forceinline__ unsigned long long tp_bits64(const uint32_t* P, int b
 }
 __device__ __forceinline__ unsigned long long mask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
 
+/* Exact no-gap acceptance test of ONE candidate (overlapanalysis.cpp:34-44): mismatches over the protected prefix
+ * pp = min(ol, 50) on the three planes; returns the count if it is within lut[ol], else -1.  Out of line: only the rare
+ * survivors of the one-plane filter below (and the few candidates whose overlap is shorter than 32 bases) get here. */
+struct OvPlanes { const uint32_t *alo, *ahi, *ann, *plo, *phi, *pnn; int f1, len1, e, len2; };
+
+__device__ __noinline__ int t_ov_exact(const OvPlanes P, int dir, int o, const int16_t* lut, int& olOut) {
+    FP_SMEM(P.alo); FP_SMEM(P.ahi); FP_SMEM(P.ann); FP_SMEM(P.plo); FP_SMEM(P.phi); FP_SMEM(P.pnn); FP_SMEM(lut);
+    unsigned long long x;
+    int ol;
+    if (dir == 0) {                                                        /* r1[o+k] vs rc(r2)[k] */
+        ol = min(P.len1 - o, P.len2);
+        const unsigned long long bnn = ((unsigned long long)__brev(tp_bits_z(P.pnn, P.e - 63)) << 32) | __brev(tp_bits_z(P.pnn, P.e - 31));
+        const unsigned long long blo = ((unsigned long long)__brev(tp_bits_z(P.plo, P.e - 63)) << 32) | __brev(tp_bits_z(P.plo, P.e - 31));
+        const unsigned long long bhi = ~(((unsigned long long)__brev(tp_bits_z(P.phi, P.e - 63)) << 32) | __brev(tp_bits_z(P.phi, P.e - 31))) & ~bnn;
+        const int bit = P.f1 + o;
+        x = (tp_bits64(P.alo, bit) ^ blo) | (tp_bits64(P.ahi, bit) ^ bhi) | (tp_bits64(P.ann, bit) ^ bnn);
+    } else {                                                               /* r1[k] vs rc(r2)[o+k]  <=>  comp(r1[pp-1-t]) vs row2[s+t] */
+        ol = min(P.len1, P.len2 - o);
+        const int pp = min(ol, 50);
+        const unsigned long long a_nn = tp_bits64(P.ann, P.f1), a_lo = tp_bits64(P.alo, P.f1), a_hi = tp_bits64(P.ahi, P.f1);
+        const unsigned long long ynn = __brevll(a_nn) >> 14, ylo = __brevll(a_lo) >> 14, yhi = ~(__brevll(a_hi) >> 14) & ~ynn;   /* Y50[t] = comp(r1[49-t]) */
+        const int sbit = P.e - o - pp + 1, ysh = 50 - pp;                   /* sbit >= front2 >= 0 */
+        x = (tp_bits64(P.plo, sbit) ^ (ylo >> ysh)) | (tp_bits64(P.phi, sbit) ^ (yhi >> ysh)) | (tp_bits64(P.pnn, sbit) ^ (ynn >> ysh));
+    }
+    const int mm = __popcll(x & mask64(min(ol, 50)));
+    olOut = ol;
+    return mm <= (int)lut[ol] ? mm : -1;
+}
+
+/* One 32-candidate word of the one-plane filter: bit sh of the result is set iff the field at bit offset sh of the word pair
+ * (W0, W1) differs from C in at most thr-1 of the positions M keeps.  The plane is X = lo ^ hi (A,G -> 0; C,T -> 1; N -> 0): two
+ * bases whose X bits differ are different bases, so this count never exceeds the true mismatch count of the candidate's first
+ * F compared bases; every acceptance limit is <= diffLimit, hence a candidate whose count exceeds diffLimit cannot be accepted.
+ * X (not lo or hi alone) because a base and its complement always differ in X: reads that end in the same homopolymer or
+ * adapter run -- the common non-random case -- do not flood the filter.  Fully unrolled, five instructions per candidate
+ * (shift, xor-and, popc, subtract, shift-in of the sign bit), no branches, so the 32 lanes stay together. */
+__device__ __forceinline__ uint32_t t_ov_word_hits(uint32_t W0, uint32_t W1, uint32_t C, uint32_t M, int thr) {
+    uint32_t hits = 0;
+    #pragma unroll
+    for (int sh = 31; sh >= 0; sh--) {
+        const int t = __popc((__funnelshift_r(W0, W1, sh) ^ C) & M) - thr;      /* negative iff the candidate survives */
+        hits = __funnelshift_l((uint32_t)t, hits, 1);                           /* hits = hits << 1 | sign(t) */
+    }
+    return hits;
+}
+
 __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRead r2, int PW, const int16_t* lut, int sub, int g) {
     FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(lut);
-    const uint32_t *alo = r1.pl, *ahi = r1.pl + PW, *ann = r1.pl + 2 * PW;
-    const uint32_t *plo = r2.pl, *phi = r2.pl + PW, *pnn = r2.pl + 2 * PW;
-    const int len1 = r1.len, len2 = r2.len, f1 = r1.front;
-    const int e = r2.front + len2 - 1;
+    OvPlanes P;
+    P.alo = r1.pl; P.ahi = r1.pl + PW; P.ann = r1.pl + 2 * PW;
+    P.plo = r2.pl; P.phi = r2.pl + PW; P.pnn = r2.pl + 2 * PW;
+    P.f1 = r1.front; P.len1 = r1.len; P.len2 = r2.len; P.e = r2.front + r2.len - 1;
+    const int len1 = r1.len, len2 = r2.len, f1 = r1.front, e = P.e;
     const int req = c_p.ov_require;
+    const int thr = c_p.ov_diff_limit + 1;       /* every lut entry is min(diffLimit, ...) <= diffLimit */
+    const int F = min(32, max(req, 1));          /* bases the filter looks at: every candidate's overlap is longer than req */
+    const uint32_t FM = low_mask(F);
     fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
-    /* any N in either window? (lets the scans skip the N plane) */
-    uint32_t anyN = 0;
-    for (int k = 0; k * 32 < len1; k++) anyN |= tp_bits(ann, f1 + 32 * k) & low_mask(len1 - 32 * k);
-    for (int k = 0; k * 32 < len2; k++) anyN |= tp_bits(pnn, r2.front + 32 * k) & low_mask(len2 - 32 * k);
     int found_dir = -1, found_o = 0, found_mm = 0, found_ol = 0;
-    const int lg = g == 4 ? 2 : (g == 2 ? 1 : 0);   /* g lanes per pair, a power of two */
-    const int dmax = c_p.ov_diff_limit;          /* every lut entry is min(diffLimit, ...) <= diffLimit */
-    /* ---- forward: offset 0 .. len1-req-1 (:48-65) ---- */
-    {
-        const unsigned long long bnn = ((unsigned long long)__brev(tp_bits_z(pnn, e - 63)) << 32) | __brev(tp_bits_z(pnn, e - 31));
-        const unsigned long long blo = ((unsigned long long)__brev(tp_bits_z(plo, e - 63)) << 32) | __brev(tp_bits_z(plo, e - 31));
-        const unsigned long long bhi = ~(((unsigned long long)__brev(tp_bits_z(phi, e - 63)) << 32) | __brev(tp_bits_z(phi, e - 31))) & ~bnn;
-        const int nfwd = len1 - req;
+    #pragma unroll 1
+    for (int dir = 0; dir < 2 && found_dir < 0; dir++) {
+        /* candidates o = 0 .. ncand-1 in the reference's order (:48-65 forward, :73-89 backward).  When the fixed read has at least F
+           bases, the first F compared bases of candidate o are an F-bit field of the MOVING read's X plane against a constant:
+             forward   r1 field at bit f1+o          vs  C = rc(r2)[0..F)  = reversed last F bases of r2 (complement flips X, so ~)
+             backward  r2 field at bit e-(F-1)-o     vs  C = reversed complemented r1[0..F)   (bit t of the field is rc(r2)[o+F-1-t])
+           The group's lanes take whole plane words (32 consecutive candidates each) in the order of increasing o. */
+        const int ncand = dir == 0 ? len1 - req : len2 - req;
+        const int lfix = dir == 0 ? len2 : len1;
+        const int nscan = lfix >= F ? max(ncand, 0) : 0;
         int my_o = 1 << 20, my_mm = 0, my_ol = 0;
-        int o = sub;
-        /* fast range: overlap >= 50 bases, so the protected prefix is exactly 50 bits; the three words under the
-           sliding window stay in registers while the offset moves inside one 32-bit word */
-        const int nfast = len2 >= 50 ? min(max(len1 - 49, 0), nfwd) : 0;
-        {
-            const uint32_t b_lo0 = (uint32_t)blo, b_lo1 = (uint32_t)(blo >> 32), b_hi0 = (uint32_t)bhi, b_hi1 = (uint32_t)(bhi >> 32),
-                           b_nn0 = (uint32_t)bnn, b_nn1 = (uint32_t)(bnn >> 32);
-            while (o < nfast && my_o == (1 << 20)) {
-                const int c = f1 + o;
-                const int w = c >> 5;
-                const uint32_t L0 = alo[w], L1 = alo[w + 1], L2 = alo[w + 2], H0 = ahi[w], H1 = ahi[w + 1], H2 = ahi[w + 2],
-                               N0 = ann[w], N1 = ann[w + 1], N2 = ann[w + 2];
-                /* candidates of this lane whose 50-bit field starts in word w.  Tight loop: only the first 32 bases against the
-                   largest limit; the rare survivor is finished (50 bases, lut) outside it and the scan resumes after it. */
-                int sh = c & 31;
-                int cnt = min((nfast - o + g - 1) >> lg, (32 - sh + g - 1) >> lg);
-                while (cnt > 0) {
-                    int mm0 = 0;
-                    for (; cnt >= 2; cnt -= 2, sh += 2 * g, o += 2 * g) {          /* two independent candidates per step (ILP); a hit is re-examined below */
-                        const uint32_t xa = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
-                        const uint32_t xb = (__funnelshift_r(L0, L1, sh + g) ^ b_lo0) | (__funnelshift_r(H0, H1, sh + g) ^ b_hi0) | (__funnelshift_r(N0, N1, sh + g) ^ b_nn0);
-                        if (min(__popc(xa), __popc(xb)) <= dmax) break;
-                    }
-                    #pragma unroll 2
-                    for (; cnt > 0; cnt--, sh += g, o += g) {
-                        const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ b_lo0) | (__funnelshift_r(H0, H1, sh) ^ b_hi0) | (__funnelshift_r(N0, N1, sh) ^ b_nn0);
-                        mm0 = __popc(x0);
-                        if (mm0 <= dmax) break;
-                    }
-                    if (cnt <= 0) break;
-                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ b_lo1) | (__funnelshift_r(H1, H2, sh) ^ b_hi1) | (__funnelshift_r(N1, N2, sh) ^ b_nn1)) & 0x3FFFFu;
-                    const int mm = mm0 + __popc(x1);
-                    const int ol = min(len1 - o, len2);
-                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
-                    cnt--; sh += g; o += g;
+        if (nscan > 0) {
+            const uint32_t *Mlo = dir == 0 ? P.alo : P.plo, *Mhi = dir == 0 ? P.ahi : P.phi;
+            /* X of the complement is ~X, except under N (0 either way; lo = hi = 0 under N in the planes) */
+            uint32_t C;
+            if (dir == 0) { const int s0 = e - 31; C = __brev(~(tp_bits_z(P.plo, s0) ^ tp_bits_z(P.phi, s0)) & ~tp_bits_z(P.pnn, s0)); }
+            else C = __brev(~(tp_bits(P.alo, f1) ^ tp_bits(P.ahi, f1)) & ~tp_bits(P.ann, f1)) >> (32 - F);
+            const int blo = dir == 0 ? f1 : e - (F - 1) - (nscan - 1), bhi = dir == 0 ? f1 + nscan - 1 : e - (F - 1);   /* field starts */
+            const int wlo = blo >> 5, whi = bhi >> 5;
+            #pragma unroll 1
+            for (int wi = sub; wi <= whi - wlo && my_o == (1 << 20); wi += g) {
+                const int w = dir == 0 ? wlo + wi : whi - wi;
+                const uint32_t W0 = Mlo[w] ^ Mhi[w], W1 = Mlo[w + 1] ^ Mhi[w + 1];
+                uint32_t hits = t_ov_word_hits(W0, W1, C, FM, thr);
+                hits &= low_mask(bhi - 32 * w + 1) & ~low_mask(blo - 32 * w);
+                /* survivors (the true overlap, rarely anything else): exact test in the reference's order.  Lanes with survivors reach
+                   this loop together, so the warp pays the test once per round, not once per survivor. */
+                while (hits) {
+                    const int sh = dir == 0 ? __ffs(hits) - 1 : 31 - __clz(hits);
+                    hits &= ~(1u << sh);
+                    const int bit = 32 * w + sh;
+                    const int o = dir == 0 ? bit - f1 : e - (F - 1) - bit;
+                    int ol;
+                    const int mm = t_ov_exact(P, dir, o, lut, ol);
+                    if (mm >= 0) { my_o = o; my_mm = mm; my_ol = ol; break; }
                 }
             }
-        }
-        for (; o < nfwd && my_o == (1 << 20); o += g) {
-            const int ol = min(len1 - o, len2);
-            const int pp = min(ol, 50);
-            const int bit = f1 + o;
-            unsigned long long x = (tp_bits64(alo, bit) ^ blo) | (tp_bits64(ahi, bit) ^ bhi);
-            if (anyN) x |= tp_bits64(ann, bit) ^ bnn;
-            const int mm = __popcll(x & mask64(pp));
-            if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
-        }
-        const int best = group_min(my_o, g);                               /* first accepted offset in the reference's order */
-        if (best < (1 << 20)) {
-            found_dir = 0; found_o = best;
-            found_mm = group_pick(my_mm, my_o == best, g); found_ol = group_pick(my_ol, my_o == best, g);
-        }
-    }
-    /* ---- backward: offset 0 .. -(len2-req-1) (:73-89) ---- */
-    if (found_dir < 0) {
-        const unsigned long long a_nn = tp_bits64(ann, f1), a_lo = tp_bits64(alo, f1), a_hi = tp_bits64(ahi, f1);
-        /* Y50[t] = comp(r1[49-t]) : 64-bit reversal >> 14 */
-        const unsigned long long ynn = __brevll(a_nn) >> 14, ylo = __brevll(a_lo) >> 14, yhi = ~(__brevll(a_hi) >> 14) & ~ynn;
-        const int nbwd = len2 - req;
-        int my_o = 1 << 20, my_mm = 0, my_ol = 0;
-        int o = sub;
-        const int nfast = len1 >= 50 ? min(max(len2 - 49, 0), nbwd) : 0;   /* overlap >= 50: row2's 50-bit field starts at e-49-o */
-        {
-            const uint32_t y_lo0 = (uint32_t)ylo, y_lo1 = (uint32_t)(ylo >> 32), y_hi0 = (uint32_t)yhi, y_hi1 = (uint32_t)(yhi >> 32),
-                           y_nn0 = (uint32_t)ynn, y_nn1 = (uint32_t)(ynn >> 32);
-            while (o < nfast && my_o == (1 << 20)) {
-                const int c = e - 49 - o;                                  /* >= front2 >= 0 */
-                const int w = c >> 5;
-                const uint32_t L0 = plo[w], L1 = plo[w + 1], L2 = plo[w + 2], H0 = phi[w], H1 = phi[w + 1], H2 = phi[w + 2],
-                               N0 = pnn[w], N1 = pnn[w + 1], N2 = pnn[w + 2];
-                int sh = c & 31;
-                int cnt = min((nfast - o + g - 1) >> lg, (sh >> lg) + 1);   /* the field start moves DOWN by g per candidate */
-                while (cnt > 0) {
-                    int mm0 = 0;
-                    for (; cnt >= 2; cnt -= 2, sh -= 2 * g, o += 2 * g) {
-                        const uint32_t xa = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
-                        const uint32_t xb = (__funnelshift_r(L0, L1, sh - g) ^ y_lo0) | (__funnelshift_r(H0, H1, sh - g) ^ y_hi0) | (__funnelshift_r(N0, N1, sh - g) ^ y_nn0);
-                        if (min(__popc(xa), __popc(xb)) <= dmax) break;
-                    }
-                    #pragma unroll 2
-                    for (; cnt > 0; cnt--, sh -= g, o += g) {
-                        const uint32_t x0 = (__funnelshift_r(L0, L1, sh) ^ y_lo0) | (__funnelshift_r(H0, H1, sh) ^ y_hi0) | (__funnelshift_r(N0, N1, sh) ^ y_nn0);
-                        mm0 = __popc(x0);
-                        if (mm0 <= dmax) break;
-                    }
-                    if (cnt <= 0) break;
-                    const uint32_t x1 = ((__funnelshift_r(L1, L2, sh) ^ y_lo1) | (__funnelshift_r(H1, H2, sh) ^ y_hi1) | (__funnelshift_r(N1, N2, sh) ^ y_nn1)) & 0x3FFFFu;
-                    const int mm = mm0 + __popc(x1);
-                    const int ol = min(len1, len2 - o);
-                    if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
-                    cnt--; sh -= g; o += g;
-                }
+        } else {
+            #pragma unroll 1
+            for (int o = sub; o < ncand; o += g) {           /* fixed read shorter than the filter: exact test of every candidate */
+                int ol;
+                const int mm = t_ov_exact(P, dir, o, lut, ol);
+                if (mm >= 0) { my_o = o; my_mm = mm; my_ol = ol; break; }
             }
-        }
-        for (; o < nbwd && my_o == (1 << 20); o += g) {
-            const int ol = min(len1, len2 - o);
-            const int pp = min(ol, 50);
-            const int sbit = e - o - pp + 1;                               /* >= front2 >= 0 */
-            const int ysh = 50 - pp;
-            unsigned long long x = (tp_bits64(plo, sbit) ^ (ylo >> ysh)) | (tp_bits64(phi, sbit) ^ (yhi >> ysh));
-            if (anyN) x |= tp_bits64(pnn, sbit) ^ (ynn >> ysh);
-            const int mm = __popcll(x & mask64(pp));
-            if (mm <= (int)lut[ol]) { my_o = o; my_mm = mm; my_ol = ol; break; }
         }
         const int best = group_min(my_o, g);
         if (best < (1 << 20)) {
-            found_dir = 1; found_o = best;
+            found_dir = dir; found_o = best;
             found_mm = group_pick(my_mm, my_o == best, g); found_ol = group_pick(my_ol, my_o == best, g);
         }
     }
@@ -344,9 +322,9 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
             const int abit = f1 + (found_dir == 0 ? found_o : 0), bbit = found_dir == 0 ? 0 : found_o;
             for (int k = 0; k * 32 < found_ol; k++) {
                 const int s0 = e - (bbit + 32 * k) - 31;
-                const uint32_t rn = __brev(tp_bits_z(pnn, s0));
-                const uint32_t rl_ = __brev(tp_bits_z(plo, s0)), rh = ~__brev(tp_bits_z(phi, s0)) & ~rn;
-                const uint32_t x = (tp_bits(alo, abit + 32 * k) ^ rl_) | (tp_bits(ahi, abit + 32 * k) ^ rh) | (tp_bits(ann, abit + 32 * k) ^ rn);
+                const uint32_t rn = __brev(tp_bits_z(P.pnn, s0));
+                const uint32_t rl_ = __brev(tp_bits_z(P.plo, s0)), rh = ~__brev(tp_bits_z(P.phi, s0)) & ~rn;
+                const uint32_t x = (tp_bits(P.alo, abit + 32 * k) ^ rl_) | (tp_bits(P.ahi, abit + 32 * k) ^ rh) | (tp_bits(P.ann, abit + 32 * k) ^ rn);
                 diff += __popc(x & low_mask(found_ol - 32 * k));
             }
         }
@@ -475,18 +453,20 @@ __device__ __noinline__ void t_patch_delta(const DeltaAcc D, unsigned long long*
                 red_add64(&G[fp_off_cycle(&L, st, 3 * 8 + bb, P)], (unsigned long long)((long long)sg * ((int)q - 33)));
             }
         }
-        /* 5-mers ending at i = P .. P+4 (stats.cpp:228-266) with the base at P set to b */
+        /* 5-mers ending at i = P .. P+4 (stats.cpp:228-266) with the base at P set to b.  The block-private table is indexed like the
+           pre-filter one (oldest base in the low digit, codes A0 C1 T2 G3; mapped to the reference's index at the flush). */
         #pragma unroll 1
         for (int i = max(P, 4); i <= min(P + 4, l0 - 1); i++) {
-            int code = 0; bool ok = true;
+            int code = 0, field = 0; bool ok = true;
             #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int pos = i - 4 + k;
-                const int v = dev_base2val(pos == P ? b : seq[pos]);
-                ok = ok && (v >= 0); code = (code << 2) | (v & 3);
+                const uint8_t bb = pos == P ? b : seq[pos];
+                const int v = dev_base2val(bb);
+                ok = ok && (v >= 0); code = (code << 2) | (v & 3); field |= ((bb >> 1) & 3) << (2 * k);
             }
             if (ok) {
-                if (clean) atomicAdd(&D.kmer[side * FP_KMER_BINS + code], sg);
+                if (clean) atomicAdd(&D.kmer[side * FP_KMER_BINS + field], sg);
                 else red_add64(&G[fp_off_kmer(&L, side * 2 + 1, code)], (unsigned long long)(long long)sg);
             }
         }
@@ -546,7 +526,7 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
                     atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);   /* diagonal only, SURVEY App. A.6 */
                     if (sink.count) {
                         const unsigned int slot = atomicAdd(sink.count, 1u);
-                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt.old_base = b2; pt.old_qual = (uint8_t)q2; pt._pad = 0; sink.patches[slot] = pt; }
                     }
                 } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
                     const uint8_t nb = dev_complement(b2);
@@ -557,7 +537,7 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
                     atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
                     if (sink.count) {
                         const unsigned int slot = atomicAdd(sink.count, 1u);
-                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt._pad[0] = pt._pad[1] = pt._pad[2] = 0; sink.patches[slot] = pt; }
+                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt.old_base = b1; pt.old_qual = (uint8_t)q1; pt._pad = 0; sink.patches[slot] = pt; }
                     }
                 }
             }
@@ -782,9 +762,6 @@ __device__ __forceinline__ fp_read_result t_make_result(const TRead& r, int verd
 /* dense pass for TWO cycles (half a word column): acc[cyc 0..1][bin][kind] */
 struct ColAcc2 { unsigned int v[2][NB][4]; };
 
-/* 2-bit codes ((base>>1)&3: A0 C1 T2 G3) of a word's 4 bases gathered into one byte: code_mul4 leaves it in byte 3 */
-__device__ __forceinline__ uint32_t code_mul4(uint32_t w) { return ((w >> 1) & 0x03030303u) * 0x01041040u; }
-__device__ __forceinline__ uint32_t pack_codes4(uint32_t w) { return code_mul4(w) >> 24; }
 /* table index used while counting (oldest base in the low digit, codes A0 C1 T2 G3) -> reference 5-mer index
    (oldest base in the high digit, base2val A0 T1 C2 G3; stats.cpp:248-266) */
 __device__ __forceinline__ int kmer_ref_index(int f) {
@@ -906,14 +883,132 @@ __device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* 
     return out;
 }
 
-/* deferred post-filter statistics request (phase C): contribution of positions [lo,hi) of one tile row */
-struct DeltaReq { int row_side; int ctx0, lo, hi; };        /* row_side = row | side<<16 | clean<<17 | (sign<0)<<18 */
+/* ------------------------------------------------------------------------------------------------
+ * Post-filter statistics of what the chain REMOVED from clean rows (failed reads, trimmed tails): the dense pass and the
+ * histogram items credited every base of the tile to pre AND post, so the removed positions [lo, hi) of a row are taken out
+ * of post again -- with the same machinery that counted them: a transposed dp4a pass over the removal list for the per-cycle
+ * counters (dense_remove) and word-parallel histogram items for qualities and 5-mers (hist_remove_chunk), both into the
+ * block-private signed accumulators.  One list per side; entry = row | lo << 8 | hi << 20; lists are zero-padded to a
+ * multiple of four entries (hi = 0: nothing).
+ * ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t rm_pack(int row, int lo, int hi) { return (uint32_t)row | ((uint32_t)lo << 8) | ((uint32_t)hi << 20); }
 
-__device__ __forceinline__ void push_delta(DeltaReq* q, int* qn, bool want, bool clean, int side, int row, int ctx0, int lo, int hi, int sign) {
+__device__ __noinline__ void dense_remove(const uint32_t* list, int n, int ifirst, int istep, const uint8_t* ts, const uint8_t* tq, int S, int w4, int my_half,
+                                          int* dc, int cycles) {
+    FP_SMEM(list); FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(dc);
+    unsigned int acc[2][NB][4];
+    #pragma unroll
+    for (int c = 0; c < 2; c++)
+        #pragma unroll
+        for (int b = 0; b < NB; b++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) acc[c][b][k] = 0;
+    const int j0 = my_half * 2;
+    const unsigned sel = my_half ? 0x7362u : 0x5140u;
+    bool any = false;
+    #pragma unroll 1
+    for (int i = ifirst; i < n; i += istep) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(list + i);
+        const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t xs[4], xq[4], anym = 0;
+        #pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int row = es[kk] & 0xFF, lo = (es[kk] >> 8) & 0xFFF, hi = es[kk] >> 20;
+            const uint32_t m = window_mask(w4, lo, hi);
+            uint32_t x = 0, q = 0;
+            if (m) {
+                x = *reinterpret_cast<const uint32_t*>(ts + row * S + w4) & m;
+                q = *reinterpret_cast<const uint32_t*>(tq + row * S + w4) & m;
+            }
+            xs[kk] = x; xq[kk] = q; anym |= m;
+        }
+        if (!anym) continue;
+        any = true;
+        const uint32_t t0 = __byte_perm(xs[0], xs[1], sel), t1 = __byte_perm(xs[2], xs[3], sel);
+        const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
+        acc_cycle(acc[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
+        acc_cycle(acc[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
+    }
+    if (!any) return;
+    #pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const int cyc = w4 + j0 + c;
+        if (cyc >= cycles) continue;
+        #pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const unsigned int nb = acc[c][b][0];
+            if (nb == 0) continue;
+            int* c4 = dc + (cyc * 5 + b) * 4;
+            atomicAdd(&c4[0], -(int)nb);
+            if (acc[c][b][1]) atomicAdd(&c4[1], -(int)acc[c][b][1]);
+            if (acc[c][b][2]) atomicAdd(&c4[2], -(int)acc[c][b][2]);
+            atomicAdd(&c4[3], -(int)(acc[c][b][3] - 33u * nb));
+        }
+    }
+}
+
+/* -1 in a block-private table at shared-window address `addr` iff bit `bit` of m is set */
+#define smem_dec_bit(addr, m, bit) asm volatile("{ .reg .pred p; .reg .b32 t; and.b32 t, %1, %2; setp.ne.u32 p, t, 0; @p red.shared.add.u32 [%0], 0xffffffff; }" :: "r"(addr), "r"(m), "r"(1u << (bit)) : "memory")
+
+/* qualities and 5-mers of the positions `rmask` of one 32-base chunk (chunk j of a clean row; sp / qp point at the chunk) out of the
+ * post-filter histograms: qaddr / kaddr = shared-window addresses of this side's signed tables (kaddr 4 KB-aligned, indexed like the
+ * pre-filter 5-mer table); nn_cur / nn_prev = N-plane words of this chunk and the one before it. */
+__device__ __noinline__ void hist_remove_chunk(const uint8_t* sp, const uint8_t* qp, int j, uint32_t rmask, uint32_t nn_cur, uint32_t nn_prev,
+                                               uint32_t qaddr, uint32_t kaddr, uint32_t kdummy) {
+    FP_SMEM(sp); FP_SMEM(qp);
+    uint32_t clo = 0, chi = 0;
+    #pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const uint2 sw = *reinterpret_cast<const uint2*>(sp + 8 * k), qw = *reinterpret_cast<const uint2*>(qp + 8 * k);
+        const uint32_t cc = __byte_perm(code_mul4(sw.x), code_mul4(sw.y), 0x7310);
+        clo = __byte_perm(clo, chi, 0x5432); chi = __byte_perm(chi, cc, 0x7632);
+        const uint32_t m8 = (rmask >> (8 * k)) & 0xFFu;
+        if (m8) {
+            #pragma unroll
+            for (int b8 = 0; b8 < 8; b8++) {
+                const uint32_t w = b8 < 4 ? qw.x : qw.y;
+                const int bb = b8 & 3;
+                const uint32_t sh = bb == 0 ? (w << 2) : (w >> (8 * bb - 2));
+                smem_dec_bit(qaddr + (sh & 0x1FCu), m8, b8);
+            }
+        }
+    }
+    /* same window arithmetic as the pre-filter items (fp_chain2_kernel phase A); a clean row's base is exact A/C/G/T iff it is not N */
+    uint32_t cz = 0, cok = 0;
+    if (j > 0) { cz = pack_codes4(*reinterpret_cast<const uint32_t*>(sp - 4)); cok = (~nn_prev >> 28) & 0xFu; }
+    const uint32_t okm = ~nn_cur;
+    const uint32_t Z0 = cz | (clo << 8), Z1 = __funnelshift_r(clo, chi, 24), Z2 = chi >> 24;
+    const uint32_t O0 = cok | (okm << 4), O1 = okm >> 28;
+    const uint32_t vwin = O0 & __funnelshift_r(O0, O1, 1) & __funnelshift_r(O0, O1, 2) & __funnelshift_r(O0, O1, 3) & __funnelshift_r(O0, O1, 4) & rmask;
+    #pragma unroll 1
+    for (int g8 = 0; g8 < 4; g8++) {
+        const uint32_t v8 = (vwin >> (8 * g8)) & 0xFFu;
+        if (!v8) continue;
+        const uint32_t W = __funnelshift_r(g8 < 2 ? Z0 : Z1, g8 < 2 ? Z1 : Z2, (g8 & 1) * 16);
+        #pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
+            asm volatile("red.shared.add.u32 [%0], 0xffffffff;" :: "r"((v8 & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy) : "memory");
+        }
+    }
+}
+
+/* deferred post-filter statistics request (phase C): contribution of positions [lo,hi) of one tile row */
+struct DeltaReq { uint32_t a, b; };        /* a = row | side<<8 | clean<<9 | (sign<0)<<10 | ctx0<<12;  b = lo | hi<<16 */
+
+struct DeltaSinks { DeltaReq* q; int* qn; uint32_t* rm; int* nrm; int T; };
+/* removals from clean rows go to the side's removal list (fast engines); re-additions of front-shifted reads and everything on
+   rows with bytes outside {A,C,G,T,N} go to the request queue (exact per-position engines) */
+__device__ __forceinline__ void push_delta(const DeltaSinks& K, bool want, bool clean, int side, int row, int ctx0, int lo, int hi, int sign) {
     if (want && hi > lo) {
-        const int slot = atomicAdd(qn, 1);
-        DeltaReq r; r.row_side = row | (side << 16) | ((clean ? 1 : 0) << 17) | ((sign < 0 ? 1 : 0) << 18); r.ctx0 = ctx0; r.lo = lo; r.hi = hi;
-        q[slot] = r;
+        if (clean && sign < 0) {
+            const int slot = atomicAdd(&K.nrm[side], 1);
+            K.rm[side * (K.T + 4) + slot] = rm_pack(row, lo, hi);
+        } else {
+            const int slot = atomicAdd(K.qn, 1);
+            DeltaReq r; r.a = (uint32_t)row | ((uint32_t)side << 8) | ((clean ? 1u : 0u) << 9) | ((sign < 0 ? 1u : 0u) << 10) | ((uint32_t)ctx0 << 12); r.b = (uint32_t)lo | ((uint32_t)hi << 16);
+            K.q[slot] = r;
+        }
     }
 }
 
@@ -948,20 +1043,26 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
     DeltaAcc D;
     D.cycles = S;
     D.cyc = reinterpret_cast<int*>(smem + sl.off_delta);
-    D.kmer = D.cyc + SIDES * S * 20;
-    D.qh = D.kmer + SIDES * FP_KMER_BINS;
+    D.kmer = reinterpret_cast<int*>(smem + sl.off_dkmer);
+    D.qh = reinterpret_cast<int*>(smem + sl.off_dqh);
+    uint32_t* s_rm = reinterpret_cast<uint32_t*>(smem + sl.off_rm);          /* [SIDES][T + 4] removal lists */
+    int* s_nrm = reinterpret_cast<int*>(s_rm + SIDES * (T + 4));             /* [SIDES] their lengths */
+    DeltaSinks sinks; sinks.rm = s_rm; sinks.nrm = s_nrm; sinks.T = T;
     int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);
     const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free lane-group-per-row access */
     uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
     DeltaReq* s_queue = reinterpret_cast<DeltaReq*>(smem + sl.off_queue);    /* [SIDES * T * 2] */
     unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
-    int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor */
+    int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
+    sinks.q = s_queue; sinks.qn = &s_qn[0];
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
     for (int i = tid; i < SIDES * T * PSTR; i += FP_CT) tile_planes[i] = 0;
     for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) s_kmer[i] = 0;
     for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_CT) s_qhist[i] = 0;
-    for (int i = tid; i < SIDES * (S * 20 + FP_KMER_BINS + FP_QUAL_BINS); i += FP_CT) D.cyc[i] = 0;
+    for (int i = tid; i < SIDES * S * 20; i += FP_CT) D.cyc[i] = 0;
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) D.kmer[i] = 0;
+    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) D.qh[i] = 0;
     for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_CT) reinterpret_cast<unsigned int*>(bc)[i] = 0;
     for (int i = tid; i < S + 2; i += FP_CT) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -1023,12 +1124,13 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
-            s_qn[0] = 0; s_qn[1] = 0;                  /* request queue: next used after the phase-A barrier */
+            s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0;     /* request queue / removal items: next used after the phase-A barrier */
         }
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
            mbarrier every thread waits on itself: no CTA barrier here */
         mbar_wait(mbar, parity);
         parity ^= 1;
+        for (int i = tid; i < SIDES * (T + 4) + SIDES; i += FP_CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
         if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
@@ -1173,8 +1275,8 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 }
                 /* post stats as a delta against pre (warp-cooperative): drop what was trimmed / failed, re-add shifted windows */
                 const bool keep_tail = counted && r1.front == 0;
-                push_delta(s_queue, &s_qn[0], active && lead, clean, 0, rr, 0, keep_tail ? r1.len : 0, len0, -1);
-                push_delta(s_queue, &s_qn[0], active && lead && counted && !keep_tail, clean, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
+                push_delta(sinks, active && lead, clean, 0, rr, 0, keep_tail ? r1.len : 0, len0, -1);
+                push_delta(sinks, active && lead && counted && !keep_tail, clean, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
             } else {
                 /* PairEndProcessor::processPairEnd loop body  peprocessor.cpp:383-643 */
                 uint8_t* rs1 = tile_seq[0] + rr * S; uint8_t* rq1 = tile_qual[0] + rr * S;
@@ -1285,31 +1387,70 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 {
                     const bool removed = false;        /* corrections were folded into the accumulators base by base (t_patch_delta) */
                     const bool keep1 = counted && r1.front == 0 && !removed;
-                    push_delta(s_queue, &s_qn[0], active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
-                    push_delta(s_queue, &s_qn[0], active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
+                    push_delta(sinks, active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
+                    push_delta(sinks, active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
                     const bool keep2 = counted && r2.front == 0 && !removed;
-                    push_delta(s_queue, &s_qn[0], active && lead && !removed, clean2, 1, rr, 0, keep2 ? r2.len : 0, l2, -1);
-                    push_delta(s_queue, &s_qn[0], active && lead && counted && !keep2, clean2, 1, rr, r2.front, r2.front, r2.front + r2.len, +1);
+                    push_delta(sinks, active && lead && !removed, clean2, 1, rr, 0, keep2 ? r2.len : 0, l2, -1);
+                    push_delta(sinks, active && lead && counted && !keep2, clean2, 1, rr, r2.front, r2.front, r2.front + r2.len, +1);
                 }
             }
         }
 
         __syncthreads();
 
-        /* ---------------- phase C: drain the post-stat request queue (all warps, dynamic) ---------------- */
+        /* ---------------- phase C: post-filter statistics of what the chain removed / shifted (all warps) ---------------- */
         {
+            /* (1) per-cycle counters of the removal lists: the column threads, transposed dp4a pass like phase A's */
+            if (col_active) {
+                const int nr = s_nrm[my_side];
+                if (nr > 0) dense_remove(s_rm + my_side * (T + 4), nr, 4 * my_part, 4 * nsplit, tile_seq[my_side], tile_qual[my_side], S, my_w * 4, my_half,
+                                         D.cyc + my_side * S * 20, S);
+            }
+            /* (2) qualities and 5-mers of the removal lists: one lane per (entry, 32-base chunk), claimed 32 at a time */
+            {
+                const int nwords = (S + 31) >> 5;
+                const int nr0 = s_nrm[0], nr1 = SIDES > 1 ? s_nrm[SIDES - 1] : 0;
+                const int total = (nr0 + nr1) * nwords;
+                const uint32_t nw_magic = 0xFFFFFFFFu / (uint32_t)nwords + 1u;
+                const uint32_t kdummy = smem_u32(s_dummy) + 4u * (uint32_t)lane;
+                #pragma unroll 1
+                for (;;) {
+                    if (total == 0) break;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_qn[3], 32);
+                    base = __shfl_sync(FULL_MASK, base, 0);
+                    if (base >= total) break;
+                    const int it = base + lane;
+                    if (it < total) {
+                        const int ei = (int)__umulhi((uint32_t)it, nw_magic), j = it - ei * nwords;
+                        const int sd = ei >= nr0 ? 1 : 0;
+                        const uint32_t e = s_rm[sd * (T + 4) + ei - sd * nr0];
+                        const int row = e & 0xFF, lo = (e >> 8) & 0xFFF, hi = e >> 20;
+                        const int a0 = max(lo - 32 * j, 0), b0 = min(hi - 32 * j, 32);
+                        if (b0 > a0) {
+                            const uint8_t* sp = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes + row * S + 32 * j;
+                            const uint32_t* pnn = tile_planes + (sd * T + row) * PSTR + 2 * PW;
+                            hist_remove_chunk(sp, sp + sl.tile_array_bytes, j, low_mask(b0) & ~low_mask(a0), pnn[j], j > 0 ? pnn[j - 1] : 0u,
+                                              smem_u32(D.qh) + (uint32_t)sd * (FP_QUAL_BINS * 4), smem_u32(D.kmer) + (uint32_t)sd * (FP_KMER_BINS * 4), kdummy);
+                        }
+                    }
+                }
+            }
+            /* (3) the request queue: re-additions of front-shifted reads, rows with bytes outside {A,C,G,T,N} (exact engines) */
             const int nreq = s_qn[0];
             #pragma unroll 1
             for (;;) {
+                if (nreq == 0) break;
                 int qi = 0;
                 if (lane == 0) qi = atomicAdd(&s_qn[1], 1);
                 qi = __shfl_sync(FULL_MASK, qi, 0);
                 if (qi >= nreq) break;
                 const DeltaReq rq = s_queue[qi];
-                const int row = rq.row_side & 0xFFFF, side = (rq.row_side >> 16) & 1, sign = ((rq.row_side >> 18) & 1) ? -1 : +1;
+                const int row = rq.a & 0xFF, side = (rq.a >> 8) & 1, sign = ((rq.a >> 10) & 1) ? -1 : +1;
+                const int ctx0 = (int)(rq.a >> 12), rlo = (int)(rq.b & 0xFFFF), rhi = (int)(rq.b >> 16);
                 const uint8_t* sq = smem + sl.off_tile + side * 2 * sl.tile_array_bytes + row * S; const uint8_t* ql = sq + sl.tile_array_bytes;
-                if ((rq.row_side >> 17) & 1) dev_stat_positions_smem(D, side, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
-                else dev_stat_positions(G, side * 2 + 1, sq, ql, rq.ctx0, rq.lo, rq.hi, sign);
+                if ((rq.a >> 9) & 1) dev_stat_positions_smem(D, side, sq, ql, ctx0, rlo, rhi, sign);
+                else dev_stat_positions(G, side * 2 + 1, sq, ql, ctx0, rlo, rhi, sign);
             }
         }
         fill_lens(tix + gridDim.x);
@@ -1362,7 +1503,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
         red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, i % FP_KMER_BINS)], (unsigned long long)(long long)v); }
+    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, kmer_ref_index(i % FP_KMER_BINS))], (unsigned long long)(long long)v); }
     #pragma unroll 1
     for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
     #pragma unroll 1

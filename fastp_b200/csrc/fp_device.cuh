@@ -295,10 +295,15 @@ __device__ __noinline__ void dev_stat_positions(unsigned long long* G, int stats
     }
 }
 
+/* 2-bit codes ((base>>1)&3: A0 C1 T2 G3) of a word's 4 bases gathered into one byte: code_mul4 leaves it in byte 3 */
+__device__ __forceinline__ uint32_t code_mul4(uint32_t w) { return ((w >> 1) & 0x03030303u) * 0x01041040u; }
+__device__ __forceinline__ uint32_t pack_codes4(uint32_t w) { return code_mul4(w) >> 24; }
+
 /* ------------------------------------------------------------------------------------------------
  * Block-private form of the same engine for CLEAN rows (bases in {A,C,G,T,N}): signed 32-bit shared-memory
  * accumulators instead of global atomics (the global block would serialise on its few hot addresses).
- *   D.cyc [side][cycle][bin A,C,T,N,G][kind count,q20,q30,qualsum]   D.kmer [side][1024]   D.qh [side][128]
+ *   D.cyc [side][cycle][bin A,C,T,N,G][kind count,q20,q30,qualsum]   D.qh [side][128]
+ *   D.kmer [side][1024], indexed like the pre-filter 5-mer table (oldest base in the low digit, codes A0 C1 T2 G3)
  * Flushed once per CTA into the POST stats of that side.
  * ------------------------------------------------------------------------------------------------ */
 struct DeltaAcc { int* cyc; int* kmer; int* qh; int cycles; };
@@ -334,10 +339,8 @@ __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side,
                 const uint32_t K = 0x01010101u;
                 const uint32_t c0 = w0 & K, c1 = (w0 >> 1) & K, c2 = (w0 >> 2) & K;
                 const uint32_t ok4 = (c0 & ~c1 & ~c2) | (c0 & c1) | (~c0 & ~c1 & c2);       /* A C G T by base&7 */
-                const uint32_t v4 = (w0 & 0x02020202u) | c2;
-                const int vb = ((b >> 1) & 1) * 2 + ((b >> 2) & 1);
                 const bool okb = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T');
-                if (ok4 == K && okb) atomicAdd(&km[((((v4 * 0x40100401u) >> 24) << 2) | vb) & 0x3FF], sign);
+                if (ok4 == K && okb) atomicAdd(&km[pack_codes4(w0) | (((uint32_t)(b >> 1) & 3u) << 8)], sign);
             }
         }
     }
@@ -349,7 +352,7 @@ __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side,
  * ------------------------------------------------------------------------------------------------ */
 struct fp_smem_layout {
     int off_dummy, off_mbar, off_next, off_tile, tile_array_bytes, off_len, off_clean, off_kmer, off_qhist, off_bc, off_lut, off_delta,
-        off_planes, off_queue, plane_words, plane_stride, total;
+        off_dkmer, off_dqh, off_rm, off_planes, off_queue, plane_words, plane_stride, total;
 };
 
 struct fp_launch_args {

@@ -15,6 +15,8 @@
  *            with p = 10^(-q/10); N bases; polyG / polyA tails; low-quality 3' tails; planted
  *            correctable mismatches (Q>=30 vs Q<=14); short / empty reads; adapter dimers.
  * profile 2  profile 1 plus single-base deletions (8 % of R2) / insertions (4 % of R1).
+ * profile 3  profile 1 plus 20 planted over-represented sequences (40..150 bases, each in about 1 % of the fragments), so that
+ *            Evaluator::computeOverRepSeq finds a non-empty candidate list (BASELINE.json configs[4]).
  */
 #ifndef FP_SYNTH_H
 #define FP_SYNTH_H
@@ -101,7 +103,7 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
         if (ins < 35) ins = 35;
         if (fp_rng_permille(&r, 3)) ins = (int)fp_rng_below(&r, 3);          /* adapter dimer: insert 0..2 */
         else if (fp_rng_permille(&r, 50)) ins = 20 + (int)fp_rng_below(&r, (uint32_t)L);   /* extra short inserts */
-        if (profile >= 2) {   /* many short inserts: only there can a gap near the overlap's end decide the outcome */
+        if (profile == 2) {   /* many short inserts: only there can a gap near the overlap's end decide the outcome */
             fp_rng rj; fp_rng_seed(&rj, seed, index, 2);
             if (fp_rng_permille(&rj, 150)) ins = 30 + (int)fp_rng_below(&rj, 40);
         }
@@ -110,6 +112,18 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
         for (int j = 0; j < ins; j++) {
             uint32_t u = fp_rng_u32(&r);
             frag[j] = lowcomplex ? fp_synth_base((u >> 13) & 1 ? 0 : (u >> 20)) : fp_synth_base(u >> 13);
+        }
+        if (profile == 3) {   /* planted over-represented sequence k: content depends on (seed, k) only */
+            fp_rng rp; fp_rng_seed(&rp, seed ^ 0x0E44E4ULL, index, 3);
+            if (fp_rng_permille(&rp, 200)) {
+                const uint32_t k = fp_rng_below(&rp, 20);
+                const int Lk = 40 + (int)((k * 37u) % 111u);
+                if (ins > Lk) {
+                    const int pos = (int)fp_rng_below(&rp, (uint32_t)(ins - Lk + 1));
+                    fp_rng rk; fp_rng_seed(&rk, seed ^ 0x51A17EDULL, (uint64_t)k, 1);
+                    for (int j = 0; j < Lk; j++) frag[pos + j] = fp_synth_base(fp_rng_u32(&rk) >> 13);
+                }
+            }
         }
         /* read lengths: mostly L; 1% arbitrary in [0, L] */
         if (fp_rng_permille(&r, 10)) n1 = (int)fp_rng_below(&r, (uint32_t)L + 1);
@@ -175,7 +189,7 @@ FP_HD void fp_synth_pair(uint64_t seed, uint64_t index, int profile, int L, int 
             }
         }
     }
-    if (profile >= 2 && seq2) {
+    if (profile == 2 && seq2) {
         /* profile 2 = enriched + single-base indels, so the one-gap overlap passes (--allow_gap_overlap_trimming) have work */
         fp_rng ri; fp_rng_seed(&ri, seed, index, 1);
         if (fp_rng_permille(&ri, 80) && n2 > 20) {                       /* deletion in R2 */

@@ -123,14 +123,19 @@ void fp_params_default(fp_params* p, int paired);
 /* One batch of reads (SE) or read pairs (PE) in fixed-stride SoA form.
  * Row i of seq1 starts at seq1 + i*stride and holds len1[i] valid bytes.
  * Bytes in [len, stride) are ignored. seq/qual are MODIFIED IN PLACE by base correction. */
+#define FP_B_INDEXED 0x1     /* fp_batch.flags: first_read_index holds the GLOBAL index of unit 0 of this batch */
 typedef struct fp_batch {
     int64_t   n;            /* reads (SE) or pairs (PE)                     */
     int32_t   stride;       /* multiple of 16, <= FP_MAX_STRIDE             */
-    int32_t   _pad;
+    int32_t   flags;        /* FP_B_*                                        */
     uint8_t  *seq1, *qual1; /* [n][stride] bases (ASCII) / phred+33 quals    */
     uint16_t *len1;         /* [n]                                          */
     uint8_t  *seq2, *qual2; /* PE only                                      */
     uint16_t *len2;
+    /* Position of unit 0 in the whole input stream (all batches, all ranks): the pre-filter over-representation
+     * sampling test is `mReads % overRepSampling == 0` on that running count (src/stats.cpp:272).  Used only with
+     * FP_B_INDEXED; without it the ctx continues its own count from the previous batch (single-process use). */
+    int64_t   first_read_index;
 } fp_batch;
 
 /* flags */
@@ -167,7 +172,9 @@ typedef struct fp_patch {
     uint8_t  which;        /* 0 = read1, 1 = read2               */
     uint8_t  base;         /* new base                           */
     uint8_t  qual;         /* new quality                        */
-    uint8_t  _pad[3];
+    uint8_t  old_base;     /* what the row held before (lets a caller that keeps its batch resident undo the pass) */
+    uint8_t  old_qual;
+    uint8_t  _pad;
 } fp_patch;                /* 12 bytes */
 
 /* ---------------- packed counter block (all int64, plain sums) ----------------
@@ -273,17 +280,44 @@ int  fp_process_pe(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read
 int  fp_process_se_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1);
 int  fp_process_pe_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2,
                         fp_ov_result* ov);
+/* Same, and the base corrections it applied to the host rows are also listed for the caller (HOST array of patch_cap entries,
+ * fp_patch.pair = index in `b`; *n_patches counts all of them and may exceed patch_cap): the reference-side shim uses it to
+ * touch only the Read objects whose bases changed (BaseCorrector rewrites r1/r2 in place, src/basecorrector.cpp:44-60). */
+int  fp_process_pe_host_patches(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                                fp_patch* patches, uint64_t patch_cap, uint64_t* n_patches);
 
 /* Counter block. fetch synchronises the ctx's streams, finalises (totals per cycle) and copies
  * layout.total int64 words to host_out. */
 int  fp_counters_reset(fp_ctx* ctx);
 int  fp_counters_fetch(fp_ctx* ctx, int64_t* host_out);
-/* Device pointer to the finalised int64 block (layout.total words) for an in-place
- * ncclAllReduce(ncclInt64, ncclSum) / torch.distributed.all_reduce by the caller (Stats::merge
- * src/stats.cpp:877-955 and FilterResult::merge src/filterresult.cpp:38-89 are element-wise sums). */
+/* Device pointer to the RAW int64 block (layout.total words; the per-cycle totals, kinds 32/33, are derived from it by
+ * fp_counters_fetch) for an in-place ncclAllReduce(ncclInt64, ncclSum) / torch.distributed.all_reduce by the caller
+ * (Stats::merge src/stats.cpp:877-955 and FilterResult::merge src/filterresult.cpp:38-89 are element-wise sums).
+ * After the all-reduce the block holds the job's totals: fetch it, then fp_counters_reset before processing more --
+ * reducing twice, or processing on top of a reduced block, counts the other ranks' reads again. */
 int  fp_counters_device_ptr(fp_ctx* ctx, int64_t** dev_ptr, int64_t* n_words);
-/* Collective form: `comm` is an ncclComm_t (void*); no-op when comm == NULL. */
+/* Collective form: `comm` is an ncclComm_t (void*); no-op when comm == NULL.  Enqueued on `stream` (NULL = the ctx's own)
+ * after everything already enqueued there, not synchronised: fp_counters_fetch waits for it. */
 int  fp_counters_allreduce(fp_ctx* ctx, void* comm, void* stream);
+
+/* Undo the base corrections of one fp_process_pe pass on a batch that stays resident in DEVICE memory: writes old_base /
+ * old_qual of the first n_patches entries of `patches` (device memory, as filled by that pass) back into the rows.
+ * A position is corrected at most once per pass, so the order of the list does not matter. */
+int  fp_patches_undo(fp_ctx* ctx, const fp_batch* b, const fp_patch* patches, const uint32_t* n_patches, uint32_t patch_cap, void* stream);
+
+/* ---- over-representation sampling across batches / ranks (src/stats.cpp:270-290) ----
+ * PRE-filter stats sample unit i iff (global index of i) % sampling == 0: pass fp_batch.first_read_index (FP_B_INDEXED).
+ * POST-filter stats sample by the running count of reads that PASSED before this one in the whole stream, which a rank
+ * only knows once every earlier shard has been filtered.  Two-phase protocol for sharded runs:
+ *   fp_overrep_defer_post(ctx, 1)     the fp_process_* calls skip the post-filter scan
+ *   fp_pass_count(...)                units of a processed batch that were counted by the post-filter Stats
+ *   (exclusive scan of the counts over batches and ranks -- one int64 per rank through ncclAllGather / all_gather)
+ *   fp_overrep_post(..., pass_base)   post-filter scan of that batch given the number of counted units before it
+ * out1/out2 are the DEVICE record arrays the fp_process_* call filled for that batch; the batch rows must still hold
+ * what that call left (corrected bases included). */
+int  fp_overrep_defer_post(fp_ctx* ctx, int32_t defer);
+int  fp_pass_count(fp_ctx* ctx, const fp_read_result* out1, int64_t n, int64_t* count, void* stream);   /* synchronises `stream` */
+int  fp_overrep_post(fp_ctx* ctx, const fp_batch* b, const fp_read_result* out1, const fp_read_result* out2, int64_t pass_base, void* stream);
 
 /* ---------------- FASTQ text <-> rows on the device ----------------
  * fp_fastq_decode  replaces FastqReader::read / getLine (src/fastqreader.cpp:240-368) for a chunk of plain FASTQ text that
@@ -336,10 +370,19 @@ int  fp_fastq_process_host(fp_ctx* ctx, const uint8_t* text1, int64_t nbytes1, c
  * (nullable) = what the reference returns for unit i when units are fed in index order, batch after batch -- deterministic, not
  * the scheduling-dependent answer plain atomicOr would give.  The bit arrays live in the ctx (1 GiB at accuracy
  * level 1, --dup_accuracy_level src/main.cpp) and are allocated by the first call; later calls must use the same level.
- * fp_dup_totals: Duplicate::mTotalReads / mDupReads (getDupRate = dups / total).  Enqueued on `stream` (NULL = the ctx's). */
+ * fp_dup_totals: Duplicate::mTotalReads / mDupReads (getDupRate = dups / total).  Enqueued on `stream` (NULL = the ctx's).
+ * Call it BEFORE fp_process_* on the same batch: the reference hashes the reads as they were read (checkPair comes before
+ * any trimming or correction, src/peprocessor.cpp:397-401), and fp_process_pe corrects bases in place. */
 int  fp_dup_check(fp_ctx* ctx, const fp_batch* b, int32_t accuracy_level, uint8_t* d_is_dup, void* stream);
 int  fp_dup_totals(fp_ctx* ctx, int64_t* total, int64_t* dups);
 int  fp_dup_reset(fp_ctx* ctx);
+
+/* Host-side pre-scan (control plane, once per input, like the reference's Evaluator): the over-representation candidate list
+ * Evaluator::computeOverRepSeq (src/evaluator.cpp:78-169) derives from the first 1.51 M bases of one input, here given as rows
+ * in HOST memory.  Writes the sequences NUL-separated in the reference's map order; *n_out = how many, *bytes_out = bytes needed
+ * (FP_E_TOOLARGE if out_cap is smaller).  seqlen = Options::seqLen1/2.  The result feeds fp_params.overrep_seqs1/2. */
+int  fp_host_overrep_candidates(const uint8_t* seq, const uint16_t* len, int64_t n, int32_t stride, int32_t seqlen,
+                                char* out, int64_t out_cap, int32_t* n_out, int64_t* bytes_out);
 
 /* Pinned host memory helpers for the staging shim. */
 int  fp_host_alloc(void** p, size_t bytes);

@@ -21,6 +21,7 @@
 #include "stats.h"
 #include "fastqreader.h"
 #include "duplicate.h"
+#include "evaluator.h"
 #include "filter.h"
 #include "filterresult.h"
 #include "polyx.h"
@@ -387,6 +388,23 @@ int64_t fp_ref_fastq_read_file(const char* path, int phred64, uint8_t* out, int6
         o += need;
         n++;
         delete r;
+    }
+    *used = o;
+    return n;
+}
+
+// The reference's own Evaluator::computeOverRepSeq (src/evaluator.cpp:78-169) over a plain FASTQ file: the candidate
+// sequences NUL-separated in map order; returns how many (*used = bytes needed).
+int fp_ref_compute_overrep(const char* path, int seqlen, char* out, int64_t cap, int64_t* used) {
+    Options opt;
+    Evaluator ev(&opt);
+    std::map<std::string, long> hot;
+    ev.computeOverRepSeq(path, hot, seqlen);
+    int64_t o = 0; int n = 0;
+    for (auto& kv : hot) {
+        const int64_t need = (int64_t)kv.first.size() + 1;
+        if (o + need <= cap) memcpy(out + o, kv.first.c_str(), (size_t)need);
+        o += need; n++;
     }
     *used = o;
     return n;
