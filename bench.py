@@ -476,7 +476,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
     sides = 2 if paired else 1
     torch.cuda.empty_cache()
     free_b, _ = torch.cuda.mem_get_info()
-    per_unit = sides * (2 * S + 2 + 16) + (8 + 6 if paired else 0)
+    per_unit = sides * (2 * S + 2 + 16) + (8 + 15 if paired else 0)
     n = int(min(units, 0.85 * free_b / per_unit))
     first = rank * n                                   # rank r owns global indices [r*n, (r+1)*n)
 
@@ -516,7 +516,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
     out2 = alloc(n * 16) if paired else None
     ov = alloc(n * 8) if paired else None
     corr = paired and bool(params.correction_enabled)
-    patch_cap = int(0.5 * n) + 4096 if corr else 0
+    patch_cap = int(1.25 * n) + 4096 if corr else 0      # measured: 0.67 corrected bases per pair on the enriched profile
     patches = alloc(patch_cap * 12) if corr else None
     npatch = torch.zeros(1, dtype=torch.int32, device=dev) if corr else None
     b = capi.Batch()
@@ -600,6 +600,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
     }
     if corr:
         checks["corrected_reads_gt0_in_timed_steps"] = bool(int(cv.filter[106]) > 0)     # FP_FR_CORRECTED_READS
+        checks["patch_list_complete"] = bool(int(npatch.item()) <= patch_cap)            # else the undo (and the next step) would be partial
     if has_ovr:
         checks["overrep_hits_gt0"] = bool(int(cv.overrep(capi.STATS_PRE1)[0].sum()) > 0)
 
@@ -669,7 +670,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         ho1 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory()
         ho2 = torch.empty(ne * 16, dtype=torch.uint8).pin_memory() if paired else None
         hov = torch.empty(ne * 8, dtype=torch.uint8).pin_memory() if paired else None
-        hp_cap = int(0.5 * ne) + 4096
+        hp_cap = int(1.25 * ne) + 4096
         hpat = np.zeros(hp_cap, capi.PATCH_DTYPE) if corr else None
         hnp = C.c_uint64()
         hbt = capi.Batch()

@@ -51,6 +51,7 @@ struct fp_ctx {
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
+    int groups = 3;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>): 3 x 8 warps on one SM; FP_GROUPS=1|2|3 overrides */
     fp_smem_layout sl{};
     uint32_t smem_base = 1024;        /* shared-window address of dynamic shared memory (probed) */
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -140,49 +141,58 @@ __global__ void fp_probe_smem_base(uint32_t* out) { extern __shared__ uint8_t pr
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static const void* chain_kernel(bool paired, int groups) {
+    if (paired) return groups == 1 ? (const void*)fp_chain2_kernel<true, 1> : groups == 2 ? (const void*)fp_chain2_kernel<true, 2> : (const void*)fp_chain2_kernel<true, 3>;
+    return groups == 1 ? (const void*)fp_chain2_kernel<false, 1> : groups == 2 ? (const void*)fp_chain2_kernel<false, 2> : (const void*)fp_chain2_kernel<false, 3>;
+}
+
 static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     const int sides = c->p.paired ? 2 : 1;
     const int S = c->stride;
     memset(&sl, 0, sizeof(sl));
+    /* ---- shared by the CTA's groups: sink, LUTs, histograms, delta accumulators, block counters ---- */
     size_t off = 0;
-    sl.off_mbar = (int)off; off += 16;
-    sl.off_next = (int)off; off += 16;                                     /* delta queue length + pop cursor */
-    off = align_up(off, 128);
     sl.off_dummy = (int)off; off += 128;
-    sl.off_len = (int)off; off += (size_t)sides * T * 2;
-    sl.off_clean = (int)off; off += (size_t)sides * T;
-    off = align_up(off, 16);
     sl.off_lut = (int)off; off += align_up((size_t)3 * (S + 2) * 2, 16);
-    /* the two histograms are addressed as (field | table address): the 5-mer table (4 KB per side) must start on a 4 KB
-       boundary of the SHARED WINDOW (c->smem_base = window address of dynamic shared memory, probed at fp_ctx_create),
-       the quality histogram (2 KB per side) follows it */
+    sl.off_delta = (int)off; off += (size_t)sides * (size_t)S * 20 * 4;      /* before the aligned tables: fills what the alignment would waste */
+    /* the two histograms are addressed as (field | table address): the 5-mer tables (4 KB per side, counts then signed deltas) must
+       start on a 4 KB boundary of the SHARED WINDOW (c->smem_base = window address of dynamic shared memory, probed at fp_ctx_create),
+       the quality histograms (2 KB per side + 512 B of deltas) follow */
     off = align_up(off + c->smem_base, 4096) - c->smem_base;
     sl.off_kmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;
     sl.off_dkmer = (int)off; off += (size_t)sides * FP_KMER_BINS * 4;       /* signed post-filter deltas, same indexing, same alignment */
     sl.off_qhist = (int)off; off += (size_t)sides * FP_QUAL_BINS * FP_QH_REP * 4;
     sl.off_dqh = (int)off; off += (size_t)sides * FP_QUAL_BINS * 4;
-    off = align_up(off, 128);
-    sl.off_tile = (int)off; sl.tile_array_bytes = T * S; off += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
     off = align_up(off, 16);
     sl.off_bc = (int)off; off += sizeof(BlockCounters);
-    off = align_up(off, 16);
-    sl.off_delta = (int)off; off += (size_t)sides * (size_t)S * 20 * 4;
-    off = align_up(off, 16);
-    sl.off_rm = (int)off; off += (size_t)sides * (T + 4) * 4 + 16;          /* removal lists (one per side, padded to 4 entries) + their lengths */
+    off = align_up(off, 128);
+    sl.off_group = (int)off;
+    /* ---- one region per group (offsets relative to it): mbarrier, cursors, lengths, tile, planes, removal lists, request queue ---- */
+    size_t g = 0;
+    sl.off_mbar = (int)g; g += 16;
+    sl.off_next = (int)g; g += 16;                                         /* queue length, pop cursor, item cursors */
+    sl.off_len = (int)g; g += (size_t)sides * T * 2;
+    sl.off_clean = (int)g; g += (size_t)sides * T;
+    g = align_up(g, 128);
+    sl.off_tile = (int)g; sl.tile_array_bytes = T * S; g += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
+    g = align_up(g, 16);
+    sl.off_rm = (int)g; g += (size_t)sides * (T + 4) * 4 + 16;             /* removal lists (one per side, padded to 4 entries) + their lengths */
     sl.plane_words = (S + 31) / 32 + 2;
     sl.plane_stride = (4 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
-    off = align_up(off, 16);
-    sl.off_planes = (int)off; off += (size_t)sides * T * sl.plane_stride * 4;
-    off = align_up(off, 16);
-    sl.off_queue = (int)off; off += (size_t)sides * T * 2 * 8;
-    sl.total = (int)align_up(off, 128);
+    g = align_up(g, 16);
+    sl.off_planes = (int)g; g += (size_t)sides * T * sl.plane_stride * 4;
+    g = align_up(g, 16);
+    sl.off_queue = (int)g; g += (size_t)sides * T * 2 * 8;
+    sl.group_stride = (int)align_up(g, 128);
+    sl.total = (int)align_up(off + (size_t)c->groups * sl.group_stride, 128);
     return (size_t)sl.total;
 }
 
-/* tile size: as large as possible (<= 64 pairs / 128 reads) while TWO CTAs still fit one SM's shared memory */
+/* tile size: as large as possible (<= 64 pairs / 128 reads) while the CTA's groups fit one SM's shared memory
+   (one CTA of 2 or 3 groups per SM; with a single group, two CTAs per SM) */
 static void make_smem_layout(fp_ctx* c) {
     const int sides = c->p.paired ? 2 : 1;
-    const size_t budget = (227 * 1024 - 2 * 1024) / 2;
+    const size_t budget = c->groups == 1 ? (227 * 1024 - 2 * 1024) / 2 : (size_t)227 * 1024;
     int T = 64 * (3 - sides);
     while (T > 16 && smem_layout_for_tile(c, T, c->sl) > budget) T -= 8;
     c->tile = T;
@@ -230,6 +240,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         CK(cudaFree(d_base));
         c->smem_base = h_base;
     }
+    if (const char* e = getenv("FP_GROUPS")) { const int g = atoi(e); if (g >= 1 && g <= 3) c->groups = g; }
     make_smem_layout(c);
 
     cudaDeviceProp prop;
@@ -338,15 +349,14 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
 
     /* kernel attributes + persistent grid size */
     int occ = 0;
-    if (p->paired) {
-        CK(cudaFuncSetAttribute(fp_chain2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<true>, FP_CT, c->sl.total));
-    } else {
-        CK(cudaFuncSetAttribute(fp_chain2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp_chain2_kernel<false>, FP_CT, c->sl.total));
+    {
+        const void* fn = chain_kernel(p->paired != 0, c->groups);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FP_CT * c->groups, c->sl.total));
     }
     if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
     c->grid_max = occ * c->num_sms;
+    if (getenv("FP_TRACE")) fprintf(stderr, "[fastp_b200] groups %d, tile %d rows, smem %d B (shared %d + %d per group), %d CTA/SM\n", c->groups, c->tile, c->sl.total, c->sl.off_group, c->sl.group_stride, occ);
     *out = c;
     return FP_OK;
 }
@@ -462,7 +472,7 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     a.counters = reinterpret_cast<unsigned long long*>(c->d_raw);
     a.n_tiles = (b->n + c->tile - 1) / c->tile;
     a.sl = c->sl;
-    int grid = (int)std::min<long long>(a.n_tiles, c->grid_max);
+    int grid = (int)std::min<long long>((a.n_tiles + c->groups - 1) / c->groups, c->grid_max);
     /* The operator parameters live in one __constant__ block per device; it is refreshed before every launch BY A KERNEL from the
        context's device copy (stream-ordered, no copy engine: a cudaMemcpyToSymbolAsync would queue behind bulk text / batch
        transfers).  Contexts running concurrently on one device must therefore share the same fp_params. */
@@ -491,8 +501,10 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
     if (c->evs.size() > 4096) { int rc = drain_events(c); if (rc) return rc; }
     CK(cudaEventRecord(ev.a, st));
-    if (c->p.paired) fp_chain2_kernel<true><<<grid, FP_CT, c->sl.total, st>>>(a);
-    else fp_chain2_kernel<false><<<grid, FP_CT, c->sl.total, st>>>(a);
+    {
+        void* kargs[] = {(void*)&a};
+        CK(cudaLaunchKernel(chain_kernel(c->p.paired != 0, c->groups), dim3(grid), dim3(FP_CT * c->groups), kargs, (size_t)c->sl.total, st));
+    }
     CK(cudaEventRecord(ev.b, st));
     c->evs.push_back(ev);
     CK(cudaGetLastError());

@@ -473,9 +473,56 @@ __device__ __noinline__ void t_patch_delta(const DeltaAcc D, unsigned long long*
     }
 }
 
+/* t_patch_delta for a CLEAN row (bases in {A,C,G,T,N}, qualities < 128), word-sized: qualities and the per-cycle counters are two
+ * signed updates each, the five 5-mers around P come from ONE pass over the nine bytes P-4 .. P+4 (2-bit codes + validity), read
+ * while seq[P] still holds the old base. */
+__device__ __noinline__ void t_patch_delta_clean(const DeltaAcc D, int side, const uint8_t* seq, int l0, int P, uint8_t ob, uint8_t oq, uint8_t nb, uint8_t nq) {
+    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);    FP_SMEM(seq);
+    atomicAdd(&D.qh[side * FP_QUAL_BINS + oq], -1);
+    atomicAdd(&D.qh[side * FP_QUAL_BINS + nq], +1);
+    if (P < D.cycles) {
+        int* c0 = D.cyc + side * D.cycles * 20 + P * 20;
+        int* co = c0 + ((0x43F21F0Fu >> (4 * (ob & 7))) & 0xF) * 4;            /* base&7: A1 C3 T4 N6 G7 -> bin 0..4 */
+        int* cn = c0 + ((0x43F21F0Fu >> (4 * (nb & 7))) & 0xF) * 4;
+        atomicAdd(&co[0], -1); atomicAdd(&cn[0], +1);
+        if (oq >= '5') atomicAdd(&co[1], -1);
+        if (nq >= '5') atomicAdd(&cn[1], +1);
+        if (oq >= '?') atomicAdd(&co[2], -1);
+        if (nq >= '?') atomicAdd(&cn[2], +1);
+        atomicAdd(&co[3], 33 - (int)oq); atomicAdd(&cn[3], (int)nq - 33);
+    }
+    uint32_t Z = 0, V = 0;                                                     /* digit k = position P-4+k */
+    #pragma unroll
+    for (int k = 0; k < 9; k++) {
+        const int pos = P - 4 + k;
+        const bool inb = pos >= 0 && pos < l0;
+        const uint32_t bb = inb ? seq[pos] : (uint32_t)'N';
+        Z |= ((bb >> 1) & 3u) << (2 * k);
+        V |= (bb != (uint32_t)'N' ? 1u : 0u) << k;
+    }
+    const uint32_t Zn = (Z & ~(3u << 8)) | ((((uint32_t)nb >> 1) & 3u) << 8), Vn = (V & ~16u) | (nb != 'N' ? 16u : 0u);
+    int* km = D.kmer + side * FP_KMER_BINS;
+    #pragma unroll
+    for (int w = 0; w < 5; w++) {                                              /* window ending at P+w = digits w .. w+4 */
+        if (((V >> w) & 31u) == 31u) atomicAdd(&km[(Z >> (2 * w)) & 0x3FFu], -1);
+        if (((Vn >> w) & 31u) == 31u) atomicAdd(&km[(Zn >> (2 * w)) & 0x3FFu], +1);
+    }
+}
+
+/* complement of a base of a clean row (util.h:16-33 restricted to A,C,G,T,N): table indexed by base & 7 */
+__device__ __forceinline__ uint8_t comp_clean(uint8_t b) {
+    /* index 1 'A'->'T'  3 'C'->'G'  4 'T'->'A'  6 'N'->'N'  7 'G'->'C' */
+    const unsigned long long tab = 0x434E4E41474E544Eull;
+    return (uint8_t)(tab >> (8 * (b & 7)));
+}
+
 /* ------------------------------------------------------------------------------------------------
- * BaseCorrector::correctByOverlapAnalysis  (basecorrector.cpp:21-83), one thread per pair, scalar over the overlap.
- * Writes the shared-memory rows, the HBM rows, the patch list and (for clean rows) updates the bit planes.
+ * BaseCorrector::correctByOverlapAnalysis  (basecorrector.cpp:21-83).  Positions are independent: a mismatching position is
+ * rewritten at most once, from the bytes and qualities of that position alone.  Two lanes of the pair's group share the work by
+ * DIRECTION: lane 0 applies "read 1 is right" (rewrites read 2, :42-50), lane 1 "read 2 is right" (rewrites read 1, :51-59) -- each
+ * read is then changed by one lane only, in increasing position, so its statistics deltas telescope exactly; the two conditions
+ * exclude each other on the original qualities and a rewritten position satisfies neither, so the lanes cannot disturb one another.
+ * Writes the shared-memory rows, the HBM rows, the patch list and (clean rows) the bit planes.  Returns (via flags) which reads changed.
  * ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void t_plane_set_base(uint32_t* pl, int PW, int pos, uint8_t base, uint8_t q) {
     const int w = pos >> 5; const uint32_t m = 1u << (pos & 31);
@@ -486,12 +533,12 @@ __device__ __forceinline__ void t_plane_set_base(uint32_t* pl, int PW, int pos, 
     pl[3 * PW + w] = (pl[3 * PW + w] & ~m) | ((q < (uint8_t)c_p.qualified_qual) ? m : 0u);
 }
 
-__device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t* pl1, uint32_t* pl2, int PW, const fp_ov_result ov,
-                                       uint8_t* g1s, uint8_t* g1q, uint8_t* g2s, uint8_t* g2q, unsigned int pair_index, const PatchSink& sink,
-                                       BlockCounters* bc, const DeltaAcc D, unsigned long long* G, int l1, int l2, bool& c1, bool& c2) {
+__device__ __noinline__ int t_correct(const TRead r1, const TRead r2, uint32_t* pl1, uint32_t* pl2, int PW, const fp_ov_result ov,
+                                      uint8_t* g1s, uint8_t* g1q, uint8_t* g2s, uint8_t* g2q, unsigned int pair_index, const PatchSink& sink,
+                                      BlockCounters* bc, const DeltaAcc D, unsigned long long* G, int l1, int l2, int role) {
     FP_SMEM(r1.seq);    FP_SMEM(r1.qual);    FP_SMEM(r2.seq);    FP_SMEM(r2.qual);    FP_SMEM(pl1);    FP_SMEM(pl2);    FP_SMEM(bc);    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);
-    c1 = c2 = false;
-    if (ov.diff == 0 || !ov.overlapped) return;                           /* :23-24 */
+    /* role 0: rewrite read 2 where read 1 is right; role 1: rewrite read 1 where read 2 is right.  Returns the number of bases this lane rewrote. */
+    if (ov.diff == 0 || !ov.overlapped) return 0;                           /* :23-24 */
     const int ol = ov.overlap_len;
     const int start1 = max(0, (int)ov.offset);
     const int start2 = r2.len - max(0, -(int)ov.offset) - 1;
@@ -501,8 +548,9 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
     int corrected = 0;
     const bool use_planes = r1.clean && r2.clean;
     const int e = r2.front + r2.len - 1, jb = r2.len - 1 - start2;          /* rc(r2) index of overlap position 0 */
+    #pragma unroll 1
     for (int k = 0; k * 32 < ol; k++) {
-        /* positions of this 32-chunk whose bases differ: from the planes (clean rows) or all of them (byte path decides) */
+        /* positions of this 32-chunk whose bases differ: from the planes (clean rows) or all of them (the byte test below decides) */
         uint32_t todo = low_mask(ol - 32 * k);
         if (use_planes) {
             const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
@@ -510,40 +558,43 @@ __device__ __noinline__ void t_correct(const TRead r1, const TRead r2, uint32_t*
             const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
             todo &= (tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn);
         }
+        #pragma unroll 1
         while (todo) {
             const int i = 32 * k + __ffs(todo) - 1;
             todo &= todo - 1;
             const int p1 = start1 + i, p2 = start2 - i;
+            const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
+            if (role == 0 ? !(q1 >= GOOD && q2 <= BAD) : !(q2 >= GOOD && q1 <= BAD)) continue;
             const uint8_t b1 = s1[p1], b2 = s2[p2];
-            if (b1 != dev_complement(b2)) {
-                const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
-                if (q1 >= GOOD && q2 <= BAD) {                                 /* use R1 :42-50 */
-                    const uint8_t nb = dev_complement(b1);
-                    t_patch_delta(D, G, r2.clean, 1, r2.seq, l2, r2.front + p2, b2, (uint8_t)q2, nb, (uint8_t)q1);
-                    s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
-                    if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
-                    corrected++; c2 = true;
-                    atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);   /* diagonal only, SURVEY App. A.6 */
-                    if (sink.count) {
-                        const unsigned int slot = atomicAdd(sink.count, 1u);
-                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt.old_base = b2; pt.old_qual = (uint8_t)q2; pt._pad = 0; sink.patches[slot] = pt; }
-                    }
-                } else if (q2 >= GOOD && q1 <= BAD) {                          /* use R2 :51-59 */
-                    const uint8_t nb = dev_complement(b2);
-                    t_patch_delta(D, G, r1.clean, 0, r1.seq, l1, r1.front + p1, b1, (uint8_t)q1, nb, (uint8_t)q2);
-                    s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
-                    if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
-                    corrected++; c1 = true;
-                    atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
-                    if (sink.count) {
-                        const unsigned int slot = atomicAdd(sink.count, 1u);
-                        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt.old_base = b1; pt.old_qual = (uint8_t)q1; pt._pad = 0; sink.patches[slot] = pt; }
-                    }
+            if (b1 == (use_planes ? comp_clean(b2) : dev_complement(b2))) continue;
+            if (role == 0) {                                                   /* use R1 :42-50 */
+                const uint8_t nb = use_planes ? comp_clean(b1) : dev_complement(b1);
+                if (r2.clean) t_patch_delta_clean(D, 1, r2.seq, l2, r2.front + p2, b2, (uint8_t)q2, nb, (uint8_t)q1);
+                else t_patch_delta(D, G, false, 1, r2.seq, l2, r2.front + p2, b2, (uint8_t)q2, nb, (uint8_t)q1);
+                s2[p2] = nb; q2p[p2] = (uint8_t)q1; g2s[p2] = nb; g2q[p2] = (uint8_t)q1;
+                if (r2.clean) t_plane_set_base(pl2, PW, r2.front + p2, nb, (uint8_t)q1);
+                corrected++;
+                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);       /* diagonal only, SURVEY App. A.6 */
+                if (sink.count) {
+                    const unsigned int slot = atomicAdd(sink.count, 1u);
+                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r2.front + p2); pt.which = 1; pt.base = nb; pt.qual = (uint8_t)q1; pt.old_base = b2; pt.old_qual = (uint8_t)q2; pt._pad = 0; sink.patches[slot] = pt; }
+                }
+            } else {                                                           /* use R2 :51-59 */
+                const uint8_t nb = use_planes ? comp_clean(b2) : dev_complement(b2);
+                if (r1.clean) t_patch_delta_clean(D, 0, r1.seq, l1, r1.front + p1, b1, (uint8_t)q1, nb, (uint8_t)q2);
+                else t_patch_delta(D, G, false, 0, r1.seq, l1, r1.front + p1, b1, (uint8_t)q1, nb, (uint8_t)q2);
+                s1[p1] = nb; q1p[p1] = (uint8_t)q2; g1s[p1] = nb; g1q[p1] = (uint8_t)q2;
+                if (r1.clean) t_plane_set_base(pl1, PW, r1.front + p1, nb, (uint8_t)q2);
+                corrected++;
+                atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);
+                if (sink.count) {
+                    const unsigned int slot = atomicAdd(sink.count, 1u);
+                    if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)(r1.front + p1); pt.which = 0; pt.base = nb; pt.qual = (uint8_t)q2; pt.old_base = b1; pt.old_qual = (uint8_t)q1; pt._pad = 0; sink.patches[slot] = pt; }
                 }
             }
         }
     }
-    if (corrected > 0) atomicAdd(&bc->fr[FP_FR_CORRECTED_READS], (c1 && c2) ? 2u : 1u);   /* :75-80 */
+    return corrected;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1019,24 +1070,30 @@ __device__ __forceinline__ void push_delta(const DeltaSinks& K, bool want, bool 
  *   B  operator chain, one lane group per read / pair; post-stat requests go to a shared-memory queue
  *   C  the queue is drained by all warps (balanced), then the tile buffer is free for the next TMA load
  * ------------------------------------------------------------------------------------------------ */
-template <bool PAIRED>
-__global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_args a) {
+template <bool PAIRED, int NG>
+__global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(const fp_launch_args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int SIDES = PAIRED ? 2 : 1;
     const fp_smem_layout& sl = a.sl;
     const int S = c_p.stride, T = c_p.tile;
-    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    /* A CTA is NG independent tile pipelines ("groups") of FP_CT threads each: own tile buffer, planes, queues, mbarrier and named
+       barrier; the histogram / delta / counter tables are shared by the groups (they are atomics anyway), which is what lets three
+       groups = 24 warps fit one SM's shared memory.  tid / warp are GROUP-local; ctid is the CTA-wide thread index. */
+    const int ctid = threadIdx.x, gid = NG == 1 ? 0 : (int)(threadIdx.x / FP_CT);
+    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x % FP_CT), lane = lane_id(), warp = tid >> 5;
+    uint8_t* const gsm = smem + sl.off_group + gid * sl.group_stride;        /* this group's private region */
+#define GSYNC() asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(FP_CT) : "memory")
     unsigned long long* G = a.counters;
     const fp_counter_layout& L = c_p.L;
 
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sl.off_mbar);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(gsm + sl.off_mbar);
     uint8_t* tile_seq[2]; uint8_t* tile_qual[2];
-    tile_seq[0] = smem + sl.off_tile;
+    tile_seq[0] = gsm + sl.off_tile;
     tile_qual[0] = tile_seq[0] + sl.tile_array_bytes;
     tile_seq[1] = tile_qual[0] + sl.tile_array_bytes;
     tile_qual[1] = tile_seq[1] + sl.tile_array_bytes;
-    uint16_t* s_len = reinterpret_cast<uint16_t*>(smem + sl.off_len);       /* [SIDES][T] */
-    uint8_t* s_clean = smem + sl.off_clean;                                 /* [SIDES][T] */
+    uint16_t* s_len = reinterpret_cast<uint16_t*>(gsm + sl.off_len);       /* [SIDES][T] */
+    uint8_t* s_clean = gsm + sl.off_clean;                                 /* [SIDES][T] */
     unsigned int* s_kmer = reinterpret_cast<unsigned int*>(smem + sl.off_kmer);    /* [SIDES][1024] */
     unsigned int* s_qhist = reinterpret_cast<unsigned int*>(smem + sl.off_qhist);  /* [SIDES][128][FP_QH_REP] */
     BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem + sl.off_bc);
@@ -1045,26 +1102,26 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
     D.cyc = reinterpret_cast<int*>(smem + sl.off_delta);
     D.kmer = reinterpret_cast<int*>(smem + sl.off_dkmer);
     D.qh = reinterpret_cast<int*>(smem + sl.off_dqh);
-    uint32_t* s_rm = reinterpret_cast<uint32_t*>(smem + sl.off_rm);          /* [SIDES][T + 4] removal lists */
+    uint32_t* s_rm = reinterpret_cast<uint32_t*>(gsm + sl.off_rm);          /* [SIDES][T + 4] removal lists */
     int* s_nrm = reinterpret_cast<int*>(s_rm + SIDES * (T + 4));             /* [SIDES] their lengths */
     DeltaSinks sinks; sinks.rm = s_rm; sinks.nrm = s_nrm; sinks.T = T;
     int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);
     const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free lane-group-per-row access */
-    uint32_t* tile_planes = reinterpret_cast<uint32_t*>(smem + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
-    DeltaReq* s_queue = reinterpret_cast<DeltaReq*>(smem + sl.off_queue);    /* [SIDES * T * 2] */
+    uint32_t* tile_planes = reinterpret_cast<uint32_t*>(gsm + sl.off_planes);             /* [SIDES][T] rows of PSTR words */
+    DeltaReq* s_queue = reinterpret_cast<DeltaReq*>(gsm + sl.off_queue);    /* [SIDES * T * 2] */
     unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
-    int* s_qn = reinterpret_cast<int*>(smem + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
+    int* s_qn = reinterpret_cast<int*>(gsm + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
     sinks.q = s_queue; sinks.qn = &s_qn[0];
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
     for (int i = tid; i < SIDES * T * PSTR; i += FP_CT) tile_planes[i] = 0;
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) s_kmer[i] = 0;
-    for (int i = tid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_CT) s_qhist[i] = 0;
-    for (int i = tid; i < SIDES * S * 20; i += FP_CT) D.cyc[i] = 0;
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) D.kmer[i] = 0;
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) D.qh[i] = 0;
-    for (int i = tid; i < (int)(sizeof(BlockCounters) / 4); i += FP_CT) reinterpret_cast<unsigned int*>(bc)[i] = 0;
-    for (int i = tid; i < S + 2; i += FP_CT) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) s_kmer[i] = 0;
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_CT * NG) s_qhist[i] = 0;
+    for (int i = ctid; i < SIDES * S * 20; i += FP_CT * NG) D.cyc[i] = 0;
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) D.kmer[i] = 0;
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) D.qh[i] = 0;
+    for (int i = ctid; i < (int)(sizeof(BlockCounters) / 4); i += FP_CT * NG) reinterpret_cast<unsigned int*>(bc)[i] = 0;
+    for (int i = ctid; i < S + 2; i += FP_CT * NG) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
@@ -1105,12 +1162,12 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
             s_clean[i] = 1;
         }
     };
-    fill_lens(blockIdx.x);
+    fill_lens((long long)blockIdx.x * NG + gid);
     __syncthreads();
     uint32_t parity = 0;
 
     #pragma unroll 1
-    for (long long tix = blockIdx.x; tix < a.n_tiles; tix += gridDim.x) {
+    for (long long tix = (long long)blockIdx.x * NG + gid; tix < a.n_tiles; tix += (long long)gridDim.x * NG) {
         const long long row0 = tix * T;
         const int rows = (int)min((long long)T, a.b.n - row0);
         /* ---------------- TMA bulk loads ---------------- */
@@ -1154,7 +1211,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                     if (rr2 < rows) {
                         const int n = (int)s_len[sd * T + rr2] - 32 * j;
                         if (n > 0) {
-                            const uint8_t* tseq_sd = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes; const uint8_t* tqual_sd = tseq_sd + sl.tile_array_bytes;
+                            const uint8_t* tseq_sd = gsm + sl.off_tile + sd * 2 * sl.tile_array_bytes; const uint8_t* tqual_sd = tseq_sd + sl.tile_array_bytes;
                             /* One pass over the chunk in four steps of 8 bases (two words): per-byte class flags of the even word in bit 0,
                                of the odd word in bit 4, so one multiply gathers 8 flags into the product's top byte (see plane_pair) and
                                PRMT shifts it into the plane word.  The same step packs the 2-bit base codes for the 5-mer windows and
@@ -1226,7 +1283,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
 
         /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
@@ -1323,17 +1380,15 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 if (active) {
                     bool dimer = false;
                     if (need_correct) {
-                        int cf = 0;
-                        if (lead) {
-                            bool c1, c2;
-                            t_correct(r1, r2, pl1, pl2, PW, ovA, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
-                                      a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, D, G, l1, l2, c1, c2);
-                            cf = (c1 ? 1 : 0) | (c2 ? 2 : 0);
-                        }
+                        int nc = 0;
+                        if (sub < 2)
+                            nc = t_correct(r1, r2, pl1, pl2, PW, ovA, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
+                                           a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, D, G, l1, l2, sub);
                         __syncwarp(gmask);                                                        /* corrected bytes / planes visible to the whole group */
-                        cf = __shfl_sync(gmask, cf, glead);
-                        if (cf & 1) flags1 |= FP_F_CORRECTED;
-                        if (cf & 2) flags2 |= FP_F_CORRECTED;
+                        const int n2 = __shfl_sync(gmask, nc, glead), n1 = __shfl_sync(gmask, nc, glead + 1);   /* lane 0 rewrote read 2, lane 1 read 1 */
+                        if (n1 > 0) flags1 |= FP_F_CORRECTED;
+                        if (n2 > 0) flags2 |= FP_F_CORRECTED;
+                        if (lead && n1 + n2 > 0) atomicAdd(&bc->fr[FP_FR_CORRECTED_READS], (n1 > 0 && n2 > 0) ? 2u : 1u);   /* :75-80 */
                     }
                     if (both && c_p.adapter_enabled) {                                            /* :457-485 */
                         bool trimmed = false;
@@ -1396,7 +1451,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
             }
         }
 
-        __syncthreads();
+        GSYNC();
 
         /* ---------------- phase C: post-filter statistics of what the chain removed / shifted (all warps) ---------------- */
         {
@@ -1428,7 +1483,7 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                         const int row = e & 0xFF, lo = (e >> 8) & 0xFFF, hi = e >> 20;
                         const int a0 = max(lo - 32 * j, 0), b0 = min(hi - 32 * j, 32);
                         if (b0 > a0) {
-                            const uint8_t* sp = smem + sl.off_tile + sd * 2 * sl.tile_array_bytes + row * S + 32 * j;
+                            const uint8_t* sp = gsm + sl.off_tile + sd * 2 * sl.tile_array_bytes + row * S + 32 * j;
                             const uint32_t* pnn = tile_planes + (sd * T + row) * PSTR + 2 * PW;
                             hist_remove_chunk(sp, sp + sl.tile_array_bytes, j, low_mask(b0) & ~low_mask(a0), pnn[j], j > 0 ? pnn[j - 1] : 0u,
                                               smem_u32(D.qh) + (uint32_t)sd * (FP_QUAL_BINS * 4), smem_u32(D.kmer) + (uint32_t)sd * (FP_KMER_BINS * 4), kdummy);
@@ -1448,16 +1503,17 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
                 const DeltaReq rq = s_queue[qi];
                 const int row = rq.a & 0xFF, side = (rq.a >> 8) & 1, sign = ((rq.a >> 10) & 1) ? -1 : +1;
                 const int ctx0 = (int)(rq.a >> 12), rlo = (int)(rq.b & 0xFFFF), rhi = (int)(rq.b >> 16);
-                const uint8_t* sq = smem + sl.off_tile + side * 2 * sl.tile_array_bytes + row * S; const uint8_t* ql = sq + sl.tile_array_bytes;
+                const uint8_t* sq = gsm + sl.off_tile + side * 2 * sl.tile_array_bytes + row * S; const uint8_t* ql = sq + sl.tile_array_bytes;
                 if ((rq.a >> 9) & 1) dev_stat_positions_smem(D, side, sq, ql, ctx0, rlo, rhi, sign);
                 else dev_stat_positions(G, side * 2 + 1, sq, ql, ctx0, rlo, rhi, sign);
             }
         }
-        fill_lens(tix + gridDim.x);
+        fill_lens(tix + (long long)gridDim.x * NG);
         if (tid == 0) s_qn[2] = 0;                     /* item counter of phase A: idle since the phase-A barrier */
-        __syncthreads();
+        GSYNC();
     }
 
+    __syncthreads();                               /* every group is done with the shared tables */
     /* ---------------- flush block-level accumulators ---------------- */
     const int BIN_SLOT[NB] = {1, 3, 4, 6, 7};      /* base & 7 of A C T N G */
     if (col_active) {
@@ -1482,19 +1538,19 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
         }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) {
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) {
         const unsigned int v = s_kmer[i];
         if (v) { const int sd = i / FP_KMER_BINS, k = kmer_ref_index(i % FP_KMER_BINS); red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) {
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) {
         unsigned int v = 0;
         #pragma unroll
         for (int c = 0; c < FP_QH_REP; c++) v += s_qhist[i * FP_QH_REP + c];
         if (v) { const int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * S * 20; i += FP_CT) {
+    for (int i = ctid; i < SIDES * S * 20; i += FP_CT * NG) {
         const int v = D.cyc[i];
         if (v == 0) continue;
         const int sd = i / (S * 20), rem = i % (S * 20), cyc = rem / 20, bin = (rem % 20) / 4, kind = rem & 3;
@@ -1503,14 +1559,14 @@ __global__ void __launch_bounds__(FP_CT, 2) fp_chain2_kernel(const fp_launch_arg
         red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
     }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_KMER_BINS; i += FP_CT) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, kmer_ref_index(i % FP_KMER_BINS))], (unsigned long long)(long long)v); }
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, kmer_ref_index(i % FP_KMER_BINS))], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = tid; i < SIDES * FP_QUAL_BINS; i += FP_CT) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = tid; i < FP_FR_WORDS; i += FP_CT) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
+    for (int i = ctid; i < FP_FR_WORDS; i += FP_CT * NG) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
     if (c_p.isize_max < FP_MAX_ISIZE_SMEM) {
         #pragma unroll 1
-        for (int i = tid; i <= c_p.isize_max; i += FP_CT) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
+        for (int i = ctid; i <= c_p.isize_max; i += FP_CT * NG) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
     }
     #pragma unroll
     for (int k = 0; k < 8; k++) {
