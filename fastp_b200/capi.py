@@ -87,6 +87,10 @@ PATCH_DTYPE = np.dtype([
 ])
 assert READ_RESULT_DTYPE.itemsize == 16 and OV_RESULT_DTYPE.itemsize == 8 and PATCH_DTYPE.itemsize == 12
 
+EVENT_DTYPE = np.dtype([("unit", "<u4"), ("start", "<u2"), ("len", "<u2"), ("key", "<u2"), ("which", "u1"), ("kind", "u1"),
+                        ("adapter", "<u2"), ("_pad", "<u2")])
+assert EVENT_DTYPE.itemsize == 16
+
 FASTQ_REC_DTYPE = np.dtype([("name_off", "<u4"), ("name_len", "<u4"), ("strand_off", "<u4"), ("strand_len", "<u4")])
 
 
@@ -112,6 +116,8 @@ SYMBOLS = {
     "fp_process_pe_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "fp_process_pe_host_patches": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                              C.POINTER(C.c_uint64)]),
+    "fp_set_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "fp_set_host_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "fp_counters_reset": (C.c_int, [C.c_void_p]),
     "fp_counters_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fp_counters_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -51,7 +51,7 @@ struct fp_ctx {
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
-    int groups = 3;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>): 3 x 8 warps on one SM; FP_GROUPS=1|2|3 overrides */
+    int groups = 2;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>) sharing the histogram tables; FP_GROUPS=1|2|3 overrides (3 x 8 warps needs <= 80 registers: measured slower) */
     fp_smem_layout sl{};
     uint32_t smem_base = 1024;        /* shared-window address of dynamic shared memory (probed) */
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -72,6 +72,12 @@ struct fp_ctx {
     int ovr_base_cur = 0;
     int64_t ovr_scratch_n = 0;
     int64_t reads_seen = 0;
+    /* adapter-string events (fp_adapter_event) */
+    fp_adapter_event* ev_dev = nullptr; uint32_t ev_cap = 0; uint32_t* ev_count = nullptr;      /* device sink (caller's memory) */
+    fp_adapter_event* ev_host = nullptr; uint64_t ev_host_cap = 0; uint64_t* ev_host_n = nullptr;  /* host sink of the *_host entry points */
+    fp_adapter_event* d_ev[2] = {nullptr, nullptr}; uint32_t* d_nev[2] = {nullptr, nullptr};        /* per chunk slot */
+    fp_adapter_event* h_ev[2] = {nullptr, nullptr}; uint32_t* h_nev[2] = {nullptr, nullptr};
+    uint32_t ev_chunk_cap = 0;
     int ovr_defer_post = 0;             /* fp_overrep_defer_post: the caller runs fp_overrep_post itself (sharded runs) */
     unsigned long long* d_pass_count = nullptr;
     cudaEvent_t ovr_ev = nullptr;       /* host pipeline: orders the post-filter sampling state between the two chunk streams */
@@ -170,7 +176,7 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     /* ---- one region per group (offsets relative to it): mbarrier, cursors, lengths, tile, planes, removal lists, request queue ---- */
     size_t g = 0;
     sl.off_mbar = (int)g; g += 16;
-    sl.off_next = (int)g; g += 16;                                         /* queue length, pop cursor, item cursors */
+    sl.off_next = (int)g; g += 32;                                         /* queue length, pop cursor, item cursors, correction list length */
     sl.off_len = (int)g; g += (size_t)sides * T * 2;
     sl.off_clean = (int)g; g += (size_t)sides * T;
     g = align_up(g, 128);
@@ -183,6 +189,11 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     sl.off_planes = (int)g; g += (size_t)sides * T * sl.plane_stride * 4;
     g = align_up(g, 16);
     sl.off_queue = (int)g; g += (size_t)sides * T * 2 * 8;
+    if (sides == 2) {                                                      /* base correction: work list + per-row masks of corrected positions */
+        sl.cm_words = (S + 31) / 32;
+        sl.off_corr = (int)g; g += (size_t)FP_CORR_CAP * 4;
+        sl.off_cm = (int)g; g += (size_t)sides * T * sl.cm_words * 4;
+    }
     sl.group_stride = (int)align_up(g, 128);
     sl.total = (int)align_up(off + (size_t)c->groups * sl.group_stride, 128);
     return (size_t)sl.total;
@@ -370,6 +381,9 @@ static void free_staging(fp_ctx* c) {
         cudaFree(c->d_ov[i]); c->d_ov[i] = nullptr;
         cudaFree(c->d_patch[i]); c->d_patch[i] = nullptr;
         cudaFree(c->d_npatch[i]); c->d_npatch[i] = nullptr;
+        cudaFree(c->d_ev[i]); c->d_ev[i] = nullptr; cudaFree(c->d_nev[i]); c->d_nev[i] = nullptr;
+        if (c->h_ev[i]) cudaFreeHost(c->h_ev[i]); c->h_ev[i] = nullptr;
+        if (c->h_nev[i]) cudaFreeHost(c->h_nev[i]); c->h_nev[i] = nullptr;
         if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
         if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
     }
@@ -469,6 +483,7 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     memset(&a, 0, sizeof(a));
     a.b = *b; a.out1 = out1; a.out2 = out2; a.ov = ov;
     a.sink.patches = patches; a.sink.cap = patches ? patch_cap : 0; a.sink.count = n_patches;
+    a.events.events = c->ev_dev; a.events.cap = c->ev_dev ? c->ev_cap : 0; a.events.count = c->ev_count;
     a.counters = reinterpret_cast<unsigned long long*>(c->d_raw);
     a.n_tiles = (b->n + c->tile - 1) / c->tile;
     a.sl = c->sl;
@@ -598,6 +613,20 @@ extern "C" int fp_overrep_post(fp_ctx* c, const fp_batch* b, const fp_read_resul
     return overrep_post_launch(c, b, out1, out2, &pass_base, stream ? (cudaStream_t)stream : c->stream[0]);
 }
 
+extern "C" int fp_set_event_sink(fp_ctx* c, fp_adapter_event* d_events, uint32_t cap, uint32_t* d_count) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    if (d_count && cap > 0 && !d_events) return set_err(FP_E_INVAL, "event list missing");
+    c->ev_dev = d_count ? d_events : nullptr; c->ev_cap = d_count ? cap : 0; c->ev_count = d_count;
+    return FP_OK;
+}
+
+extern "C" int fp_set_host_event_sink(fp_ctx* c, fp_adapter_event* h_events, uint64_t cap, uint64_t* n_events) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    if (n_events && cap > 0 && !h_events) return set_err(FP_E_INVAL, "event list missing");
+    c->ev_host = n_events ? h_events : nullptr; c->ev_host_cap = n_events ? cap : 0; c->ev_host_n = n_events;
+    return FP_OK;
+}
+
 /* ---------------- host-buffer pipeline ---------------- */
 static int ensure_staging(fp_ctx* c) {
     if (c->chunk) return FP_OK;
@@ -634,9 +663,34 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     const int64_t n = b->n, CH = c->chunk;
     const int64_t nchunks = (n + CH - 1) / CH;
     struct Pending { int64_t lo, cnt; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    const bool want_ev = c->ev_host_n != nullptr;
+    if (want_ev) {
+        *c->ev_host_n = 0;
+        if (!c->d_ev[0]) {
+            c->ev_chunk_cap = (uint32_t)std::min<int64_t>(CH * 4 + 1024, (int64_t)1 << 24);   /* a unit gives at most 2 events + 2 per fasta adapter */
+            for (int i = 0; i < 2; i++) {
+                CK(cudaMalloc(&c->d_ev[i], (size_t)c->ev_chunk_cap * sizeof(fp_adapter_event))); CK(cudaMalloc(&c->d_nev[i], 4));
+                CK(cudaMallocHost(&c->h_ev[i], (size_t)c->ev_chunk_cap * sizeof(fp_adapter_event))); CK(cudaMallocHost(&c->h_nev[i], 4));
+            }
+        }
+    }
+    /* the device sink of fp_set_event_sink (if any) is put back when this call returns */
+    fp_adapter_event* const saved_dev = c->ev_dev; const uint32_t saved_cap = c->ev_cap; uint32_t* const saved_cnt = c->ev_count;
+    struct Restore { fp_ctx* c; fp_adapter_event* d; uint32_t cap; uint32_t* n; ~Restore() { c->ev_dev = d; c->ev_cap = cap; c->ev_count = n; } } restore{c, saved_dev, saved_cap, saved_cnt};
+    if (!want_ev) { c->ev_dev = nullptr; c->ev_cap = 0; c->ev_count = nullptr; }
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return FP_OK;
         CK(cudaStreamSynchronize(c->stream[slot]));
+        if (want_ev) {
+            const uint32_t ne = *c->h_nev[slot];
+            const uint32_t have = std::min(ne, c->ev_chunk_cap);
+            if (have > 0) CK(cudaMemcpy(c->h_ev[slot], c->d_ev[slot], (size_t)have * sizeof(fp_adapter_event), cudaMemcpyDeviceToHost));
+            for (uint32_t k = 0; k < have; k++) {
+                if (*c->ev_host_n < c->ev_host_cap) { c->ev_host[*c->ev_host_n] = c->h_ev[slot][k]; c->ev_host[*c->ev_host_n].unit = (uint32_t)(pend[slot].lo + c->h_ev[slot][k].unit); }
+                (*c->ev_host_n)++;
+            }
+            if (ne > have) *c->ev_host_n += ne - have;           /* more events than the chunk buffer holds: counted, not listed */
+        }
         if (pe && c->p.correction_enabled) {
             uint32_t np = *c->h_npatch[slot];
             const int64_t lo = pend[slot].lo;
@@ -681,9 +735,14 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             CK(cudaMemcpyAsync(c->d_stage_len[slot][1], b->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st));
         }
+        if (want_ev) {
+            CK(cudaMemsetAsync(c->d_nev[slot], 0, 4, st));
+            c->ev_dev = c->d_ev[slot]; c->ev_cap = c->ev_chunk_cap; c->ev_count = c->d_nev[slot];
+        }
         fp_batch db;
         memset(&db, 0, sizeof(db));
         db.n = cnt; db.stride = S;
+        if (b->flags & FP_B_INDEXED) { db.flags = FP_B_INDEXED; db.first_read_index = b->first_read_index + lo; }
         db.seq1 = c->d_stage[slot][0]; db.qual1 = c->d_stage[slot][1]; db.len1 = c->d_stage_len[slot][0];
         if (pe) { db.seq2 = c->d_stage[slot][2]; db.qual2 = c->d_stage[slot][3]; db.len2 = c->d_stage_len[slot][1]; }
         /* the over-representation sampling state (running counts, rank scratch) is one per ctx: chunk k+1's kernels wait for chunk
@@ -696,6 +755,7 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                           pe ? c->d_patch[slot] : nullptr, c->patch_cap, pe ? c->d_npatch[slot] : nullptr, st);
         if (rc) return rc;
         if (c->p.overrep_enabled) CK(cudaEventRecord(c->ovr_ev, st));
+        if (want_ev) CK(cudaMemcpyAsync(c->h_nev[slot], c->d_nev[slot], 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out1 + lo, c->d_out[slot][0], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
         if (pe) {
             CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));

@@ -598,6 +598,124 @@ __device__ __noinline__ int t_correct(const TRead r1, const TRead r2, uint32_t* 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Base correction, distributed form (clean pairs).  A pair with a 3' low-quality tail inside its overlap can have dozens of
+ * correctable positions; one lane working through them holds back its whole warp -- and, behind the tile's barrier, the CTA.
+ * So the pair's lanes only DECIDE (which mismatching positions are rewritten, from the two quality bytes) and put every
+ * correction on the tile's work list; then ONE LANE PER CORRECTION (all warps of the group) does the statistics deltas, the
+ * patch entry and, after a barrier, the rewrite.  Everything about one correction is independent of the others except the
+ * 5-mer delta of corrections less than five bases apart on one read: each affected window (ending at x in [P, P+4]) is taken
+ * by the LAST corrected position not beyond x (the per-row mask of corrected positions tells), with its old bases from the
+ * still unmodified row and its new bases from the partner read (position y of the rewritten read faces c - y of the other).
+ * entry = row | which << 7 | P << 8 | Pp << 18   (which = the read that is rewritten, P its row position, Pp the partner's)
+ * ------------------------------------------------------------------------------------------------ */
+#define FP_CORR_CAP 1024
+__device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, int PW, const fp_ov_result ov, int row, int sub, int g,
+                                              uint32_t* list, int* nlist, uint32_t* cm1, uint32_t* cm2) {
+    FP_SMEM(r1.qual);    FP_SMEM(r2.qual);    FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(list);    FP_SMEM(nlist);    FP_SMEM(cm1);    FP_SMEM(cm2);
+    bool overflow = false;
+    const int ol = ov.overlap_len;
+    const int start1 = max(0, (int)ov.offset);
+    const int start2 = r2.len - max(0, -(int)ov.offset) - 1;
+    const uint8_t* q1p = r1.qual + r1.front; const uint8_t* q2p = r2.qual + r2.front;
+    const signed char GOOD = 33 + 30, BAD = 33 + 14;                          /* basecorrector.cpp:26-27 */
+    const uint32_t *pl1 = r1.pl, *pl2 = r2.pl;
+    const int e = r2.front + r2.len - 1, jb = r2.len - 1 - start2;           /* rc(r2) index of overlap position 0 */
+    #pragma unroll 1
+    for (int k = sub; k * 32 < ol; k += g) {                                 /* the group's lanes take the 32-position chunks in turn */
+        const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
+        const uint32_t rn = __brev(tp_bits_z(pl2 + 2 * PW, s0));
+        const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
+        uint32_t todo = ((tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn)) & low_mask(ol - 32 * k);
+        #pragma unroll 1
+        while (todo) {
+            const int i = 32 * k + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int p1 = start1 + i, p2 = start2 - i;
+            const signed char q1 = (signed char)q1p[p1], q2 = (signed char)q2p[p2];
+            int which;
+            if (q1 >= GOOD && q2 <= BAD) which = 1;                            /* read 1 is right: rewrite read 2 (:42-50) */
+            else if (q2 >= GOOD && q1 <= BAD) which = 0;                       /* read 2 is right: rewrite read 1 (:51-59) */
+            else continue;
+            const int P1 = r1.front + p1, P2 = r2.front + p2;
+            const int slot = atomicAdd(nlist, 1);
+            if (slot >= FP_CORR_CAP) { overflow = true; continue; }            /* left to the sequential path after the distributed one */
+            list[slot] = (uint32_t)row | ((uint32_t)which << 7) | ((uint32_t)(which ? P2 : P1) << 8) | ((uint32_t)(which ? P1 : P2) << 18);
+            if (which) atomicOr(&cm2[P2 >> 5], 1u << (P2 & 31)); else atomicOr(&cm1[P1 >> 5], 1u << (P1 & 31));
+        }
+    }
+    return overflow;
+}
+
+/* one correction: statistics deltas (post-filter), patch entry, correction matrix.  Rows are still unmodified. */
+__device__ __noinline__ void t_correct_item(uint32_t entry, const uint8_t* tile0, int tile_array_bytes, int S, int T, const uint16_t* s_len, const uint32_t* cm,
+                                            int CMW, const DeltaAcc D, BlockCounters* bc, const PatchSink& sink, unsigned int pair_index) {
+    FP_SMEM(tile0);    FP_SMEM(s_len);    FP_SMEM(cm);    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);    FP_SMEM(bc);
+    const int row = entry & 0x7F, which = (entry >> 7) & 1, P = (entry >> 8) & 0x3FF, Pp = (entry >> 18) & 0x3FF;
+    const uint8_t* mseq = tile0 + (which * 2) * tile_array_bytes + row * S; const uint8_t* mqual = mseq + tile_array_bytes;
+    const uint8_t* pseq = tile0 + ((which ^ 1) * 2) * tile_array_bytes + row * S; const uint8_t* pqual = pseq + tile_array_bytes;
+    const uint32_t* mcm = cm + (which * T + row) * CMW;
+    const int l0 = s_len[which * T + row], c = P + Pp;
+    const uint8_t ob = mseq[P], oq = mqual[P], nb = comp_clean(pseq[Pp]), nq = pqual[Pp];
+    const int side = which;
+    atomicAdd(&D.qh[side * FP_QUAL_BINS + oq], -1);
+    atomicAdd(&D.qh[side * FP_QUAL_BINS + nq], +1);
+    if (P < D.cycles) {
+        int* c0 = D.cyc + side * D.cycles * 20 + P * 20;
+        int* co = c0 + ((0x43F21F0Fu >> (4 * (ob & 7))) & 0xF) * 4;            /* base&7: A1 C3 T4 N6 G7 -> bin 0..4 */
+        int* cn = c0 + ((0x43F21F0Fu >> (4 * (nb & 7))) & 0xF) * 4;
+        atomicAdd(&co[0], -1); atomicAdd(&cn[0], +1);
+        if (oq >= '5') atomicAdd(&co[1], -1);
+        if (nq >= '5') atomicAdd(&cn[1], +1);
+        if (oq >= '?') atomicAdd(&co[2], -1);
+        if (nq >= '?') atomicAdd(&cn[2], +1);
+        atomicAdd(&co[3], 33 - (int)oq); atomicAdd(&cn[3], (int)nq - 33);
+    }
+    /* 5-mers: digit k = position P-4+k; old codes from the row, new codes with every corrected position of the window taken from the partner */
+    uint32_t Z = 0, V = 0, Zn = 0, Vn = 0, CMB = 0;
+    #pragma unroll
+    for (int k = 0; k < 9; k++) {
+        const int pos = P - 4 + k;
+        const bool inb = pos >= 0 && pos < l0;
+        const uint32_t bb = inb ? mseq[pos] : (uint32_t)'N';
+        const bool corr = inb && ((mcm[pos >> 5] >> (pos & 31)) & 1u);
+        const int pp = c - pos;
+        const uint32_t nn_ = corr ? (uint32_t)comp_clean(pseq[pp]) : bb;       /* a corrected position faces a valid partner position */
+        Z |= ((bb >> 1) & 3u) << (2 * k); V |= (bb != (uint32_t)'N' ? 1u : 0u) << k;
+        Zn |= ((nn_ >> 1) & 3u) << (2 * k); Vn |= (nn_ != (uint32_t)'N' ? 1u : 0u) << k;
+        CMB |= (corr ? 1u : 0u) << k;
+    }
+    int* km = D.kmer + side * FP_KMER_BINS;
+    #pragma unroll
+    for (int w = 0; w < 5; w++) {                                              /* window ending at P+w = digits w .. w+4; mine iff no corrected position in (P, P+w] */
+        if ((CMB >> 5) & ((1u << w) - 1u)) continue;
+        if (((V >> w) & 31u) == 31u) atomicAdd(&km[(Z >> (2 * w)) & 0x3FFu], -1);
+        if (((Vn >> w) & 31u) == 31u) atomicAdd(&km[(Zn >> (2 * w)) & 0x3FFu], +1);
+    }
+    atomicAdd(&bc->fr[FP_FR_CORRECTION + (nb & 7) * 9], 1u);                   /* diagonal only, SURVEY App. A.6 */
+    if (sink.count) {
+        const unsigned int slot = atomicAdd(sink.count, 1u);
+        if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)P; pt.which = (uint8_t)which; pt.base = nb; pt.qual = nq; pt.old_base = ob; pt.old_qual = oq; pt._pad = 0; sink.patches[slot] = pt; }
+    }
+}
+
+/* the rewrite itself: shared-memory row, HBM row, bit planes (other lanes may touch the same plane words: atomics) */
+__device__ __forceinline__ void t_correct_apply(uint32_t entry, uint8_t* tile0, int tile_array_bytes, int S, int T, uint32_t* planes, int PSTR, int PW,
+                                                uint8_t* gseq, uint8_t* gqual) {
+    const int row = entry & 0x7F, which = (entry >> 7) & 1, P = (entry >> 8) & 0x3FF, Pp = (entry >> 18) & 0x3FF;
+    uint8_t* mseq = tile0 + (which * 2) * tile_array_bytes + row * S; uint8_t* mqual = mseq + tile_array_bytes;
+    const uint8_t* pseq = tile0 + ((which ^ 1) * 2) * tile_array_bytes + row * S; const uint8_t* pqual = pseq + tile_array_bytes;
+    const uint8_t nb = comp_clean(pseq[Pp]), nq = pqual[Pp];
+    mseq[P] = nb; mqual[P] = nq; gseq[P] = nb; gqual[P] = nq;
+    uint32_t* pl = planes + (which * T + row) * PSTR + (P >> 5);
+    const uint32_t m = 1u << (P & 31);
+    const int c2 = (nb >> 1) & 3; const bool n = (nb == 'N');
+    if (!n && (c2 & 1)) atomicOr(&pl[0], m); else atomicAnd(&pl[0], ~m);
+    if (!n && (c2 & 2)) atomicOr(&pl[PW], m); else atomicAnd(&pl[PW], ~m);
+    if (n) atomicOr(&pl[2 * PW], m); else atomicAnd(&pl[2 * PW], ~m);
+    if (nq < (uint8_t)c_p.qualified_qual) atomicOr(&pl[3 * PW], m); else atomicAnd(&pl[3 * PW], ~m);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * AdapterTrimmer::trimBySequence  (adaptertrimmer.cpp:64-157), one thread per read.
  * Scan 1 on planes (clean read + clean adapter) or bytes; scans 2/3 in the closed form of dev_gap_scan,
  * evaluated sequentially (O(alen)).
@@ -629,8 +747,10 @@ __device__ __forceinline__ bool gap_may_hit(unsigned long long D1, unsigned long
     return v <= cmax / 8 - 1;
 }
 
+struct EvCtx { EventSink sink; unsigned int unit; int which; };
+
 __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, int alen, int matchReq, int aidx, int PW,
-                                                int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
+                                                int& posOut, int& basesOut, BlockCounters* bc, int sub, int g, const EvCtx& ec) {
     FP_SMEM(r.seq);    FP_SMEM(r.pl);    FP_SMEM(bc);
     const int rlen = r.len;
     const uint8_t* rdata = r.seq + r.front;
@@ -737,17 +857,23 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
         int abases;
         if (pos < 0) { abases = alen + pos; r.len = 0; }
         else { abases = rlen - pos; if (pos <= r.len) r.len = pos; }
-        if (abases > 0 && sub == 0) atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)abases);
+        if (abases > 0 && sub == 0) {
+            atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)abases);
+            /* the string FilterResult::addAdapterTrimmed histograms (:139-152): a prefix of the adapter, or the read's tail */
+            const int key = (aidx < 2 ? 0 : 2048) + ec.which * 1024 + (aidx < 2 ? 0 : aidx - 2);
+            if (pos < 0) push_event(ec.sink, ec.unit, ec.which, FP_EV_ADAPTER, key, 0, abases, aidx);
+            else push_event(ec.sink, ec.unit, ec.which, FP_EV_READ, key, r.front + pos, abases, aidx);
+        }
         posOut = pos; basesOut += max(abases, 0);
         return true;
     }
     return false;
 }
 
-__device__ __forceinline__ bool t_trim_by_multi(TRead& r, int PW, int& posOut, int& basesOut, BlockCounters* bc, int sub, int g) {
+__device__ __forceinline__ bool t_trim_by_multi(TRead& r, int PW, int& posOut, int& basesOut, BlockCounters* bc, int sub, int g, const EvCtx& ec) {
     bool trimmed = false;                                                 /* adaptertrimmer.cpp:48-62 */
     for (int i = 0; i < c_p.n_fasta; i++)
-        trimmed |= t_trim_by_sequence(r, c_p.adapters + c_p.fasta_off[i], c_p.fasta_len[i], c_p.fasta_match_req, 2 + i, PW, posOut, basesOut, bc, sub, g);
+        trimmed |= t_trim_by_sequence(r, c_p.adapters + c_p.fasta_off[i], c_p.fasta_len[i], c_p.fasta_match_req, 2 + i, PW, posOut, basesOut, bc, sub, g, ec);
     return trimmed;
 }
 
@@ -1112,6 +1238,9 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
     unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
     int* s_qn = reinterpret_cast<int*>(gsm + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
     sinks.q = s_queue; sinks.qn = &s_qn[0];
+    uint32_t* s_corr = reinterpret_cast<uint32_t*>(gsm + sl.off_corr);      /* [FP_CORR_CAP] base-correction work list (PE); its length is s_qn[4] */
+    uint32_t* s_cm = reinterpret_cast<uint32_t*>(gsm + sl.off_cm);          /* [SIDES][T][CMW] corrected positions of every row */
+    const int CMW = sl.cm_words;
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
     for (int i = tid; i < SIDES * T * PSTR; i += FP_CT) tile_planes[i] = 0;
@@ -1181,13 +1310,14 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
-            s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0;     /* request queue / removal items: next used after the phase-A barrier */
+            s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0; s_qn[4] = 0;     /* request queue / removal items / correction list: next used after the phase-A barrier */
         }
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
            mbarrier every thread waits on itself: no CTA barrier here */
         mbar_wait(mbar, parity);
         parity ^= 1;
         for (int i = tid; i < SIDES * (T + 4) + SIDES; i += FP_CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
+        if (PAIRED && c_p.correction) for (int i = tid; i < SIDES * T * CMW; i += FP_CT) s_cm[i] = 0;
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
         if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
@@ -1287,7 +1417,8 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
 
         /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
-        for (int rbase = warp * UPW; rbase < rows; rbase += FP_CW * UPW) {
+        for (int rb0 = 0; rb0 < rows; rb0 += FP_CW * UPW) {            /* same trip count for every warp: the loop body holds group barriers */
+            const int rbase = rb0 + warp * UPW;
             const int r = rbase + lane / GL;
             const bool active = r < rows;
             const int rr = active ? r : 0;
@@ -1307,8 +1438,9 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     bool dimer = false;
                     if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
                         bool trimmed = false;
-                        if (c_p.has_r1) trimmed = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos, abases, bc, sub, GL);
-                        if (c_p.n_fasta > 0) trimmed |= t_trim_by_multi(r1, PW, apos, abases, bc, sub, GL);
+                        EvCtx ec; ec.sink = a.events; ec.unit = (unsigned int)gi; ec.which = 0;
+                        if (c_p.has_r1) trimmed = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos, abases, bc, sub, GL, ec);
+                        if (c_p.n_fasta > 0) trimmed |= t_trim_by_multi(r1, PW, apos, abases, bc, sub, GL, ec);
                         if (trimmed) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags |= FP_F_ADAPTER_TRIMMED; }
                         if (trimmed && r1.len <= c_p.dimer_max_len) dimer = true;
                     }
@@ -1375,17 +1507,44 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     else ovA = ov;
                     need_correct = both && c_p.correction && !ovA.has_gap && ovA.overlapped && ovA.diff != 0;       /* :443,:453-456 */
                 }
+                /* ---- base correction (:453-456): the pair's lanes decide, the whole group works the list, one lane per correction ---- */
+                bool corr_overflow = false;
+                const bool distributed = need_correct && clean1 && clean2;
+                if (PAIRED && c_p.correction) {
+                    if (distributed)
+                        corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, s_corr, &s_qn[4], s_cm + rr * CMW, s_cm + (T + rr) * CMW);
+                    GSYNC();
+                    const int ncorr = min(s_qn[4], FP_CORR_CAP);
+                    for (int i = tid; i < ncorr; i += FP_CT)
+                        t_correct_item(s_corr[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (s_corr[i] & 0x7F)));
+                    GSYNC();
+                    for (int i = tid; i < ncorr; i += FP_CT) {
+                        const uint32_t en = s_corr[i];
+                        const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
+                        t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
+                                        (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
+                    }
+                    GSYNC();
+                    if (tid == 0) s_qn[4] = 0;                 /* next round of this tile (if any) starts an empty list; read again only after the next barrier */
+                }
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
                 if (active) {
                     bool dimer = false;
                     if (need_correct) {
+                        /* sequential path: pairs with bytes outside {A,C,G,T,N}, and what did not fit the work list (those positions still mismatch) */
+                        corr_overflow = (__ballot_sync(gmask, corr_overflow) != 0u);
                         int nc = 0;
-                        if (sub < 2)
+                        if ((!distributed || corr_overflow) && sub < 2)
                             nc = t_correct(r1, r2, pl1, pl2, PW, ovA, a.b.seq1 + gi * S + r1.front, a.b.qual1 + gi * S + r1.front,
                                            a.b.seq2 + gi * S + r2.front, a.b.qual2 + gi * S + r2.front, (unsigned int)gi, a.sink, bc, D, G, l1, l2, sub);
                         __syncwarp(gmask);                                                        /* corrected bytes / planes visible to the whole group */
-                        const int n2 = __shfl_sync(gmask, nc, glead), n1 = __shfl_sync(gmask, nc, glead + 1);   /* lane 0 rewrote read 2, lane 1 read 1 */
+                        int n2 = __shfl_sync(gmask, nc, glead), n1 = __shfl_sync(gmask, nc, glead + 1);   /* lane 0 rewrote read 2, lane 1 read 1 */
+                        if (distributed) {                                                        /* + what the work list rewrote */
+                            uint32_t any1 = 0, any2 = 0;
+                            for (int k = 0; k < CMW; k++) { any1 |= s_cm[rr * CMW + k]; any2 |= s_cm[(T + rr) * CMW + k]; }
+                            n1 += any1 ? 1 : 0; n2 += any2 ? 1 : 0;
+                        }
                         if (n1 > 0) flags1 |= FP_F_CORRECTED;
                         if (n2 > 0) flags2 |= FP_F_CORRECTED;
                         if (lead && n1 + n2 > 0) atomicAdd(&bc->fr[FP_FR_CORRECTED_READS], (n1 > 0 && n2 > 0) ? 2u : 1u);   /* :75-80 */
@@ -1396,17 +1555,22 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                             const int ol = ovA.overlap_len;
                             const int nl1 = min(r1.len, ol + r2.front), nl2 = min(r2.len, ol + r1.front);
                             const int a1 = r1.len - nl1, a2 = r2.len - nl2;
+                            if (lead) {
+                                atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)(a1 + a2));
+                                push_event(a.events, (unsigned int)gi, 0, FP_EV_PAIR, 0, r1.front + nl1, a1, 0);      /* addAdapterTrimmed(adapter1, adapter2) */
+                                push_event(a.events, (unsigned int)gi, 1, FP_EV_PAIR, 1, r2.front + nl2, a2, 0);
+                            }
                             r1.len = nl1; r2.len = nl2;
-                            if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_BASES], (unsigned)(a1 + a2));
                             ab1 += a1; ab2 += a2;
                             trimmed = true;
                         }
                         bool t1 = trimmed, t2 = trimmed;
+                        EvCtx ec1, ec2; ec1.sink = a.events; ec1.unit = (unsigned int)gi; ec1.which = 0; ec2 = ec1; ec2.which = 1;
                         if (!trimmed) {                                                           /* :461-466 */
-                            if (c_p.has_r1) t1 = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos1, ab1, bc, sub, GL);
-                            if (c_p.has_r2) t2 = t_trim_by_sequence(r2, c_p.adapters + c_p.adapter_r2_off, c_p.adapter_r2_len, 4, 1, PW, apos2, ab2, bc, sub, GL);
+                            if (c_p.has_r1) t1 = t_trim_by_sequence(r1, c_p.adapters + c_p.adapter_r1_off, c_p.adapter_r1_len, 4, 0, PW, apos1, ab1, bc, sub, GL, ec1);
+                            if (c_p.has_r2) t2 = t_trim_by_sequence(r2, c_p.adapters + c_p.adapter_r2_off, c_p.adapter_r2_len, 4, 1, PW, apos2, ab2, bc, sub, GL, ec2);
                         }
-                        if (c_p.n_fasta > 0) { t1 |= t_trim_by_multi(r1, PW, apos1, ab1, bc, sub, GL); t2 |= t_trim_by_multi(r2, PW, apos2, ab2, bc, sub, GL); }   /* :467-470 */
+                        if (c_p.n_fasta > 0) { t1 |= t_trim_by_multi(r1, PW, apos1, ab1, bc, sub, GL, ec1); t2 |= t_trim_by_multi(r2, PW, apos2, ab2, bc, sub, GL, ec2); }   /* :467-470 */
                         if (t1) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags1 |= FP_F_ADAPTER_TRIMMED; }   /* :472-475 */
                         if (t2) { if (lead) atomicAdd(&bc->fr[FP_FR_ADAPTER_READS], 1u); flags2 |= FP_F_ADAPTER_TRIMMED; }
                         if ((t1 || t2) && r1.len <= c_p.dimer_max_len && r2.len <= c_p.dimer_max_len) dimer = true;   /* :480-484 */

@@ -75,6 +75,7 @@ size_t fp_abi_sizeof(int which) {
         case 5: return sizeof(fp_counter_layout);
         case 6: return sizeof(fp_fastq_rec);
         case 7: return sizeof(fp_fastq_info);
+        case 8: return sizeof(fp_adapter_event);
         default: return 0;
     }
 }

@@ -156,6 +156,18 @@ __device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, 
 /* ballot-based rebuild of one row's planes (used after base correction rewrote the row; rare) */
 /* sink of the base-correction patch list (fp_patch entries, capacity, running count) */
 struct PatchSink { fp_patch* patches; unsigned int cap; unsigned int* count; };
+/* sink of the adapter-string events (fp_adapter_event entries, capacity, running count; count == nullptr: off) */
+struct EventSink { fp_adapter_event* events; unsigned int cap; unsigned int* count; };
+__device__ __forceinline__ void push_event(const EventSink& sk, unsigned int unit, int which, int kind, int key, int start, int len, int adapter) {
+    if (!sk.count) return;
+    const unsigned int slot = atomicAdd(sk.count, 1u);
+    if (slot < sk.cap) {
+        fp_adapter_event e;
+        e.unit = unit; e.start = (uint16_t)start; e.len = (uint16_t)len; e.key = (uint16_t)key; e.which = (uint8_t)which; e.kind = (uint8_t)kind;
+        e.adapter = (uint16_t)adapter; e._pad = 0;
+        sk.events[slot] = e;
+    }
+}
 
 /* ------------------------------------------------------------------------------------------------
  * Column-pass statistics (Stats::statRead per-base part, stats.cpp:204-268).
@@ -353,7 +365,7 @@ __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side,
 struct fp_smem_layout {
     int off_dummy, off_mbar, off_next, off_tile, tile_array_bytes, off_len, off_clean, off_kmer, off_qhist, off_bc, off_lut, off_delta,
         off_dkmer, off_dqh, off_rm, off_planes, off_queue, plane_words, plane_stride, total,
-        off_group, group_stride;     /* off_mbar, off_next, off_len, off_clean, off_tile, off_rm, off_planes, off_queue are relative to a group's region */
+        off_group, group_stride, off_corr, off_cm, cm_words;     /* off_mbar, off_next, off_len, off_clean, off_tile, off_rm, off_planes, off_queue are relative to a group's region */
 };
 
 struct fp_launch_args {
@@ -362,6 +374,7 @@ struct fp_launch_args {
     fp_read_result* out2;
     fp_ov_result* ov;
     PatchSink sink;
+    EventSink events;
     unsigned long long* counters;    /* global int64 block (two's complement adds) */
     long long n_tiles;
     fp_smem_layout sl;

@@ -177,6 +177,29 @@ typedef struct fp_patch {
     uint8_t  _pad;
 } fp_patch;                /* 12 bytes */
 
+/* One call of FilterResult::addAdapterTrimmed (src/filterresult.cpp:124-180) as the chain made it -- the adapter STRINGS the reference
+ * histograms (`adapter_cutting.read1_adapter_counts` of the JSON report) are substrings of the read rows or prefixes of the configured
+ * adapters, so the device records where they are and the host rebuilds the maps in input order with the reference's own caps
+ * (MAX_ADAPTER_REC / LOW_COMPLEXITY_SKIP are applied in arrival order, src/filterresult.cpp:7-8,135).  Events are appended to the list
+ * in no particular order: sort by (unit, key).  Within a unit the calls come in the order of `key`.
+ *   FP_EV_PAIR    trimByOverlapAnalysis (src/adaptertrimmer.cpp:17-46): addAdapterTrimmed(adapter1, adapter2) -- two events of one unit
+ *                 (which = 0 and 1, len may be 0); the string is row[start, start+len) of that read (current, i.e. corrected, bytes)
+ *   FP_EV_READ    trimBySequence hit at pos >= 0 (:147-152): addAdapterTrimmed(row[start, start+len), isR2 = which)
+ *   FP_EV_ADAPTER trimBySequence hit at pos < 0 (:139-146): the string is the first `len` bases of adapter number `adapter`
+ *                 (0 = adapter_seq_r1, 1 = adapter_seq_r2, 2+i = fasta_adapters[i])                                            */
+#define FP_EV_PAIR    0
+#define FP_EV_READ    1
+#define FP_EV_ADAPTER 2
+typedef struct fp_adapter_event {
+    uint32_t unit;         /* index in the batch (host entry points: in the whole host batch) */
+    uint16_t start, len;
+    uint16_t key;          /* order of the calls inside one unit */
+    uint8_t  which;        /* 0 = read1, 1 = read2 */
+    uint8_t  kind;         /* FP_EV_* */
+    uint16_t adapter;      /* FP_EV_ADAPTER: which adapter */
+    uint16_t _pad;
+} fp_adapter_event;        /* 16 bytes */
+
 /* ---------------- packed counter block (all int64, plain sums) ----------------
  * stats[s], s in {0:pre1, 1:post1, 2:pre2, 3:post2}  (SE uses 0,1):
  *     cycle[34][C]   kinds in the reference's order (stats.cpp:54-63); slot = base & 7
@@ -285,6 +308,13 @@ int  fp_process_pe_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp
  * touch only the Read objects whose bases changed (BaseCorrector rewrites r1/r2 in place, src/basecorrector.cpp:44-60). */
 int  fp_process_pe_host_patches(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
                                 fp_patch* patches, uint64_t patch_cap, uint64_t* n_patches);
+
+/* Adapter-string events (above).  Device form: `events` (capacity `cap`) and `count` are DEVICE memory that later fp_process_se / _pe
+ * calls append to (*count keeps counting past cap; the caller zeroes it); NULL switches the recording off (the default).
+ * Host form: the fp_process_*_host calls append to a HOST array with fp_adapter_event.unit relative to the host batch and set
+ * *n_events (which may exceed cap) -- what the reference-side shim feeds to FilterResult::addAdapterTrimmed after sorting by (unit, key). */
+int  fp_set_event_sink(fp_ctx* ctx, fp_adapter_event* d_events, uint32_t cap, uint32_t* d_count);
+int  fp_set_host_event_sink(fp_ctx* ctx, fp_adapter_event* h_events, uint64_t cap, uint64_t* n_events);
 
 /* Counter block. fetch synchronises the ctx's streams, finalises (totals per cycle) and copies
  * layout.total int64 words to host_out. */

@@ -1,17 +1,13 @@
 """-m gpu: the duplication bloom filter on the device (fp_dup_check) against the sequential C port, which is pinned
-to the reference's Duplicate object (tests/test_duplicate_oracle.py).
-
-Status: the per-thread bodies (fastp_b200/csrc/fp_dup.h) are validated on the host -- run one thread at a time in shuffled order they
-reproduce the oracle -- but round 1 ran out of GPU minutes before the CUDA wrappers saw hardware.  So this first on-device comparison
-(a) runs in a CHILD PROCESS (tests/_gpu_dup_worker.py): a fault cannot poison the CUDA context of the rest of the suite, and
-(b) is marked xfail(strict=False): a pass shows up as XPASS, a difference as xfail, neither hides behind a green tick."""
+to the reference's Duplicate object (tests/test_duplicate_oracle.py).  First ran on a B200 at the end of round 1 (equal); a plain test
+since.  It still runs in a child process (tests/_gpu_dup_worker.py) so that its multi-GiB bit arrays are released at once."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of the fp_dup kernels (host-emulated so far)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

@@ -118,3 +118,89 @@ def test_random_option_sets(gpu, paired):
         want = T.run_cpu("oracle", p, arrs, 160)
         got = gpu.run_gpu(p, arrs, 160, mode="device")
         T.assert_results_equal(got, want, paired, what=f"random set {k}: {kw}")
+
+
+def _dev_tensors(torch, n, paired, with_patches):
+    t = {"out1": torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device="cuda:0")}
+    if paired:
+        t["out2"] = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device="cuda:0")
+        t["ov"] = torch.zeros(max(n, 1) * 8, dtype=torch.uint8, device="cuda:0")
+        if with_patches:
+            t["patches"] = torch.zeros((4 * n + 16) * 12, dtype=torch.uint8, device="cuda:0")
+            t["np"] = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    return t
+
+
+def test_patches_undo_restores_the_rows(gpu):
+    """fp_patches_undo plays a pass's patch list backwards: the resident rows are pristine again, a second pass gives the same
+    records, counters and patch list (bench.py relies on it so that every timed step of configs[2] corrects bases)."""
+    import ctypes as C
+    import torch
+    p = T.config_params("cfg3_overlap_correction", 1)
+    n = 9000
+    _, arrs = T.synth_host(n, 160, 1, 0, 17, 1, 150)
+    want = T.run_cpu("oracle", p, arrs, 160)
+    ctx = gpu.GpuCtx(p, n, 160, 160)
+    lib = ctx.lib
+    b, t = gpu.device_batch({k: v.copy() for k, v in arrs.items()})
+    d = _dev_tensors(torch, n, 1, True)
+    cap = 4 * n + 16
+    for rep in range(2):
+        ctx.reset()
+        d["np"].zero_()
+        capi.check(lib.fp_process_pe(ctx.h, C.byref(b), d["out1"].data_ptr(), d["out2"].data_ptr(), d["ov"].data_ptr(), d["patches"].data_ptr(), cap,
+                                     d["np"].data_ptr(), None), lib)
+        torch.cuda.synchronize()
+        npatch = int(d["np"].item())
+        assert 0 < npatch <= cap
+        got = {"out1": d["out1"].cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n], "out2": d["out2"].cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n],
+               "ov": d["ov"].cpu().numpy().view(capi.OV_RESULT_DTYPE)[:n], "counters": ctx.counters(), "arrs": {k: t[k].cpu().numpy() for k in arrs}, "layout": ctx.L}
+        T.assert_results_equal(got, want, 1, what=f"pass {rep}")
+        pts = d["patches"].cpu().numpy().view(capi.PATCH_DTYPE)[:npatch]
+        for pt in pts[:200]:                                   # old values are the ORIGINAL bytes
+            side = "2" if pt["which"] else "1"
+            assert arrs["seq" + side][pt["pair"], pt["pos"]] == pt["old_base"] and arrs["qual" + side][pt["pair"], pt["pos"]] == pt["old_qual"]
+        capi.check(lib.fp_patches_undo(ctx.h, C.byref(b), d["patches"].data_ptr(), d["np"].data_ptr(), cap, None), lib)
+        torch.cuda.synchronize()
+        for k in ("seq1", "qual1", "seq2", "qual2"):
+            assert (t[k].cpu().numpy() == arrs[k]).all(), k
+    ctx.close()
+
+
+@pytest.mark.parametrize("nshards", [2, 3])
+def test_sharded_overrepresentation_equals_single_stream(gpu, nshards):
+    """shards of ONE stream processed by separate contexts (as separate ranks would), pre-filter sampling by the
+    global read index (fp_batch.first_read_index), post-filter sampling by the exclusive scan of the shards' pass counts
+    (fp_overrep_defer_post / fp_pass_count / fp_overrep_post); the SUM of the shards' counter blocks == the block of the whole
+    stream processed as `--thread 1` would (the oracle)."""
+    import ctypes as C
+    import torch
+    L, S, n = 250, 256, 9000
+    _, arrs = T.synth_host(n, S, 1, 0, 11, 3, L)
+    p = T.overrep_params("cfg3_overlap_correction", 1, arrs, L, 20)
+    want = T.run_cpu("oracle", p, arrs, S)
+    assert int(want["counters"].overrep(1)[0].sum()) > 5 and int(want["counters"].overrep(3)[0].sum()) > 5
+    bounds = [n * i // nshards + (3 if 0 < i < nshards else 0) for i in range(nshards + 1)]      # uneven cuts, not multiples of the sampling step
+    ctxs, outs, batches, counts = [], [], [], []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        ctx = gpu.GpuCtx(p, hi - lo, S, S)
+        capi.check(ctx.lib.fp_overrep_defer_post(ctx.h, 1), ctx.lib)
+        b, t = gpu.device_batch({k: np.ascontiguousarray(v[lo:hi]) for k, v in arrs.items()})
+        b.flags, b.first_read_index = 1, lo
+        d = _dev_tensors(torch, hi - lo, 1, False)
+        capi.check(ctx.lib.fp_process_pe(ctx.h, C.byref(b), d["out1"].data_ptr(), d["out2"].data_ptr(), d["ov"].data_ptr(), None, 0, None, None), ctx.lib)
+        c = C.c_int64()
+        capi.check(ctx.lib.fp_pass_count(ctx.h, d["out1"].data_ptr(), hi - lo, C.byref(c), None), ctx.lib)
+        ctxs.append(ctx); outs.append(d); batches.append((b, t)); counts.append(c.value)
+    total = np.zeros(ctxs[0].L.total, np.int64)
+    base = 0
+    for ctx, d, (b, t), c in zip(ctxs, outs, batches, counts):
+        capi.check(ctx.lib.fp_overrep_post(ctx.h, C.byref(b), d["out1"].data_ptr(), d["out2"].data_ptr(), base, None), ctx.lib)
+        base += c
+        total += ctx.counters().data
+    assert base == int(want["counters"].stats(capi.STATS_POST1)["reads"])
+    got = capi.CounterView(ctxs[0].L, total)
+    # per-cycle totals (kinds 32/33) are derived per fetch, so they add up as well
+    T.assert_counters_equal(got, want["counters"], what=f"{nshards} shards")
+    for ctx in ctxs:
+        ctx.close()

@@ -37,3 +37,23 @@ def test_sharded_allreduce_equals_single_process(tmp_path, world, mode):
     _, arrs = T.synth_host(n, 160, 1, 0, 42, 1, 150)
     want = T.run_cpu("oracle", p, arrs, 160)["counters"].data
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_overrepresentation_sampling_equals_single_process(tmp_path, world):
+    """the pass-count exclusive scan (sharding.exclusive_pass_base) over gloo: all-reduced over-representation counts of N shards ==
+    the single-process `--thread 1` block (src/stats.cpp:270-290)"""
+    from fastp_b200 import capi
+    total = 4003
+    out = str(tmp_path / "o.npy")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world), os.path.join(HERE, "_gloo_worker.py"), str(total), out, "overrep"]
+    subprocess.run(cmd, check=True, env=env, timeout=600, capture_output=True)
+    got = np.load(out)
+    _, arrs = T.synth_host(total, 160, 1, 0, 42, 3, 150)
+    p = T.overrep_params("cfg3_overlap_correction", 1, arrs, 150, 20)
+    want = T.run_cpu("oracle", p, arrs, 160)["counters"]
+    assert int(want.overrep(capi.STATS_POST1)[0].sum()) > 3
+    # the finalised per-cycle totals (kinds 32/33) are part of the oracle's block; the raw sums carry them too
+    assert (got == want.data).all()
