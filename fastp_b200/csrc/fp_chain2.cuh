@@ -206,29 +206,31 @@ __device__ __forceinline__ unsigned long long tp_bits64(const uint32_t* P, int b
 __device__ __forceinline__ unsigned long long mask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
 
 /* Exact no-gap acceptance test of ONE candidate (overlapanalysis.cpp:34-44): mismatches over the protected prefix
- * pp = min(ol, 50) on the three planes; returns the count if it is within lut[ol], else -1.  Out of line: only the rare
- * survivors of the one-plane filter below (and the few candidates whose overlap is shorter than 32 bases) get here. */
+ * pp = min(ol, 50) on the three planes; returns the count if it is within lut[ol], else -1.  The 64-base constant side of the
+ * comparison (K*) is prepared once per pair and direction by every lane together (OvConst); only the few survivors of the
+ * one-plane filter below (and candidates of pairs too short for it) get here, so the divergent part is three plane fields. */
 struct OvPlanes { const uint32_t *alo, *ahi, *ann, *plo, *phi, *pnn; int f1, len1, e, len2; };
+struct OvConst { unsigned long long klo, khi, knn; };
 
-__device__ __noinline__ int t_ov_exact(const OvPlanes P, int dir, int o, const int16_t* lut, int& olOut) {
-    FP_SMEM(P.alo); FP_SMEM(P.ahi); FP_SMEM(P.ann); FP_SMEM(P.plo); FP_SMEM(P.phi); FP_SMEM(P.pnn); FP_SMEM(lut);
-    unsigned long long x;
-    int ol;
-    if (dir == 0) {                                                        /* r1[o+k] vs rc(r2)[k] */
-        ol = min(P.len1 - o, P.len2);
-        const unsigned long long bnn = ((unsigned long long)__brev(tp_bits_z(P.pnn, P.e - 63)) << 32) | __brev(tp_bits_z(P.pnn, P.e - 31));
-        const unsigned long long blo = ((unsigned long long)__brev(tp_bits_z(P.plo, P.e - 63)) << 32) | __brev(tp_bits_z(P.plo, P.e - 31));
-        const unsigned long long bhi = ~(((unsigned long long)__brev(tp_bits_z(P.phi, P.e - 63)) << 32) | __brev(tp_bits_z(P.phi, P.e - 31))) & ~bnn;
-        const int bit = P.f1 + o;
-        x = (tp_bits64(P.alo, bit) ^ blo) | (tp_bits64(P.ahi, bit) ^ bhi) | (tp_bits64(P.ann, bit) ^ bnn);
-    } else {                                                               /* r1[k] vs rc(r2)[o+k]  <=>  comp(r1[pp-1-t]) vs row2[s+t] */
-        ol = min(P.len1, P.len2 - o);
-        const int pp = min(ol, 50);
+__device__ __forceinline__ OvConst t_ov_const(const OvPlanes& P, int dir) {
+    OvConst K;
+    if (dir == 0) {                                                        /* rc(r2)[0..64): reversed tail of r2, hi complemented */
+        K.knn = ((unsigned long long)__brev(tp_bits_z(P.pnn, P.e - 63)) << 32) | __brev(tp_bits_z(P.pnn, P.e - 31));
+        K.klo = ((unsigned long long)__brev(tp_bits_z(P.plo, P.e - 63)) << 32) | __brev(tp_bits_z(P.plo, P.e - 31));
+        K.khi = ~(((unsigned long long)__brev(tp_bits_z(P.phi, P.e - 63)) << 32) | __brev(tp_bits_z(P.phi, P.e - 31))) & ~K.knn;
+    } else {                                                               /* Y50[t] = comp(r1[49-t]) */
         const unsigned long long a_nn = tp_bits64(P.ann, P.f1), a_lo = tp_bits64(P.alo, P.f1), a_hi = tp_bits64(P.ahi, P.f1);
-        const unsigned long long ynn = __brevll(a_nn) >> 14, ylo = __brevll(a_lo) >> 14, yhi = ~(__brevll(a_hi) >> 14) & ~ynn;   /* Y50[t] = comp(r1[49-t]) */
-        const int sbit = P.e - o - pp + 1, ysh = 50 - pp;                   /* sbit >= front2 >= 0 */
-        x = (tp_bits64(P.plo, sbit) ^ (ylo >> ysh)) | (tp_bits64(P.phi, sbit) ^ (yhi >> ysh)) | (tp_bits64(P.pnn, sbit) ^ (ynn >> ysh));
+        K.knn = __brevll(a_nn) >> 14; K.klo = __brevll(a_lo) >> 14; K.khi = ~(__brevll(a_hi) >> 14) & ~K.knn;
     }
+    return K;
+}
+
+__device__ __forceinline__ int t_ov_exact(const OvPlanes& P, const OvConst& K, int dir, int o, const int16_t* lut, int& olOut) {
+    int ol, bit, sh;
+    if (dir == 0) { ol = min(P.len1 - o, P.len2); bit = P.f1 + o; sh = 0; }                       /* r1[o+k] vs rc(r2)[k] */
+    else { ol = min(P.len1, P.len2 - o); const int pp = min(ol, 50); bit = P.e - o - pp + 1; sh = 50 - pp; }   /* comp(r1[pp-1-t]) vs row2[bit+t] */
+    const uint32_t *Mlo = dir == 0 ? P.alo : P.plo, *Mhi = dir == 0 ? P.ahi : P.phi, *Mnn = dir == 0 ? P.ann : P.pnn;
+    const unsigned long long x = (tp_bits64(Mlo, bit) ^ (K.klo >> sh)) | (tp_bits64(Mhi, bit) ^ (K.khi >> sh)) | (tp_bits64(Mnn, bit) ^ (K.knn >> sh));
     const int mm = __popcll(x & mask64(min(ol, 50)));
     olOut = ol;
     return mm <= (int)lut[ol] ? mm : -1;
@@ -275,6 +277,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
         const int lfix = dir == 0 ? len2 : len1;
         const int nscan = lfix >= F ? max(ncand, 0) : 0;
         int my_o = 1 << 20, my_mm = 0, my_ol = 0;
+        const OvConst K = t_ov_const(P, dir);
         if (nscan > 0) {
             const uint32_t *Mlo = dir == 0 ? P.alo : P.plo, *Mhi = dir == 0 ? P.ahi : P.phi;
             /* X of the complement is ~X, except under N (0 either way; lo = hi = 0 under N in the planes) */
@@ -297,7 +300,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
                     const int bit = 32 * w + sh;
                     const int o = dir == 0 ? bit - f1 : e - (F - 1) - bit;
                     int ol;
-                    const int mm = t_ov_exact(P, dir, o, lut, ol);
+                    const int mm = t_ov_exact(P, K, dir, o, lut, ol);
                     if (mm >= 0) { my_o = o; my_mm = mm; my_ol = ol; break; }
                 }
             }
@@ -305,7 +308,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
             #pragma unroll 1
             for (int o = sub; o < ncand; o += g) {           /* fixed read shorter than the filter: exact test of every candidate */
                 int ol;
-                const int mm = t_ov_exact(P, dir, o, lut, ol);
+                const int mm = t_ov_exact(P, K, dir, o, lut, ol);
                 if (mm >= 0) { my_o = o; my_mm = mm; my_ol = ol; break; }
             }
         }

@@ -349,6 +349,26 @@ int fp_ref_process(const fp_params* p, const fp_counter_layout* L, const fp_batc
     return FP_OK;
 }
 
+// Single worker over the whole batch + the reference's own adapter-string histograms (FilterResult::mAdapter1 / mAdapter2,
+// src/filterresult.cpp:124-180) serialised as "1\tSEQ\tCOUNT\n" / "2\t..." lines in map order.  Returns the number of lines.
+int fp_ref_process_maps(const fp_params* p, const fp_counter_layout* L, const fp_batch* b, int64_t* counters, char* out, int64_t cap, int64_t* used) {
+    Worker w(p, L->cycles);
+    fp_read_result t1, t2;
+    for (int64_t i = 0; i < b->n; i++) {
+        if (p->paired)
+            pe_one(w, p, b->seq1 + i * b->stride, b->qual1 + i * b->stride, b->len1[i], b->seq2 + i * b->stride, b->qual2 + i * b->stride, b->len2[i], &t1, &t2, NULL);
+        else
+            se_one(w, p, b->seq1 + i * b->stride, b->qual1 + i * b->stride, b->len1[i], &t1);
+    }
+    dump_worker(w, p, L, counters);
+    std::string o; int n = 0;
+    for (auto& kv : w.fr->mAdapter1) { o += "1\t" + kv.first + "\t" + std::to_string(kv.second) + "\n"; n++; }
+    for (auto& kv : w.fr->mAdapter2) { o += "2\t" + kv.first + "\t" + std::to_string(kv.second) + "\n"; n++; }
+    *used = (int64_t)o.size();
+    if ((int64_t)o.size() <= cap) memcpy(out, o.data(), o.size());
+    return n;
+}
+
 // Multi-threaded form for the CPU baseline: `nthreads` workers over contiguous ranges, private
 // Stats/FilterResult per worker, summed at the end (what Stats::merge / FilterResult::merge do).
 // out1/out2/ov may be NULL (baseline timing).

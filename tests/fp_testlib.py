@@ -417,3 +417,72 @@ def random_params(rng, paired, lib=None):
         if coin(0.5):
             kw["adapter_seq_r2"] = TRUSEQ_R2[: R(6, len(TRUSEQ_R2))]
     return capi.default_params(paired, lib=lib or oracle(), **kw), kw
+
+
+# ---------------- adapter-string histograms ----------------
+MAX_ADAPTER_REC, LOW_COMPLEXITY_SKIP = 20000, 5000          # src/filterresult.cpp:7-8
+
+
+def _low_complexity(a):                                    # FilterResult::isLowComplexity src/filterresult.cpp:116-123
+    return sum(1 for i in range(len(a) - 1) if a[i] != a[i + 1]) < len(a) // 2
+
+
+def rebuild_adapter_maps(events, arrs, adapters):
+    """What the reference-side shim does with the device's fp_adapter_event list: sort by (unit, key) and replay
+    FilterResult::addAdapterTrimmed (src/filterresult.cpp:124-180) in input order, with its caps and its early return.
+    arrs = the rows AFTER the pass (corrected bytes); adapters = [adapter_seq_r1, adapter_seq_r2, fasta...]."""
+    maps = ({}, {})
+
+    def add(m, s):          # returns False when the reference `return`s out of the whole call
+        if s in m:
+            m[s] += 1
+            return True
+        if len(m) > MAX_ADAPTER_REC or (len(m) > LOW_COMPLEXITY_SKIP and _low_complexity(s)):
+            return False
+        m[s] = 1
+        return True
+
+    def text(e):
+        if e["kind"] == 2:
+            return adapters[e["adapter"]][: e["len"]]
+        row = arrs["seq2" if e["which"] else "seq1"][e["unit"]]
+        return bytes(row[e["start"]: e["start"] + e["len"]]).decode()
+    ev = np.sort(events, order=["unit", "key"])
+    i = 0
+    while i < len(ev):
+        e = ev[i]
+        if e["kind"] == 0:                                   # addAdapterTrimmed(adapter1, adapter2): two events of one unit
+            e2 = ev[i + 1]
+            assert e2["kind"] == 0 and e2["unit"] == e["unit"] and e["which"] == 0 and e2["which"] == 1
+            a1, a2 = text(e), text(e2)
+            ok = True
+            if a1:
+                ok = add(maps[0], a1)
+            if ok and a2:                                    # an early return on adapter1 skips adapter2 (SURVEY App. A.7)
+                add(maps[1], a2)
+            i += 2
+        else:
+            s = text(e)
+            if s:
+                add(maps[1] if e["which"] else maps[0], s)
+            i += 1
+    return maps
+
+
+def ref_adapter_maps(params, arrs, cycles):
+    """The reference's own mAdapter1 / mAdapter2 after a single-worker pass (oracle/_ref)."""
+    a = {k: v.copy() for k, v in arrs.items()}
+    b = capi.batch_from_arrays(a)
+    paired = bool(params.paired)
+    L = capi.make_layout(oracle(), paired, cycles, params.insert_size_max, params=params)
+    cnt = np.zeros(L.total, np.int64)
+    out = C.create_string_buffer(1 << 26); used = C.c_int64()
+    r = ref()
+    r.fp_ref_process_maps.restype = C.c_int
+    r.fp_ref_process_maps.argtypes = [C.POINTER(capi.Params), C.POINTER(capi.CounterLayout), C.POINTER(capi.Batch), C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    r.fp_ref_process_maps(C.byref(params), C.byref(L), C.byref(b), cnt.ctypes.data, out, len(out), C.byref(used))
+    maps = ({}, {})
+    for line in out.raw[:used.value].decode().splitlines():
+        w, s, c = line.split("\t")
+        maps[int(w) - 1][s] = int(c)
+    return maps, capi.CounterView(L, cnt)

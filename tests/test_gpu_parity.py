@@ -204,3 +204,41 @@ def test_sharded_overrepresentation_equals_single_stream(gpu, nshards):
     T.assert_counters_equal(got, want["counters"], what=f"{nshards} shards")
     for ctx in ctxs:
         ctx.close()
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("mode", ["device", "host"])
+@pytest.mark.parametrize("name,paired", [("default", 1), ("cfg4_full", 1), ("fasta_adapters", 1), ("cfg4_full", 0), ("fasta_adapters", 0), ("short_adapter", 1)])
+def test_adapter_string_histograms_equal_reference(gpu, name, paired, mode):
+    """SURVEY 8(f) rank 3: the device records every FilterResult::addAdapterTrimmed call as an fp_adapter_event; replayed on the host in
+    input order they give the reference's mAdapter1 / mAdapter2 maps (`adapter_cutting.read*_adapter_counts` of the JSON report)."""
+    import ctypes as C
+    import torch
+    n, S = 20000, 160
+    p = T.config_params(name, paired)
+    _, arrs = T.synth_host(n, S, paired, 0, 77, 1, 150)
+    want, wcnt = T.ref_adapter_maps(p, arrs, S)
+    assert len(want[0]) > 3
+    ctx = gpu.GpuCtx(p, n, S, S)
+    lib = ctx.lib
+    if mode == "device":
+        cap = 8 * n
+        d_ev = torch.zeros(cap * 16, dtype=torch.uint8, device="cuda:0"); d_n = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+        capi.check(lib.fp_set_event_sink(ctx.h, d_ev.data_ptr(), cap, d_n.data_ptr()), lib)
+        got = gpu.run_gpu(p, arrs, S, mode="device", ctx=ctx)
+        ne = int(d_n.item())
+        ev = d_ev.cpu().numpy().view(capi.EVENT_DTYPE)[:ne].copy()
+    else:
+        cap = 8 * n
+        h_ev = np.zeros(cap, capi.EVENT_DTYPE); h_n = C.c_uint64()
+        capi.check(lib.fp_set_host_event_sink(ctx.h, h_ev.ctypes.data, cap, C.byref(h_n)), lib)
+        got = gpu.run_gpu(p, arrs, S, mode="host", ctx=ctx)
+        ne = h_n.value
+        ev = h_ev[:ne].copy()
+    assert 0 < ne <= cap
+    adapters = [(p.adapter_seq_r1 or b"").decode(), (p.adapter_seq_r2 or b"").decode()] + [p.fasta_adapters[i].decode() for i in range(p.n_fasta_adapters)]
+    maps = T.rebuild_adapter_maps(ev, got["arrs"], adapters)
+    assert maps[0] == want[0]
+    assert maps[1] == want[1]
+    T.assert_counters_equal(got["counters"], wcnt, what="counters")
+    ctx.close()
