@@ -63,6 +63,16 @@ class Batch(C.Structure):
     ]
 
 
+class PackedBatch(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("pitch_b", C.c_int32), ("pitch_q", C.c_int32),
+        ("bases1", C.c_void_p), ("qual1", C.c_void_p), ("len1", C.c_void_p),
+        ("bases2", C.c_void_p), ("qual2", C.c_void_p), ("len2", C.c_void_p),
+        ("npos", C.c_void_p), ("n_npos", C.c_int64), ("npos_cap", C.c_int64),
+        ("flags", C.c_int32), ("_pad", C.c_int32), ("first_read_index", C.c_int64),
+    ]
+
+
 class CounterLayout(C.Structure):
     _fields_ = [
         ("cycles", C.c_int32), ("n_stats", C.c_int32), ("isize_bins", C.c_int32), ("_pad", C.c_int32),
@@ -118,6 +128,10 @@ SYMBOLS = {
                                              C.POINTER(C.c_uint64)]),
     "fp_set_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "fp_set_host_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "fp_host_pack_rows": (C.c_int, [C.POINTER(Batch), C.c_int, C.POINTER(PackedBatch), C.c_int]),
+    "fp_process_se_host_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.c_void_p]),
+    "fp_process_pe_host_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_uint64)]),
     "fp_counters_reset": (C.c_int, [C.c_void_p]),
     "fp_counters_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fp_counters_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
@@ -128,6 +142,13 @@ SYMBOLS = {
     "fp_overrep_post": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "fp_host_overrep_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "fp_gz_is_bgzf": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fp_gz_inflate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
+    "fp_gz_deflate_bound": (C.c_int64, [C.c_int64, C.c_int64]),
+    "fp_gz_deflate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int64, C.c_int, C.c_int]),
+    "fp_gz_open": (C.c_void_p, [C.c_char_p]),
+    "fp_gz_read": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "fp_gz_close": (None, [C.c_void_p]),
     "fp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fp_host_free": (C.c_int, [C.c_void_p]),
     "fp_synth_fill": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),

@@ -93,6 +93,9 @@ struct fp_ctx {
     fp_patch* h_patch[2] = {nullptr, nullptr};
     unsigned int* h_npatch[2] = {nullptr, nullptr};
     uint32_t patch_cap = 0;
+    uint8_t* d_pk[2][4] = {{nullptr}};          /* packed staging per chunk slot: bases1 qual1 bases2 qual2 */
+    fp_npos* d_npos[2] = {nullptr, nullptr};
+    size_t pk_cap_b = 0, pk_cap_q = 0, npos_cap = 0;
     /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
@@ -381,13 +384,15 @@ static void free_staging(fp_ctx* c) {
         cudaFree(c->d_ov[i]); c->d_ov[i] = nullptr;
         cudaFree(c->d_patch[i]); c->d_patch[i] = nullptr;
         cudaFree(c->d_npatch[i]); c->d_npatch[i] = nullptr;
+        for (int k = 0; k < 4; k++) { cudaFree(c->d_pk[i][k]); c->d_pk[i][k] = nullptr; }
+        cudaFree(c->d_npos[i]); c->d_npos[i] = nullptr;
         cudaFree(c->d_ev[i]); c->d_ev[i] = nullptr; cudaFree(c->d_nev[i]); c->d_nev[i] = nullptr;
         if (c->h_ev[i]) cudaFreeHost(c->h_ev[i]); c->h_ev[i] = nullptr;
         if (c->h_nev[i]) cudaFreeHost(c->h_nev[i]); c->h_nev[i] = nullptr;
         if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
         if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
     }
-    c->chunk = 0;
+    c->chunk = 0; c->pk_cap_b = c->pk_cap_q = c->npos_cap = 0;
 }
 
 extern "C" void fp_ctx_destroy(fp_ctx* c) {
@@ -627,6 +632,120 @@ extern "C" int fp_set_host_event_sink(fp_ctx* c, fp_adapter_event* h_events, uin
     return FP_OK;
 }
 
+/* ---------------- packed host rows (fp_packed_batch) ---------------- */
+/* one thread per (read, 16 bases): 4 packed bytes -> 16 ASCII bases, 16 qualities re-pitched; zero fill beyond the read */
+__global__ void fp_unpack_kernel(const uint8_t* __restrict__ pb, const uint8_t* __restrict__ pq, const uint16_t* __restrict__ len, long long n,
+                                 int pitch_b, int pitch_q, int stride, uint8_t* __restrict__ seq, uint8_t* __restrict__ qual) {
+    const int gpr = stride >> 4;                                           /* 16-byte groups per row */
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * gpr) return;
+    const long long r = t / gpr; const int g = (int)(t - r * gpr);
+    const int L = min((int)len[r], stride);
+    const uint8_t* b = pb + r * pitch_b + g * 4; const uint8_t* q = pq + r * pitch_q + g * 16;
+    uint32_t so[4], qo[4];
+    #pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const int p0 = g * 16 + w * 4;
+        uint32_t sv = 0, qv = 0;
+        if (p0 < L) {
+            const uint32_t c = b[w];
+            #pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (p0 + k < L) { sv |= ((0x47544341u >> (8 * ((c >> (2 * k)) & 3u))) & 0xFFu) << (8 * k); qv |= (uint32_t)q[w * 4 + k] << (8 * k); }
+        }
+        so[w] = sv; qo[w] = qv;
+    }
+    *reinterpret_cast<uint4*>(seq + r * stride + g * 16) = make_uint4(so[0], so[1], so[2], so[3]);
+    *reinterpret_cast<uint4*>(qual + r * stride + g * 16) = make_uint4(qo[0], qo[1], qo[2], qo[3]);
+}
+__global__ void fp_unpack_n_kernel(const fp_npos* __restrict__ np, long long cnt, long long unit0, int stride, uint8_t* seq1, uint8_t* seq2) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const fp_npos e = np[i];
+    (e.which ? seq2 : seq1)[((long long)e.unit - unit0) * stride + e.pos] = 'N';
+}
+
+#include <thread>
+extern "C" int fp_host_pack_rows(const fp_batch* rows, int paired, fp_packed_batch* out, int threads) {
+    if (!rows || !out || !out->bases1 || !out->qual1 || !out->len1 || (paired && (!out->bases2 || !out->qual2 || !out->len2))) return set_err(FP_E_INVAL, "null argument");
+    if (rows->n >= ((int64_t)1 << 32)) return set_err(FP_E_TOOLARGE, "batch larger than 2^32");
+    const int64_t n = rows->n; const int S = rows->stride, pb = out->pitch_b, pq = out->pitch_q;
+    if (threads < 1) threads = 1;
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / 4096));
+    std::vector<std::vector<fp_npos>> nl(threads);
+    std::vector<int> bad(threads, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        for (int sd = 0; sd < (paired ? 2 : 1); sd++) {
+            const uint8_t* seq = sd ? rows->seq2 : rows->seq1; const uint8_t* qual = sd ? rows->qual2 : rows->qual1; const uint16_t* len = sd ? rows->len2 : rows->len1;
+            uint8_t* ob = sd ? out->bases2 : out->bases1; uint8_t* oq = sd ? out->qual2 : out->qual1; uint16_t* ol = sd ? out->len2 : out->len1;
+            for (int64_t r = lo; r < hi; r++) {
+                const int L = len[r];
+                if ((L + 3) / 4 > pb || L > pq) { bad[t] = 2; return; }
+                const uint8_t* s = seq + r * S; uint8_t* d = ob + r * pb;
+                int k = 0;
+                for (; k + 8 <= L; k += 8) {                               /* 8 bases per step: all of them A/C/G/T ? -> 16 bits by one multiply */
+                    uint64_t x; memcpy(&x, s + k, 8);
+                    const uint64_t K = 0x0101010101010101ull;
+                    const uint64_t common = (x & 0xE8E8E8E8E8E8E8E8ull) ^ 0x4040404040404040ull;          /* bits 7,6,5 = 010, bit 3 = 0 */
+                    const uint64_t v1 = ((x >> 4) ^ x) & K;                                                  /* bit4 != bit0  (T <-> bit4) */
+                    const uint64_t v2 = ((((x >> 2) & ~(x >> 1)) ^ x)) & K;                                  /* (bit2 & !bit1) != bit0 */
+                    if (common == 0 && v1 == K && v2 == K) {
+                        const uint64_t c2 = (x >> 1) & 0x0303030303030303ull;                                 /* 2-bit codes, one per byte */
+                        const uint32_t lo4 = (uint32_t)c2, hi4 = (uint32_t)(c2 >> 32);                         /* four codes -> one byte by a multiply */
+                        d[k >> 2] = (uint8_t)((lo4 * 0x01041040u) >> 24);
+                        d[(k >> 2) + 1] = (uint8_t)((hi4 * 0x01041040u) >> 24);
+                        continue;
+                    }
+                    for (int j = 0; j < 8; j += 4) {                       /* an N (or something else) in this group: byte by byte */
+                        uint8_t o = 0;
+                        for (int i = 0; i < 4; i++) {
+                            const uint8_t ch = s[k + j + i];
+                            if (ch == 'N') nl[t].push_back(fp_npos{(uint32_t)r, (uint16_t)(k + j + i), (uint8_t)sd, 0});
+                            else if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { bad[t] = 1; return; }
+                            else o |= (uint8_t)(((ch >> 1) & 3) << (2 * i));
+                        }
+                        d[(k + j) >> 2] = o;
+                    }
+                }
+                for (; k < L; k += 4) {
+                    uint8_t o = 0;
+                    for (int i = 0; i < 4 && k + i < L; i++) {
+                        const uint8_t ch = s[k + i];
+                        if (ch == 'N') nl[t].push_back(fp_npos{(uint32_t)r, (uint16_t)(k + i), (uint8_t)sd, 0});
+                        else if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { bad[t] = 1; return; }
+                        else o |= (uint8_t)(((ch >> 1) & 3) << (2 * i));
+                    }
+                    d[k >> 2] = o;
+                }
+                memcpy(oq + r * pq, qual + r * S, L);
+                ol[r] = (uint16_t)L;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < threads; t++) {
+        if (bad[t] == 1) return set_err(FP_E_UNSUPPORTED, "a base outside {A,C,G,T,N}: not representable in packed rows");
+        if (bad[t] == 2) return set_err(FP_E_INVAL, "a read is longer than the packed pitch");
+    }
+    /* exception list sorted by unit: every thread's entries come side by side (read1 then read2 of its range), ranges are in order */
+    int64_t total = 0;
+    for (auto& v : nl) total += (int64_t)v.size();
+    out->n_npos = total;
+    if (total > out->npos_cap) return set_err(FP_E_TOOLARGE, "N exception list too small (n_npos holds the size needed)");
+    int64_t o = 0;
+    for (auto& v : nl) {
+        std::stable_sort(v.begin(), v.end(), [](const fp_npos& a, const fp_npos& b) { return a.unit < b.unit; });
+        if (!v.empty()) memcpy(out->npos + o, v.data(), v.size() * sizeof(fp_npos));
+        o += (int64_t)v.size();
+    }
+    out->n = n; out->flags = rows->flags; out->first_read_index = rows->first_read_index;
+    return FP_OK;
+}
+
 /* ---------------- host-buffer pipeline ---------------- */
 static int ensure_staging(fp_ctx* c) {
     if (c->chunk) return FP_OK;
@@ -649,15 +768,25 @@ static int ensure_staging(fp_ctx* c) {
     return FP_OK;
 }
 
-static const uint32_t PFAST = 16384;   /* patches copied back without waiting for their count */
+/* the whole patch buffer of a chunk rides along with its results (about 2 % of the chunk's input bytes): no second round trip for its count */
 
 static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
-                        fp_patch* hp_out = nullptr, uint64_t hp_cap = 0, uint64_t* hp_n = nullptr) {
+                        fp_patch* hp_out = nullptr, uint64_t hp_cap = 0, uint64_t* hp_n = nullptr, const fp_packed_batch* pk = nullptr) {
     if (hp_n) *hp_n = 0;
     CK(cudaSetDevice(c->device));
     int rc = ensure_staging(c);
     if (rc) return rc;
     if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    if (pk) {                                                  /* packed input: staging for one chunk of packed rows + its N exceptions */
+        if (pk->pitch_b <= 0 || pk->pitch_q <= 0) return set_err(FP_E_INVAL, "bad packed pitch");
+        const size_t nb = (size_t)c->chunk * pk->pitch_b + 64, nq = (size_t)c->chunk * pk->pitch_q + 64;
+        if (nb > c->pk_cap_b || nq > c->pk_cap_q) {
+            CK(cudaDeviceSynchronize());
+            for (int i = 0; i < 2; i++)
+                for (int k = 0; k < (c->p.paired ? 4 : 2); k++) { cudaFree(c->d_pk[i][k]); CK(cudaMalloc(&c->d_pk[i][k], (k & 1) ? nq : nb)); }
+            c->pk_cap_b = nb; c->pk_cap_q = nq;
+        }
+    }
     const bool pe = c->p.paired;
     const int S = c->stride;
     const int64_t n = b->n, CH = c->chunk;
@@ -694,19 +823,21 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         if (pe && c->p.correction_enabled) {
             uint32_t np = *c->h_npatch[slot];
             const int64_t lo = pend[slot].lo;
-            if (np > PFAST && np <= c->patch_cap)
-                CK(cudaMemcpy(c->h_patch[slot] + PFAST, c->d_patch[slot] + PFAST, (size_t)(np - PFAST) * sizeof(fp_patch), cudaMemcpyDeviceToHost));
             if (np <= c->patch_cap) {
                 for (uint32_t k = 0; k < np; k++) {
                     const fp_patch& pt = c->h_patch[slot][k];
-                    uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * S;
-                    uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * S;
-                    sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
+                    if (!pk) {
+                        uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * S;
+                        uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * S;
+                        sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
+                    }
                     if (hp_n) {                                  /* caller's list: pair index relative to the whole host batch */
                         if (*hp_n < hp_cap) { hp_out[*hp_n] = pt; hp_out[*hp_n].pair = (uint32_t)(lo + pt.pair); }
                         (*hp_n)++;
                     }
                 }
+            } else if (pk) {
+                if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
             } else {   /* patch list overflow: take the corrected rows wholesale */
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
                 const size_t bytes = (size_t)pend[slot].cnt * S;
@@ -726,6 +857,38 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         const int64_t lo = ci * CH, cnt = std::min(CH, n - lo);
         cudaStream_t st = c->stream[slot];
         const size_t bytes = (size_t)cnt * S;
+        if (pk) {
+            /* packed rows up, then a small kernel restores the stride rows in HBM (6 TB/s: nothing next to the PCIe transfer) */
+            const size_t bb = (size_t)cnt * pk->pitch_b, qb = (size_t)cnt * pk->pitch_q;
+            CK(cudaMemcpyAsync(c->d_pk[slot][0], pk->bases1 + lo * pk->pitch_b, bb, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_pk[slot][1], pk->qual1 + lo * pk->pitch_q, qb, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_stage_len[slot][0], pk->len1 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+            if (pe) {
+                CK(cudaMemcpyAsync(c->d_pk[slot][2], pk->bases2 + lo * pk->pitch_b, bb, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(c->d_pk[slot][3], pk->qual2 + lo * pk->pitch_q, qb, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(c->d_stage_len[slot][1], pk->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st));
+            }
+            const long long thr = (long long)cnt * (S >> 4);
+            fp_unpack_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(c->d_pk[slot][0], c->d_pk[slot][1], c->d_stage_len[slot][0], cnt, pk->pitch_b, pk->pitch_q, S,
+                                                                          c->d_stage[slot][0], c->d_stage[slot][1]);
+            if (pe) fp_unpack_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(c->d_pk[slot][2], c->d_pk[slot][3], c->d_stage_len[slot][1], cnt, pk->pitch_b, pk->pitch_q, S,
+                                                                                  c->d_stage[slot][2], c->d_stage[slot][3]);
+            /* the chunk's slice of the sorted 'N' list */
+            const fp_npos* nb0 = std::lower_bound(pk->npos, pk->npos + pk->n_npos, (uint32_t)lo, [](const fp_npos& e, uint32_t v) { return e.unit < v; });
+            const fp_npos* nb1 = std::lower_bound(nb0, (const fp_npos*)(pk->npos + pk->n_npos), (uint32_t)(lo + cnt), [](const fp_npos& e, uint32_t v) { return e.unit < v; });
+            const long long nn = nb1 - nb0;
+            if (nn > 0) {
+                if ((size_t)nn > c->npos_cap) {
+                    CK(cudaDeviceSynchronize());
+                    for (int i = 0; i < 2; i++) { cudaFree(c->d_npos[i]); CK(cudaMalloc(&c->d_npos[i], (size_t)(nn + nn / 2 + 1024) * sizeof(fp_npos))); }
+                    c->npos_cap = (size_t)(nn + nn / 2 + 1024);
+                }
+                CK(cudaMemcpyAsync(c->d_npos[slot], nb0, (size_t)nn * sizeof(fp_npos), cudaMemcpyHostToDevice, st));
+                fp_unpack_n_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(c->d_npos[slot], nn, lo, S, c->d_stage[slot][0], pe ? c->d_stage[slot][2] : nullptr);
+            }
+            CK(cudaGetLastError());
+        } else {
         CK(cudaMemcpyAsync(c->d_stage[slot][0], b->seq1 + lo * S, bytes, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(c->d_stage[slot][1], b->qual1 + lo * S, bytes, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(c->d_stage_len[slot][0], b->len1 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
@@ -734,6 +897,7 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             CK(cudaMemcpyAsync(c->d_stage[slot][3], b->qual2 + lo * S, bytes, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->d_stage_len[slot][1], b->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st));
+        }
         }
         if (want_ev) {
             CK(cudaMemsetAsync(c->d_nev[slot], 0, 4, st));
@@ -761,9 +925,8 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
             if (ov) CK(cudaMemcpyAsync(ov + lo, c->d_ov[slot], (size_t)cnt * sizeof(fp_ov_result), cudaMemcpyDeviceToHost, st));
             if (c->p.correction_enabled) {
-                /* count + the first PFAST patches ride along asynchronously (corrections are sparse); finish() fetches the rest if any */
                 CK(cudaMemcpyAsync(c->h_npatch[slot], c->d_npatch[slot], 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)std::min<uint32_t>(PFAST, c->patch_cap) * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)c->patch_cap * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
             }
         }
         pend[slot].lo = lo; pend[slot].cnt = cnt; pend[slot].active = true;
@@ -782,6 +945,23 @@ extern "C" int fp_process_pe_host(fp_ctx* c, const fp_batch* b, fp_read_result* 
     if (!c || !b || !out1 || !out2) return set_err(FP_E_INVAL, "null argument");
     if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
     return process_host(c, b, out1, out2, ov);
+}
+
+extern "C" int fp_process_se_host_packed(fp_ctx* c, const fp_packed_batch* pb, fp_read_result* out1) {
+    if (!c || !pb || !out1) return set_err(FP_E_INVAL, "null argument");
+    if (c->p.paired) return set_err(FP_E_INVAL, "ctx was created for paired-end data");
+    fp_batch b; memset(&b, 0, sizeof(b));
+    b.n = pb->n; b.stride = c->stride; b.flags = pb->flags; b.first_read_index = pb->first_read_index;
+    return process_host(c, &b, out1, nullptr, nullptr, nullptr, 0, nullptr, pb);
+}
+
+extern "C" int fp_process_pe_host_packed(fp_ctx* c, const fp_packed_batch* pb, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                                         fp_patch* patches, uint64_t patch_cap, uint64_t* n_patches) {
+    if (!c || !pb || !out1 || !out2 || (patch_cap > 0 && (!patches || !n_patches))) return set_err(FP_E_INVAL, "null argument");
+    if (!c->p.paired) return set_err(FP_E_INVAL, "ctx was created for single-end data");
+    fp_batch b; memset(&b, 0, sizeof(b));
+    b.n = pb->n; b.stride = c->stride; b.flags = pb->flags; b.first_read_index = pb->first_read_index;
+    return process_host(c, &b, out1, out2, ov, patches, patch_cap, n_patches, pb);
 }
 
 extern "C" int fp_process_pe_host_patches(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,

@@ -76,6 +76,8 @@ size_t fp_abi_sizeof(int which) {
         case 6: return sizeof(fp_fastq_rec);
         case 7: return sizeof(fp_fastq_info);
         case 8: return sizeof(fp_adapter_event);
+        case 9: return sizeof(fp_packed_batch);
+        case 10: return sizeof(fp_npos);
         default: return 0;
     }
 }

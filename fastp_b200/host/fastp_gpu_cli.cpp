@@ -10,6 +10,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <vector>
 #include "fastp_host.h"
 
 using namespace fastp_b200;
@@ -28,6 +29,7 @@ int main(int argc, char** argv) {
     std::string in1, in2, out1, out2, json;
     int packSize = 1 << 16, maxLen = 0;
     bool deviceFastq = false, phred64 = false;
+    int zlevel = 4, zthreads = 8;          /* -z / --compression (src/main.cpp:50), host threads for .gz output */
     size_t chunkBytes = 0;                 /* text path: bytes read per side per step (default: about one device batch) */
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -60,6 +62,7 @@ int main(int argc, char** argv) {
         else if (a == "--overlap_diff_percent_limit") opt.overlapDiffPercentLimit = atoi(next());
         else if (a == "--device_fastq") deviceFastq = true; else if (a == "-6" || a == "--phred64") phred64 = true;
         else if (a == "--chunk_bytes") chunkBytes = (size_t)atoll(next());
+        else if (a == "-z" || a == "--compression") zlevel = std::min(9, std::max(1, atoi(next()))); else if (a == "--zthreads") zthreads = std::max(1, atoi(next()));
         else if (a == "--max_read_len") maxLen = atoi(next()); else if (a == "--pack_size") packSize = atoi(next());
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -68,9 +71,16 @@ int main(int argc, char** argv) {
     std::ifstream f1(in1), f2;
     if (opt.paired) f2.open(in2);
     if (!f1 || (opt.paired && !f2)) { fprintf(stderr, "cannot open input\n"); return 1; }
+    if (!deviceFastq && ((in1.size() > 3 && in1.compare(in1.size() - 3, 3, ".gz") == 0))) { fprintf(stderr, "compressed input needs --device_fastq\n"); return 2; }
     if (maxLen == 0) {                                  /* Evaluator::evaluateSeqLen peeks at the first records (src/evaluator.cpp:54-76) */
-        std::ifstream peek(in1); std::string l; int n = 0; maxLen = 151;
-        while (n < 4000 && std::getline(peek, l)) { if (n % 4 == 1) maxLen = std::max(maxLen, (int)l.size()); n++; }
+        std::vector<uint8_t> head(1 << 20);
+        void* gp = fp_gz_open(in1.c_str());
+        const int64_t got = gp ? fp_gz_read(gp, head.data(), (int64_t)head.size()) : 0;
+        fp_gz_close(gp);
+        maxLen = 151;
+        int n = 0; size_t ls = 0;
+        for (size_t i = 0; i < (size_t)std::max<int64_t>(got, 0) && n < 4000; i++)
+            if (head[i] == '\n') { if (n % 4 == 1) maxLen = std::max(maxLen, (int)(i - ls)); n++; ls = i + 1; }
         maxLen += 64;
     }
     if (chunkBytes == 0) chunkBytes = (size_t)packSize * (size_t)(2 * maxLen + 64);
@@ -82,32 +92,51 @@ int main(int argc, char** argv) {
     if (deviceFastq) {
         /* text path: raw file chunks go to the device, which parses, filters and re-encodes them (fp_fastq_process_host);
            whatever a chunk's last, incomplete record (or the longer side of a pair) leaves over is carried into the next chunk */
+        /* .gz / BGZF inputs are inflated on the host (fp_gz_open: zlib streaming reader, plain files pass through), .gz outputs are written as
+           one gzip member per round, compressed by `zthreads` host threads (what the reference's writer threads do per pack,
+           src/writerthread.cpp:118-168) */
         std::string buf1, buf2;
         bool eof1 = false, eof2 = !opt.paired;
-        auto fill = [&](std::ifstream& f, std::string& buf, bool& eof) {
+        void* g1 = fp_gz_open(in1.c_str()); void* g2 = opt.paired ? fp_gz_open(in2.c_str()) : nullptr;
+        if (!g1 || (opt.paired && !g2)) { fprintf(stderr, "cannot open input\n"); return 1; }
+        auto fill = [&](void* g, std::string& buf, bool& eof) {
             if (eof) return;
             const size_t old = buf.size();
             buf.resize(old + chunkBytes);
-            f.read(&buf[old], (std::streamsize)chunkBytes);
-            const size_t got = (size_t)f.gcount();
-            buf.resize(old + got);
-            if (got < chunkBytes) eof = true;
+            const int64_t got = fp_gz_read(g, reinterpret_cast<uint8_t*>(&buf[old]), (int64_t)chunkBytes);
+            if (got < 0) { fprintf(stderr, "fastp_gpu_cli: corrupt compressed input\n"); exit(1); }
+            buf.resize(old + (size_t)got);
+            if ((size_t)got < chunkBytes) eof = true;
+        };
+        auto gz_name = [](const std::string& n) { return n.size() > 3 && n.compare(n.size() - 3, 3, ".gz") == 0; };
+        const bool zout1 = gz_name(out1), zout2 = gz_name(out2);
+        std::vector<uint8_t> zbuf;
+        auto emit = [&](std::ofstream& o, const std::string& t, bool z) {
+            if (!o.is_open() || t.empty()) return;
+            if (!z) { o << t; return; }
+            int64_t nz = 0;
+            zbuf.resize((size_t)fp_gz_deflate_bound((int64_t)t.size(), 1 << 20));
+            if (fp_gz_deflate(reinterpret_cast<const uint8_t*>(t.data()), (int64_t)t.size(), zbuf.data(), (int64_t)zbuf.size(), &nz, 1 << 20, zlevel, zthreads) != FP_OK) {
+                fprintf(stderr, "fastp_gpu_cli: gzip output failed\n"); exit(1);
+            }
+            o.write(reinterpret_cast<const char*>(zbuf.data()), (std::streamsize)nz);
         };
         for (;;) {
-            fill(f1, buf1, eof1);
-            if (opt.paired) fill(f2, buf2, eof2);
+            fill(g1, buf1, eof1);
+            if (opt.paired) fill(g2, buf2, eof2);
             const bool final = eof1 && eof2;
             std::string s1, s2; size_t c1 = 0, c2 = 0; long units = 0;
             if (!worker.processFastqText(buf1.data(), buf1.size(), buf2.data(), buf2.size(), final, phred64, &s1, &s2, &c1, &c2, &units)) {
                 fprintf(stderr, "fastp_gpu_cli: %s\n", worker.error().c_str()); return 1;
             }
-            if (o1.is_open()) o1 << s1;
-            if (o2.is_open()) o2 << s2;
+            emit(o1, s1, zout1);
+            emit(o2, s2, zout2);
             buf1.erase(0, c1); if (opt.paired) buf2.erase(0, c2);
             if (worker.inputEnded()) break;                    /* a reader gave up on a record: the reference stops reading there */
             if (final && (units == 0 || (buf1.empty() && buf2.empty()))) break;
             if (final && c1 == 0 && c2 == 0) break;
         }
+        fp_gz_close(g1); fp_gz_close(g2);
     } else
     for (;;) {
         ReadPack* lp = new ReadPack{new Read*[packSize], 0};

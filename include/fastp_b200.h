@@ -316,6 +316,32 @@ int  fp_process_pe_host_patches(fp_ctx* ctx, const fp_batch* b, fp_read_result* 
 int  fp_set_event_sink(fp_ctx* ctx, fp_adapter_event* d_events, uint32_t cap, uint32_t* d_count);
 int  fp_set_host_event_sink(fp_ctx* ctx, fp_adapter_event* h_events, uint64_t cap, uint64_t* n_events);
 
+/* ---------------- packed host rows: the end-to-end path is PCIe-bound, so send fewer bytes ----------------
+ * 2 bits per base (code = (ascii >> 1) & 3: A0 C1 T2 G3; base k of a read in bits 2(k&3) of byte k>>2), qualities as they are, rows at
+ * the caller's pitch (no padding to the device stride), 'N' positions as a sorted exception list: 2x150 bp -> about 385 bytes per
+ * pair instead of 644.  fp_host_pack_rows packs host SoA rows with `threads` host threads (word-at-a-time fast path for runs of
+ * A/C/G/T; FP_E_UNSUPPORTED if a base outside {A,C,G,T,N} turns up -- send that batch through fp_process_*_host instead).
+ * fp_process_*_host_packed = fp_process_*_host on packed input: H2D of the packed arrays, a small kernel restores the stride rows in
+ * HBM, then the same chain.  The packed buffers are never modified; base corrections come back as the patch list only.        */
+typedef struct fp_npos { uint32_t unit; uint16_t pos; uint8_t which; uint8_t _pad; } fp_npos;   /* base `pos` of read `which` of unit `unit` is 'N' */
+typedef struct fp_packed_batch {
+    int64_t   n;
+    int32_t   pitch_b, pitch_q;     /* bytes per read in bases* / qual* (pitch_b >= (longest read + 3) / 4, pitch_q >= longest read) */
+    uint8_t  *bases1, *qual1;       /* [n][pitch_b], [n][pitch_q] */
+    uint16_t *len1;
+    uint8_t  *bases2, *qual2;       /* PE only */
+    uint16_t *len2;
+    fp_npos  *npos;                 /* sorted by unit */
+    int64_t   n_npos, npos_cap;
+    int32_t   flags;                /* FP_B_INDEXED as in fp_batch */
+    int32_t   _pad;
+    int64_t   first_read_index;
+} fp_packed_batch;
+int  fp_host_pack_rows(const fp_batch* rows, int paired, fp_packed_batch* out, int threads);
+int  fp_process_se_host_packed(fp_ctx* ctx, const fp_packed_batch* pb, fp_read_result* out1);
+int  fp_process_pe_host_packed(fp_ctx* ctx, const fp_packed_batch* pb, fp_read_result* out1, fp_read_result* out2, fp_ov_result* ov,
+                               fp_patch* patches, uint64_t patch_cap, uint64_t* n_patches);
+
 /* Counter block. fetch synchronises the ctx's streams, finalises (totals per cycle) and copies
  * layout.total int64 words to host_out. */
 int  fp_counters_reset(fp_ctx* ctx);
@@ -413,6 +439,20 @@ int  fp_dup_reset(fp_ctx* ctx);
  * (FP_E_TOOLARGE if out_cap is smaller).  seqlen = Options::seqLen1/2.  The result feeds fp_params.overrep_seqs1/2. */
 int  fp_host_overrep_candidates(const uint8_t* seq, const uint16_t* len, int64_t n, int32_t stride, int32_t seqlen,
                                 char* out, int64_t out_cap, int32_t* n_out, int64_t* bytes_out);
+
+/* ---------------- gzip / BGZF either side of the text path (host code on zlib) ----------------
+ * fp_gz_inflate: a whole compressed buffer -> text; BGZF (src/bgzf.h:165-195) block-parallel on `threads` host threads, other gzip streams
+ * member after member (src/fastqreader.cpp:88-209).  *n_out = decompressed size (FP_E_TOOLARGE if cap is smaller, BGZF only knows it upfront).
+ * fp_gz_deflate: text -> concatenated gzip members of member_bytes input bytes each, compressed in parallel -- one member per output pack
+ * is what the reference's writer threads produce (src/writerthread.cpp:118-168).  fp_gz_open / _read / _close: streaming reader (plain
+ * files pass through) for callers that feed fp_fastq_process_host chunk by chunk.                                                  */
+int     fp_gz_is_bgzf(const uint8_t* in, int64_t n);
+int     fp_gz_inflate(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t cap, int64_t* n_out, int threads);
+int64_t fp_gz_deflate_bound(int64_t n_in, int64_t member_bytes);
+int     fp_gz_deflate(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t cap, int64_t* n_out, int64_t member_bytes, int level, int threads);
+void*   fp_gz_open(const char* path);
+int64_t fp_gz_read(void* h, uint8_t* buf, int64_t cap);
+void    fp_gz_close(void* h);
 
 /* Pinned host memory helpers for the staging shim. */
 int  fp_host_alloc(void** p, size_t bytes);

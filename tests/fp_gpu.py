@@ -62,6 +62,25 @@ def device_batch(arrs, device=0):
     return b, t
 
 
+def pack_rows(lib, b, arrs, paired, threads=4):
+    """fp_host_pack_rows into fresh numpy buffers; returns (PackedBatch, keepalive dict)."""
+    n, S = arrs["seq1"].shape
+    L = int(max(arrs["len1"].max(initial=0), arrs["len2"].max(initial=0) if paired else 0))
+    pitch_b, pitch_q = (L + 3) // 4 + 1, L + 2
+    keep = {"npos": np.zeros(max(2 * n, 1024) * 8 + 64, np.uint8)}
+    pb = capi.PackedBatch()
+    pb.pitch_b, pb.pitch_q = pitch_b, pitch_q
+    for sd in ("1", "2")[: 2 if paired else 1]:
+        keep["bases" + sd] = np.zeros(max(n, 1) * pitch_b + 64, np.uint8); keep["qual" + sd] = np.zeros(max(n, 1) * pitch_q + 64, np.uint8)
+        keep["len" + sd] = np.zeros(max(n, 1), np.uint16)
+        setattr(pb, "bases" + sd, keep["bases" + sd].ctypes.data); setattr(pb, "qual" + sd, keep["qual" + sd].ctypes.data); setattr(pb, "len" + sd, keep["len" + sd].ctypes.data)
+    pb.npos = keep["npos"].ctypes.data; pb.npos_cap = keep["npos"].size // 8
+    capi.check(lib.fp_host_pack_rows(C.byref(b), 1 if paired else 0, C.byref(pb), threads), lib)
+    keep["bytes"] = (2 if paired else 1) * n * (pitch_b + pitch_q + 2) + pb.n_npos * 8
+    pb._keep = keep
+    return pb, keep
+
+
 def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
     """Run the CUDA hot path over a COPY of arrs; same return shape as fp_testlib.run_cpu."""
     torch = _torch()
@@ -107,6 +126,20 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
         for k in a:
             a[k] = t[k].cpu().numpy()
         extra = {"patches": patches, "n_patches": npatch} if paired else {}
+    elif mode == "packed":
+        # fp_host_pack_rows -> fp_process_*_host_packed; the corrected rows are rebuilt from the returned patch list
+        b = capi.batch_from_arrays(a)
+        pb, keep = pack_rows(lib, b, a, paired)
+        cap = 4 * n + 16
+        hp = np.zeros(cap, capi.PATCH_DTYPE); hn = C.c_uint64()
+        if paired:
+            capi.check(lib.fp_process_pe_host_packed(ctx.h, C.byref(pb), out1.ctypes.data, out2.ctypes.data, ov.ctypes.data, hp.ctypes.data, cap, C.byref(hn)), lib)
+            for pt in hp[:hn.value]:
+                side = "2" if pt["which"] else "1"
+                a["seq" + side][pt["pair"], pt["pos"]] = pt["base"]; a["qual" + side][pt["pair"], pt["pos"]] = pt["qual"]
+        else:
+            capi.check(lib.fp_process_se_host_packed(ctx.h, C.byref(pb), out1.ctypes.data), lib)
+        extra = {"packed_bytes": keep["bytes"]}
     else:
         b = capi.batch_from_arrays(a)
         if paired:

@@ -242,3 +242,15 @@ def test_adapter_string_histograms_equal_reference(gpu, name, paired, mode):
     assert maps[1] == want[1]
     T.assert_counters_equal(got["counters"], wcnt, what="counters")
     ctx.close()
+
+
+@pytest.mark.parametrize("name,paired,L,S", [("cfg3_overlap_correction", 1, 150, 160), ("cfg4_full", 1, 150, 160), ("cfg2_cut_right_polyg", 0, 150, 160),
+                                             ("cfg4_full", 1, 250, 256), ("default", 1, 100, 112)])
+def test_packed_host_rows(gpu, name, paired, L, S):
+    """the packed end-to-end entry points (2-bit bases, N exception list, unpadded qualities; H2D of ~60 % of the bytes, rows restored
+    on the device) give the same records, counters and -- through the patch list -- corrected rows as the oracle"""
+    p = T.config_params(name, paired)
+    _, arrs = T.synth_host(300000 if L == 150 and paired else 20000, S, paired, 5, 44, 1, L)      # the large one crosses a host chunk
+    want = T.run_cpu("oracle", p, arrs, S)
+    got = gpu.run_gpu(p, arrs, S, mode="packed")
+    T.assert_results_equal(got, want, paired, what=f"packed {name}")
