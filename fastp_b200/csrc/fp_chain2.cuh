@@ -1366,12 +1366,22 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                                 clo = __byte_perm(clo, chi, 0x5432); chi = __byte_perm(chi, cc, 0x7632);
                                 const int rem = n - 8 * k;                   /* valid bases from this step on */
                                 if (!((qw.x | qw.y) & 0x80808080u)) {        /* every quality < 128 (else the exact loop below) */
-                                    #pragma unroll
-                                    for (int b8 = 0; b8 < 8; b8++) {
-                                        const uint32_t w = b8 < 4 ? qw.x : qw.y;
-                                        const int bb = b8 & 3;
-                                        const uint32_t sh = bb == 0 ? (w << 4) : (w >> (8 * bb - 4));
-                                        smem_inc_gt(qaddr | (sh & 0xFF0u), rem, b8);
+                                    if (rem >= 8) {                          /* the usual step: all eight bases count, no predicates */
+                                        #pragma unroll
+                                        for (int b8 = 0; b8 < 8; b8++) {
+                                            const uint32_t w = b8 < 4 ? qw.x : qw.y;
+                                            const int bb = b8 & 3;
+                                            const uint32_t sh = bb == 0 ? (w << 4) : (w >> (8 * bb - 4));
+                                            smem_inc(qaddr | (sh & 0xFF0u));
+                                        }
+                                    } else {
+                                        #pragma unroll
+                                        for (int b8 = 0; b8 < 8; b8++) {
+                                            const uint32_t w = b8 < 4 ? qw.x : qw.y;
+                                            const int bb = b8 & 3;
+                                            const uint32_t sh = bb == 0 ? (w << 4) : (w >> (8 * bb - 4));
+                                            smem_inc_gt(qaddr | (sh & 0xFF0u), rem, b8);
+                                        }
                                     }
                                 } else {
                                     #pragma unroll 1
@@ -1402,11 +1412,19 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                             #pragma unroll 1
                             for (int g8 = 0; g8 < 4; g8++) {               /* 8 windows per step: W = Z bits [16*g8, 16*g8 + 32) */
                                 const uint32_t W = __funnelshift_r(g8 < 2 ? Z0 : Z1, g8 < 2 ? Z1 : Z2, (g8 & 1) * 16);
-                                const uint32_t v8 = vwin >> (8 * g8);
-                                #pragma unroll
-                                for (int pp = 0; pp < 8; pp++) {           /* byte offset of the bin = field*4 | side*4096 */
-                                    const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
-                                    smem_inc((v8 & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy);
+                                const uint32_t v8 = (vwin >> (8 * g8)) & 0xFFu;
+                                if (v8 == 0xFFu) {                         /* the usual step: eight countable windows, no selects */
+                                    #pragma unroll
+                                    for (int pp = 0; pp < 8; pp++) {       /* byte offset of the bin = field*4 | side*4096 */
+                                        const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
+                                        smem_inc(kaddr | (f4 & 0xFFCu));
+                                    }
+                                } else if (v8) {
+                                    #pragma unroll
+                                    for (int pp = 0; pp < 8; pp++) {
+                                        const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
+                                        smem_inc((v8 & (1u << pp)) ? (kaddr | (f4 & 0xFFCu)) : kdummy);
+                                    }
                                 }
                             }
                         }
