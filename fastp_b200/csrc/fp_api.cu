@@ -194,7 +194,7 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     sl.off_queue = (int)g; g += (size_t)sides * T * 2 * 8;
     if (sides == 2) {                                                      /* base correction: work list + per-row masks of corrected positions */
         sl.cm_words = (S + 31) / 32;
-        sl.off_corr = (int)g; g += (size_t)FP_CORR_CAP * 4;
+        sl.off_corr = (int)g; g += (size_t)FP_CW * FP_CORR_CAP * 4 + FP_CW * 4;      /* one list (+ length) per warp */
         sl.off_cm = (int)g; g += (size_t)sides * T * sl.cm_words * 4;
     }
     sl.group_stride = (int)align_up(g, 128);

@@ -611,7 +611,7 @@ __device__ __noinline__ int t_correct(const TRead r1, const TRead r2, uint32_t* 
  * still unmodified row and its new bases from the partner read (position y of the rewritten read faces c - y of the other).
  * entry = row | which << 7 | P << 8 | Pp << 18   (which = the read that is rewritten, P its row position, Pp the partner's)
  * ------------------------------------------------------------------------------------------------ */
-#define FP_CORR_CAP 1024
+#define FP_CORR_CAP 128                /* corrections of ONE warp-step (8 pairs); more go the sequential way */
 __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, int PW, const fp_ov_result ov, int row, int sub, int g,
                                               uint32_t* list, int* nlist, uint32_t* cm1, uint32_t* cm2) {
     FP_SMEM(r1.qual);    FP_SMEM(r2.qual);    FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(list);    FP_SMEM(nlist);    FP_SMEM(cm1);    FP_SMEM(cm2);
@@ -624,11 +624,14 @@ __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, in
     const uint32_t *pl1 = r1.pl, *pl2 = r2.pl;
     const int e = r2.front + r2.len - 1, jb = r2.len - 1 - start2;           /* rc(r2) index of overlap position 0 */
     #pragma unroll 1
-    for (int k = sub; k * 32 < ol; k += g) {                                 /* the group's lanes take the 32-position chunks in turn */
+    for (int k = 0; k * 32 < ol; k++) {
         const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
         const uint32_t rn = __brev(tp_bits_z(pl2 + 2 * PW, s0));
         const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
         uint32_t todo = ((tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn)) & low_mask(ol - 32 * k);
+        /* a low-quality tail puts its mismatches side by side: the group's lanes take the positions i with i % g == sub, so one
+           bad tail is shared by all of them */
+        todo &= (g == 4 ? 0x11111111u : g == 2 ? 0x55555555u : 0xFFFFFFFFu) << sub;
         #pragma unroll 1
         while (todo) {
             const int i = 32 * k + __ffs(todo) - 1;
@@ -1241,7 +1244,8 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
     unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
     int* s_qn = reinterpret_cast<int*>(gsm + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
     sinks.q = s_queue; sinks.qn = &s_qn[0];
-    uint32_t* s_corr = reinterpret_cast<uint32_t*>(gsm + sl.off_corr);      /* [FP_CORR_CAP] base-correction work list (PE); its length is s_qn[4] */
+    uint32_t* s_corr = reinterpret_cast<uint32_t*>(gsm + sl.off_corr) + warp * FP_CORR_CAP;   /* [FP_CW][FP_CORR_CAP] base-correction work list of each warp (PE) */
+    int* s_ncorr = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(gsm + sl.off_corr) + FP_CW * FP_CORR_CAP) + warp;   /* its length */
     uint32_t* s_cm = reinterpret_cast<uint32_t*>(gsm + sl.off_cm);          /* [SIDES][T][CMW] corrected positions of every row */
     const int CMW = sl.cm_words;
 
@@ -1313,7 +1317,7 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                 tma_bulk_g2s(tile_seq[1], a.b.seq2 + row0 * S, bytes, mbar);
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
-            s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0; s_qn[4] = 0;     /* request queue / removal items / correction list: next used after the phase-A barrier */
+            s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0;     /* request queue / removal items: next used after the phase-A barrier */
         }
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
            mbarrier every thread waits on itself: no CTA barrier here */
@@ -1528,25 +1532,27 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     else ovA = ov;
                     need_correct = both && c_p.correction && !ovA.has_gap && ovA.overlapped && ovA.diff != 0;       /* :443,:453-456 */
                 }
-                /* ---- base correction (:453-456): the pair's lanes decide, the whole group works the list, one lane per correction ---- */
+                /* ---- base correction (:453-456): the pairs' lanes decide, then the WARP works its own list, one lane per correction
+                        (everything a correction touches belongs to one of this warp's pairs: warp-level synchronisation is enough) ---- */
                 bool corr_overflow = false;
                 const bool distributed = need_correct && clean1 && clean2;
                 if (PAIRED && c_p.correction) {
+                    if (lane == 0) *s_ncorr = 0;
+                    __syncwarp();
                     if (distributed)
-                        corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, s_corr, &s_qn[4], s_cm + rr * CMW, s_cm + (T + rr) * CMW);
-                    GSYNC();
-                    const int ncorr = min(s_qn[4], FP_CORR_CAP);
-                    for (int i = tid; i < ncorr; i += FP_CT)
+                        corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, s_corr, s_ncorr, s_cm + rr * CMW, s_cm + (T + rr) * CMW);
+                    __syncwarp();
+                    const int ncorr = min(*s_ncorr, FP_CORR_CAP);
+                    for (int i = lane; i < ncorr; i += 32)
                         t_correct_item(s_corr[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (s_corr[i] & 0x7F)));
-                    GSYNC();
-                    for (int i = tid; i < ncorr; i += FP_CT) {
+                    __syncwarp();
+                    for (int i = lane; i < ncorr; i += 32) {
                         const uint32_t en = s_corr[i];
                         const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
                         t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
                                         (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
                     }
-                    GSYNC();
-                    if (tid == 0) s_qn[4] = 0;                 /* next round of this tile (if any) starts an empty list; read again only after the next barrier */
+                    __syncwarp();
                 }
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
