@@ -24,7 +24,7 @@ def lib():
 def declared_symbols():
     h = open(os.path.join(ROOT, "include", "fastp_b200.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    names = set(re.findall(r"^\s*(?:int|void|size_t|const char\*)\s+\*?\s*(fp_\w+)\s*\(", h, flags=re.M))
+    names = set(re.findall(r"^\s*(?:int|void|void\*|size_t|int64_t|const char\*)\s+\*?\s*(fp_\w+)\s*\(", h, flags=re.M))
     return names
 
 
@@ -43,6 +43,9 @@ def test_struct_sizes_match(lib):
     assert lib.fp_abi_sizeof(3) == capi.OV_RESULT_DTYPE.itemsize == 8
     assert lib.fp_abi_sizeof(4) == capi.PATCH_DTYPE.itemsize == 12
     assert lib.fp_abi_sizeof(5) == C.sizeof(capi.CounterLayout)
+    assert lib.fp_abi_sizeof(8) == capi.EVENT_DTYPE.itemsize == 16
+    assert lib.fp_abi_sizeof(9) == C.sizeof(capi.PackedBatch)
+    assert lib.fp_abi_sizeof(10) == 8
 
 
 def test_defaults_mirror_reference_options(lib):
