@@ -157,6 +157,8 @@ SYMBOLS = {
     "fp_dup_check": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p]),
     "fp_dup_totals": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fp_dup_reset": (C.c_int, [C.c_void_p]),
+    "fp_set_dup_flags": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fp_fastq_set_dedup": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "fp_fastq_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.POINTER(FastqInfo)]),
     "fp_fastq_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

@@ -109,6 +109,9 @@ struct fp_ctx {
     uint64_t* d_dup_primes = nullptr;
     unsigned long long* d_dup_count = nullptr;
     int64_t dup_total = 0;
+    const uint8_t* dup_flags = nullptr;     /* fp_set_dup_flags: --dedup flags of the batch the next launch works on */
+    int fq_dup_level = 0, fq_dedup = 0;     /* fp_fastq_set_dedup */
+    Buf fq_dupflags;
     Buf dup_pos, dup_keys, dup_vals;
     /* kernel timing */
     std::vector<EvPair> evs;
@@ -404,7 +407,7 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
         fp_ctx::Buf* all[] = {&c->fq_term, &c->fq_bcnt, &c->fq_agg, &c->fq_bstate, &c->fq_brec, &c->fq_recline, &c->fq_recend, &c->fq_info, &c->fq_bsum,
                               &c->fqh_text[0], &c->fqh_text[1], &c->fqh_seq[0], &c->fqh_seq[1], &c->fqh_qual[0], &c->fqh_qual[1], &c->fqh_len[0], &c->fqh_len[1],
                               &c->fqh_recs[0], &c->fqh_recs[1], &c->fqh_res[0], &c->fqh_res[1], &c->fqh_ov, &c->fqh_out[0], &c->fqh_out[1],
-                              &c->fqh_outbuf[0][0], &c->fqh_outbuf[0][1], &c->fqh_outbuf[1][0], &c->fqh_outbuf[1][1], &c->fqh_recend[0], &c->fqh_recend[1]};
+                              &c->fqh_outbuf[0][0], &c->fqh_outbuf[0][1], &c->fqh_outbuf[1][0], &c->fqh_outbuf[1][1], &c->fqh_recend[0], &c->fqh_recend[1], &c->fq_dupflags};
         if (c->dup.bits) cudaFree(c->dup.bits);
         cudaFree(c->d_dup_primes); cudaFree(c->d_dup_count);
         fq_free(c->dup_pos); fq_free(c->dup_keys); fq_free(c->dup_vals);
@@ -488,6 +491,7 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     memset(&a, 0, sizeof(a));
     a.b = *b; a.out1 = out1; a.out2 = out2; a.ov = ov;
     a.sink.patches = patches; a.sink.cap = patches ? patch_cap : 0; a.sink.count = n_patches;
+    a.is_dup = c->dup_flags;
     a.events.events = c->ev_dev; a.events.cap = c->ev_dev ? c->ev_cap : 0; a.events.count = c->ev_count;
     a.counters = reinterpret_cast<unsigned long long*>(c->d_raw);
     a.n_tiles = (b->n + c->tile - 1) / c->tile;
@@ -1167,8 +1171,15 @@ extern "C" int fp_fastq_process_host(fp_ctx* c, const uint8_t* text1, int64_t nb
             fp_batch b; memset(&b, 0, sizeof(b));
             b.n = n; b.stride = c->stride;
             b.seq1 = (uint8_t*)c->fqh_seq[0].p; b.qual1 = (uint8_t*)c->fqh_qual[0].p; b.len1 = (uint16_t*)c->fqh_len[0].p;
+            if (sides == 2) { b.seq2 = (uint8_t*)c->fqh_seq[1].p; b.qual2 = (uint8_t*)c->fqh_qual[1].p; b.len2 = (uint16_t*)c->fqh_len[1].p; }
+            const uint8_t* saved_flags = c->dup_flags;
+            if (c->fq_dup_level > 0) {                            /* Duplicate::checkRead / checkPair on the reads as read, before the chain (:397-401) */
+                if ((rc = fq_ensure(c->fq_dupflags, (size_t)cap))) return rc;
+                if ((rc = fp_dup_check(c, &b, c->fq_dup_level, (uint8_t*)c->fq_dupflags.p, st))) return rc;
+                if (c->fq_dedup) c->dup_flags = (const uint8_t*)c->fq_dupflags.p;
+            }
+            struct FlagsBack { fp_ctx* c; const uint8_t* f; ~FlagsBack() { c->dup_flags = f; } } flags_back{c, saved_flags};
             if (sides == 2) {
-                b.seq2 = (uint8_t*)c->fqh_seq[1].p; b.qual2 = (uint8_t*)c->fqh_qual[1].p; b.len2 = (uint16_t*)c->fqh_len[1].p;
                 rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, (fp_read_result*)c->fqh_res[1].p, nullptr, nullptr, 0, nullptr, st);
             } else rc = launch_chain(c, &b, (fp_read_result*)c->fqh_res[0].p, nullptr, nullptr, nullptr, 0, nullptr, st);
             if (rc) return rc;
@@ -1225,12 +1236,16 @@ extern "C" int fp_dup_check(fp_ctx* c, const fp_batch* b, int32_t accuracy_level
         fp_dup_sizes(accuracy_level, &buf_bytes, &buf_num);
         std::vector<uint64_t> primes((size_t)buf_num * FP_DUP_PRIME_LEN);
         fp_dup_primes(primes.data(), (int)primes.size());
-        CK(cudaMalloc(&c->dup.bits, (size_t)buf_num * buf_bytes));
-        CK(cudaMemset(c->dup.bits, 0, (size_t)buf_num * buf_bytes));
-        CK(cudaMalloc(&c->d_dup_primes, primes.size() * 8));
-        CK(cudaMemcpy(c->d_dup_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&c->d_dup_count, 8));
-        CK(cudaMemset(c->d_dup_count, 0, 8));
+        /* built in locals and committed only when every step has succeeded (a 32 GiB level-6 allocation can fail) */
+        uint32_t* bits = nullptr; uint64_t* d_primes = nullptr; unsigned long long* d_count = nullptr;
+        cudaError_t e1 = cudaMalloc(&bits, (size_t)buf_num * buf_bytes);
+        if (e1 == cudaSuccess) e1 = cudaMemset(bits, 0, (size_t)buf_num * buf_bytes);
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_primes, primes.size() * 8);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(d_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice);
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_count, 8);
+        if (e1 == cudaSuccess) e1 = cudaMemset(d_count, 0, 8);
+        if (e1 != cudaSuccess) { cudaFree(bits); cudaFree(d_primes); cudaFree(d_count); return set_err(FP_E_CUDA, "duplicate filter state: %s", cudaGetErrorString(e1)); }
+        c->dup.bits = bits; c->d_dup_primes = d_primes; c->d_dup_count = d_count;
         c->dup.buf_num = buf_num; c->dup.buf_bits = buf_bytes << 3; c->dup.offset_mask = (uint64_t)FP_DUP_PRIME_LEN * buf_num - 1;
         c->dup.primes = c->d_dup_primes;
         c->dup_level = accuracy_level; c->dup_total = 0;
@@ -1249,12 +1264,25 @@ extern "C" int fp_dup_check(fp_ctx* c, const fp_batch* b, int32_t accuracy_level
     CK(cudaMemsetAsync(S.keys, 0xFF, (size_t)cap * 8, st));    /* FP_DUP_EMPTY */
     CK(cudaMemsetAsync(S.vals, 0xFF, (size_t)cap * 4, st));
     const unsigned gu = (unsigned)((n + 255) / 256), gt = (unsigned)((total + 255) / 256);
-    fp_dup_hash_kernel<<<gu, 256, 0, st>>>(S, n, b->seq1, b->len1, b->seq2, b->len2, b->stride, paired);
+    fp_dup_hash_warp_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(S, n, b->seq1, b->len1, b->seq2, b->len2, b->stride, paired);
     fp_dup_first_kernel<<<gt, 256, 0, st>>>(S, total);
     fp_dup_decide_kernel<<<gu, 256, 0, st>>>(S, n, d_is_dup, c->d_dup_count);
     fp_dup_commit_kernel<<<gt, 256, 0, st>>>(S, total);
     CK(cudaGetLastError());
     c->dup_total += n;
+    return FP_OK;
+}
+
+extern "C" int fp_set_dup_flags(fp_ctx* c, const uint8_t* d_is_dup) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    c->dup_flags = d_is_dup;
+    return FP_OK;
+}
+
+extern "C" int fp_fastq_set_dedup(fp_ctx* c, int32_t accuracy_level, int32_t dedup) {
+    if (!c) return set_err(FP_E_INVAL, "null argument");
+    if (accuracy_level < 0 || accuracy_level > 6) return set_err(FP_E_INVAL, "dup accuracy level must be 0 (off) .. 6");
+    c->fq_dup_level = accuracy_level; c->fq_dedup = dedup ? 1 : 0;
     return FP_OK;
 }
 

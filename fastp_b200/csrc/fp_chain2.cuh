@@ -1480,7 +1480,9 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     if (!r1.null && c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;   /* :268-271 */
                     result = t_pass_filter(r1, PW, s_lut);                                        /* :273 */
                     if (dimer) { result = FP_FAIL_ADAPTER_DIMER; flags |= FP_F_ADAPTER_DIMER; }
-                    counted = !r1.null && result == FP_PASS_FILTER;                               /* :281-286 */
+                    const bool dupout = a.is_dup && a.is_dup[gi];                                 /* dedupOut :280 */
+                    if (dupout) flags |= FP_F_DUPLICATE;
+                    counted = !r1.null && result == FP_PASS_FILTER && !dupout;                    /* :281-286 */
                     if (lead) {
                         atomicAdd(&bc->fr[FP_FR_READSTATS + result], 1u);                          /* :278 */
                         if (counted) { rl[2] += 1; rl[3] += r1.len; }
@@ -1620,7 +1622,9 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);      /* :565-566 */
                     if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
                     const int pv = max(res1, res2);
-                    counted = !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER;   /* :577-591 */
+                    const bool dupout = a.is_dup && a.is_dup[gi];                                 /* dedupOut :575 */
+                    if (dupout) { flags1 |= FP_F_DUPLICATE; flags2 |= FP_F_DUPLICATE; }
+                    counted = !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER && !dupout;   /* :577-591 */
                     if (lead) {
                         atomicAdd(&bc->fr[FP_FR_READSTATS + pv], 2u);                              /* :573 */
                         if (counted) { rl[2] += 1; rl[3] += r1.len; rl[6] += 1; rl[7] += r2.len; }

@@ -375,6 +375,7 @@ struct fp_launch_args {
     fp_ov_result* ov;
     PatchSink sink;
     EventSink events;
+    const uint8_t* is_dup;           /* --dedup: units flagged by the duplicate filter (nullable) */
     unsigned long long* counters;    /* global int64 block (two's complement adds) */
     long long n_tiles;
     fp_smem_layout sl;

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(FQ_T) fq_size_blocksum_kernel(const fq_rec* re
     unsigned long long c = 0;
     for (int k = threadIdx.x; k < FQ_SCAN_ITEMS; k += FQ_T) {
         const long long i = b0 + k;
-        if (i < n && res[i].pair_verdict == FP_PASS_FILTER) c += (unsigned long long)(recs[i].name_len & 0x0FFFFFFFu) + recs[i].strand_len + 2ull * res[i].len + 4ull;
+        if (i < n && res[i].pair_verdict == FP_PASS_FILTER && !(res[i].flags & FP_F_DUPLICATE)) c += (unsigned long long)(recs[i].name_len & 0x0FFFFFFFu) + recs[i].strand_len + 2ull * res[i].len + 4ull;
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(FQ_T) fq_encode_kernel(const uint8_t* text, co
         /* sizes of 256 consecutive records, exclusive scan inside the block */
         const long long i = b0 + k0 + threadIdx.x;
         unsigned long long sz = 0;
-        if (i < n && res[i].pair_verdict == FP_PASS_FILTER) sz = (unsigned long long)(recs[i].name_len & 0x0FFFFFFFu) + recs[i].strand_len + 2ull * res[i].len + 4ull;
+        if (i < n && res[i].pair_verdict == FP_PASS_FILTER && !(res[i].flags & FP_F_DUPLICATE)) sz = (unsigned long long)(recs[i].name_len & 0x0FFFFFFFu) + recs[i].strand_len + 2ull * res[i].len + 4ull;
         unsigned long long inc = sz;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL_MASK, inc, o); if (lane >= o) inc += t; }
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(FQ_T) fq_encode_kernel(const uint8_t* text, co
             const long long ri = b0 + k0 + j;
             if (ri >= n) break;
             const fp_read_result rr = res[ri];
-            if (rr.pair_verdict != FP_PASS_FILTER) continue;
+            if (rr.pair_verdict != FP_PASS_FILTER || (rr.flags & FP_F_DUPLICATE)) continue;
             const fq_rec rc = recs[ri];
             const unsigned int nl = rc.name_len & 0x0FFFFFFFu;
             unsigned long long o = s_sz[j];

@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
     std::string in1, in2, out1, out2, json;
     int packSize = 1 << 16, maxLen = 0;
     bool deviceFastq = false, phred64 = false;
+    bool dedup = false, evalDup = true; int dupLevel = 0;     /* src/main.cpp:200-209 */
     int zlevel = 4, zthreads = 8;          /* -z / --compression (src/main.cpp:50), host threads for .gz output */
     size_t chunkBytes = 0;                 /* text path: bytes read per side per step (default: about one device batch) */
     for (int i = 1; i < argc; i++) {
@@ -62,6 +63,8 @@ int main(int argc, char** argv) {
         else if (a == "--overlap_diff_percent_limit") opt.overlapDiffPercentLimit = atoi(next());
         else if (a == "--device_fastq") deviceFastq = true; else if (a == "-6" || a == "--phred64") phred64 = true;
         else if (a == "--chunk_bytes") chunkBytes = (size_t)atoll(next());
+        else if (a == "-D" || a == "--dedup") dedup = true; else if (a == "--dup_calc_accuracy") dupLevel = std::min(6, std::max(1, atoi(next())));
+        else if (a == "--dont_eval_duplication") evalDup = false;
         else if (a == "-z" || a == "--compression") zlevel = std::min(9, std::max(1, atoi(next()))); else if (a == "--zthreads") zthreads = std::max(1, atoi(next()));
         else if (a == "--max_read_len") maxLen = atoi(next()); else if (a == "--pack_size") packSize = atoi(next());
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
@@ -90,6 +93,9 @@ int main(int argc, char** argv) {
     if (!out1.empty()) o1.open(out1);
     if (!out2.empty()) o2.open(out2);
     if (deviceFastq) {
+        if (evalDup || dedup) {                            /* accuracy level: 3 with --dedup, else 1, unless given (src/main.cpp:203-209) */
+            if (!worker.setDedup(dupLevel ? dupLevel : (dedup ? 3 : 1), dedup)) { fprintf(stderr, "fastp_gpu_cli: duplicate filter: %s\n", fp_last_error()); return 1; }
+        }
         /* text path: raw file chunks go to the device, which parses, filters and re-encodes them (fp_fastq_process_host);
            whatever a chunk's last, incomplete record (or the longer side of a pair) leaves over is carried into the next chunk */
         /* .gz / BGZF inputs are inflated on the host (fp_gz_open: zlib streaming reader, plain files pass through), .gz outputs are written as
@@ -158,6 +164,8 @@ int main(int argc, char** argv) {
     }
     Stats pre1, post1, pre2, post2; FilterResult fr; std::vector<long> isize;
     if (!worker.finish(&pre1, &post1, &pre2, &post2, &fr, &isize)) { fprintf(stderr, "fastp_gpu_cli: %s\n", worker.error().c_str()); return 1; }
+    long dupTotal = 0, dupCount = 0;
+    if (deviceFastq && (evalDup || dedup)) worker.dupTotals(&dupTotal, &dupCount);
     if (!json.empty()) {
         std::ofstream js(json);
         auto tot = [&](long Stats::*m) { return pre1.*m + (opt.paired ? pre2.*m : 0); };
@@ -171,6 +179,7 @@ int main(int argc, char** argv) {
            << ", \"too_long_reads\": " << fr.mFilterReadStats[FP_FAIL_TOO_LONG] << ", \"low_complexity_reads\": " << fr.mFilterReadStats[FP_FAIL_COMPLEXITY]
            << ", \"adapter_dimer_reads\": " << fr.mFilterReadStats[FP_FAIL_ADAPTER_DIMER] << "},\n"
            << " \"adapter_cutting\": {\"adapter_trimmed_reads\": " << fr.mTrimmedAdapterRead << ", \"adapter_trimmed_bases\": " << fr.mTrimmedAdapterBases << "},\n"
+           << " \"duplication\": {\"total\": " << dupTotal << ", \"duplicates\": " << dupCount << "},\n"
            << " \"corrected_reads\": " << fr.mCorrectedReads << ",\n \"insert_size_unknown\": " << (isize.empty() ? 0 : isize.back()) << "\n}\n";
     }
     return 0;

@@ -97,6 +97,9 @@ public:
     /* true once a reader rejected a record (strand line not '+', |quality| != |sequence|): like FastqReader::read returning NULL the
      * input ENDS there -- the caller stops feeding chunks (src/fastqreader.cpp:349-364) */
     bool inputEnded() const { return mInputEnded; }
+    /* text path: Duplicate::checkRead / checkPair on the device at `accuracyLevel` (src/main.cpp:200-209; 0 = off); dedup: drop duplicates (-D) */
+    bool setDedup(int accuracyLevel, bool dedup) { return mCtx && fp_fastq_set_dedup(mCtx, accuracyLevel, dedup ? 1 : 0) == FP_OK; }
+    bool dupTotals(long* total, long* dups) { int64_t t = 0, d = 0; if (!mCtx || fp_dup_totals(mCtx, &t, &d) != FP_OK) return false; *total = (long)t; *dups = (long)d; return true; }
     bool processFastqText(const char* text1, size_t n1, const char* text2, size_t n2, bool final, bool phred64,
                           std::string* outstr1, std::string* outstr2, size_t* consumed1, size_t* consumed2, long* units);
 

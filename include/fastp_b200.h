@@ -145,6 +145,7 @@ typedef struct fp_batch {
 #define FP_F_CORRECTED        0x08  /* at least one base of this read was overwritten          */
 #define FP_F_POLYG_TRIMMED    0x10  /* trimPolyG shortened the read                            */
 #define FP_F_ADAPTER_DIMER    0x20
+#define FP_F_DUPLICATE        0x40  /* dedupOut: flagged by the duplicate filter with --dedup on; not written, not in the post-filter stats (peprocessor.cpp:397-401,575) */
 
 typedef struct fp_read_result {
     uint16_t front;        /* frontTrimmed: bases removed at the 5' end by trimAndCut          */
@@ -432,6 +433,12 @@ int  fp_fastq_process_host(fp_ctx* ctx, const uint8_t* text1, int64_t nbytes1, c
 int  fp_dup_check(fp_ctx* ctx, const fp_batch* b, int32_t accuracy_level, uint8_t* d_is_dup, void* stream);
 int  fp_dup_totals(fp_ctx* ctx, int64_t* total, int64_t* dups);
 int  fp_dup_reset(fp_ctx* ctx);
+/* --dedup (src/options.h duplicate.dedup): `d_is_dup` = DEVICE flags of the batch the next fp_process_se / _pe call works on (as fp_dup_check
+ * wrote them); flagged units keep their verdict counters but are left out of the post-filter stats and marked FP_F_DUPLICATE, which
+ * fp_fastq_encode skips.  NULL switches it off.  fp_fastq_set_dedup: the text path (fp_fastq_process_host) runs the duplicate filter at
+ * `accuracy_level` on every round's decoded rows before the chain (0 = off) and drops duplicates from the output when `dedup` is set. */
+int  fp_set_dup_flags(fp_ctx* ctx, const uint8_t* d_is_dup);
+int  fp_fastq_set_dedup(fp_ctx* ctx, int32_t accuracy_level, int32_t dedup);
 
 /* Host-side pre-scan (control plane, once per input, like the reference's Evaluator): the over-representation candidate list
  * Evaluator::computeOverRepSeq (src/evaluator.cpp:78-169) derives from the first 1.51 M bases of one input, here given as rows

@@ -112,3 +112,36 @@ def test_device_fastq_text_path_equals_object_path(cli, tmp_path, paired, chunk)
     assert outs["text"] == outs["obj"]
     assert len(outs["text"][0]) > 1000000
     assert json.load(open(tmp_path / "text.json")) == json.load(open(tmp_path / "obj.json"))
+
+
+@pytest.mark.skipif(not (T.have_ref() and os.path.exists(T.REF_CLI)), reason="oracle/_ref not built")
+@pytest.mark.parametrize("paired", [1, 0])
+def test_dedup_on_the_text_path_equals_reference_cli(cli, tmp_path, paired):
+    """-D / --dedup: the duplicate filter runs on the device on the decoded rows (fp_dup_check, accuracy level 3 as the reference
+    picks with --dedup), duplicates are dropped from the output and left out of the post-filter stats (src/peprocessor.cpp:397-401,575);
+    output files and the filter / duplication numbers equal the unmodified reference CLI at --thread 1.  Also through .gz in and out."""
+    import gzip
+    from test_duplicate_oracle import planted
+    arrs = planted(paired, n=30000, seed=91 + paired)
+    write_fastq(tmp_path / "r1.fq", arrs["seq1"], arrs["qual1"], arrs["len1"])
+    ref = [T.REF_CLI, "-i", str(tmp_path / "r1.fq"), "-o", str(tmp_path / "ref1.fq"), "-w", "1", "-D", "-j", str(tmp_path / "ref.json"), "-h", str(tmp_path / "ref.html")]
+    gz_in = tmp_path / "r1.fq.gz"
+    gz_in.write_bytes(gzip.compress((tmp_path / "r1.fq").read_bytes()[:1500000]) + gzip.compress((tmp_path / "r1.fq").read_bytes()[1500000:]))
+    mine = [cli, "-i", str(gz_in), "-o", str(tmp_path / "gpu1.fq.gz"), "--device_fastq", "-D", "-j", str(tmp_path / "gpu.json"), "--pack_size", "8192", "--max_read_len", "150"]
+    if paired:
+        write_fastq(tmp_path / "r2.fq", arrs["seq2"], arrs["qual2"], arrs["len2"])
+        ref += ["-I", str(tmp_path / "r2.fq"), "-O", str(tmp_path / "ref2.fq")]
+        mine += ["-I", str(tmp_path / "r2.fq"), "-O", str(tmp_path / "gpu2.fq")]
+    else:                       # single-end: the reference would auto-detect an adapter (Evaluator, host control plane) -- keep it out of the comparison
+        ref += ["-A"]; mine += ["-A"]
+    subprocess.run(ref, check=True, capture_output=True, cwd=tmp_path, timeout=600)
+    subprocess.run(mine, check=True, timeout=600)
+    assert gzip.decompress((tmp_path / "gpu1.fq.gz").read_bytes()) == (tmp_path / "ref1.fq").read_bytes()
+    if paired:
+        assert (tmp_path / "gpu2.fq").read_bytes() == (tmp_path / "ref2.fq").read_bytes()
+    jr, jg = json.load(open(tmp_path / "ref.json")), json.load(open(tmp_path / "gpu.json"))
+    for k in ("passed_filter_reads", "low_quality_reads", "too_many_N_reads", "too_short_reads"):
+        assert jg["filtering_result"][k] == jr["filtering_result"][k]
+    assert jg["after_filtering"]["total_reads"] == jr["summary"]["after_filtering"]["total_reads"]
+    assert jg["duplication"]["duplicates"] > 100
+    assert abs(jg["duplication"]["duplicates"] / jg["duplication"]["total"] - jr["duplication"]["rate"]) < 1e-6
