@@ -654,6 +654,36 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         "clocks": clocks,
     }
 
+    # ---- duplicate filter on the resident rows: Duplicate::checkRead / checkPair for every unit, in index order ----
+    if with_e2e and rank == 0:
+        try:
+            nd = int(min(n, 20_000_000))
+            bd = capi.Batch(); bd.n, bd.stride = nd, S
+            for k, v in t.items():
+                setattr(bd, k, v.data_ptr())
+            flags_d = alloc(nd)
+            capi.check(lib.fp_dup_check(h, C.byref(bd), 1, flags_d.data_ptr(), sp), lib)       # allocates the 1 GiB of bit arrays, warms up
+            torch.cuda.synchronize()
+            capi.check(lib.fp_dup_reset(h), lib)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                capi.check(lib.fp_dup_check(h, C.byref(bd), 1, flags_d.data_ptr(), sp), lib)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dms = e0.elapsed_time(e1) / 3
+            tot_d, dup_d = C.c_int64(), C.c_int64()
+            capi.check(lib.fp_dup_totals(h, C.byref(tot_d), C.byref(dup_d)), lib)
+            dbytes = sides * L_ + 1
+            res["dup_filter"] = {"value": nd / (dms / 1e3), "unit": unit, "units": nd, "ms": dms, "accuracy_level": 1,
+                                 "algorithmic_bytes_per_unit": dbytes, "achieved_GBps": nd * dbytes / (dms / 1e3) / 1e9,
+                                 "frac_of_hbm_peak": nd * dbytes / (dms / 1e3) / 1e9 / measured_peak()[0],
+                                 "duplicates_second_and_third_pass": int(dup_d.value),
+                                 "note": "fp_dup_check: warp-per-unit hash + first-toucher table + commit (4 kernels); the second and third timed passes see every unit again, so all of them are duplicates"}
+            del flags_d
+        except Exception as e:
+            res["dup_filter"] = {"value": None, "error": repr(e)}
+
     # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region) ----
     if with_e2e:
         ne = int(min(args.e2e_units, n))
@@ -662,9 +692,10 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         if world > 1:        # the parity pass above regenerated a prefix in place: refill this rank's own rows
             capi.check(lib.fp_synth_fill(h, C.byref(b), first, SEED, profile, L_, None), lib)
             torch.cuda.synchronize()
+        HP = L_                                             # host row pitch = read length: no padding bytes over PCIe (re-pitched in HBM)
         for k in keys:
-            hb[k] = torch.empty(ne * S, dtype=torch.uint8).pin_memory()
-            hb[k].copy_(t[k][: ne * S])
+            hb[k] = torch.empty(ne * HP, dtype=torch.uint8).pin_memory()
+            hb[k].view(ne, HP).copy_(t[k][: ne * S].view(ne, S)[:, :HP])
         for k in (["len1", "len2"] if paired else ["len1"]):
             hb[k] = torch.empty(ne * 2, dtype=torch.uint8).pin_memory()
             hb[k].copy_(t[k][: ne * 2])
@@ -675,10 +706,10 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         hpat = np.zeros(hp_cap, capi.PATCH_DTYPE) if corr else None
         hnp = C.c_uint64()
         hbt = capi.Batch()
-        hbt.n, hbt.stride, hbt.flags, hbt.first_read_index = ne, S, 1, first
+        hbt.n, hbt.stride, hbt.flags, hbt.first_read_index = ne, HP, 1, first
         for k, v in hb.items():
             setattr(hbt, k, v.data_ptr())
-        views = {k: hb[k].numpy().reshape(ne, S) for k in keys}
+        views = {k: hb[k].numpy().reshape(ne, HP) for k in keys}
 
         def e2e_step():
             capi.check(lib.fp_counters_reset(h), lib)
@@ -714,7 +745,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
             tt_ = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
             dt = float(tt_.item())
-        h2d = ne * (sides * 2 * S + sides * 2)
+        h2d = ne * (sides * 2 * HP + sides * 2)
         d2h = ne * ((32 + 8) if paired else 16)
         e2e_val = ne * world * steps / dt
         PCIE_PEAK = 63.0
@@ -776,7 +807,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         res["e2e"] = dict(best)
         res["e2e"].update({"units_per_step_per_gpu": ne, "pcie_peak_GBps": PCIE_PEAK, "pcie_peak_source": "PCIe Gen5 x16, 63 GB/s per direction nominal",
                            "soa_rows": soa, "packed_rows": pk,
-                           "note": "pinned host SoA rows -> (packed path: 2-bit bases + N list + unpadded qualities, packed inside the clock) -> chunked H2D on two "
+                           "host_row_pitch": HP, "note": "pinned host SoA rows at pitch = read length -> (packed path: 2-bit bases + N list + unpadded qualities, packed inside the clock) -> chunked H2D on two "
                                    "streams -> kernel -> D2H of per-read records + correction patches; the headline value is the faster of the two host formats"})
     lib.fp_ctx_destroy(h)
     del t, out1, out2, ov, patches

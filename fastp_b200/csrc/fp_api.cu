@@ -662,6 +662,24 @@ __global__ void fp_unpack_kernel(const uint8_t* __restrict__ pb, const uint8_t* 
     *reinterpret_cast<uint4*>(seq + r * stride + g * 16) = make_uint4(so[0], so[1], so[2], so[3]);
     *reinterpret_cast<uint4*>(qual + r * stride + g * 16) = make_uint4(qo[0], qo[1], qo[2], qo[3]);
 }
+/* host rows at a tighter pitch than the device stride (no padding over PCIe): one thread per (read, 16 output bytes) */
+__global__ void fp_repitch_kernel(const uint8_t* __restrict__ in, const uint16_t* __restrict__ len, long long n, int pitch, int stride, uint8_t* __restrict__ out) {
+    const int gpr = stride >> 4;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * gpr) return;
+    const long long r = t / gpr; const int g = (int)(t - r * gpr);
+    const int L = min((int)len[r], min(stride, pitch));
+    const uint8_t* s = in + r * pitch + g * 16;
+    uint32_t o[4];
+    #pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t v = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) { const int p = g * 16 + w * 4 + k; if (p < L) v |= (uint32_t)s[w * 4 + k] << (8 * k); }
+        o[w] = v;
+    }
+    *reinterpret_cast<uint4*>(out + r * stride + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+}
 __global__ void fp_unpack_n_kernel(const fp_npos* __restrict__ np, long long cnt, long long unit0, int stride, uint8_t* seq1, uint8_t* seq2) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= cnt) return;
@@ -780,7 +798,19 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     CK(cudaSetDevice(c->device));
     int rc = ensure_staging(c);
     if (rc) return rc;
-    if (b->stride != c->stride) return set_err(FP_E_INVAL, "batch stride differs from the ctx stride");
+    /* host rows may be tighter than the device stride (pitch = read length: no padding bytes over PCIe); they are re-pitched in HBM */
+    const int HP = b->stride;
+    if (HP > c->stride || HP <= 0) return set_err(FP_E_INVAL, "host row pitch must be in (0, ctx stride]");
+    const bool repitch = !pk && HP != c->stride;
+    if (repitch) {
+        const size_t nb = (size_t)c->chunk * HP + 64;
+        if (nb > c->pk_cap_b || nb > c->pk_cap_q) {
+            CK(cudaDeviceSynchronize());
+            for (int i = 0; i < 2; i++)
+                for (int k = 0; k < (c->p.paired ? 4 : 2); k++) { cudaFree(c->d_pk[i][k]); c->d_pk[i][k] = nullptr; CK(cudaMalloc(&c->d_pk[i][k], nb)); }
+            c->pk_cap_b = c->pk_cap_q = nb;
+        }
+    }
     if (pk) {                                                  /* packed input: staging for one chunk of packed rows + its N exceptions */
         if (pk->pitch_b <= 0 || pk->pitch_q <= 0) return set_err(FP_E_INVAL, "bad packed pitch");
         const size_t nb = (size_t)c->chunk * pk->pitch_b + 64, nq = (size_t)c->chunk * pk->pitch_q + 64;
@@ -831,8 +861,8 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 for (uint32_t k = 0; k < np; k++) {
                     const fp_patch& pt = c->h_patch[slot][k];
                     if (!pk) {
-                        uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * S;
-                        uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * S;
+                        uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * HP;
+                        uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * HP;
                         sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
                     }
                     if (hp_n) {                                  /* caller's list: pair index relative to the whole host batch */
@@ -842,13 +872,11 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 }
             } else if (pk) {
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
-            } else {   /* patch list overflow: take the corrected rows wholesale */
+            } else {   /* patch list overflow: take the corrected rows wholesale (row by row when the host pitch differs) */
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
-                const size_t bytes = (size_t)pend[slot].cnt * S;
-                CK(cudaMemcpy(b->seq1 + lo * S, c->d_stage[slot][0], bytes, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(b->qual1 + lo * S, c->d_stage[slot][1], bytes, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(b->seq2 + lo * S, c->d_stage[slot][2], bytes, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(b->qual2 + lo * S, c->d_stage[slot][3], bytes, cudaMemcpyDeviceToHost));
+                uint8_t* dst[4] = {b->seq1, b->qual1, b->seq2, b->qual2};
+                for (int k = 0; k < 4; k++)
+                    CK(cudaMemcpy2D(dst[k] + lo * HP, (size_t)HP, c->d_stage[slot][k], (size_t)S, (size_t)HP, (size_t)pend[slot].cnt, cudaMemcpyDeviceToHost));
             }
         }
         pend[slot].active = false;
@@ -890,6 +918,17 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 }
                 CK(cudaMemcpyAsync(c->d_npos[slot], nb0, (size_t)nn * sizeof(fp_npos), cudaMemcpyHostToDevice, st));
                 fp_unpack_n_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(c->d_npos[slot], nn, lo, S, c->d_stage[slot][0], pe ? c->d_stage[slot][2] : nullptr);
+            }
+            CK(cudaGetLastError());
+        } else if (repitch) {
+            const size_t hb = (size_t)cnt * HP;
+            const uint8_t* src[4] = {b->seq1, b->qual1, b->seq2, b->qual2};
+            CK(cudaMemcpyAsync(c->d_stage_len[slot][0], b->len1 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+            if (pe) { CK(cudaMemcpyAsync(c->d_stage_len[slot][1], b->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st)); }
+            const long long thr = (long long)cnt * (S >> 4);
+            for (int k = 0; k < (pe ? 4 : 2); k++) {
+                CK(cudaMemcpyAsync(c->d_pk[slot][k], src[k] + lo * HP, hb, cudaMemcpyHostToDevice, st));
+                fp_repitch_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(c->d_pk[slot][k], c->d_stage_len[slot][k >> 1], cnt, HP, S, c->d_stage[slot][k]);
             }
             CK(cudaGetLastError());
         } else {

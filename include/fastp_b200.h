@@ -299,7 +299,8 @@ int  fp_process_pe(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read
                    fp_ov_result* ov, fp_patch* patches, uint32_t patch_cap, uint32_t* n_patches, void* stream);
 
 /* Host-buffer entry points (the call the reference-side shim makes): every pointer is HOST memory
- * (pinned or pageable). Copies inputs H2D in chunks on two streams, runs the kernels, copies the
+ * (pinned or pageable).  b->stride is the HOST row pitch here: any value from the longest read up to the ctx stride (a pitch equal to the
+ * read length sends no padding bytes over PCIe; the rows are re-pitched in HBM). Copies inputs H2D in chunks on two streams, runs the kernels, copies the
  * per-read records back and applies base-correction patches to the host seq/qual rows. Synchronous. */
 int  fp_process_se_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1);
 int  fp_process_pe_host(fp_ctx* ctx, const fp_batch* b, fp_read_result* out1, fp_read_result* out2,

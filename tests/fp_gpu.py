@@ -126,6 +126,20 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
         for k in a:
             a[k] = t[k].cpu().numpy()
         extra = {"patches": patches, "n_patches": npatch} if paired else {}
+    elif mode == "host_tight":
+        # host rows at pitch = longest read (no padding bytes over PCIe); corrected rows come back at that pitch
+        Lmax = int(max(a["len1"].max(initial=1), a["len2"].max(initial=1) if paired else 1))
+        tight = {k: (np.ascontiguousarray(v[:, :Lmax]) if v.ndim == 2 else v) for k, v in a.items()}
+        b = capi.batch_from_arrays(tight)
+        assert b.stride == Lmax
+        if paired:
+            capi.check(lib.fp_process_pe_host(ctx.h, C.byref(b), out1.ctypes.data, out2.ctypes.data, ov.ctypes.data), lib)
+        else:
+            capi.check(lib.fp_process_se_host(ctx.h, C.byref(b), out1.ctypes.data), lib)
+        for k, v in tight.items():
+            if v.ndim == 2:
+                a[k][:, :Lmax] = v
+        extra = {}
     elif mode == "packed":
         # fp_host_pack_rows -> fp_process_*_host_packed; the corrected rows are rebuilt from the returned patch list
         b = capi.batch_from_arrays(a)

@@ -254,3 +254,14 @@ def test_packed_host_rows(gpu, name, paired, L, S):
     want = T.run_cpu("oracle", p, arrs, S)
     got = gpu.run_gpu(p, arrs, S, mode="packed")
     T.assert_results_equal(got, want, paired, what=f"packed {name}")
+
+
+@pytest.mark.parametrize("name,paired", [("cfg3_overlap_correction", 1), ("cfg2_cut_right_polyg", 0)])
+def test_host_rows_at_a_tight_pitch(gpu, name, paired):
+    """fp_process_*_host with fp_batch.stride = the longest read (150) instead of the device stride (160): same results, corrected rows
+    patched at the caller's pitch"""
+    p = T.config_params(name, paired)
+    _, arrs = T.synth_host(300000, 160, paired, 5, 46, 1, 150)
+    want = T.run_cpu("oracle", p, arrs, 160)
+    got = gpu.run_gpu(p, arrs, 160, mode="host_tight")
+    T.assert_results_equal(got, want, paired, what=f"tight pitch {name}")
