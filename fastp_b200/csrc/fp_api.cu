@@ -51,6 +51,7 @@ struct fp_ctx {
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
+    int group_threads = 256;            /* FP_GROUP_THREADS=512: one 16-warp group per SM */
     int groups = 2;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>) sharing the histogram tables; FP_GROUPS=1|2|3 overrides (3 x 8 warps needs <= 80 registers: measured slower) */
     fp_smem_layout sl{};
     uint32_t smem_base = 1024;        /* shared-window address of dynamic shared memory (probed) */
@@ -153,9 +154,13 @@ __global__ void fp_probe_smem_base(uint32_t* out) { extern __shared__ uint8_t pr
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static const void* chain_kernel(bool paired, int groups) {
-    if (paired) return groups == 1 ? (const void*)fp_chain2_kernel<true, 1> : groups == 2 ? (const void*)fp_chain2_kernel<true, 2> : (const void*)fp_chain2_kernel<true, 3>;
-    return groups == 1 ? (const void*)fp_chain2_kernel<false, 1> : groups == 2 ? (const void*)fp_chain2_kernel<false, 2> : (const void*)fp_chain2_kernel<false, 3>;
+/* kernel shapes: groups x threads per group.  (2, 256) = two 8-warp tile pipelines per CTA, one CTA per SM (the default);
+   (1, 256) = round 1's shape, two CTAs per SM; (3, 256) = 24 warps per SM at <= 80 registers; (1, 512) = ONE 16-warp pipeline per SM
+   with 128-pair tiles: every warp of the SM is in the same phase, i.e. one hot code region at a time (instruction cache). */
+static const void* chain_kernel(bool paired, int groups, int ct) {
+    if (ct == 512) return paired ? (const void*)fp_chain2_kernel<true, 1, 512> : (const void*)fp_chain2_kernel<false, 1, 512>;
+    if (paired) return groups == 1 ? (const void*)fp_chain2_kernel<true, 1, 256> : groups == 2 ? (const void*)fp_chain2_kernel<true, 2, 256> : (const void*)fp_chain2_kernel<true, 3, 256>;
+    return groups == 1 ? (const void*)fp_chain2_kernel<false, 1, 256> : groups == 2 ? (const void*)fp_chain2_kernel<false, 2, 256> : (const void*)fp_chain2_kernel<false, 3, 256>;
 }
 
 static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
@@ -197,7 +202,7 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     sl.off_queue = (int)g; g += (size_t)sides * T * 2 * 8;
     if (sides == 2) {                                                      /* base correction: work list + per-row masks of corrected positions */
         sl.cm_words = (S + 31) / 32;
-        sl.off_corr = (int)g; g += (size_t)FP_CW * FP_CORR_CAP * 4 + FP_CW * 4;      /* one list (+ length) per warp */
+        sl.off_corr = (int)g; g += (size_t)FP_CORR_CAP * 4 + 16;                        /* the tile's list + its length */
         sl.off_cm = (int)g; g += (size_t)sides * T * sl.cm_words * 4;
     }
     sl.group_stride = (int)align_up(g, 128);
@@ -209,8 +214,9 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
    (one CTA of 2 or 3 groups per SM; with a single group, two CTAs per SM) */
 static void make_smem_layout(fp_ctx* c) {
     const int sides = c->p.paired ? 2 : 1;
-    const size_t budget = c->groups == 1 ? (227 * 1024 - 2 * 1024) / 2 : (size_t)227 * 1024;
-    int T = 64 * (3 - sides);
+    const size_t budget = (c->groups == 1 && c->group_threads == 256) ? (227 * 1024 - 2 * 1024) / 2 : (size_t)227 * 1024;
+    int T = 64 * (3 - sides) * (c->group_threads / 256);
+    if (T > 128) T = 128;                                   /* row indices in the work lists are 7 bits */
     while (T > 16 && smem_layout_for_tile(c, T, c->sl) > budget) T -= 8;
     c->tile = T;
     smem_layout_for_tile(c, T, c->sl);
@@ -222,7 +228,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     if (cycles <= 0) cycles = stride;
     if (p->allow_gap_overlap_trimming && p->overlap_require < 2) return set_err(FP_E_INVAL, "allow_gap_overlap_trimming needs overlap_require >= 2");
     if (p->insert_size_max < 0 || p->insert_size_max > (1 << 20)) return set_err(FP_E_INVAL, "insert_size_max out of range");
-    if ((p->paired ? 2 : 1) * (stride / 2) > FP_CT) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
+    if ((p->paired ? 2 : 1) * (stride / 2) > 256) return set_err(FP_E_INVAL, "stride too large for the column pass (PE: <= 256, SE: <= 512)");
     if (p->cut_front_window < 1 || p->cut_tail_window < 1 || p->cut_right_window < 1) return set_err(FP_E_INVAL, "cut window must be >= 1");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -258,6 +264,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         c->smem_base = h_base;
     }
     if (const char* e = getenv("FP_GROUPS")) { const int g = atoi(e); if (g >= 1 && g <= 3) c->groups = g; }
+    if (const char* e = getenv("FP_GROUP_THREADS")) { if (atoi(e) == 512) { c->group_threads = 512; c->groups = 1; } }
     make_smem_layout(c);
 
     cudaDeviceProp prop;
@@ -367,13 +374,13 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     /* kernel attributes + persistent grid size */
     int occ = 0;
     {
-        const void* fn = chain_kernel(p->paired != 0, c->groups);
+        const void* fn = chain_kernel(p->paired != 0, c->groups, c->group_threads);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FP_CT * c->groups, c->sl.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, c->group_threads * c->groups, c->sl.total));
     }
     if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
     c->grid_max = occ * c->num_sms;
-    if (getenv("FP_TRACE")) fprintf(stderr, "[fastp_b200] groups %d, tile %d rows, smem %d B (shared %d + %d per group), %d CTA/SM\n", c->groups, c->tile, c->sl.total, c->sl.off_group, c->sl.group_stride, occ);
+    if (getenv("FP_TRACE")) fprintf(stderr, "[fastp_b200] groups %d x %d threads, tile %d rows, smem %d B (shared %d + %d per group), %d CTA/SM\n", c->groups, c->group_threads, c->tile, c->sl.total, c->sl.off_group, c->sl.group_stride, occ);
     *out = c;
     return FP_OK;
 }
@@ -527,7 +534,7 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     CK(cudaEventRecord(ev.a, st));
     {
         void* kargs[] = {(void*)&a};
-        CK(cudaLaunchKernel(chain_kernel(c->p.paired != 0, c->groups), dim3(grid), dim3(FP_CT * c->groups), kargs, (size_t)c->sl.total, st));
+        CK(cudaLaunchKernel(chain_kernel(c->p.paired != 0, c->groups, c->group_threads), dim3(grid), dim3(c->group_threads * c->groups), kargs, (size_t)c->sl.total, st));
     }
     CK(cudaEventRecord(ev.b, st));
     c->evs.push_back(ev);

@@ -611,7 +611,7 @@ __device__ __noinline__ int t_correct(const TRead r1, const TRead r2, uint32_t* 
  * still unmodified row and its new bases from the partner read (position y of the rewritten read faces c - y of the other).
  * entry = row | which << 7 | P << 8 | Pp << 18   (which = the read that is rewritten, P its row position, Pp the partner's)
  * ------------------------------------------------------------------------------------------------ */
-#define FP_CORR_CAP 128                /* corrections of ONE warp-step (8 pairs); more go the sequential way */
+#define FP_CORR_CAP 1024               /* corrections of one tile; more go the sequential way */
 __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, int PW, const fp_ov_result ov, int row, int sub, int g,
                                               uint32_t* list, int* nlist, uint32_t* cm1, uint32_t* cm2) {
     FP_SMEM(r1.qual);    FP_SMEM(r2.qual);    FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(list);    FP_SMEM(nlist);    FP_SMEM(cm1);    FP_SMEM(cm2);
@@ -1202,19 +1202,19 @@ __device__ __forceinline__ void push_delta(const DeltaSinks& K, bool want, bool 
  *   B  operator chain, one lane group per read / pair; post-stat requests go to a shared-memory queue
  *   C  the queue is drained by all warps (balanced), then the tile buffer is free for the next TMA load
  * ------------------------------------------------------------------------------------------------ */
-template <bool PAIRED, int NG>
-__global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(const fp_launch_args a) {
+template <bool PAIRED, int NG, int CT>
+__global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_chain2_kernel(const fp_launch_args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int SIDES = PAIRED ? 2 : 1;
     const fp_smem_layout& sl = a.sl;
     const int S = c_p.stride, T = c_p.tile;
-    /* A CTA is NG independent tile pipelines ("groups") of FP_CT threads each: own tile buffer, planes, queues, mbarrier and named
+    /* A CTA is NG independent tile pipelines ("groups") of CT threads each: own tile buffer, planes, queues, mbarrier and named
        barrier; the histogram / delta / counter tables are shared by the groups (they are atomics anyway), which is what lets three
        groups = 24 warps fit one SM's shared memory.  tid / warp are GROUP-local; ctid is the CTA-wide thread index. */
-    const int ctid = threadIdx.x, gid = NG == 1 ? 0 : (int)(threadIdx.x / FP_CT);
-    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x % FP_CT), lane = lane_id(), warp = tid >> 5;
+    const int ctid = threadIdx.x, gid = NG == 1 ? 0 : (int)(threadIdx.x / CT);
+    const int tid = NG == 1 ? (int)threadIdx.x : (int)(threadIdx.x % CT), lane = lane_id(), warp = tid >> 5;
     uint8_t* const gsm = smem + sl.off_group + gid * sl.group_stride;        /* this group's private region */
-#define GSYNC() asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(FP_CT) : "memory")
+#define GSYNC() asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(CT) : "memory")
     unsigned long long* G = a.counters;
     const fp_counter_layout& L = c_p.L;
 
@@ -1244,26 +1244,26 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
     unsigned int* s_dummy = reinterpret_cast<unsigned int*>(smem + sl.off_dummy);   /* [32] write-only sink */
     int* s_qn = reinterpret_cast<int*>(gsm + sl.off_next);                  /* [0] queue length, [1] pop cursor, [2] phase-A item cursor, [3] removal item cursor */
     sinks.q = s_queue; sinks.qn = &s_qn[0];
-    uint32_t* s_corr = reinterpret_cast<uint32_t*>(gsm + sl.off_corr) + warp * FP_CORR_CAP;   /* [FP_CW][FP_CORR_CAP] base-correction work list of each warp (PE) */
-    int* s_ncorr = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(gsm + sl.off_corr) + FP_CW * FP_CORR_CAP) + warp;   /* its length */
+    uint32_t* s_corr = reinterpret_cast<uint32_t*>(gsm + sl.off_corr);      /* [FP_CORR_CAP] base-correction work list of the tile (PE) */
+    int* s_ncorr = reinterpret_cast<int*>(s_corr + FP_CORR_CAP);            /* its length */
     uint32_t* s_cm = reinterpret_cast<uint32_t*>(gsm + sl.off_cm);          /* [SIDES][T][CMW] corrected positions of every row */
     const int CMW = sl.cm_words;
 
     if (((smem_u32(smem) + (uint32_t)sl.off_kmer) & 4095u) != 0u) __trap();   /* layout was built for another shared-window base */
-    for (int i = tid; i < SIDES * T * PSTR; i += FP_CT) tile_planes[i] = 0;
-    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) s_kmer[i] = 0;
-    for (int i = ctid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += FP_CT * NG) s_qhist[i] = 0;
-    for (int i = ctid; i < SIDES * S * 20; i += FP_CT * NG) D.cyc[i] = 0;
-    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) D.kmer[i] = 0;
-    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) D.qh[i] = 0;
-    for (int i = ctid; i < (int)(sizeof(BlockCounters) / 4); i += FP_CT * NG) reinterpret_cast<unsigned int*>(bc)[i] = 0;
-    for (int i = ctid; i < S + 2; i += FP_CT * NG) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
+    for (int i = tid; i < SIDES * T * PSTR; i += CT) tile_planes[i] = 0;
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += CT * NG) s_kmer[i] = 0;
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS * FP_QH_REP; i += CT * NG) s_qhist[i] = 0;
+    for (int i = ctid; i < SIDES * S * 20; i += CT * NG) D.cyc[i] = 0;
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += CT * NG) D.kmer[i] = 0;
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += CT * NG) D.qh[i] = 0;
+    for (int i = ctid; i < (int)(sizeof(BlockCounters) / 4); i += CT * NG) reinterpret_cast<unsigned int*>(bc)[i] = 0;
+    for (int i = ctid; i < S + 2; i += CT * NG) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
     const int HPR = S >> 1;
-    const int ncols = SIDES * HPR;                /* host guarantees ncols <= FP_CT */
-    const int nsplit = FP_CT / ncols;             /* row groups are dealt round-robin to nsplit threads per column */
+    const int ncols = SIDES * HPR;                /* host guarantees ncols <= CT */
+    const int nsplit = CT / ncols;             /* row groups are dealt round-robin to nsplit threads per column */
     const bool col_active = tid < ncols * nsplit;
     const int my_part = col_active ? tid / ncols : 0, my_col = col_active ? tid % ncols : 0;
     const int my_side = my_col / HPR, my_hc = my_col % HPR;
@@ -1290,7 +1290,7 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
         if (t >= a.n_tiles) return;
         const long long r0 = t * T;
         const int nr = (int)min((long long)T, a.b.n - r0);
-        for (int i = tid; i < SIDES * T; i += FP_CT) {
+        for (int i = tid; i < SIDES * T; i += CT) {
             const int sd = i / T, r = i % T;
             uint16_t ln = 0;
             if (r < nr) { ln = (sd == 0 ? a.b.len1 : a.b.len2)[r0 + r]; if (ln > S) ln = (uint16_t)S; }
@@ -1318,13 +1318,14 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
             s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0;     /* request queue / removal items: next used after the phase-A barrier */
+            if (PAIRED && c_p.correction) *s_ncorr = 0;
         }
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
            mbarrier every thread waits on itself: no CTA barrier here */
         mbar_wait(mbar, parity);
         parity ^= 1;
-        for (int i = tid; i < SIDES * (T + 4) + SIDES; i += FP_CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
-        if (PAIRED && c_p.correction) for (int i = tid; i < SIDES * T * CMW; i += FP_CT) s_cm[i] = 0;
+        for (int i = tid; i < SIDES * (T + 4) + SIDES; i += CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
+        if (PAIRED && c_p.correction) for (int i = tid; i < SIDES * T * CMW; i += CT) s_cm[i] = 0;
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
         if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
@@ -1442,7 +1443,7 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
 
         /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
-        for (int rb0 = 0; rb0 < rows; rb0 += FP_CW * UPW) {            /* same trip count for every warp: the loop body holds group barriers */
+        for (int rb0 = 0; rb0 < rows; rb0 += (CT / 32) * UPW) {            /* same trip count for every warp: the loop body holds group barriers */
             const int rbase = rb0 + warp * UPW;
             const int r = rbase + lane / GL;
             const bool active = r < rows;
@@ -1534,27 +1535,28 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
                     else ovA = ov;
                     need_correct = both && c_p.correction && !ovA.has_gap && ovA.overlapped && ovA.diff != 0;       /* :443,:453-456 */
                 }
-                /* ---- base correction (:453-456): the pairs' lanes decide, then the WARP works its own list, one lane per correction
-                        (everything a correction touches belongs to one of this warp's pairs: warp-level synchronisation is enough) ---- */
+                /* ---- base correction (:453-456): the pairs' lanes decide, then the whole GROUP works the tile's list, one lane per correction.
+                        Group barriers on purpose: a per-warp variant (warp-level syncs only) was measured 35 % slower -- eight warps running the
+                        correction code at eight different times thrash the instruction cache (no-instruction stalls 1.1 -> 3.5 per issue), while
+                        phase-synchronous warps share one hot region at a time. ---- */
                 bool corr_overflow = false;
                 const bool distributed = need_correct && clean1 && clean2;
                 if (PAIRED && c_p.correction) {
-                    if (lane == 0) *s_ncorr = 0;
-                    __syncwarp();
                     if (distributed)
                         corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, s_corr, s_ncorr, s_cm + rr * CMW, s_cm + (T + rr) * CMW);
-                    __syncwarp();
+                    GSYNC();
                     const int ncorr = min(*s_ncorr, FP_CORR_CAP);
-                    for (int i = lane; i < ncorr; i += 32)
+                    for (int i = tid; i < ncorr; i += CT)
                         t_correct_item(s_corr[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (s_corr[i] & 0x7F)));
-                    __syncwarp();
-                    for (int i = lane; i < ncorr; i += 32) {
+                    GSYNC();
+                    for (int i = tid; i < ncorr; i += CT) {
                         const uint32_t en = s_corr[i];
                         const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
                         t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
                                         (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
                     }
-                    __syncwarp();
+                    GSYNC();
+                    if (tid == 0) *s_ncorr = 0;                /* (a PE tile is one round of this loop: 8 warps x 8 pairs >= T) */
                 }
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
@@ -1733,19 +1735,19 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
         }
     }
     #pragma unroll 1
-    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) {
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += CT * NG) {
         const unsigned int v = s_kmer[i];
         if (v) { const int sd = i / FP_KMER_BINS, k = kmer_ref_index(i % FP_KMER_BINS); red_add64(&G[fp_off_kmer(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_kmer(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) {
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += CT * NG) {
         unsigned int v = 0;
         #pragma unroll
         for (int c = 0; c < FP_QH_REP; c++) v += s_qhist[i * FP_QH_REP + c];
         if (v) { const int sd = i / FP_QUAL_BINS, k = i % FP_QUAL_BINS; red_add64(&G[fp_off_qualhist(&L, sd * 2, k)], (unsigned long long)v); red_add64(&G[fp_off_qualhist(&L, sd * 2 + 1, k)], (unsigned long long)v); }
     }
     #pragma unroll 1
-    for (int i = ctid; i < SIDES * S * 20; i += FP_CT * NG) {
+    for (int i = ctid; i < SIDES * S * 20; i += CT * NG) {
         const int v = D.cyc[i];
         if (v == 0) continue;
         const int sd = i / (S * 20), rem = i % (S * 20), cyc = rem / 20, bin = (rem % 20) / 4, kind = rem & 3;
@@ -1754,14 +1756,14 @@ __global__ void __launch_bounds__(FP_CT * NG, NG == 1 ? 2 : 1) fp_chain2_kernel(
         red_add64(&G[fp_off_cycle(&L, sd * 2 + 1, gk * 8 + BIN_SLOT[bin], cyc)], (unsigned long long)(long long)v);
     }
     #pragma unroll 1
-    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += FP_CT * NG) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, kmer_ref_index(i % FP_KMER_BINS))], (unsigned long long)(long long)v); }
+    for (int i = ctid; i < SIDES * FP_KMER_BINS; i += CT * NG) { const int v = D.kmer[i]; if (v) red_add64(&G[fp_off_kmer(&L, (i / FP_KMER_BINS) * 2 + 1, kmer_ref_index(i % FP_KMER_BINS))], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += FP_CT * NG) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
+    for (int i = ctid; i < SIDES * FP_QUAL_BINS; i += CT * NG) { const int v = D.qh[i]; if (v) red_add64(&G[fp_off_qualhist(&L, (i / FP_QUAL_BINS) * 2 + 1, i % FP_QUAL_BINS)], (unsigned long long)(long long)v); }
     #pragma unroll 1
-    for (int i = ctid; i < FP_FR_WORDS; i += FP_CT * NG) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
+    for (int i = ctid; i < FP_FR_WORDS; i += CT * NG) { const unsigned int v = bc->fr[i]; if (v) red_add64(&G[L.off_filter + i], (unsigned long long)v); }
     if (c_p.isize_max < FP_MAX_ISIZE_SMEM) {
         #pragma unroll 1
-        for (int i = ctid; i <= c_p.isize_max; i += FP_CT * NG) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
+        for (int i = ctid; i <= c_p.isize_max; i += CT * NG) { const unsigned int v = bc->isize[i]; if (v) red_add64(&G[L.off_isize + i], (unsigned long long)v); }
     }
     #pragma unroll
     for (int k = 0; k < 8; k++) {

@@ -68,5 +68,6 @@ def test_ten_million_units_equal_reference(name, paired):
            "ov": ov.cpu().numpy().view(capi.OV_RESULT_DTYPE)[:n if paired else 0], "counters": ctx.counters(),
            "arrs": {k: v.cpu().numpy().reshape(arrs[k].shape) for k, v in t.items()}, "layout": ctx.L}
     want = {"out1": w1, "out2": w2, "ov": wov, "counters": capi.CounterView(Lr, want_cnt), "arrs": a, "layout": Lr}
-    T.assert_results_equal(got, want, paired, what=f"{name} {n} units")
+    # adapter_pos is a device-side extra (where trimBySequence hit); the reference harness has no such field
+    T.assert_results_equal(got, want, paired, skip=("adapter_pos",), what=f"{name} {n} units")
     ctx.close()
