@@ -92,8 +92,10 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
             /* window of 4 = one 32-bit field: the group's lanes take consecutive aligned words (4 window starts each), the window sum is
                one dp4a; rounds advance together so the group-min picks the first start in the reference's order */
             const int smax = l - tail - w;                                /* window starts s in [front, smax) */
+            const int thr = c_p.cr_thr;
+            const unsigned gm = group_mask(g);
             int best = 1 << 20;
-            for (int wb = (front >> 2) + sub; (wb - sub) * 4 < smax && best == (1 << 20); wb += g) {
+            for (int wb = (front >> 2) + sub; (wb - sub) * 4 < smax; wb += g) {
                 const int b0 = wb * 4;
                 int mine = 1 << 20;
                 if (b0 < smax) {
@@ -102,10 +104,10 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
                     for (int k = 3; k >= 0; k--) {
                         const int sk = b0 + k;
                         const int tot = __dp4a((int)__funnelshift_r(W0, W1, 8 * k), 0x01010101, 0);       /* signed chars, like the reference's char sum */
-                        if (sk >= front && sk < smax && tot < c_p.cr_thr) mine = sk;
+                        if (sk >= front && sk < smax && tot < thr) mine = sk;
                     }
                 }
-                best = group_min(mine, g);
+                if (__any_sync(gm, mine != (1 << 20))) { best = group_min(mine, g); break; }   /* one vote per round; the min only when someone hit */
             }
             if (best < (1 << 20)) { found = true; s = best; }
         } else
@@ -137,6 +139,29 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
     if (rlen <= 0 || front >= l - 1) return false;                        /* :196-197 */
     frontOut = front; lenOut = rlen;
     return true;
+}
+
+/* Plane tests that settle the usual case of the two poly-tail trimmers without walking the tail (clean rows only).
+ * trimPolyG (polyx.cpp:16-42) trims only if its scan gets past index minLen-1; more than five non-G among the last minLen bases
+ * stop it before that (`mismatch > 5`), and so does a read shorter than minLen.
+ * trimPolyX (:49-116) with minLen >= 10 cannot stop before pos 8 and trims only if it stops at pos+1 >= minLen: if no base (N counts
+ * for every base) fills 8 of the last 9 positions, `needToBreak` holds at pos 8 and the scan ends there without trimming. */
+__device__ __forceinline__ bool t_polyg_cannot_trim(const TRead& r, int PW, int minLen) {
+    if (r.len < minLen) return true;
+    if (!r.clean || minLen > 32 || minLen < 1) return false;
+    const int bit = r.front + r.len - minLen;
+    const uint32_t g = tp_bits(r.pl, bit) & tp_bits(r.pl + PW, bit);           /* G: code 3 (lo = hi = 1; both 0 under N) */
+    return __popc(~g & low_mask(minLen)) > 5;
+}
+__device__ __forceinline__ bool t_polyx_cannot_trim(const TRead& r, int PW, int minLen) {
+    if (minLen < 10) return false;
+    if (r.len < 9) return true;
+    if (!r.clean) return false;
+    const int bit = r.front + r.len - 9;
+    const uint32_t lo = tp_bits(r.pl, bit), hi = tp_bits(r.pl + PW, bit), nn = tp_bits(r.pl + 2 * PW, bit), m = 0x1FFu;
+    const int cA = __popc((~lo & ~hi) & m), cC = __popc((lo & ~hi | nn) & m), cT = __popc((~lo & hi | nn) & m), cG = __popc((lo & hi | nn) & m);
+    /* ~lo & ~hi is A or N (both planes are 0 under N): already counts N for A */
+    return max(max(cA, cC), max(cT, cG)) <= 7;
 }
 
 /* PolyX::trimPolyG  (polyx.cpp:16-42): returns the new length */
@@ -261,9 +286,7 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
     P.f1 = r1.front; P.len1 = r1.len; P.len2 = r2.len; P.e = r2.front + r2.len - 1;
     const int len1 = r1.len, len2 = r2.len, f1 = r1.front, e = P.e;
     const int req = c_p.ov_require;
-    const int thr = c_p.ov_diff_limit + 1;       /* every lut entry is min(diffLimit, ...) <= diffLimit */
-    const int F = min(32, max(req, 1));          /* bases the filter looks at: every candidate's overlap is longer than req */
-    const uint32_t FM = low_mask(F);
+    const int Fmax = min(32, max(req, 1));       /* bases the filter looks at: every candidate's overlap is longer than req ... */
     fp_ov_result ov; ov.overlapped = 0; ov.has_gap = 0; ov.offset = 0; ov.overlap_len = 0; ov.diff = 0;
     int found_dir = -1, found_o = 0, found_mm = 0, found_ol = 0;
     #pragma unroll 1
@@ -274,8 +297,13 @@ __device__ __noinline__ fp_ov_result t_analyze_planes(const TRead r1, const TRea
              backward  r2 field at bit e-(F-1)-o     vs  C = reversed complemented r1[0..F)   (bit t of the field is rc(r2)[o+F-1-t])
            The group's lanes take whole plane words (32 consecutive candidates each) in the order of increasing o. */
         const int ncand = dir == 0 ? len1 - req : len2 - req;
-        const int lfix = dir == 0 ? len2 : len1;
-        const int nscan = lfix >= F ? max(ncand, 0) : 0;
+        const int lfix = dir == 0 ? len2 : len1, lmov = dir == 0 ? len1 : len2;
+        /* ... unless the fixed read itself is shorter (quality trimming): then every candidate overlaps all of it.  The acceptance limit
+           grows with the overlap length, so the largest overlap of this direction bounds them all. */
+        const int F = min(Fmax, lfix);
+        const uint32_t FM = low_mask(F);
+        const int thr = (int)lut[min(lmov, lfix)] + 1;
+        const int nscan = F >= 1 ? max(ncand, 0) : 0;
         int my_o = 1 << 20, my_mm = 0, my_ol = 0;
         const OvConst K = t_ov_const(P, dir);
         if (nscan > 0) {
@@ -743,14 +771,24 @@ __device__ __forceinline__ int t_gap_scan(const uint8_t* ins, const uint8_t* nor
     return best;
 }
 
-/* can the one-gap scan over lengths <= cmax accept anything?  D1 / D2: aligned / shifted mismatch bits (bit j = position j) */
-__device__ __forceinline__ bool gap_may_hit(unsigned long long D1, unsigned long long D2, int cmax) {
-    if (cmax < 8) return false;                                           /* c/8 - 1 < 0 for every c < 8 */
-    const uint32_t d1 = (uint32_t)D1 & 0xFFu, d2 = (uint32_t)D2 & 0xFFu;
-    int v = 8;
-    #pragma unroll
-    for (int i = 0; i <= 8; i++) v = min(v, __popc(d1 & ((1u << i) - 1u)) + __popc(d2 & ~((1u << i) - 1u)));
-    return v <= cmax / 8 - 1;
+/* can the one-gap scan over lengths <= cmax accept anything?  D1 / D2: aligned / shifted mismatch bits (bit j = position j).
+ * A length c in [8k, 8k+7] is accepted only if some split i has (aligned mismatches before i) + (shifted mismatches from i to c) <= k - 1;
+ * the same quantity over the first K = 8k positions only, B_K = min_i popc(D1 & low(i)) + popc(D2 & low(K) & ~low(i)), is a lower bound for
+ * every c >= K and grows with K.  So: some k with B_8k <= k - 1 must exist, and once B_K exceeds the largest allowance nothing longer can hit.
+ * Random sequence fails at K = 8 nine times out of ten; what passes there is checked at 16, 24, 32 ... before the byte scan is paid. */
+__device__ __noinline__ bool gap_may_hit(unsigned long long D1, unsigned long long D2, int cmax) {
+    const int amax = cmax / 8 - 1;                                        /* c/8 - 1 < 0 for every c < 8 */
+    #pragma unroll 1
+    for (int k = 1; 8 * k <= min(cmax, 64); k++) {
+        const int K = 8 * k;
+        const unsigned long long mk = mask64(K);
+        int v = 1 << 20;
+        #pragma unroll 1
+        for (int i = 0; i <= K; i++) v = min(v, __popcll(D1 & mask64(i)) + __popcll(D2 & mk & ~mask64(i)));
+        if (v <= k - 1) return true;
+        if (v > amax) return false;
+    }
+    return false;
 }
 
 struct EvCtx { EventSink sink; unsigned int unit; int which; };
@@ -803,33 +841,41 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
                 }
                 return mm <= cmplen / 8;
             };
-            /* main range: the first min(alen,32) adapter bases lie inside the read, so their mismatch count alone (one sliding 32-bit
-               field per plane, constant mask) already exceeds the largest allowance alen/8 for almost every position */
+            /* main range: the first a0 = min(alen,32) adapter bases lie inside the read.  Same one-plane word filter as the overlap scan
+               (t_ov_word_hits on X = lo ^ hi: bases whose X bits differ are different bases; allowance alen/8 bounds every position's own):
+               a lane takes a whole plane word = 32 consecutive positions, branch-free; survivors get the exact three-plane count. */
             const int a0 = min(alen, 32);
             const int pmain = min(npos, rlen - a0 + 1);
             const uint32_t M0 = low_mask(a0), A_lo = __ldg(alo), A_hi = __ldg(ahi), A_nn = __ldg(ann);
             const int amax = alen / 8;
-            const int lg = g == 4 ? 2 : (g == 2 ? 1 : 0);
-            int p = sub;
-            while (p < pmain && my_p == (1 << 20)) {
-                const int c = r.front + p;
-                const int w = c >> 5;
-                const uint32_t L0 = plo[w], L1 = plo[w + 1], H0 = phi[w], H1 = phi[w + 1], N0 = pnn[w], N1 = pnn[w + 1];
-                int sh = c & 31;
-                int cnt = min((pmain - p + g - 1) >> lg, (32 - sh + g - 1) >> lg);
-                while (cnt > 0) {
-                    #pragma unroll 2
-                    for (; cnt > 0; cnt--, sh += g, p += g) {
-                        const uint32_t x0 = ((__funnelshift_r(L0, L1, sh) ^ A_lo) | (__funnelshift_r(H0, H1, sh) ^ A_hi) | (__funnelshift_r(N0, N1, sh) ^ A_nn)) & M0;
-                        if (__popc(x0) <= amax) break;
+            if (pmain > 0) {
+                const uint32_t AX = (A_lo ^ A_hi) & M0;
+                const int blo = r.front, bhi = r.front + pmain - 1;
+                #pragma unroll 1
+                for (int w = (blo >> 5) + sub; w <= (bhi >> 5) && my_p == (1 << 20); w += g) {
+                    const uint32_t W0 = plo[w] ^ phi[w], W1 = plo[w + 1] ^ phi[w + 1];
+                    uint32_t hits = t_ov_word_hits(W0, W1, AX, M0, amax + 1);
+                    hits &= low_mask(bhi - 32 * w + 1) & ~low_mask(blo - 32 * w);
+                    while (hits) {
+                        const int sh = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int p = 32 * w + sh - r.front;
+                        if (full_check(p)) { my_p = p; break; }
                     }
-                    if (cnt <= 0) break;
-                    if (full_check(p)) { my_p = p; break; }
-                    cnt--; sh += g; p += g;
                 }
             }
-            for (; p < npos && my_p == (1 << 20); p += g)                  /* tail: the adapter runs past the read end */
-                if (full_check(p)) { my_p = p; break; }
+            /* tail: the adapter runs past the read end, position p compares the read's last c = rlen - p bases with the adapter's first c.
+               The read's last 32 bases are one constant field per plane; c goes down as p goes up. */
+            if (group_min(my_p, g) == (1 << 20) && npos > pmain) {
+                const int tb = r.front + rlen - 32;
+                const uint32_t T_lo = tp_bits_z(plo, tb), T_hi = tp_bits_z(phi, tb), T_nn = tp_bits_z(pnn, tb);
+                #pragma unroll 1
+                for (int pp = max(pmain, 0) + sub; pp < npos; pp += g) {
+                    const int c = rlen - pp;                               /* matchReq < c < a0 <= 32 */
+                    const uint32_t x = (((T_lo >> (32 - c)) ^ A_lo) | ((T_hi >> (32 - c)) ^ A_hi) | ((T_nn >> (32 - c)) ^ A_nn)) & low_mask(c);
+                    if (__popc(x) <= c / 8) { my_p = pp; break; }
+                }
+            }
         } else {
             for (int p = sub; p < npos; p += g) {
                 const int cmplen = min(rlen - p, alen), allowed = cmplen / 8;
@@ -1460,7 +1506,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 bool counted = false;
                 if (active) {
                     r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :235 */
-                    if (!r1.null && c_p.polyg) { const int nl = t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
+                    if (!r1.null && c_p.polyg && !t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
                     bool dimer = false;
                     if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
                         bool trimmed = false;
@@ -1472,7 +1518,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                     }
                     if (!r1.null && c_p.polyx) {                                                  /* :263-266 */
                         int nl;
-                        if (t_trim_polyx(rs + r1.front, r1.len, c_p.polyx_min, nl, pbase, plen)) {
+                        if (!t_polyx_cannot_trim(r1, PW, c_p.polyx_min) && t_trim_polyx(rs + r1.front, r1.len, c_p.polyx_min, nl, pbase, plen)) {
                             r1.len = nl;
                             if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pbase], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pbase], (unsigned)plen); }
                             flags |= FP_F_POLYX_TRIMMED;
@@ -1514,8 +1560,8 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                     r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len, sub, GL);
                     both = !r1.null && !r2.null;
                     if (both && c_p.polyg) {                                                      /* :428-431 */
-                        int nl = t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; }
-                        nl = t_trim_polyg(rs2 + r2.front, r2.len, c_p.polyg_min); if (nl != r2.len) { r2.len = nl; flags2 |= FP_F_POLYG_TRIMMED; }
+                        if (!t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; } }
+                        if (!t_polyg_cannot_trim(r2, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs2 + r2.front, r2.len, c_p.polyg_min); if (nl != r2.len) { r2.len = nl; flags2 |= FP_F_POLYG_TRIMMED; } }
                     }
                     if (both && (c_p.adapter_enabled || c_p.correction || c_p.thread0)) {         /* :438-441 */
                         ov = (clean1 && clean2) ? t_analyze_planes(r1, r2, PW, s_lut, sub, GL) : t_analyze_bytes(r1, r2, s_lut);
@@ -1608,11 +1654,11 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                     }
                     if (both && c_p.polyx) {                                                      /* :506-509 */
                         int nl;
-                        if (t_trim_polyx(rs1 + r1.front, r1.len, c_p.polyx_min, nl, pb1, pl1n)) {
+                        if (!t_polyx_cannot_trim(r1, PW, c_p.polyx_min) && t_trim_polyx(rs1 + r1.front, r1.len, c_p.polyx_min, nl, pb1, pl1n)) {
                             r1.len = nl; flags1 |= FP_F_POLYX_TRIMMED;
                             if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pb1], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pb1], (unsigned)pl1n); }
                         }
-                        if (t_trim_polyx(rs2 + r2.front, r2.len, c_p.polyx_min, nl, pb2, pl2n)) {
+                        if (!t_polyx_cannot_trim(r2, PW, c_p.polyx_min) && t_trim_polyx(rs2 + r2.front, r2.len, c_p.polyx_min, nl, pb2, pl2n)) {
                             r2.len = nl; flags2 |= FP_F_POLYX_TRIMMED;
                             if (lead) { atomicAdd(&bc->fr[FP_FR_POLYX_READS + pb2], 1u); atomicAdd(&bc->fr[FP_FR_POLYX_BASES + pb2], (unsigned)pl2n); }
                         }
