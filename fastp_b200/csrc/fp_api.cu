@@ -51,8 +51,8 @@ struct fp_ctx {
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
-    int group_threads = 256;            /* FP_GROUP_THREADS=512: one 16-warp group per SM */
-    int groups = 2;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>) sharing the histogram tables; FP_GROUPS=1|2|3 overrides (3 x 8 warps needs <= 80 registers: measured slower) */
+    int group_threads = 512;            /* one 16-warp group per SM (FP_GROUP_THREADS=256: 8-warp groups, FP_GROUPS of them) */
+    int groups = 1;                     /* tile pipelines per CTA (fp_chain2_kernel<.., NG>) sharing the histogram tables; FP_GROUPS=1|2|3 overrides (3 x 8 warps needs <= 80 registers: measured slower) */
     fp_smem_layout sl{};
     uint32_t smem_base = 1024;        /* shared-window address of dynamic shared memory (probed) */
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -264,7 +264,8 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         c->smem_base = h_base;
     }
     if (const char* e = getenv("FP_GROUPS")) { const int g = atoi(e); if (g >= 1 && g <= 3) c->groups = g; }
-    if (const char* e = getenv("FP_GROUP_THREADS")) { if (atoi(e) == 512) { c->group_threads = 512; c->groups = 1; } }
+    if (const char* e = getenv("FP_GROUP_THREADS")) { if (atoi(e) == 256) { c->group_threads = 256; if (!getenv("FP_GROUPS")) c->groups = 2; } }
+    if (c->group_threads == 512) c->groups = 1;
     make_smem_layout(c);
 
     cudaDeviceProp prop;
