@@ -216,7 +216,7 @@ static void make_smem_layout(fp_ctx* c) {
     const int sides = c->p.paired ? 2 : 1;
     const size_t budget = (c->groups == 1 && c->group_threads == 256) ? (227 * 1024 - 2 * 1024) / 2 : (size_t)227 * 1024;
     int T = 64 * (3 - sides) * (c->group_threads / 256);
-    if (T > 128) T = 128;                                   /* row indices in the work lists are 7 bits */
+    if (T > (sides == 2 ? 128 : 256)) T = sides == 2 ? 128 : 256;   /* row indices: 7 bits in the correction list (PE), 8 bits in the removal lists */
     while (T > 16 && smem_layout_for_tile(c, T, c->sl) > budget) T -= 8;
     c->tile = T;
     smem_layout_for_tile(c, T, c->sl);

@@ -34,6 +34,12 @@ __device__ __forceinline__ uint32_t tp_bits(const uint32_t* P, int bit) {      /
     return __funnelshift_r(P[w], P[w + 1], bit & 31);
 }
 
+__device__ __forceinline__ uint32_t tp_bits_z(const uint32_t* P, int s0) {   /* tp_bits with zeros below bit 0 */
+    if (s0 >= 0) return tp_bits(P, s0);
+    if (s0 > -32) return P[0] << (-s0);
+    return 0u;
+}
+
 /* A read / pair is served by a GROUP of g adjacent lanes (g = 4 for PE, 2 for SE): all lanes run the scalar operators
  * redundantly (same shared-memory addresses -> broadcasts), the long candidate scans (overlap offsets, adapter
  * positions) are split round-robin over the g lanes and combined with group_min, and every side effect (atomics,
@@ -177,6 +183,39 @@ __device__ __noinline__ int t_trim_polyg(const uint8_t* data, int rlen, int minL
     return rlen;
 }
 
+/* trimPolyG on the planes (clean rows): the scan's state only changes at non-G bases, so hop from one to the next (at most six before
+ * `mismatch > 5` ends it) instead of walking every base.  i counts from the tail (base rlen-1-i); on a run of G's with m mismatches behind it
+ * the stop condition `m > (i+1)/8 && i >= minLen-1` holds exactly for max(run start, minLen-1) <= i <= 8m-2. */
+__device__ __noinline__ int t_trim_polyg_planes(const uint32_t* pl, int PW, int front, int rlen, int minLen) {
+    FP_SMEM(pl);
+    auto ng_word = [&](int w) -> uint32_t {                                 /* bit t: base i = 32w + t is not G (valid i only) */
+        const int bit = front + rlen - 32 * (w + 1);
+        const uint32_t g = __brev(tp_bits_z(pl, bit) & tp_bits_z(pl + PW, bit));
+        return ~g & low_mask(rlen - 32 * w);
+    };
+    int i = 0, m = 0, lastG = -1, brk = -1;
+    #pragma unroll 1
+    while (i < rlen) {
+        int w = i >> 5;
+        uint32_t x = ng_word(w) & ~low_mask(i & 31);
+        while (!x && 32 * (w + 1) < rlen) { w++; x = ng_word(w); }
+        const int nxt = x ? 32 * w + __ffs(x) - 1 : rlen;                  /* next non-G at or after i */
+        if (nxt > i) {                                                     /* G's on [i, nxt-1] */
+            const int ib = max(i, minLen - 1);
+            if (m > 0 && ib <= min(nxt - 1, 8 * m - 2)) { brk = ib; lastG = ib; break; }
+            lastG = nxt - 1;
+        }
+        if (nxt >= rlen) break;
+        m++;
+        if (m > 5 || (m > (nxt + 1) / 8 && nxt >= minLen - 1)) { brk = nxt; break; }
+        i = nxt + 1;
+    }
+    const int iend = brk >= 0 ? brk : rlen;
+    const int firstGPos = lastG >= 0 ? rlen - 1 - lastG : rlen - 1;
+    if (iend >= minLen && firstGPos >= 0 && firstGPos <= rlen) return firstGPos;
+    return rlen;
+}
+
 /* PolyX::trimPolyX  (polyx.cpp:49-116): returns true if addPolyXTrimmed is called */
 __device__ __noinline__ bool t_trim_polyx(const uint8_t* data, int rlen, int minLen, int& newLen, int& polyOut, int& nOut) {
     FP_SMEM(data);
@@ -218,11 +257,6 @@ __device__ __noinline__ bool t_trim_polyx(const uint8_t* data, int rlen, int min
  *   backward offset o: r1[k] vs rc(r2)[o+k]          -> equivalently comp(r1[pp-1-t]) vs row2[s+t], s = e-o-pp+1:
  *                      the reversed-complemented r1 prefix Y is constant, row2's field moves (never negative).
  * ------------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ uint32_t tp_bits_z(const uint32_t* P, int s0) {   /* tp_bits with zeros below bit 0 */
-    if (s0 >= 0) return tp_bits(P, s0);
-    if (s0 > -32) return P[0] << (-s0);
-    return 0u;
-}
 __device__ __forceinline__ unsigned long long tp_bits64(const uint32_t* P, int bit) {
     const int w = bit >> 5, sh = bit & 31;
     const uint32_t lo = __funnelshift_r(P[w], P[w + 1], sh), hi = __funnelshift_r(P[w + 1], P[w + 2], sh);
@@ -781,10 +815,15 @@ __device__ __noinline__ bool gap_may_hit(unsigned long long D1, unsigned long lo
     #pragma unroll 1
     for (int k = 1; 8 * k <= min(cmax, 64); k++) {
         const int K = 8 * k;
-        const unsigned long long mk = mask64(K);
-        int v = 1 << 20;
+        /* B_K = min over the split i = 0..K of (aligned mismatches below i) + (shifted mismatches from i to K-1): walk i, one bit in, one bit out */
+        int a = 0, b = __popcll(D2 & mask64(K)), v = b;
+        unsigned long long d1 = D1, d2 = D2;
         #pragma unroll 1
-        for (int i = 0; i <= K; i++) v = min(v, __popcll(D1 & mask64(i)) + __popcll(D2 & mk & ~mask64(i)));
+        for (int i = 0; i < K; i++) {
+            a += (int)(d1 & 1ull); b -= (int)(d2 & 1ull);
+            d1 >>= 1; d2 >>= 1;
+            v = min(v, a + b);
+        }
         if (v <= k - 1) return true;
         if (v > amax) return false;
     }
@@ -1506,7 +1545,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 bool counted = false;
                 if (active) {
                     r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :235 */
-                    if (!r1.null && c_p.polyg && !t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
+                    if (!r1.null && c_p.polyg && !t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = r1.clean ? t_trim_polyg_planes(r1.pl, PW, r1.front, r1.len, c_p.polyg_min) : t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
                     bool dimer = false;
                     if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
                         bool trimmed = false;
@@ -1560,8 +1599,8 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                     r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len, sub, GL);
                     both = !r1.null && !r2.null;
                     if (both && c_p.polyg) {                                                      /* :428-431 */
-                        if (!t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; } }
-                        if (!t_polyg_cannot_trim(r2, PW, c_p.polyg_min)) { const int nl = t_trim_polyg(rs2 + r2.front, r2.len, c_p.polyg_min); if (nl != r2.len) { r2.len = nl; flags2 |= FP_F_POLYG_TRIMMED; } }
+                        if (!t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = r1.clean ? t_trim_polyg_planes(r1.pl, PW, r1.front, r1.len, c_p.polyg_min) : t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; } }
+                        if (!t_polyg_cannot_trim(r2, PW, c_p.polyg_min)) { const int nl = r2.clean ? t_trim_polyg_planes(r2.pl, PW, r2.front, r2.len, c_p.polyg_min) : t_trim_polyg(rs2 + r2.front, r2.len, c_p.polyg_min); if (nl != r2.len) { r2.len = nl; flags2 |= FP_F_POLYG_TRIMMED; } }
                     }
                     if (both && (c_p.adapter_enabled || c_p.correction || c_p.thread0)) {         /* :438-441 */
                         ov = (clean1 && clean2) ? t_analyze_planes(r1, r2, PW, s_lut, sub, GL) : t_analyze_bytes(r1, r2, s_lut);
