@@ -195,7 +195,7 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     g = align_up(g, 16);
     sl.off_rm = (int)g; g += (size_t)sides * (T + 4) * 4 + 16;             /* removal lists (one per side, padded to 4 entries) + their lengths */
     sl.plane_words = (S + 31) / 32 + 2;
-    sl.plane_stride = (4 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
+    sl.plane_stride = (5 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
     g = align_up(g, 16);
     sl.off_planes = (int)g; g += (size_t)sides * T * sl.plane_stride * 4;
     g = align_up(g, 16);

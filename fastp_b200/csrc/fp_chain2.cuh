@@ -61,8 +61,8 @@ __device__ __forceinline__ int group_pick(int v, bool mine, int g) {
 /* ------------------------------------------------------------------------------------------------
  * Filter::trimAndCut  (filter.cpp:68-207), scalar per thread.  Returns false for NULL.
  * ------------------------------------------------------------------------------------------------ */
-__device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut, int sub, int g) {
-    FP_SMEM(seq);    FP_SMEM(qualu);
+__device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* qualu, int l0, int front, int tail, int& frontOut, int& lenOut, int sub, int g, const uint32_t* cqp) {
+    FP_SMEM(seq);    FP_SMEM(qualu);    FP_SMEM(cqp);
     frontOut = 0; lenOut = l0;
     const bool anycut = c_p.cut_front || c_p.cut_tail || c_p.cut_right;
     if (front == 0 && tail == 0 && !anycut) return true;                  /* :71-72 */
@@ -94,7 +94,34 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
         int total = 0;
         for (int i = 0; i < w - 1; i++) total += q[s + i];
         bool found = false;
-        if (w == 4) {
+        if (cqp && w <= 8 && c_p.cr_q >= 0 && c_p.cr_q <= 127) {
+            /* plane 4 marks the bases below the per-base threshold 33+Q; a window without one sums to at least w*(33+Q).  So only windows
+               holding a marked base are summed -- none at all for most reads.  The group's lanes take 32 window starts (one plane word)
+               each per round, in the reference's order; one vote per round. */
+            const int smax = l - tail - w;                                /* window starts s in [front, smax) */
+            const int thr = c_p.cr_thr;
+            const unsigned gm = group_mask(g);
+            int best = 1 << 20;
+            for (int wb = (front >> 5) + sub; 32 * (wb - sub) < smax; wb += g) {
+                int mine = 1 << 20;
+                if (32 * wb < smax) {
+                    const uint32_t c0 = cqp[wb], c1 = cqp[wb + 1];
+                    uint32_t cand = c0;
+                    for (int k = 1; k < w; k++) cand |= __funnelshift_r(c0, c1, k);
+                    cand &= low_mask(smax - 32 * wb) & ~low_mask(front - 32 * wb);
+                    while (cand) {
+                        const int sk = 32 * wb + __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        int tot = 0;
+                        if (w == 4) tot = __dp4a((int)ld_u32_unaligned(qualu + sk), 0x01010101, 0);     /* qualities < 128 on clean rows */
+                        else for (int k = 0; k < w; k++) tot += q[sk + k];
+                        if (tot < thr) { mine = sk; break; }
+                    }
+                }
+                if (__any_sync(gm, mine != (1 << 20))) { best = group_min(mine, g); break; }
+            }
+            if (best < (1 << 20)) { found = true; s = best; }
+        } else if (w == 4) {
             /* window of 4 = one 32-bit field: the group's lanes take consecutive aligned words (4 window starts each), the window sum is
                one dp4a; rounds advance together so the group-min picks the first start in the reference's order */
             const int smax = l - tail - w;                                /* window starts s in [front, smax) */
@@ -1418,6 +1445,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
         {   /* bit planes + validation: 32-item batches claimed dynamically -- warps without columns start at once, the dense warps join */
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
+            const uint32_t cq4 = (uint32_t)(min(max(c_p.cr_q, 0), 127)) * 0x01010101u;      /* plane 4: quality below cut_right's per-base threshold */
             const int total = SIDES * T * nwords;              /* pad words of the planes stay zero (cleared once at kernel start) */
             const uint32_t nw_magic = 0xFFFFFFFFu / (uint32_t)nwords + 1u;   /* it / nwords == umulhi(it, magic) for it < 2^16 */
             #pragma unroll 1
@@ -1430,7 +1458,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 if (it < total) {
                     const int rowi = (int)__umulhi((uint32_t)it, nw_magic), j = it - rowi * nwords;
                     const int sd = rowi >= T ? 1 : 0, rr2 = rowi - sd * T;
-                    uint32_t lo = 0, hi = 0, nn = 0, lq = 0;
+                    uint32_t lo = 0, hi = 0, nn = 0, lq = 0, cqw = 0;
                     if (rr2 < rows) {
                         const int n = (int)s_len[sd * T + rr2] - 32 * j;
                         if (n > 0) {
@@ -1448,8 +1476,9 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                             #pragma unroll 1
                             for (int k = 0; k < 4; k++) {
                                 const uint2 sw = *reinterpret_cast<const uint2*>(sp + 8 * k), qw = *reinterpret_cast<const uint2*>(qp + 8 * k);
-                                uint32_t f_lo, f_hi, f_nn, f_lq, f_ok, f_bad;
-                                plane_pair(sw.x, sw.y, qw.x, qw.y, qq4, f_lo, f_hi, f_nn, f_lq, f_ok, f_bad);
+                                uint32_t f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, f_cq;
+                                plane_pair(sw.x, sw.y, qw.x, qw.y, qq4, f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, cq4, f_cq);
+                                cqw = __byte_perm(cqw, f_cq, 0x7321);
                                 lo = __byte_perm(lo, f_lo, 0x7321); hi = __byte_perm(hi, f_hi, 0x7321); nn = __byte_perm(nn, f_nn, 0x7321);
                                 lq = __byte_perm(lq, f_lq, 0x7321); okm = __byte_perm(okm, f_ok, 0x7321); bad = __byte_perm(bad, f_bad, 0x7321);
                                 const uint32_t cc = __byte_perm(code_mul4(sw.x), code_mul4(sw.y), 0x7310);   /* bytes 2,3 = codes of the two words */
@@ -1482,7 +1511,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                                 }
                             }
                             const uint32_t vm = low_mask(n);
-                            lo &= vm; hi &= vm; nn &= vm; lq &= vm; okm &= vm;
+                            lo &= vm; hi &= vm; nn &= vm; lq &= vm; okm &= vm; cqw &= vm;
                             if (bad & vm) s_clean[sd * T + rr2] = 0;
                             /* pre-filter 5-mer counts (stats.cpp:228-266): a 5-mer counts iff its five bases are exact A/C/G/T.
                                Z = 2-bit codes of the 4 bases before this chunk and its 32 bases, 2 bits per base; the 5-mer ending
@@ -1520,7 +1549,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                         }
                     }
                     uint32_t* pr = tile_planes + (sd * T + rr2) * PSTR + j;
-                    pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq;
+                    pr[0] = lo; pr[PW] = hi; pr[2 * PW] = nn; pr[3 * PW] = lq; pr[4 * PW] = cqw;
                 }
             }
         }
@@ -1544,7 +1573,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 int flags = 0, apos = 0, abases = 0, pbase = 255, plen = 0, result = FP_FAIL_LENGTH;
                 bool counted = false;
                 if (active) {
-                    r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :235 */
+                    r1.null = !t_trim_and_cut(rs, rq, len0, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL, clean ? r1.pl + 4 * PW : nullptr);   /* :235 */
                     if (!r1.null && c_p.polyg && !t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = r1.clean ? t_trim_polyg_planes(r1.pl, PW, r1.front, r1.len, c_p.polyg_min) : t_trim_polyg(rs + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags |= FP_F_POLYG_TRIMMED; } }
                     bool dimer = false;
                     if (!r1.null && c_p.adapter_enabled) {                                        /* :243-260 */
@@ -1595,8 +1624,8 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 fp_ov_result ovA = ov;                    /* ovForAdapter */
                 bool both = false, need_correct = false;
                 if (active) {
-                    r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL);   /* :425-426 */
-                    r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len, sub, GL);
+                    r1.null = !t_trim_and_cut(rs1, rq1, l1, c_p.trim_front1, c_p.trim_tail1, r1.front, r1.len, sub, GL, clean1 ? pl1 + 4 * PW : nullptr);   /* :425-426 */
+                    r2.null = !t_trim_and_cut(rs2, rq2, l2, c_p.trim_front2, c_p.trim_tail2, r2.front, r2.len, sub, GL, clean2 ? pl2 + 4 * PW : nullptr);
                     both = !r1.null && !r2.null;
                     if (both && c_p.polyg) {                                                      /* :428-431 */
                         if (!t_polyg_cannot_trim(r1, PW, c_p.polyg_min)) { const int nl = r1.clean ? t_trim_polyg_planes(r1.pl, PW, r1.front, r1.len, c_p.polyg_min) : t_trim_polyg(rs1 + r1.front, r1.len, c_p.polyg_min); if (nl != r1.len) { r1.len = nl; flags1 |= FP_F_POLYG_TRIMMED; } }

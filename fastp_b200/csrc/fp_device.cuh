@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t gather_top4(uint32_t m0, uint32_t m1, uint32
 /* flags of 8 bases (even word a, odd word b; qualities qa, qb): each f_* holds the 8 flags in its TOP byte
  * (bit 24+i = base i of a, bit 28+i = base i of b).  f_bad: byte outside {A,C,G,T,N} or quality bit 7 set. */
 __device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, uint32_t qb, uint32_t qq4,
-                                           uint32_t& f_lo, uint32_t& f_hi, uint32_t& f_nn, uint32_t& f_lq, uint32_t& f_ok, uint32_t& f_bad) {
+                                           uint32_t& f_lo, uint32_t& f_hi, uint32_t& f_nn, uint32_t& f_lq, uint32_t& f_ok, uint32_t& f_bad, uint32_t cq4, uint32_t& f_cq) {
     const uint32_t K = 0x01010101u, K4 = 0x10101010u, M = 0x01020408u;
     /* even word: bit j of every byte moved to bit 0 */
     const uint32_t a1 = a >> 1, a2 = a >> 2, a3 = a >> 3, a4 = a >> 4;
@@ -150,6 +150,10 @@ __device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, 
     f_nn = np * M;
     f_ok = okp * M;                                                                   /* exact: byte is one of 'A','C','G','T' */
     f_lq = (((ta >> 7) & K) | ((tb >> 3) & K4)) * M;
+    {   /* q < cut_right's per-base threshold 33+Q (filter.cpp:159): a window without such a base cannot fall below w*(33+Q) */
+        const uint32_t ca = ~((qa | 0x80808080u) - cq4), cb = ~((qb | 0x80808080u) - cq4);
+        f_cq = (((ca >> 7) & K) | ((cb >> 3) & K4)) * M;
+    }
     f_bad = ((~(okp | np) & (K | K4)) | ((qa >> 7) & K) | ((qb >> 3) & K4)) * M;
 }
 
