@@ -91,32 +91,31 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
         const int w = c_p.cr_w;
         int s = front;
         if (l - front - tail - w <= 0) return false;
-        int total = 0;
-        for (int i = 0; i < w - 1; i++) total += q[s + i];
         bool found = false;
         if (cqp && w <= 8 && c_p.cr_q >= 0 && c_p.cr_q <= 127) {
             /* plane 4 marks the bases below the per-base threshold 33+Q; a window without one sums to at least w*(33+Q).  So only windows
-               holding a marked base are summed -- none at all for most reads.  The group's lanes take 32 window starts (one plane word)
-               each per round, in the reference's order; one vote per round. */
+               holding a marked base are summed -- none at all for most reads.  Every lane of the group walks the plane words in the
+               reference's order and takes the candidate starts congruent to its own index (a low-quality stretch is shared evenly);
+               one vote per word. */
             const int smax = l - tail - w;                                /* window starts s in [front, smax) */
             const int thr = c_p.cr_thr;
             const unsigned gm = group_mask(g);
+            const uint32_t share = (g == 4 ? 0x11111111u : g == 2 ? 0x55555555u : 0xFFFFFFFFu) << (g <= 4 ? sub : 0);
             int best = 1 << 20;
-            for (int wb = (front >> 5) + sub; 32 * (wb - sub) < smax; wb += g) {
+            for (int wb = front >> 5; 32 * wb < smax; wb++) {
                 int mine = 1 << 20;
-                if (32 * wb < smax) {
-                    const uint32_t c0 = cqp[wb], c1 = cqp[wb + 1];
-                    uint32_t cand = c0;
-                    for (int k = 1; k < w; k++) cand |= __funnelshift_r(c0, c1, k);
-                    cand &= low_mask(smax - 32 * wb) & ~low_mask(front - 32 * wb);
-                    while (cand) {
-                        const int sk = 32 * wb + __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        int tot = 0;
-                        if (w == 4) tot = __dp4a((int)ld_u32_unaligned(qualu + sk), 0x01010101, 0);     /* qualities < 128 on clean rows */
-                        else for (int k = 0; k < w; k++) tot += q[sk + k];
-                        if (tot < thr) { mine = sk; break; }
-                    }
+                const uint32_t c0 = cqp[wb], c1 = cqp[wb + 1];
+                uint32_t cand = c0;
+                for (int k = 1; k < w; k++) cand |= __funnelshift_r(c0, c1, k);
+                cand &= low_mask(smax - 32 * wb) & ~low_mask(front - 32 * wb);
+                if (g > 4) { if (sub) cand = 0; } else cand &= share;
+                while (cand) {
+                    const int sk = 32 * wb + __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    int tot = 0;
+                    if (w == 4) tot = __dp4a((int)ld_u32_unaligned(qualu + sk), 0x01010101, 0);     /* qualities < 128 on clean rows */
+                    else for (int k = 0; k < w; k++) tot += q[sk + k];
+                    if (tot < thr) { mine = sk; break; }
                 }
                 if (__any_sync(gm, mine != (1 << 20))) { best = group_min(mine, g); break; }
             }
@@ -143,11 +142,14 @@ __device__ __noinline__ bool t_trim_and_cut(const uint8_t* seq, const uint8_t* q
                 if (__any_sync(gm, mine != (1 << 20))) { best = group_min(mine, g); break; }   /* one vote per round; the min only when someone hit */
             }
             if (best < (1 << 20)) { found = true; s = best; }
-        } else
-        for (s = front; s + w < l - tail; s++) {
-            total += q[s + w - 1];
-            if (s > front) total -= q[s - 1];
-            if (total < c_p.cr_thr) { found = true; break; }
+        } else {
+            int total = 0;
+            for (int i = 0; i < w - 1; i++) total += q[s + i];
+            for (s = front; s + w < l - tail; s++) {
+                total += q[s + w - 1];
+                if (s > front) total -= q[s - 1];
+                if (total < c_p.cr_thr) { found = true; break; }
+            }
         }
         if (found) {
             while (s < l - 1 && q[s] >= c_p.cr_q) s++;
@@ -839,18 +841,17 @@ __device__ __forceinline__ int t_gap_scan(const uint8_t* ins, const uint8_t* nor
  * Random sequence fails at K = 8 nine times out of ten; what passes there is checked at 16, 24, 32 ... before the byte scan is paid. */
 __device__ __noinline__ bool gap_may_hit(unsigned long long D1, unsigned long long D2, int cmax) {
     const int amax = cmax / 8 - 1;                                        /* c/8 - 1 < 0 for every c < 8 */
+    const int kmax = min(cmax, 64) >> 3;
+    /* B_K = popc(D2 & low(K)) + min_{0<=i<=K} S(i),  S(i) = popc(D1 & low(i)) - popc(D2 & low(i)): one walk over the bits, checked every 8 */
+    int S = 0, M = 0, c2 = 0;
     #pragma unroll 1
-    for (int k = 1; 8 * k <= min(cmax, 64); k++) {
-        const int K = 8 * k;
-        /* B_K = min over the split i = 0..K of (aligned mismatches below i) + (shifted mismatches from i to K-1): walk i, one bit in, one bit out */
-        int a = 0, b = __popcll(D2 & mask64(K)), v = b;
-        unsigned long long d1 = D1, d2 = D2;
-        #pragma unroll 1
-        for (int i = 0; i < K; i++) {
-            a += (int)(d1 & 1ull); b -= (int)(d2 & 1ull);
-            d1 >>= 1; d2 >>= 1;
-            v = min(v, a + b);
-        }
+    for (int k = 1; k <= kmax; k++) {
+        const uint32_t b1 = (uint32_t)D1 & 0xFFu, b2 = (uint32_t)D2 & 0xFFu;
+        D1 >>= 8; D2 >>= 8;
+        c2 += __popc(b2);
+        #pragma unroll
+        for (int i = 0; i < 8; i++) { S += (int)((b1 >> i) & 1u) - (int)((b2 >> i) & 1u); M = min(M, S); }
+        const int v = c2 + M;
         if (v <= k - 1) return true;
         if (v > amax) return false;
     }
@@ -957,19 +958,30 @@ __device__ __noinline__ bool t_trim_by_sequence(TRead& r, const uint8_t* adata, 
        <= c/8 - 1, which is negative below c = 8 and at most cmax/8 - 1 overall; the same quantity restricted to the first 8
        positions is a lower bound for every c >= 8, so when even that exceeds the largest allowance the scan cannot hit. */
     const unsigned long long D1 = (R_lo ^ A_lo) | (R_hi ^ A_hi) | (R_nn ^ A_nn);                                  /* read[j] != adapter[j] */
+    const int cmax2 = min(rlen - 1, alen), cmax3 = min(rlen, alen - 1);
+    bool may2 = true, may3 = true;
+    if (planes64 && !found && rlen - matchReq > 0) {
+        /* both quick rejects at once: even lanes of the group test scan 2 (read[j+1] != adapter[j]), odd lanes scan 3 (adapter[j+1] != read[j]) */
+        const bool odd = (g >= 2) && (sub & 1);
+        const unsigned long long D2 = odd ? (((A_lo >> 1) ^ R_lo) | ((A_hi >> 1) ^ R_hi) | ((A_nn >> 1) ^ R_nn))
+                                          : (((R_lo >> 1) ^ A_lo) | ((R_hi >> 1) ^ A_hi) | ((R_nn >> 1) ^ A_nn));
+        const bool m = gap_may_hit(D1, D2, odd ? cmax3 : cmax2);
+        if (g >= 2) {
+            const unsigned gm = group_mask(g);
+            const int l0 = lane_id() & ~(g - 1);
+            may2 = __shfl_sync(gm, (int)m, l0) != 0; may3 = __shfl_sync(gm, (int)m, l0 + 1) != 0;
+        } else {
+            may2 = m;
+            may3 = gap_may_hit(D1, ((A_lo >> 1) ^ R_lo) | ((A_hi >> 1) ^ R_hi) | ((A_nn >> 1) ^ R_nn), cmax3);
+        }
+    }
     if (!found && rlen - matchReq - 1 > 0) {                              /* scan 2 (:105-118) */
-        const int cmax = min(rlen - 1, alen);
-        bool may = true;
-        if (planes64) may = gap_may_hit(D1, ((R_lo >> 1) ^ A_lo) | ((R_hi >> 1) ^ A_hi) | ((R_nn >> 1) ^ A_nn), cmax);   /* read[j+1] != adapter[j] */
-        const int c = may ? t_gap_scan(rdata, adata, cmax, matchReq + 1) : -1;
-        if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - 1 - c; }
+        const int c = may2 ? t_gap_scan(rdata, adata, cmax2, matchReq + 1) : -1;
+        if (c >= 0) { found = true; pos = (c == cmax2) ? 0 : rlen - 1 - c; }
     }
     if (!found && rlen - matchReq > 0) {                                  /* scan 3 (:122-135) */
-        const int cmax = min(rlen, alen - 1);
-        bool may = true;
-        if (planes64) may = gap_may_hit(D1, ((A_lo >> 1) ^ R_lo) | ((A_hi >> 1) ^ R_hi) | ((A_nn >> 1) ^ R_nn), cmax);   /* adapter[j+1] != read[j] */
-        const int c = may ? t_gap_scan(adata, rdata, cmax, matchReq + 1) : -1;
-        if (c >= 0) { found = true; pos = (c == cmax) ? 0 : rlen - c; }
+        const int c = may3 ? t_gap_scan(adata, rdata, cmax3, matchReq + 1) : -1;
+        if (c >= 0) { found = true; pos = (c == cmax3) ? 0 : rlen - c; }
     }
     if (found) {                                                          /* :137-154 */
         int abases;
@@ -1447,7 +1459,13 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
             const uint32_t cq4 = (uint32_t)(min(max(c_p.cr_q, 0), 127)) * 0x01010101u;      /* plane 4: quality below cut_right's per-base threshold */
             const int total = SIDES * T * nwords;              /* pad words of the planes stay zero (cleared once at kernel start) */
-            const uint32_t nw_magic = 0xFFFFFFFFu / (uint32_t)nwords + 1u;   /* it / nwords == umulhi(it, magic) for it < 2^16 */
+            /* item order.  Word-major: the lanes of a warp hold the SAME word index of 32 different rows, so with reads of one length the
+               row-end word (partial steps, predicated counts) is taken by whole warps instead of one lane in five.  The lanes then read
+               shared memory one row pitch apart: not when the pitch is a multiple of 16 words (the 256-byte rows of 250 bp reads would
+               all hit one bank) -- those tiles keep the row-major order (consecutive words of a row on consecutive lanes). */
+            const bool word_major = ((S >> 2) & 15) != 0;
+            const uint32_t it_div = word_major ? (uint32_t)(SIDES * T) : (uint32_t)nwords;
+            const uint32_t it_magic = 0xFFFFFFFFu / it_div + 1u;             /* it / it_div == umulhi(it, magic) for it < 2^16 */
             #pragma unroll 1
             for (;;) {
                 int base = 0;
@@ -1456,7 +1474,8 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 if (base >= total) break;
                 const int it = base + lane;
                 if (it < total) {
-                    const int rowi = (int)__umulhi((uint32_t)it, nw_magic), j = it - rowi * nwords;
+                    const int qd = (int)__umulhi((uint32_t)it, it_magic), rd = it - qd * (int)it_div;
+                    const int j = word_major ? qd : rd, rowi = word_major ? rd : qd;
                     const int sd = rowi >= T ? 1 : 0, rr2 = rowi - sd * T;
                     uint32_t lo = 0, hi = 0, nn = 0, lq = 0, cqw = 0;
                     if (rr2 < rows) {

@@ -454,7 +454,12 @@ struct fp_overrep_side {
     const unsigned long long* thash;  /* [table_size] hash of the candidate, 0 = empty slot */
     const int32_t* tidx;              /* [table_size] candidate index                       */
     int table_mask, K, eval_len;
+    const uint32_t* bitmap;           /* bit (slot & bitmap_mask) set iff some slot folding there is occupied (copied to shared memory) */
+    int bitmap_mask;                  /* bits - 1, bits <= FP_OVERREP_BM_BITS; -1 without candidates */
+    int steps[5];                     /* 10, 20, 40, 100, min(150, eval_len - 2)            */
+    unsigned long long bpow[5];       /* FP_OVERREP_HASH_B ^ steps[i]                       */
 };
+#define FP_OVERREP_BM_BITS 32768
 
 struct fp_overrep_args {
     fp_batch b;
@@ -469,14 +474,20 @@ struct fp_overrep_args {
     const unsigned int* list_n;
 };
 
-__device__ __forceinline__ unsigned long long overrep_pow(int step) {
+static inline unsigned long long fp_overrep_pow(int step) {
     unsigned long long r = 1, b = FP_OVERREP_HASH_B;
-    for (int e = step; e; e >>= 1) { if (e & 1) r *= b; b *= b; }
+    for (int e = step; e > 0; e >>= 1) { if (e & 1) r *= b; b *= b; }
     return r;
 }
 
 __global__ void __launch_bounds__(256) fp_overrep_kernel(const fp_overrep_args a) {
     __shared__ unsigned long long s_pref[8][FP_MAX_STRIDE + 1];
+    __shared__ uint32_t s_bm[2][FP_OVERREP_BM_BITS / 32];
+    /* nearly every window is no candidate: the occupancy bits of the hash table sit in shared memory, the table itself is read only
+       for a window whose home slot is taken */
+    for (int sd = 0; sd < a.sides; sd++)
+        for (int i = threadIdx.x; i <= (a.side[sd].bitmap_mask >> 5); i += blockDim.x) s_bm[sd][i] = a.side[sd].bitmap[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * 8 + warp;             /* one warp per (sampled read, side) */
     const long long unit = gw / a.sides;
@@ -496,39 +507,51 @@ __global__ void __launch_bounds__(256) fp_overrep_kernel(const fp_overrep_args a
     if (a.post) { const fp_read_result r = a.res[sd][row]; seq += r.front; len = r.len; }
     if (len > a.b.stride) len = a.b.stride;
     unsigned long long* pref = s_pref[warp];
-    if (lane == 0) {
-        unsigned long long h = 0;
-        pref[0] = 0;
-        for (int i = 0; i < len; i++) { h = h * FP_OVERREP_HASH_B + (unsigned long long)(seq[i] + 1); pref[i + 1] = h; }
+    {
+        /* prefix hashes, 32 chunks at once: a chunk is the affine map h -> h*m + a; an inclusive warp scan of the
+         * compositions gives every lane the hash in front of its chunk (same values as the serial recurrence) */
+        const int c = (len + 31) >> 5;
+        const int j0 = min(lane * c, len), j1 = min(j0 + c, len);
+        unsigned long long m = 1, av = 0;
+        for (int j = j0; j < j1; j++) { av = av * FP_OVERREP_HASH_B + (unsigned long long)(seq[j] + 1); m *= FP_OVERREP_HASH_B; }
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long pm = __shfl_up_sync(FULL_MASK, m, o), pa = __shfl_up_sync(FULL_MASK, av, o);
+            if (lane >= o) { av = pa * m + av; m = pm * m; }
+        }
+        unsigned long long h = __shfl_up_sync(FULL_MASK, av, 1);
+        if (lane == 0) { h = 0; pref[0] = 0; }
+        for (int j = j0; j < j1; j++) { h = h * FP_OVERREP_HASH_B + (unsigned long long)(seq[j] + 1); pref[j + 1] = h; }
     }
     __syncwarp();
     const int stats = sd * 2 + a.post;
-    const int steps[5] = {10, 20, 40, 100, min(150, S.eval_len - 2)};
+    const uint32_t* bm = s_bm[sd];
+    #pragma unroll 1
     for (int s5 = 0; s5 < 5; s5++) {
-        const int step = steps[s5];
+        const int step = S.steps[s5];
         if (step <= 0) continue;
-        const unsigned long long bp = overrep_pow(step);
+        const unsigned long long bp = S.bpow[s5];
         const int npos = len - step;                                   /* i in [0, npos) */
         int allowed = 0;
         for (int base = 0; base < npos; base += 32) {
             const int i = base + lane;
+            /* every lane: the first slot whose hash and length match (bytes not compared yet) */
             int hit = -1;
+            unsigned int hslot = 0;
+            unsigned long long h = 0;
             if (i < npos) {
-                unsigned long long h = pref[i + step] - pref[i] * bp;
+                h = pref[i + step] - pref[i] * bp;
                 if (h == 0) h = 1;
-                for (unsigned int slot = (unsigned int)(h ^ (h >> 32)) & S.table_mask;; slot = (slot + 1) & S.table_mask) {
-                    const unsigned long long th = S.thash[slot];
-                    if (th == 0) break;
-                    if (th == h) {
-                        const int k = S.tidx[slot];
-                        if (S.len[k] == step) {
-                            const uint8_t* c = S.blob + S.off[k];
-                            bool eq = true;
-                            for (int j = 0; j < step && eq; j++) eq = (c[j] == seq[i + j]);
-                            if (eq) { hit = k; break; }
+                const unsigned int home = (unsigned int)(h ^ (h >> 32)) & S.table_mask, bi = home & (unsigned int)S.bitmap_mask;
+                if ((bm[bi >> 5] >> (bi & 31)) & 1u)
+                    for (unsigned int slot = home;; slot = (slot + 1) & S.table_mask) {
+                        const unsigned long long th = S.thash[slot];
+                        if (th == 0) break;
+                        if (th == h) {
+                            const int k = S.tidx[slot];
+                            if (S.len[k] == step) { hit = k; hslot = slot; break; }
                         }
                     }
-                }
             }
             unsigned m = __ballot_sync(FULL_MASK, hit >= 0);
             while (m) {                                                /* accept hits in increasing i under the skip rule */
@@ -536,7 +559,30 @@ __global__ void __launch_bounds__(256) fp_overrep_kernel(const fp_overrep_args a
                 m &= m - 1;
                 const int hi = base + bit;
                 if (hi >= allowed) {
-                    const int k = __shfl_sync(FULL_MASK, hit, bit);
+                    /* only a window that can be accepted is compared byte by byte, by the whole warp */
+                    int k = __shfl_sync(FULL_MASK, hit, bit);
+                    const uint8_t* c = S.blob + S.off[k];
+                    bool eq = true;
+                    for (int j = lane; j < step; j += 32) eq = eq && (c[j] == seq[hi + j]);
+                    if (!__all_sync(FULL_MASK, eq)) {
+                        /* a 64-bit hash collision: the owning lane walks on alone, comparing bytes itself */
+                        if (lane == bit) {
+                            hit = -1;
+                            for (unsigned int slot = (hslot + 1) & S.table_mask;; slot = (slot + 1) & S.table_mask) {
+                                const unsigned long long th = S.thash[slot];
+                                if (th == 0) break;
+                                if (th != h) continue;
+                                const int k2 = S.tidx[slot];
+                                if (S.len[k2] != step) continue;
+                                const uint8_t* c2 = S.blob + S.off[k2];
+                                bool e2 = true;
+                                for (int j = 0; j < step && e2; j++) e2 = (c2[j] == seq[hi + j]);
+                                if (e2) { hit = k2; break; }
+                            }
+                        }
+                        k = __shfl_sync(FULL_MASK, hit, bit);
+                        if (k < 0) continue;
+                    }
                     if (lane == 0) red_add64(&a.counters[fp_off_overrep_count(&a.L, stats, k)], 1ull);
                     for (int q = hi + lane; q < hi + step && q < S.eval_len; q += 32) red_add64(&a.counters[fp_off_overrep_dist(&a.L, stats, k, q)], 1ull);
                     allowed = hi + step + 1;
