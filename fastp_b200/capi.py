@@ -110,6 +110,9 @@ class FastqInfo(C.Structure):
 
 
 # name -> (restype, argtypes): every symbol include/fastp_b200.h declares
+FP_B_INDEXED = 0x1          # fp_batch.flags
+FP_B_PACK2BIT = 0x2
+
 SYMBOLS = {
     "fp_params_default": (None, [C.POINTER(Params), C.c_int]),
     "fp_counter_layout_make": (None, [C.POINTER(CounterLayout), C.c_int, C.c_int, C.c_int]),
@@ -128,6 +131,7 @@ SYMBOLS = {
                                              C.POINTER(C.c_uint64)]),
     "fp_set_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "fp_set_host_event_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "fp_set_host_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "fp_host_pack_rows": (C.c_int, [C.POINTER(Batch), C.c_int, C.POINTER(PackedBatch), C.c_int]),
     "fp_process_se_host_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.c_void_p]),
     "fp_process_pe_host_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,

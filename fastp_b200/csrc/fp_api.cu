@@ -68,6 +68,7 @@ struct fp_ctx {
     uint8_t* d_ovr_blob[2] = {nullptr, nullptr};
     int32_t *d_ovr_off[2] = {nullptr, nullptr}, *d_ovr_len[2] = {nullptr, nullptr}, *d_ovr_tidx[2] = {nullptr, nullptr};
     unsigned long long* d_ovr_thash[2] = {nullptr, nullptr};
+    uint32_t* d_ovr_bitmap[2] = {nullptr, nullptr};
     unsigned int *d_ovr_blocksum = nullptr, *d_ovr_list = nullptr, *d_ovr_list_n = nullptr;
     unsigned long long* d_ovr_base = nullptr;      /* [2] ping-pong: counted reads seen before this batch */
     int ovr_base_cur = 0;
@@ -97,6 +98,11 @@ struct fp_ctx {
     uint8_t* d_pk[2][4] = {{nullptr}};          /* packed staging per chunk slot: bases1 qual1 bases2 qual2 */
     fp_npos* d_npos[2] = {nullptr, nullptr};
     size_t pk_cap_b = 0, pk_cap_q = 0, npos_cap = 0;
+    /* FP_B_PACK2BIT: pinned host staging of the packing team (4 slots so that it runs two chunks ahead of the copies) */
+    uint8_t* h_pkb[4][2] = {{nullptr}};
+    fp_npos* h_np[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_pkb_cap = 0, h_np_cap = 0;
+    int host_threads = 0;                       /* 0 = default_host_threads() */
     /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
@@ -323,7 +329,10 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
             if (S.K == 0) continue;
             std::vector<uint8_t> blob; std::vector<int32_t> off, len;
             for (auto& q : cs) { off.push_back((int32_t)blob.size()); len.push_back((int32_t)q.size()); blob.insert(blob.end(), q.begin(), q.end()); }
-            int tsize = 64; while (tsize < 4 * S.K) tsize <<= 1;
+            /* sparse table (1/16 full while the occupancy bits fit the kernel's shared-memory copy, never more than 1/4) */
+            int tsize = 64;
+            while (tsize < 16 * S.K && tsize < FP_OVERREP_BM_BITS) tsize <<= 1;
+            while (tsize < 4 * S.K) tsize <<= 1;
             std::vector<unsigned long long> th(tsize, 0); std::vector<int32_t> ti(tsize, -1);
             for (int k = 0; k < S.K; k++) {
                 unsigned long long h = 0;
@@ -334,6 +343,14 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
                 th[slot] = h; ti[slot] = k;
             }
             S.table_mask = tsize - 1;
+            const int bm_bits = std::min(tsize, FP_OVERREP_BM_BITS);
+            std::vector<uint32_t> bm(bm_bits / 32, 0);
+            for (int slot = 0; slot < tsize; slot++) if (th[slot]) { const int bi = slot & (bm_bits - 1); bm[bi >> 5] |= 1u << (bi & 31); }
+            S.bitmap_mask = bm_bits - 1;
+            const int st5[5] = {10, 20, 40, 100, std::min(150, S.eval_len - 2)};
+            for (int i = 0; i < 5; i++) { S.steps[i] = st5[i]; S.bpow[i] = fp_overrep_pow(st5[i]); }
+            CK(cudaMalloc(&c->d_ovr_bitmap[sd], bm.size() * 4)); CK(cudaMemcpy(c->d_ovr_bitmap[sd], bm.data(), bm.size() * 4, cudaMemcpyHostToDevice));
+            S.bitmap = c->d_ovr_bitmap[sd];
             CK(cudaMalloc(&c->d_ovr_blob[sd], blob.size() + 16)); CK(cudaMemcpy(c->d_ovr_blob[sd], blob.data(), blob.size(), cudaMemcpyHostToDevice));
             CK(cudaMalloc(&c->d_ovr_off[sd], off.size() * 4)); CK(cudaMemcpy(c->d_ovr_off[sd], off.data(), off.size() * 4, cudaMemcpyHostToDevice));
             CK(cudaMalloc(&c->d_ovr_len[sd], len.size() * 4)); CK(cudaMemcpy(c->d_ovr_len[sd], len.data(), len.size() * 4, cudaMemcpyHostToDevice));
@@ -403,6 +420,12 @@ static void free_staging(fp_ctx* c) {
         if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
         if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
     }
+    for (int i = 0; i < 4; i++) {
+        for (int k = 0; k < 2; k++) { if (c->h_pkb[i][k]) cudaFreeHost(c->h_pkb[i][k]); c->h_pkb[i][k] = nullptr; }
+        if (c->h_np[i]) cudaFreeHost(c->h_np[i]);
+        c->h_np[i] = nullptr;
+    }
+    c->h_pkb_cap = c->h_np_cap = 0;
     c->chunk = 0; c->pk_cap_b = c->pk_cap_q = c->npos_cap = 0;
 }
 
@@ -427,7 +450,7 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     cudaFree(c->d_ovlimit); cudaFree(c->d_lowq); cudaFree(c->d_mindiff); cudaFree(c->d_adapters);
     cudaFree(c->d_fasta_off); cudaFree(c->d_fasta_len); cudaFree(c->d_raw); cudaFree(c->d_fin);
     cudaFree(c->d_aplanes); cudaFree(c->d_aclean);
-    for (int sd = 0; sd < 2; sd++) { cudaFree(c->d_ovr_blob[sd]); cudaFree(c->d_ovr_off[sd]); cudaFree(c->d_ovr_len[sd]); cudaFree(c->d_ovr_thash[sd]); cudaFree(c->d_ovr_tidx[sd]); }
+    for (int sd = 0; sd < 2; sd++) { cudaFree(c->d_ovr_blob[sd]); cudaFree(c->d_ovr_off[sd]); cudaFree(c->d_ovr_len[sd]); cudaFree(c->d_ovr_thash[sd]); cudaFree(c->d_ovr_tidx[sd]); cudaFree(c->d_ovr_bitmap[sd]); }
     cudaFree(c->d_ovr_blocksum); cudaFree(c->d_ovr_list); cudaFree(c->d_ovr_list_n); cudaFree(c->d_ovr_base); cudaFree(c->d_pass_count);
     if (c->ovr_ev) cudaEventDestroy(c->ovr_ev);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -696,6 +719,36 @@ __global__ void fp_unpack_n_kernel(const fp_npos* __restrict__ np, long long cnt
 }
 
 #include <thread>
+#include <atomic>
+#include <memory>
+#include <sched.h>
+#include "fp_hostpack.h"
+
+/* CPUs this process may really use: the affinity mask, cut by a cgroup CPU quota (a container with 16 CPUs of a 128-core box) */
+static int usable_cpus() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64]; long long period = 0;
+        if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) n = std::min<long long>(n, std::max<long long>(1, atoll(q) / period));
+        fclose(f);
+    } else {
+        long long quota = -1, period = 0;
+        if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(g, "%lld", &quota) != 1) quota = -1; fclose(g); }
+        if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(g, "%lld", &period) != 1) period = 0; fclose(g); }
+        if (quota > 0 && period > 0) n = std::min<long long>(n, std::max<long long>(1, quota / period));
+    }
+    return std::max(n, 1);
+}
+static int default_host_threads() { return std::min(std::max(usable_cpus() - 1, 1), 32); }
+
+extern "C" int fp_set_host_threads(fp_ctx* c, int threads) {
+    if (!c || threads < 0) return set_err(FP_E_INVAL, "bad argument");
+    c->host_threads = threads;
+    return FP_OK;
+}
+
 extern "C" int fp_host_pack_rows(const fp_batch* rows, int paired, fp_packed_batch* out, int threads) {
     if (!rows || !out || !out->bases1 || !out->qual1 || !out->len1 || (paired && (!out->bases2 || !out->qual2 || !out->len2))) return set_err(FP_E_INVAL, "null argument");
     if (rows->n >= ((int64_t)1 << 32)) return set_err(FP_E_TOOLARGE, "batch larger than 2^32");
@@ -706,52 +759,16 @@ extern "C" int fp_host_pack_rows(const fp_batch* rows, int paired, fp_packed_bat
     std::vector<int> bad(threads, 0);
     auto work = [&](int t) {
         const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
-        for (int sd = 0; sd < (paired ? 2 : 1); sd++) {
-            const uint8_t* seq = sd ? rows->seq2 : rows->seq1; const uint8_t* qual = sd ? rows->qual2 : rows->qual1; const uint16_t* len = sd ? rows->len2 : rows->len1;
-            uint8_t* ob = sd ? out->bases2 : out->bases1; uint8_t* oq = sd ? out->qual2 : out->qual1; uint16_t* ol = sd ? out->len2 : out->len1;
-            for (int64_t r = lo; r < hi; r++) {
+        for (int64_t r = lo; r < hi; r++)                                  /* read 1 then read 2 of a unit: the list comes out sorted by unit */
+            for (int sd = 0; sd < (paired ? 2 : 1); sd++) {
+                const uint8_t* seq = sd ? rows->seq2 : rows->seq1; const uint8_t* qual = sd ? rows->qual2 : rows->qual1; const uint16_t* len = sd ? rows->len2 : rows->len1;
+                uint8_t* ob = sd ? out->bases2 : out->bases1; uint8_t* oq = sd ? out->qual2 : out->qual1; uint16_t* ol = sd ? out->len2 : out->len1;
                 const int L = len[r];
-                if ((L + 3) / 4 > pb || L > pq) { bad[t] = 2; return; }
-                const uint8_t* s = seq + r * S; uint8_t* d = ob + r * pb;
-                int k = 0;
-                for (; k + 8 <= L; k += 8) {                               /* 8 bases per step: all of them A/C/G/T ? -> 16 bits by one multiply */
-                    uint64_t x; memcpy(&x, s + k, 8);
-                    const uint64_t K = 0x0101010101010101ull;
-                    const uint64_t common = (x & 0xE8E8E8E8E8E8E8E8ull) ^ 0x4040404040404040ull;          /* bits 7,6,5 = 010, bit 3 = 0 */
-                    const uint64_t v1 = ((x >> 4) ^ x) & K;                                                  /* bit4 != bit0  (T <-> bit4) */
-                    const uint64_t v2 = ((((x >> 2) & ~(x >> 1)) ^ x)) & K;                                  /* (bit2 & !bit1) != bit0 */
-                    if (common == 0 && v1 == K && v2 == K) {
-                        const uint64_t c2 = (x >> 1) & 0x0303030303030303ull;                                 /* 2-bit codes, one per byte */
-                        const uint32_t lo4 = (uint32_t)c2, hi4 = (uint32_t)(c2 >> 32);                         /* four codes -> one byte by a multiply */
-                        d[k >> 2] = (uint8_t)((lo4 * 0x01041040u) >> 24);
-                        d[(k >> 2) + 1] = (uint8_t)((hi4 * 0x01041040u) >> 24);
-                        continue;
-                    }
-                    for (int j = 0; j < 8; j += 4) {                       /* an N (or something else) in this group: byte by byte */
-                        uint8_t o = 0;
-                        for (int i = 0; i < 4; i++) {
-                            const uint8_t ch = s[k + j + i];
-                            if (ch == 'N') nl[t].push_back(fp_npos{(uint32_t)r, (uint16_t)(k + j + i), (uint8_t)sd, 0});
-                            else if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { bad[t] = 1; return; }
-                            else o |= (uint8_t)(((ch >> 1) & 3) << (2 * i));
-                        }
-                        d[(k + j) >> 2] = o;
-                    }
-                }
-                for (; k < L; k += 4) {
-                    uint8_t o = 0;
-                    for (int i = 0; i < 4 && k + i < L; i++) {
-                        const uint8_t ch = s[k + i];
-                        if (ch == 'N') nl[t].push_back(fp_npos{(uint32_t)r, (uint16_t)(k + i), (uint8_t)sd, 0});
-                        else if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { bad[t] = 1; return; }
-                        else o |= (uint8_t)(((ch >> 1) & 3) << (2 * i));
-                    }
-                    d[k >> 2] = o;
-                }
+                if ((L + 3) / 4 > pb || L > pq || L > S) { bad[t] = 2; return; }
+                if (fp_pack_bases_row(seq + r * S, L, ob + r * pb, (uint32_t)r, sd, nl[t])) { bad[t] = 1; return; }
                 memcpy(oq + r * pq, qual + r * S, L);
                 ol[r] = (uint16_t)L;
             }
-        }
     };
     std::vector<std::thread> th;
     for (int t = 1; t < threads; t++) th.emplace_back(work, t);
@@ -768,7 +785,6 @@ extern "C" int fp_host_pack_rows(const fp_batch* rows, int paired, fp_packed_bat
     if (total > out->npos_cap) return set_err(FP_E_TOOLARGE, "N exception list too small (n_npos holds the size needed)");
     int64_t o = 0;
     for (auto& v : nl) {
-        std::stable_sort(v.begin(), v.end(), [](const fp_npos& a, const fp_npos& b) { return a.unit < b.unit; });
         if (!v.empty()) memcpy(out->npos + o, v.data(), v.size() * sizeof(fp_npos));
         o += (int64_t)v.size();
     }
@@ -809,7 +825,24 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     /* host rows may be tighter than the device stride (pitch = read length: no padding bytes over PCIe); they are re-pitched in HBM */
     const int HP = b->stride;
     if (HP > c->stride || HP <= 0) return set_err(FP_E_INVAL, "host row pitch must be in (0, ctx stride]");
-    const bool repitch = !pk && HP != c->stride;
+    const bool packfly = !pk && (b->flags & FP_B_PACK2BIT) != 0;
+    const bool repitch = !pk && !packfly && HP != c->stride;
+    const int PB = ((((HP + 3) >> 2) + 3) & ~3);                 /* packed bases of one row, FP_B_PACK2BIT */
+    const int NS = 4;                                          /* host staging slots of the packing team */
+    if (packfly) {
+        const size_t nb = (size_t)c->chunk * PB + 64, nq = (size_t)c->chunk * HP + 64;
+        if (nb > c->pk_cap_b || nq > c->pk_cap_q) {
+            CK(cudaDeviceSynchronize());
+            for (int i = 0; i < 2; i++)
+                for (int k = 0; k < (c->p.paired ? 4 : 2); k++) { cudaFree(c->d_pk[i][k]); c->d_pk[i][k] = nullptr; CK(cudaMalloc(&c->d_pk[i][k], (k & 1) ? nq : nb)); }
+            c->pk_cap_b = nb; c->pk_cap_q = nq;
+        }
+        if (nb > c->h_pkb_cap) {
+            for (int i = 0; i < NS; i++)
+                for (int k = 0; k < (c->p.paired ? 2 : 1); k++) { if (c->h_pkb[i][k]) cudaFreeHost(c->h_pkb[i][k]); c->h_pkb[i][k] = nullptr; CK(cudaMallocHost(&c->h_pkb[i][k], nb)); }
+            c->h_pkb_cap = nb;
+        }
+    }
     if (repitch) {
         const size_t nb = (size_t)c->chunk * HP + 64;
         if (nb > c->pk_cap_b || nb > c->pk_cap_q) {
@@ -890,10 +923,51 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         pend[slot].active = false;
         return FP_OK;
     };
+    /* FP_B_PACK2BIT: a team of host threads packs the bases of chunk k into pinned slot k % NS, up to two chunks ahead of the chunk whose
+       copies are being issued; a slot is free again once finish() has seen the chunk that used it */
+    struct Team {
+        std::vector<std::thread> th;
+        std::atomic<int64_t> allowed{-1};
+        std::atomic<int> stop{0}, bad{0};
+        std::unique_ptr<std::atomic<int>[]> done;
+        std::vector<std::vector<fp_npos>> nl;                  /* [thread * NS + slot] */
+        ~Team() { stop.store(1); for (auto& t : th) t.join(); }
+    } team;
+    const int NT = packfly ? (c->host_threads > 0 ? c->host_threads : default_host_threads()) : 0;
+    if (packfly) {
+        team.done.reset(new std::atomic<int>[(size_t)nchunks]);
+        for (int64_t k = 0; k < nchunks; k++) team.done[(size_t)k].store(0);
+        team.nl.resize((size_t)NT * NS);
+        team.allowed.store(1);
+        const int sides = pe ? 2 : 1;
+        for (int t = 0; t < NT; t++)
+            team.th.emplace_back([&, t]() {
+                for (int64_t k = 0; k < nchunks; k++) {
+                    while (team.allowed.load(std::memory_order_acquire) < k) { if (team.stop.load()) return; std::this_thread::yield(); }
+                    const int64_t lo = k * CH, cnt = std::min(CH, n - lo);
+                    const int64_t r0 = cnt * t / NT, r1 = cnt * (t + 1) / NT;
+                    std::vector<fp_npos>& nl = team.nl[(size_t)t * NS + (size_t)(k % NS)];
+                    nl.clear();
+                    for (int64_t r = r0; r < r1; r++)
+                        for (int sd = 0; sd < sides; sd++) {
+                            const int L = (sd ? b->len2 : b->len1)[lo + r];
+                            if (L > HP) { team.bad.store(2); break; }
+                            if (fp_pack_bases_row((sd ? b->seq2 : b->seq1) + (lo + r) * HP, L, c->h_pkb[k % NS][sd] + r * PB, (uint32_t)r, sd, nl)) { team.bad.store(1); break; }
+                        }
+                    team.done[(size_t)k].fetch_add(1, std::memory_order_release);
+                }
+            });
+    }
     for (int64_t ci = 0; ci < nchunks; ci++) {
         const int slot = (int)(ci & 1);
         rc = finish(slot);
         if (rc) return rc;
+        if (packfly) {
+            team.allowed.store(ci + 2, std::memory_order_release);
+            while (team.done[(size_t)ci].load(std::memory_order_acquire) < NT) std::this_thread::yield();
+            if (team.bad.load() == 1) return set_err(FP_E_UNSUPPORTED, "a base outside {A,C,G,T,N}: not representable in packed rows (FP_B_PACK2BIT)");
+            if (team.bad.load() == 2) return set_err(FP_E_INVAL, "a read is longer than the host row pitch");
+        }
         const int64_t lo = ci * CH, cnt = std::min(CH, n - lo);
         cudaStream_t st = c->stream[slot];
         const size_t bytes = (size_t)cnt * S;
@@ -926,6 +1000,41 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 }
                 CK(cudaMemcpyAsync(c->d_npos[slot], nb0, (size_t)nn * sizeof(fp_npos), cudaMemcpyHostToDevice, st));
                 fp_unpack_n_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(c->d_npos[slot], nn, lo, S, c->d_stage[slot][0], pe ? c->d_stage[slot][2] : nullptr);
+            }
+            CK(cudaGetLastError());
+        } else if (packfly) {
+            const int hs = (int)(ci % NS);
+            size_t nn = 0;
+            for (int t = 0; t < NT; t++) nn += team.nl[(size_t)t * NS + hs].size();
+            if (nn > c->h_np_cap) {                                /* the slots' older chunks are done (finish above): safe to re-allocate */
+                CK(cudaDeviceSynchronize());
+                const size_t cap = nn + nn / 2 + 4096;
+                for (int i = 0; i < NS; i++) { if (c->h_np[i]) cudaFreeHost(c->h_np[i]); c->h_np[i] = nullptr; CK(cudaMallocHost(&c->h_np[i], cap * sizeof(fp_npos))); }
+                c->h_np_cap = cap;
+            }
+            if (nn > c->npos_cap) {
+                CK(cudaDeviceSynchronize());
+                for (int i = 0; i < 2; i++) { cudaFree(c->d_npos[i]); c->d_npos[i] = nullptr; CK(cudaMalloc(&c->d_npos[i], (nn + nn / 2 + 1024) * sizeof(fp_npos))); }
+                c->npos_cap = nn + nn / 2 + 1024;
+            }
+            size_t o = 0;
+            for (int t = 0; t < NT; t++) { const auto& v = team.nl[(size_t)t * NS + hs]; if (!v.empty()) memcpy(c->h_np[hs] + o, v.data(), v.size() * sizeof(fp_npos)); o += v.size(); }
+            const size_t bb = (size_t)cnt * PB, qb = (size_t)cnt * HP;
+            CK(cudaMemcpyAsync(c->d_pk[slot][0], c->h_pkb[hs][0], bb, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_pk[slot][1], b->qual1 + lo * HP, qb, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_stage_len[slot][0], b->len1 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+            if (pe) {
+                CK(cudaMemcpyAsync(c->d_pk[slot][2], c->h_pkb[hs][1], bb, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(c->d_pk[slot][3], b->qual2 + lo * HP, qb, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(c->d_stage_len[slot][1], b->len2 + lo, (size_t)cnt * 2, cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(c->d_npatch[slot], 0, 4, st));
+            }
+            const long long thr = (long long)cnt * (S >> 4);
+            fp_unpack_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(c->d_pk[slot][0], c->d_pk[slot][1], c->d_stage_len[slot][0], cnt, PB, HP, S, c->d_stage[slot][0], c->d_stage[slot][1]);
+            if (pe) fp_unpack_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(c->d_pk[slot][2], c->d_pk[slot][3], c->d_stage_len[slot][1], cnt, PB, HP, S, c->d_stage[slot][2], c->d_stage[slot][3]);
+            if (nn > 0) {
+                CK(cudaMemcpyAsync(c->d_npos[slot], c->h_np[hs], nn * sizeof(fp_npos), cudaMemcpyHostToDevice, st));
+                fp_unpack_n_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(c->d_npos[slot], (long long)nn, 0, S, c->d_stage[slot][0], pe ? c->d_stage[slot][2] : nullptr);
             }
             CK(cudaGetLastError());
         } else if (repitch) {

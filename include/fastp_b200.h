@@ -124,6 +124,10 @@ void fp_params_default(fp_params* p, int paired);
  * Row i of seq1 starts at seq1 + i*stride and holds len1[i] valid bytes.
  * Bytes in [len, stride) are ignored. seq/qual are MODIFIED IN PLACE by base correction. */
 #define FP_B_INDEXED 0x1     /* fp_batch.flags: first_read_index holds the GLOBAL index of unit 0 of this batch */
+#define FP_B_PACK2BIT 0x2    /* fp_batch.flags, host entry points only: the library's host threads (fp_set_host_threads) pack the bases to
+                              * 2 bits (+ a list of the 'N's) chunk by chunk, overlapped with the copies, so that 0.25 instead of 1 byte
+                              * per base crosses PCIe; qualities go up from the caller's rows as they are.  Rows must hold A/C/G/T/N only
+                              * (else FP_E_UNSUPPORTED); results, corrected rows and patch lists are the same as without the flag. */
 typedef struct fp_batch {
     int64_t   n;            /* reads (SE) or pairs (PE)                     */
     int32_t   stride;       /* multiple of 16, <= FP_MAX_STRIDE             */
@@ -317,6 +321,9 @@ int  fp_process_pe_host_patches(fp_ctx* ctx, const fp_batch* b, fp_read_result* 
  * *n_events (which may exceed cap) -- what the reference-side shim feeds to FilterResult::addAdapterTrimmed after sorting by (unit, key). */
 int  fp_set_event_sink(fp_ctx* ctx, fp_adapter_event* d_events, uint32_t cap, uint32_t* d_count);
 int  fp_set_host_event_sink(fp_ctx* ctx, fp_adapter_event* h_events, uint64_t cap, uint64_t* n_events);
+/* Host threads the library may use for FP_B_PACK2BIT (the reference's counterpart is its `-w` worker count, src/options.h:thread).
+ * 0 (the default) = the CPUs this process can really use (affinity mask, cgroup quota) minus one. */
+int  fp_set_host_threads(fp_ctx* ctx, int threads);
 
 /* ---------------- packed host rows: the end-to-end path is PCIe-bound, so send fewer bytes ----------------
  * 2 bits per base (code = (ascii >> 1) & 3: A0 C1 T2 G3; base k of a read in bits 2(k&3) of byte k>>2), qualities as they are, rows at

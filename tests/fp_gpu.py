@@ -126,12 +126,15 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
         for k in a:
             a[k] = t[k].cpu().numpy()
         extra = {"patches": patches, "n_patches": npatch} if paired else {}
-    elif mode == "host_tight":
-        # host rows at pitch = longest read (no padding bytes over PCIe); corrected rows come back at that pitch
+    elif mode in ("host_tight", "host_tight_pack2bit"):
+        # host rows at pitch = longest read (no padding bytes over PCIe); corrected rows come back at that pitch.
+        # _pack2bit: FP_B_PACK2BIT, the library's host threads pack the bases chunk by chunk under the copies
         Lmax = int(max(a["len1"].max(initial=1), a["len2"].max(initial=1) if paired else 1))
         tight = {k: (np.ascontiguousarray(v[:, :Lmax]) if v.ndim == 2 else v) for k, v in a.items()}
         b = capi.batch_from_arrays(tight)
         assert b.stride == Lmax
+        if mode.endswith("pack2bit"):
+            b.flags |= capi.FP_B_PACK2BIT
         if paired:
             capi.check(lib.fp_process_pe_host(ctx.h, C.byref(b), out1.ctypes.data, out2.ctypes.data, ov.ctypes.data), lib)
         else:
@@ -156,6 +159,8 @@ def run_gpu(params, arrs, cycles, mode="device", ctx=None, splits=1):
         extra = {"packed_bytes": keep["bytes"]}
     else:
         b = capi.batch_from_arrays(a)
+        if mode == "host_pack2bit":
+            b.flags |= capi.FP_B_PACK2BIT
         if paired:
             capi.check(lib.fp_process_pe_host(ctx.h, C.byref(b), out1.ctypes.data, out2.ctypes.data, ov.ctypes.data), lib)
         else:

@@ -265,3 +265,25 @@ def test_host_rows_at_a_tight_pitch(gpu, name, paired):
     want = T.run_cpu("oracle", p, arrs, 160)
     got = gpu.run_gpu(p, arrs, 160, mode="host_tight")
     T.assert_results_equal(got, want, paired, what=f"tight pitch {name}")
+
+
+@pytest.mark.parametrize("name,paired,mode", [("cfg3_overlap_correction", 1, "host_tight_pack2bit"), ("cfg4_full", 1, "host_pack2bit"),
+                                              ("cfg2_cut_right_polyg", 0, "host_tight_pack2bit")])
+def test_host_rows_packed_on_the_fly(gpu, name, paired, mode):
+    """FP_B_PACK2BIT: the library's host threads pack the bases to 2 bits chunk by chunk while the previous chunks are copied (1.2 M units =
+    five chunks, so the staging slots of the packing team are re-used); results, counters and the corrected rows in the caller's buffers
+    are the same as without the flag"""
+    p = T.config_params(name, paired)
+    _, arrs = T.synth_host(1200000, 160, paired, 5, 47, 1, 150)
+    want = T.run_cpu("oracle", p, arrs, 160)
+    got = gpu.run_gpu(p, arrs, 160, mode=mode)
+    T.assert_results_equal(got, want, paired, what=f"{mode} {name}")
+
+
+def test_pack2bit_rejects_other_bytes(gpu):
+    """a base outside {A,C,G,T,N} cannot be packed: FP_E_UNSUPPORTED, not a wrong answer"""
+    p = T.config_params("default", 1)
+    _, arrs = T.synth_host(5000, 160, 1, 5, 48, 1, 150)
+    arrs["seq1"][1234, 7] = ord("R")
+    with pytest.raises(Exception):
+        gpu.run_gpu(p, arrs, 160, mode="host_pack2bit")
