@@ -51,6 +51,7 @@ class Params(C.Structure):
         ("overrep_enabled", C.c_int32), ("overrep_sampling", C.c_int32),
         ("n_overrep1", C.c_int32), ("overrep_seqs1", C.POINTER(C.c_char_p)),
         ("n_overrep2", C.c_int32), ("overrep_seqs2", C.POINTER(C.c_char_p)),
+        ("merge_enabled", C.c_int32), ("merge_include_unmerged", C.c_int32),
     ]
 
 

@@ -103,6 +103,7 @@ struct fp_ctx {
     fp_npos* h_np[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_pkb_cap = 0, h_np_cap = 0;
     int host_threads = 0;                       /* 0 = default_host_threads() */
+    cudaEvent_t chunk_done[2] = {nullptr, nullptr};   /* end of a host chunk's work on its stream (cudaEventBlockingSync) */
     /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
@@ -128,20 +129,22 @@ struct fp_ctx {
 };
 
 static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov, std::vector<int16_t>& lowq, std::vector<int16_t>& mind) {
-    ov.assign(stride + 2, 0); lowq.assign(stride + 2, 0); mind.assign(stride + 2, 0);
+    /* the two passFilter tables cover merged reads as well (up to two rows long); the kernel's shared-memory copy takes the first stride + 2 */
+    const int maxlen = 2 * stride;
+    ov.assign(stride + 2, 0); lowq.assign(maxlen + 2, 0); mind.assign(maxlen + 2, 0);
     const double diffPercentLimit = p->overlap_diff_percent_limit / 100.0;        /* peprocessor.cpp:439 */
     for (int ol = 0; ol <= stride; ol++) {
         int v = std::min(p->overlap_diff_limit, (int)(ol * diffPercentLimit));    /* overlapanalysis.cpp:51 */
         ov[ol] = (int16_t)v;
     }
-    for (int rlen = 0; rlen <= stride; rlen++) {
+    for (int rlen = 0; rlen <= maxlen; rlen++) {
         /* lowQualNum > (unqualifiedPercentLimit * rlen / 100.0)   filter.cpp:37 : largest int NOT exceeding the bound */
         double bound = p->unqualified_percent_limit * rlen / 100.0;
         int n = 0;
-        while (n <= stride && !((double)n > bound)) n++;       /* first n with n > bound */
+        while (n <= maxlen && !((double)n > bound)) n++;       /* first n with n > bound */
         lowq[rlen] = (int16_t)(n - 1);
     }
-    for (int len = 0; len <= stride; len++) {
+    for (int len = 0; len <= maxlen; len++) {
         /* pass iff (double)diff/(double)(len-1) >= threshold   filter.cpp:65 */
         int d = len + 1;
         if (len > 1) {
@@ -253,6 +256,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     for (auto& s : c->fasta) if (s.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
     if (c->ad1.size() > FP_MAX_ADAPTER_LEN || c->ad2.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
     c->max_batch = max_batch; c->stride = stride; c->cycles = cycles;
+    if (p->merge_enabled && p->paired && p->overrep_enabled) { delete c; return set_err(FP_E_UNSUPPORTED, "merge mode together with over-representation analysis is not built"); }
     if (p->overrep_enabled) {
         if (p->overrep_sampling < 1) { delete c; return set_err(FP_E_INVAL, "overrep_sampling must be >= 1"); }
         for (int i = 0; i < p->n_overrep1; i++) c->overrep[0].push_back(p->overrep_seqs1[i]);
@@ -277,7 +281,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CK(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventBlockingSync | cudaEventDisableTiming)); }
 
     /* LUTs */
     std::vector<int16_t> ov, lowq, mind;
@@ -378,6 +382,7 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     d.n_fasta = (int)c->fasta.size();
     d.fasta_match_req = d.n_fasta > 256 ? 6 : d.n_fasta > 16 ? 5 : 4;                                /* adaptertrimmer.cpp:49-53 */
     d.dimer_max_len = p->dimer_max_len;
+    d.merge = p->merge_enabled && p->paired; d.merge_unmerged = p->merge_include_unmerged;
     d.correction = p->correction_enabled; d.ov_require = p->overlap_require; d.allow_gap = p->allow_gap_overlap_trimming; d.ov_diff_limit = p->overlap_diff_limit;
     d.qual_filter = p->qual_filter_enabled; d.qualified_qual = p->qualified_qual & 0xFF; d.n_base_limit = p->n_base_limit; d.avg_qual_req = p->avg_qual_req;
     d.length_filter = p->length_filter_enabled; d.length_required = p->length_required; d.length_limit = p->length_limit;
@@ -455,7 +460,7 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     if (c->ovr_ev) cudaEventDestroy(c->ovr_ev);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    for (int i = 0; i < 2; i++) { if (c->stream[i]) cudaStreamDestroy(c->stream[i]); if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]); }
     delete c;
 }
 
@@ -721,6 +726,8 @@ __global__ void fp_unpack_n_kernel(const fp_npos* __restrict__ np, long long cnt
 #include <thread>
 #include <atomic>
 #include <memory>
+#include <mutex>
+#include <condition_variable>
 #include <sched.h>
 #include "fp_hostpack.h"
 
@@ -884,7 +891,7 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     if (!want_ev) { c->ev_dev = nullptr; c->ev_cap = 0; c->ev_count = nullptr; }
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return FP_OK;
-        CK(cudaStreamSynchronize(c->stream[slot]));
+        CK(cudaEventSynchronize(c->chunk_done[slot]));           /* blocking-sync event: the waiting thread sleeps instead of spinning */
         if (want_ev) {
             const uint32_t ne = *c->h_nev[slot];
             const uint32_t have = std::min(ne, c->ev_chunk_cap);
@@ -927,23 +934,29 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
        copies are being issued; a slot is free again once finish() has seen the chunk that used it */
     struct Team {
         std::vector<std::thread> th;
-        std::atomic<int64_t> allowed{-1};
-        std::atomic<int> stop{0}, bad{0};
-        std::unique_ptr<std::atomic<int>[]> done;
+        std::mutex mu;
+        std::condition_variable cv_allowed, cv_done;           /* blocking waits: spinning threads would eat the CPU quota the packers need */
+        int64_t allowed = -1;
+        bool stop = false;
+        std::atomic<int> bad{0};
+        std::vector<int> done;                                 /* [chunk] threads that finished it (under mu) */
         std::vector<std::vector<fp_npos>> nl;                  /* [thread * NS + slot] */
-        ~Team() { stop.store(1); for (auto& t : th) t.join(); }
+        ~Team() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv_allowed.notify_all(); for (auto& t : th) t.join(); }
     } team;
     const int NT = packfly ? (c->host_threads > 0 ? c->host_threads : default_host_threads()) : 0;
     if (packfly) {
-        team.done.reset(new std::atomic<int>[(size_t)nchunks]);
-        for (int64_t k = 0; k < nchunks; k++) team.done[(size_t)k].store(0);
+        team.done.assign((size_t)nchunks, 0);
         team.nl.resize((size_t)NT * NS);
-        team.allowed.store(1);
-        const int sides = pe ? 2 : 1;
+        team.allowed = 1;
         for (int t = 0; t < NT; t++)
             team.th.emplace_back([&, t]() {
+                const int sides = pe ? 2 : 1;
                 for (int64_t k = 0; k < nchunks; k++) {
-                    while (team.allowed.load(std::memory_order_acquire) < k) { if (team.stop.load()) return; std::this_thread::yield(); }
+                    {
+                        std::unique_lock<std::mutex> lk(team.mu);
+                        team.cv_allowed.wait(lk, [&] { return team.stop || team.allowed >= k; });
+                        if (team.stop) return;
+                    }
                     const int64_t lo = k * CH, cnt = std::min(CH, n - lo);
                     const int64_t r0 = cnt * t / NT, r1 = cnt * (t + 1) / NT;
                     std::vector<fp_npos>& nl = team.nl[(size_t)t * NS + (size_t)(k % NS)];
@@ -954,7 +967,9 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                             if (L > HP) { team.bad.store(2); break; }
                             if (fp_pack_bases_row((sd ? b->seq2 : b->seq1) + (lo + r) * HP, L, c->h_pkb[k % NS][sd] + r * PB, (uint32_t)r, sd, nl)) { team.bad.store(1); break; }
                         }
-                    team.done[(size_t)k].fetch_add(1, std::memory_order_release);
+                    bool last;
+                    { std::lock_guard<std::mutex> lk(team.mu); last = ++team.done[(size_t)k] == NT; }
+                    if (last) team.cv_done.notify_all();
                 }
             });
     }
@@ -963,8 +978,9 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         rc = finish(slot);
         if (rc) return rc;
         if (packfly) {
-            team.allowed.store(ci + 2, std::memory_order_release);
-            while (team.done[(size_t)ci].load(std::memory_order_acquire) < NT) std::this_thread::yield();
+            { std::lock_guard<std::mutex> lk(team.mu); team.allowed = ci + 2; }
+            team.cv_allowed.notify_all();
+            { std::unique_lock<std::mutex> lk(team.mu); team.cv_done.wait(lk, [&] { return team.done[(size_t)ci] >= NT; }); }
             if (team.bad.load() == 1) return set_err(FP_E_UNSUPPORTED, "a base outside {A,C,G,T,N}: not representable in packed rows (FP_B_PACK2BIT)");
             if (team.bad.load() == 2) return set_err(FP_E_INVAL, "a read is longer than the host row pitch");
         }
@@ -1089,6 +1105,7 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)c->patch_cap * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
             }
         }
+        CK(cudaEventRecord(c->chunk_done[slot], st));
         pend[slot].lo = lo; pend[slot].cnt = cnt; pend[slot].active = true;
     }
     for (int s = 0; s < 2; s++) { rc = finish(s); if (rc) return rc; }

@@ -15,6 +15,15 @@
 #pragma once
 #include "fp_device.cuh"
 
+/* unroll factors of the two hottest loops (plane / histogram items, dense column pass): measured, see profiles/README.md */
+#ifndef FP_ITEM_UNROLL
+#define FP_ITEM_UNROLL 1
+#endif
+#ifndef FP_DENSE_UNROLL
+#define FP_DENSE_UNROLL 1
+#endif
+static constexpr int kItemUnroll = FP_ITEM_UNROLL, kDenseUnroll = FP_DENSE_UNROLL;   /* (#pragma unroll does not expand macros) */
+
 /* thread-level view of one read: row pointers (smem), plane pointers, current window */
 /* shared-memory counter += 1 at a 32-bit shared-window address, optionally predicated (no branch, no return value) */
 __device__ __forceinline__ void smem_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory"); }
@@ -1057,6 +1066,73 @@ __device__ __noinline__ int t_pass_filter(const TRead r, int PW, const int16_t* 
     return FP_PASS_FILTER;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * --merge (peprocessor.cpp:519-560).  The merged read is never materialised: it is a view over the two tile rows
+ * (OverlapAnalysis::merge, overlapanalysis.cpp:148-179): positions [0, n1) are s1[0, n1) (read 1 from its trimmed start), position
+ * n1 + k is the complement of s2[n2 - 1 - k] with that base's quality (read 2 from its trimmed start).  n2 = 0: a plain read (the
+ * unmerged reads of --include_unmerged).  A feature path, not a tuned one: the group's lanes share the positions, the Stats go to
+ * the global block by RED (a merged read can be two rows long, longer than the block-private accumulators).
+ * ------------------------------------------------------------------------------------------------ */
+struct MView { const uint8_t *s1, *q1, *s2, *q2; int n1, n2; };
+__device__ __forceinline__ uint8_t mv_base(const MView& v, int j) { return j < v.n1 ? v.s1[j] : dev_complement(v.s2[v.n2 - 1 - (j - v.n1)]); }
+__device__ __forceinline__ uint8_t mv_qual(const MView& v, int j) { return j < v.n1 ? v.q1[j] : v.q2[v.n2 - 1 - (j - v.n1)]; }
+__device__ __forceinline__ int group_sum(int v, int g) {
+    const unsigned gm = group_mask(g);
+    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
+    return v;
+}
+
+/* Filter::passFilter (filter.cpp:15-57) of a view */
+__device__ __noinline__ int t_pass_filter_view(const MView v, int sub, int g) {
+    const int rlen = v.n1 + v.n2;
+    if (rlen == 0) return FP_FAIL_LENGTH;
+    int lowq = 0, nb = 0, tq = 0, adj = 0;
+    const uint8_t qq = (uint8_t)c_p.qualified_qual;
+    for (int i = sub; i < rlen; i += g) {
+        const uint8_t b = mv_base(v, i), q = mv_qual(v, i);
+        lowq += (q < qq); nb += (b == 'N'); tq += (int)q - 33;
+        if (i + 1 < rlen) adj += (b != mv_base(v, i + 1));
+    }
+    lowq = group_sum(lowq, g); nb = group_sum(nb, g); tq = group_sum(tq, g); adj = group_sum(adj, g);
+    if (c_p.qual_filter) {
+        if (lowq > (int)c_p.lut_lowq[rlen]) return FP_FAIL_QUALITY;
+        if (c_p.avg_qual_req > 0 && (tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
+        if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
+    }
+    if (c_p.length_filter) {
+        if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
+        if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
+    }
+    if (c_p.complexity_filter) {
+        if (rlen <= 1) return FP_FAIL_COMPLEXITY;
+        if (adj < (int)c_p.lut_mindiff[rlen]) return FP_FAIL_COMPLEXITY;
+    }
+    return FP_PASS_FILTER;
+}
+
+/* Stats::statRead (stats.cpp:191-268, without the over-representation scan) of a view, into Stats `stats` of the global block */
+__device__ __noinline__ void t_stat_view(unsigned long long* G, int stats, const MView v, int sub, int g) {
+    const fp_counter_layout& L = c_p.L;
+    const int rlen = v.n1 + v.n2;
+    for (int i = sub; i < rlen; i += g) {
+        const uint8_t base = mv_base(v, i), q = mv_qual(v, i);
+        const int b = base & 7;
+        if (q < FP_QUAL_BINS) red_add64(&G[fp_off_qualhist(&L, stats, q)], 1ull);
+        if (i < L.cycles) {
+            if (q >= '?') { red_add64(&G[fp_off_cycle(&L, stats, 0 * 8 + b, i)], 1ull); red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, i)], 1ull); }
+            else if (q >= '5') red_add64(&G[fp_off_cycle(&L, stats, 1 * 8 + b, i)], 1ull);
+            red_add64(&G[fp_off_cycle(&L, stats, 2 * 8 + b, i)], 1ull);
+            red_add64(&G[fp_off_cycle(&L, stats, 3 * 8 + b, i)], (unsigned long long)(long long)((int)q - 33));
+        }
+        if (i >= 4) {
+            int code = 0; bool ok = true;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) { const int val = dev_base2val(mv_base(v, i - 4 + k)); ok = ok && (val >= 0); code = (code << 2) | (val & 3); }
+            if (ok) red_add64(&G[fp_off_kmer(&L, stats, code)], 1ull);
+        }
+    }
+}
+
 __device__ __forceinline__ fp_read_result t_make_result(const TRead& r, int verdict, int pv, int flags, int apos, int abases, int pbase, int plen) {
     fp_read_result o;
     if (r.null) { o.front = 0; o.len = 0; flags |= FP_F_DROPPED; }
@@ -1142,7 +1218,7 @@ __device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* 
             for (int k = 0; k < 4; k++) acc[c][b][k] = acc_in.v[c][b][k];
     const int j0 = my_half * 2;
     const unsigned sel = my_half ? 0x7362u : 0x5140u;
-    #pragma unroll 1
+    #pragma unroll (kDenseUnroll)
     for (int r0 = rfirst; r0 < rows; r0 += rstep) {
         /* rows beyond the tile have length 0, so the minimum also covers a partial tile */
         const uint2 l4 = *reinterpret_cast<const uint2*>(lens + r0);
@@ -1492,7 +1568,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                             const uint32_t qsel = ((uint32_t)(lane & (FP_QH_REP - 1)) << 2) | ((uint32_t)sd * (FP_QUAL_BINS * FP_QH_REP * 4));
                             const uint32_t qaddr = smem_u32(qhb) + qsel;          /* tables 2 KB-aligned: the bin offset (bits 4..10) ORs in */
                             uint32_t okm = 0, bad = 0, clo = 0, chi = 0;
-                            #pragma unroll 1
+                            #pragma unroll (kItemUnroll)
                             for (int k = 0; k < 4; k++) {
                                 const uint2 sw = *reinterpret_cast<const uint2*>(sp + 8 * k), qw = *reinterpret_cast<const uint2*>(qp + 8 * k);
                                 uint32_t f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, f_cq;
@@ -1547,7 +1623,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                             uint8_t* khb = smem + sl.off_kmer;
                             const uint32_t kaddr = smem_u32(khb) + (uint32_t)sd * (FP_KMER_BINS * 4);     /* 4 KB-aligned: the field (bits 2..11) ORs in */
                             const uint32_t kdummy = smem_u32(s_dummy) + 4u * (uint32_t)lane;                /* windows that do not count land here */
-                            #pragma unroll 1
+                            #pragma unroll (kItemUnroll)
                             for (int g8 = 0; g8 < 4; g8++) {               /* 8 windows per step: W = Z bits [16*g8, 16*g8 + 32) */
                                 const uint32_t W = __funnelshift_r(g8 < 2 ? Z0 : Z1, g8 < 2 ? Z1 : Z2, (g8 & 1) * 16);
                                 const uint32_t v8 = (vwin >> (8 * g8)) & 0xFFu;
@@ -1754,14 +1830,51 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                         if (c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;
                         if (c_p.max_len2 > 0 && c_p.max_len2 < r2.len) r2.len = c_p.max_len2;
                     }
-                    res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);      /* :565-566 */
-                    if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
-                    const int pv = max(res1, res2);
                     const bool dupout = a.is_dup && a.is_dup[gi];                                 /* dedupOut :575 */
                     if (dupout) { flags1 |= FP_F_DUPLICATE; flags2 |= FP_F_DUPLICATE; }
-                    counted = !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER && !dupout;   /* :577-591 */
+                    int pv = 0;
+                    bool merge_done = false;
+                    if (c_p.merge && both) {                                                      /* merging mode :519-560 */
+                        ov = (clean1 && clean2) ? t_analyze_planes(r1, r2, PW, s_lut, sub, GL) : t_analyze_bytes(r1, r2, s_lut);   /* :523, on the trimmed reads */
+                        if (ov.overlapped) {
+                            MView v; v.s1 = rs1 + r1.front; v.q1 = rq1 + r1.front; v.s2 = rs2 + r2.front; v.q2 = rq2 + r2.front;
+                            v.n1 = ov.overlap_len + max(0, (int)ov.offset); v.n2 = ov.offset > 0 ? r2.len - ov.overlap_len : 0;
+                            const int mres = t_pass_filter_view(v, sub, GL);                      /* :526 */
+                            if (mres == FP_PASS_FILTER) {                                         /* :528-534 */
+                                t_stat_view(G, 1, v, sub, GL);
+                                if (lead) { atomicAdd(&bc->fr[FP_FR_MERGED_PAIRS], 1u); rl[2] += 1; rl[3] += v.n1 + v.n2; }
+                            }
+                            if (lead) atomicAdd(&bc->fr[FP_FR_READSTATS + mres], 2u);             /* :527 */
+                            res1 = res2 = pv = mres;
+                            flags1 |= FP_F_MERGED; flags2 |= FP_F_MERGED;
+                            merge_done = true;
+                        } else if (c_p.merge_unmerged) {                                          /* :537-560: read by read, both into read 1's post Stats */
+                            res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);
+                            if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
+                            if (lead) { atomicAdd(&bc->fr[FP_FR_READSTATS + res1], 1u); atomicAdd(&bc->fr[FP_FR_READSTATS + res2], 1u); }
+                            if (res1 == FP_PASS_FILTER && !dupout) {
+                                MView v; v.s1 = rs1 + r1.front; v.q1 = rq1 + r1.front; v.s2 = v.s1; v.q2 = v.q1; v.n1 = r1.len; v.n2 = 0;
+                                t_stat_view(G, 1, v, sub, GL);
+                                if (lead) { rl[2] += 1; rl[3] += r1.len; }
+                            }
+                            if (res2 == FP_PASS_FILTER && !dupout) {
+                                MView v; v.s1 = rs2 + r2.front; v.q1 = rq2 + r2.front; v.s2 = v.s1; v.q2 = v.q1; v.n1 = r2.len; v.n2 = 0;
+                                t_stat_view(G, 1, v, sub, GL);
+                                if (lead) { rl[2] += 1; rl[3] += r2.len; }
+                            }
+                            pv = max(res1, res2);
+                            merge_done = true;
+                        }
+                    }
+                    if (!merge_done) {
+                        res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);  /* :565-566 */
+                        if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
+                        pv = max(res1, res2);
+                        /* merging mode keeps the post-filter Stats for merged (and --include_unmerged) reads only (:588-591) */
+                        counted = !c_p.merge && !r1.null && res1 == FP_PASS_FILTER && !r2.null && res2 == FP_PASS_FILTER && !dupout;   /* :577-591 */
+                        if (lead) atomicAdd(&bc->fr[FP_FR_READSTATS + pv], 2u);                   /* :573 */
+                    }
                     if (lead) {
-                        atomicAdd(&bc->fr[FP_FR_READSTATS + pv], 2u);                              /* :573 */
                         if (counted) { rl[2] += 1; rl[3] += r1.len; rl[6] += 1; rl[7] += r2.len; }
                         a.out1[gi] = t_make_result(r1, res1, pv, flags1, apos1, ab1, pb1, pl1n);
                         a.out2[gi] = t_make_result(r2, res2, pv, flags2, apos2, ab2, pb2, pl2n);

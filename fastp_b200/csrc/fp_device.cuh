@@ -31,6 +31,7 @@ struct fp_dev_params {
     int cf_w, cf_thr, ct_w, ct_thr, cr_w, cr_thr, cr_q;      /* thr = w*(33+Q); cr_q = 33+Q */
     int polyg, polyg_min, polyx, polyx_min;
     int adapter_enabled, has_r1, has_r2, n_fasta, fasta_match_req, dimer_max_len;
+    int merge, merge_unmerged;                               /* --merge / --include_unmerged (PE) */
     int correction, ov_require, allow_gap, ov_diff_limit;   /* ov_diff_limit: upper bound of every lut_ovlimit entry */
     int qual_filter, qualified_qual, n_base_limit, avg_qual_req;
     int length_filter, length_required, length_limit;
@@ -40,8 +41,8 @@ struct fp_dev_params {
     int adapter_r1_off, adapter_r1_len, adapter_r2_off, adapter_r2_len;   /* into adapters blob */
     /* global-memory tables */
     const int16_t* lut_ovlimit;     /* [stride+1]  min(diffLimit, (int)(ol * (pct/100.0)))  overlapanalysis.cpp:51 */
-    const int16_t* lut_lowq;        /* [stride+1]  floor(unqualifiedPercentLimit*rlen/100.0) filter.cpp:37          */
-    const int16_t* lut_mindiff;     /* [stride+1]  smallest diff with diff/(len-1) >= threshold filter.cpp:65      */
+    const int16_t* lut_lowq;        /* [2*stride+1] floor(unqualifiedPercentLimit*rlen/100.0) filter.cpp:37 (merged reads included) */
+    const int16_t* lut_mindiff;     /* [2*stride+1] smallest diff with diff/(len-1) >= threshold filter.cpp:65     */
     const uint8_t* adapters;        /* blob of adapter strings, each padded to a multiple of 4 + 8               */
     const int32_t* fasta_off;       /* [n_fasta] offsets into blob */
     const int32_t* fasta_len;       /* [n_fasta] */

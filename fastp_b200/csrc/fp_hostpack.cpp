@@ -70,7 +70,21 @@ int pack_avx2(const uint8_t* s, int L, uint8_t* d, uint32_t unit, int which, std
         const uint32_t lo = (uint32_t)_mm256_extract_epi32(r, 0), hi = (uint32_t)_mm256_extract_epi32(r, 4);
         memcpy(d + (k >> 2), &lo, 4); memcpy(d + (k >> 2) + 4, &hi, 4);
     }
-    return pack_swar(s, k, L, d, unit, which, nl);
+    const int tail = L - k;
+    if (tail > 0) {
+        /* the row's last 1..31 bases: same block on a copy padded with 'A' (never reads past the row), only the bytes of the tail are stored */
+        alignas(32) uint8_t buf[32];
+        memset(buf, 'A', 32); memcpy(buf, s + k, (size_t)tail);
+        const __m256i x = _mm256_load_si256(reinterpret_cast<const __m256i*>(buf));
+        const __m256i c = _mm256_and_si256(_mm256_srli_epi16(x, 1), m3);
+        const __m256i y = _mm256_shuffle_epi8(tbl, c);
+        if (_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, y)) != -1) return pack_swar(s, k, L, d, unit, which, nl);
+        const __m256i r = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(c, w1), w2), gather);
+        const uint32_t lo = (uint32_t)_mm256_extract_epi32(r, 0), hi = (uint32_t)_mm256_extract_epi32(r, 4);
+        uint8_t o[8]; memcpy(o, &lo, 4); memcpy(o + 4, &hi, 4);
+        memcpy(d + (k >> 2), o, (size_t)((tail + 3) >> 2));
+    }
+    return 0;
 }
 #endif
 

@@ -14,8 +14,9 @@
  * pinned SoA rows  ->  fp_process_*_host (the whole operator chain on the device)  ->  unstage: apply trim windows and corrected
  * bases to the Read objects, replay the adapter-string events through the reference's own FilterResult::addAdapterTrimmed, add the
  * device's counter block to this worker's Stats / FilterResult objects, then the unchanged tail of the reference loop (output
- * strings, writers, recycling).  Option sets the device path does not cover (merge, overlapped_out, UMI, over-representation
- * analysis, reads longer than FP_MAX_STRIDE) are handed to the stock body.
+ * strings, writers, recycling).  Merging mode (--merge / --include_unmerged, :519-560) runs on the device too: the merged Read is built
+ * by the reference's own OverlapAnalysis::merge from the device's second overlap record.  Option sets the device path does not
+ * cover (overlapped_out, UMI, over-representation analysis, reads longer than FP_MAX_STRIDE) are handed to the stock body.
  */
 #include <algorithm>
 #include <cstdio>
@@ -32,6 +33,9 @@
 #include "duplicate.h"
 #include "filter.h"
 #include "filterresult.h"
+#include "overlapanalysis.h"
+/* Stats::extendBuffer (private) is called below before the block of merged reads -- up to two reads long -- is added to the post-filter
+   Stats; this file is built with -fno-access-control (oracle/Makefile).  A maintainer would rather add the block-adding function to Stats. */
 #include "stats.h"
 #include "threadconfig.h"
 #include "umiprocessor.h"
@@ -91,6 +95,7 @@ void fill_params(fp_params* p, Options* o, bool paired, int tid, GpuWorker* w) {
     p->complexity_filter_enabled = o->complexityFilter.enabled; p->complexity_threshold = o->complexityFilter.threshold;
     p->insert_size_max = o->insertSizeMax; p->seq_len1 = o->seqLen1; p->seq_len2 = o->seqLen2;
     p->overrep_enabled = 0;
+    p->merge_enabled = paired && o->merge.enabled; p->merge_include_unmerged = o->merge.includeUnmerged;
     w->adapters.clear();
     w->adapters.push_back(o->adapter.sequence); w->adapters.push_back(o->adapter.sequenceR2);
     for (auto& s : o->adapter.seqsInFasta) w->adapters.push_back(s);
@@ -110,7 +115,8 @@ GpuWorker* worker_for(const void* proc, Options* o, bool paired, int tid, int ne
     if (paired && w->stride > 256) w->stride = 256;                            /* the column pass covers 2 x 256 cycles (fp_ctx_create) */
     w->cap = std::max<int64_t>(need_cap, 4096);
     const char* dev = getenv("FASTP_B200_DEVICE");
-    if (fp_ctx_create(&w->params, dev ? atoi(dev) : 0, w->cap, w->stride, w->stride, &w->ctx) != FP_OK) die("fp_ctx_create");
+    /* merged reads are up to two rows long: the counter block covers 2 x stride cycles then */
+    if (fp_ctx_create(&w->params, dev ? atoi(dev) : 0, w->cap, w->stride, w->params.merge_enabled ? 2 * w->stride : w->stride, &w->ctx) != FP_OK) die("fp_ctx_create");
     fp_ctx_layout(w->ctx, &w->L);
     w->block.resize(w->L.total);
     const int sides = paired ? 2 : 1;
@@ -126,7 +132,7 @@ GpuWorker* worker_for(const void* proc, Options* o, bool paired, int tid, int ne
 }
 
 bool supported(Options* o, bool hasOverlappedWriter) {
-    return !o->merge.enabled && !hasOverlappedWriter && !o->umi.enabled && !o->overRepAnalysis.enabled;
+    return !hasOverlappedWriter && !o->umi.enabled && !o->overRepAnalysis.enabled;
 }
 
 void stage(GpuWorker* w, int side, int64_t i, Read* r) {
@@ -152,6 +158,9 @@ Read* unstage(GpuWorker* w, int side, int64_t i, Read* r) {
 /* add the device's counter block to this worker's Stats / FilterResult (what statRead / addFilterResult / addPolyXTrimmed ...
  * would have accumulated), then clear it on the device */
 void add_stats(Stats* s, const int64_t* B, const fp_counter_layout& L, int which) {
+    int used = 0;                                                              /* cycles the block really holds (merged reads: beyond the buffer) */
+    for (int c = 0; c < (int)L.cycles; c++) if (B[fp_off_cycle(&L, which, 32, c)]) used = c + 1;
+    if (used > s->mBufLen) s->extendBuffer(std::max(used + 100, (int)(used * 1.5)));   /* what statRead does for a longer read (stats.cpp:195-197) */
     const int n = std::min(s->mBufLen, (int)L.cycles);
     for (int b = 0; b < 8; b++)
         for (int c = 0; c < n; c++) {
@@ -181,6 +190,7 @@ void add_counters(GpuWorker* w, ThreadConfig* config, bool paired, std::atomic_l
     for (int b = 0; b < 4; b++) { fr->mTrimmedPolyXReads[b] += F[FP_FR_POLYX_READS + b]; fr->mTrimmedPolyXBases[b] += F[FP_FR_POLYX_BASES + b]; }
     for (int i = 0; i < 64; i++) fr->mCorrectionMatrix[i] += F[FP_FR_CORRECTION + i];
     fr->mCorrectedReads += F[FP_FR_CORRECTED_READS];
+    fr->mMergedPairs += F[FP_FR_MERGED_PAIRS];                                 /* config->addMergedPairs(mergedCount) :693-695 */
     if (isize) for (int i = 0; i < w->L.isize_bins; i++) if (B[w->L.off_isize + i]) isize[i] += B[w->L.off_isize + i];
     if (fp_counters_reset(w->ctx) != FP_OK) die("fp_counters_reset");
 }
@@ -336,7 +346,27 @@ bool PairEndProcessor::processPairEnd(ReadPack* leftPack, ReadPack* rightPack, T
                other read keeps what trimAndCut did to it: the device reports exactly that window */
         }
         const int result1 = w->res[0][i].verdict, result2 = w->res[1][i].verdict;
-        if (!dedup[p]) {
+        bool mergeProcessed = false;
+        if (mOptions->merge.enabled && r1 && r2) {                             /* merging mode :519-560 */
+            if (w->res[0][i].flags & FP_F_MERGED) {
+                if (result1 == PASS_FILTER) {
+                    OverlapResult ov;
+                    ov.overlapped = true; ov.hasGap = false;
+                    ov.offset = w->ov[i].offset; ov.overlap_len = w->ov[i].overlap_len; ov.diff = w->ov[i].diff;
+                    Read* merged = OverlapAnalysis::merge(r1, r2, ov);         /* the reference's own string work (names included) */
+                    merged->appendToString(&mergedOutput);
+                    readPassed++;
+                    recycleToPool1(tid, merged);
+                }
+                mergeProcessed = true;
+            } else if (mOptions->merge.includeUnmerged) {
+                if (result1 == PASS_FILTER && !dedup[p]) r1->appendToString(&mergedOutput);
+                if (result2 == PASS_FILTER && !dedup[p]) r2->appendToString(&mergedOutput);
+                if (result1 == PASS_FILTER && result2 == PASS_FILTER) readPassed++;
+                mergeProcessed = true;
+            }
+        }
+        if (!mergeProcessed && !dedup[p]) {
             if (r1 != NULL && result1 == PASS_FILTER && r2 != NULL && result2 == PASS_FILTER) {
                 if (mOptions->outputToSTDOUT && !mOptions->merge.enabled) { r1->appendToString(&singleOutput); r2->appendToString(&singleOutput); }
                 else { r1->appendToString(&outstr1); r2->appendToString(&outstr2); }
@@ -379,7 +409,8 @@ bool PairEndProcessor::processPairEnd(ReadPack* leftPack, ReadPack* rightPack, T
         mLeftWriter->input(tid, new string(std::move(outstr1)));
         mRightWriter->input(tid, new string(std::move(outstr2)));
     } else if (mLeftWriter) {
-        mLeftWriter->input(tid, new string(std::move(singleOutput)));
+        if (mOptions->merge.enabled && mOptions->outputToSTDOUT) mLeftWriter->input(tid, new string(std::move(mergedOutput)));   /* :672-675 */
+        else mLeftWriter->input(tid, new string(std::move(singleOutput)));
     }
     if (mUnpairedLeftWriter && mUnpairedRightWriter) {
         mUnpairedLeftWriter->input(tid, new string(std::move(unpairedOut1)));

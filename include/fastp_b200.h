@@ -114,6 +114,15 @@ typedef struct fp_params {
     const char* const* overrep_seqs1;       /* keys of overRepSeqs1 (any order; the layout keeps this order) */
     int32_t n_overrep2;
     const char* const* overrep_seqs2;
+    /* MergeOptions options.h:104-121 (PE only).  After the chain the pair is analysed again on the trimmed reads (peprocessor.cpp:521-523);
+     * an overlapped pair becomes ONE read, r1[0, len1) + reverse complement of r2[0, len2) with len1 = overlap_len + max(0, offset),
+     * len2 = offset > 0 ? len(r2) - overlap_len : 0 (OverlapAnalysis::merge, overlapanalysis.cpp:148-179); that read is filtered
+     * (weight 2 in the FilterResult counters) and, when it passes, is what the post-filter Stats of read 1 see.  The post-filter Stats of
+     * read 2 stay empty in this mode (peprocessor.cpp:588-591).  Records of a merged pair carry FP_F_MERGED, the merged read's verdict in
+     * verdict / pair_verdict and the (trimmed) windows of r1 and r2; fp_ov_result holds the second analysis, from which len1 / len2 follow
+     * (fp_merged_lens).  Size the counter block for merged reads: `cycles` of fp_ctx_create >= 2 * read length. */
+    int32_t merge_enabled;                  /* --merge; main.cpp also forces correction_enabled (options.cpp:120-121): the caller's job */
+    int32_t merge_include_unmerged;         /* --include_unmerged: pairs that did not merge are filtered read by read and both counted in read 1's post Stats */
 } fp_params;
 
 /* Fill with the reference's defaults: Options::Options() (options.cpp:9-32) + nested
@@ -149,6 +158,7 @@ typedef struct fp_batch {
 #define FP_F_CORRECTED        0x08  /* at least one base of this read was overwritten          */
 #define FP_F_POLYG_TRIMMED    0x10  /* trimPolyG shortened the read                            */
 #define FP_F_ADAPTER_DIMER    0x20
+#define FP_F_MERGED           0x80  /* --merge: the pair overlapped and was merged (on both records); verdict = the merged read's */
 #define FP_F_DUPLICATE        0x40  /* dedupOut: flagged by the duplicate filter with --dedup on; not written, not in the post-filter stats (peprocessor.cpp:397-401,575) */
 
 typedef struct fp_read_result {
@@ -169,6 +179,13 @@ typedef struct fp_ov_result {
     uint8_t overlapped, has_gap;
     int16_t offset, overlap_len, diff;
 } fp_ov_result;            /* 8 bytes */
+
+/* --merge: the two pieces of a merged read (OverlapAnalysis::merge, overlapanalysis.cpp:149-157): merged = r1[0, len1) followed by the
+ * reverse complement of r2[0, len2), both in TRIMMED coordinates (add fp_read_result.front for the row index); r2_len = out2.len. */
+static inline void fp_merged_lens(const fp_ov_result* ov, int r2_len, int* len1, int* len2) {
+    *len1 = ov->overlap_len + (ov->offset > 0 ? ov->offset : 0);
+    *len2 = ov->offset > 0 ? r2_len - ov->overlap_len : 0;
+}
 
 /* A base overwritten by BaseCorrector (basecorrector.cpp:44-60). */
 typedef struct fp_patch {

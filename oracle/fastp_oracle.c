@@ -611,7 +611,7 @@ static void process_se_one(const fp_params* p, const fp_counter_layout* L, int64
 }
 
 /* ------------------------------------------------------------------------------------------
- * PairEndProcessor::processPairEnd loop body  src/peprocessor.cpp:383-643 (no merge / overlapped_out /
+ * PairEndProcessor::processPairEnd loop body  src/peprocessor.cpp:383-643 (incl. merging mode :519-560; no overlapped_out /
  * dedup / index filter / UMI) + statInsertSize :710-723
  * ------------------------------------------------------------------------------------------ */
 static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64_t* C,
@@ -713,21 +713,66 @@ static void process_pe_one(const fp_params* p, const fp_counter_layout* L, int64
         if (p->max_len1 > 0 && p->max_len1 < r1.len) read_resize(&r1, p->max_len1);
         if (p->max_len2 > 0 && p->max_len2 < r2.len) read_resize(&r2, p->max_len2);
     }
-    int result1 = pass_filter(p, &r1);                                  /* :565-566 */
-    int result2 = pass_filter(p, &r2);
-    if (isAdapterDimer) {                                               /* :568-571 */
-        result1 = result2 = FP_FAIL_ADAPTER_DIMER;
-        flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER;
+    int result1, result2, pv;
+    int mergeProcessed = 0;
+    if (p->merge_enabled && both) {                                     /* :519-560 merging mode */
+        /* :523 the overlap is always computed again on the trimmed reads */
+        ov = analyze(&r1, &r2, p->overlap_diff_limit, p->overlap_require, p->overlap_diff_percent_limit / 100.0, 0);
+        ovComputed = 1;
+        if (ov.overlapped) {
+            /* OverlapAnalysis::merge overlapanalysis.cpp:148-179: r1[0,len1) + reverseComplement(r2)[ol, ol+len2) */
+            const int ol = ov.overlap_len;
+            const int mlen1 = ol + imax(0, ov.offset);
+            const int mlen2 = ov.offset > 0 ? r2.len - ol : 0;
+            uint8_t mseq[2 * FP_MAX_STRIDE], mqual[2 * FP_MAX_STRIDE];
+            memcpy(mseq, r1.seq, (size_t)mlen1); memcpy(mqual, r1.qual, (size_t)mlen1);
+            for (int k = 0; k < mlen2; k++) {                           /* rr2[ol + k] = complement(r2[len2 - 1 - ol - k]), quality reversed */
+                mseq[mlen1 + k] = complement(r2.seq[r2.len - 1 - ol - k]);
+                mqual[mlen1 + k] = r2.qual[r2.len - 1 - ol - k];
+            }
+            oread m = {mseq, mqual, mlen1 + mlen2, 0};
+            const int result = pass_filter(p, &m);                      /* :526 */
+            FR[FP_FR_READSTATS + result] += 2;                          /* :527 */
+            if (result == FP_PASS_FILTER) {                             /* :528-534 */
+                stat_read(p, C, L, FP_STATS_POST1, mseq, mqual, m.len);
+                FR[FP_FR_MERGED_PAIRS] += 1;                            /* mergedCount -> addMergedPairs :694 */
+            }
+            result1 = result2 = pv = result;
+            flags1 |= FP_F_MERGED; flags2 |= FP_F_MERGED;
+            mergeProcessed = 1;
+        } else if (p->merge_include_unmerged) {                         /* :537-560 */
+            result1 = pass_filter(p, &r1);
+            result2 = pass_filter(p, &r2);
+            if (isAdapterDimer) {
+                result1 = result2 = FP_FAIL_ADAPTER_DIMER;
+                flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER;
+            }
+            FR[FP_FR_READSTATS + result1] += 1;
+            if (result1 == FP_PASS_FILTER) stat_read(p, C, L, FP_STATS_POST1, r1.seq, r1.qual, r1.len);
+            FR[FP_FR_READSTATS + result2] += 1;
+            if (result2 == FP_PASS_FILTER) stat_read(p, C, L, FP_STATS_POST1, r2.seq, r2.qual, r2.len);   /* read 2 into read 1's Stats: :555 */
+            pv = imax(result1, result2);
+            mergeProcessed = 1;
+        }
     }
-    int pv = imax(result1, result2);
-    FR[FP_FR_READSTATS + pv] += 2;                                      /* :573 */
-    if (!r1.is_null && result1 == FP_PASS_FILTER && !r2.is_null && result2 == FP_PASS_FILTER) {   /* :577-591 */
-        stat_read(p, C, L, FP_STATS_POST1, r1.seq, r1.qual, r1.len);
-        stat_read(p, C, L, FP_STATS_POST2, r2.seq, r2.qual, r2.len);
+    if (!mergeProcessed) {
+        result1 = pass_filter(p, &r1);                                  /* :565-566 */
+        result2 = pass_filter(p, &r2);
+        if (isAdapterDimer) {                                           /* :568-571 */
+            result1 = result2 = FP_FAIL_ADAPTER_DIMER;
+            flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER;
+        }
+        pv = imax(result1, result2);
+        FR[FP_FR_READSTATS + pv] += 2;                                  /* :573 */
+        if (!p->merge_enabled && !r1.is_null && result1 == FP_PASS_FILTER && !r2.is_null && result2 == FP_PASS_FILTER) {   /* :577-591 */
+            stat_read(p, C, L, FP_STATS_POST1, r1.seq, r1.qual, r1.len);
+            stat_read(p, C, L, FP_STATS_POST2, r2.seq, r2.qual, r2.len);
+        }
     }
     fill_result(out1, &r1, seq1, result1, pv, flags1, apos1, ab1, pb1, pl1);
     fill_result(out2, &r2, seq2, result2, pv, flags2, apos2, ab2, pb2, pl2);
     if (ovOut) *ovOut = ov;
+    (void)ovComputed;
 }
 
 int fp_oracle_process(const fp_params* p, const fp_counter_layout* L, const fp_batch* b,

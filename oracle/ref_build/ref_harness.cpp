@@ -56,6 +56,7 @@ void fill_options(Options& o, const fp_params* p) {
     o.adapter.allowGapOverlapTrimming = p->allow_gap_overlap_trimming;
     o.adapter.dimerMaxLen = p->dimer_max_len;
     o.correction.enabled = p->correction_enabled;
+    o.merge.enabled = p->merge_enabled != 0; o.merge.includeUnmerged = p->merge_include_unmerged != 0;
     o.overlapRequire = p->overlap_require; o.overlapDiffLimit = p->overlap_diff_limit;
     o.overlapDiffPercentLimit = p->overlap_diff_percent_limit;
     o.qualfilter.enabled = p->qual_filter_enabled; o.qualfilter.qualifiedQual = (char)p->qualified_qual;
@@ -260,14 +261,42 @@ void pe_one(Worker& w, const fp_params* p, uint8_t* seq1, uint8_t* qual1, int le
         if (mOptions->trim.maxLen1 > 0 && mOptions->trim.maxLen1 < r1->length()) r1->resize(mOptions->trim.maxLen1);
         if (mOptions->trim.maxLen2 > 0 && mOptions->trim.maxLen2 < r2->length()) r2->resize(mOptions->trim.maxLen2);
     }
-    int result1 = w.filter->passFilter(r1);                                   // :565-566
-    int result2 = w.filter->passFilter(r2);
-    if (isAdapterDimer) { result1 = FAIL_ADAPTER_DIMER; result2 = FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
-    int pv = std::max(result1, result2);
-    w.fr->addFilterResult(pv, 2);                                             // :573
-    if (r1 != NULL && result1 == PASS_FILTER && r2 != NULL && result2 == PASS_FILTER) {   // :577-591
-        w.post1->statRead(r1);
-        w.post2->statRead(r2);
+    int result1 = 0, result2 = 0, pv = 0;
+    bool mergeProcessed = false;
+    if (mOptions->merge.enabled && r1 && r2) {                                // :519-560
+        ov = OverlapAnalysis::analyze(r1, r2, mOptions->overlapDiffLimit, mOptions->overlapRequire, mOptions->overlapDiffPercentLimit / 100.0);
+        ovComputed = true;
+        if (ov.overlapped) {
+            Read* merged = OverlapAnalysis::merge(r1, r2, ov);
+            int result = w.filter->passFilter(merged);
+            w.fr->addFilterResult(result, 2);
+            if (result == PASS_FILTER) { w.post1->statRead(merged); w.fr->addMergedPairs(1); }
+            delete merged;
+            result1 = result2 = pv = result;
+            flags1 |= FP_F_MERGED; flags2 |= FP_F_MERGED;
+            mergeProcessed = true;
+        } else if (mOptions->merge.includeUnmerged) {
+            result1 = w.filter->passFilter(r1);
+            result2 = w.filter->passFilter(r2);
+            if (isAdapterDimer) { result1 = FAIL_ADAPTER_DIMER; result2 = FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
+            w.fr->addFilterResult(result1, 1);
+            if (result1 == PASS_FILTER) w.post1->statRead(r1);
+            w.fr->addFilterResult(result2, 1);
+            if (result2 == PASS_FILTER) w.post1->statRead(r2);
+            pv = std::max(result1, result2);
+            mergeProcessed = true;
+        }
+    }
+    if (!mergeProcessed) {
+        result1 = w.filter->passFilter(r1);                                   // :565-566
+        result2 = w.filter->passFilter(r2);
+        if (isAdapterDimer) { result1 = FAIL_ADAPTER_DIMER; result2 = FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
+        pv = std::max(result1, result2);
+        w.fr->addFilterResult(pv, 2);                                         // :573
+        if (!mOptions->merge.enabled && r1 != NULL && result1 == PASS_FILTER && r2 != NULL && result2 == PASS_FILTER) {   // :577-591
+            w.post1->statRead(r1);
+            w.post2->statRead(r2);
+        }
     }
     fill_result(out1, r1, len1, frontTrimmed1, result1, pv, flags1, ab1, pb1, pl1);
     fill_result(out2, r2, len2, frontTrimmed2, result2, pv, flags2, ab2, pb2, pl2);

@@ -188,6 +188,10 @@ def config_params(name, paired, lib=None):
         p = config_params(name[4:], paired, lib)
         capi.set_params(p, allow_gap_overlap_trimming=1)
         return p
+    if name.startswith("merge_") or name.startswith("mergeu_"):   # --merge (forces --correction, options.cpp:120-121) [+ --include_unmerged]
+        p = config_params(name.split("_", 1)[1], paired, lib)
+        capi.set_params(p, merge_enabled=1, correction_enabled=1, merge_include_unmerged=1 if name.startswith("mergeu_") else 0)
+        return p
     if name == "tight_overlap":               # stricter overlap thresholds + correction + gap passes
         return P(correction_enabled=1, allow_gap_overlap_trimming=1, overlap_require=20, overlap_diff_limit=3,
                  overlap_diff_percent_limit=10, adapter_seq_r1=TRUSEQ_R1, adapter_seq_r2=TRUSEQ_R2)
@@ -251,6 +255,8 @@ def overrep_params(name, paired, arrs, L, sampling=20, lib=None):
 CONFIG_NAMES = ["default", "cfg2_cut_right_polyg", "cfg3_overlap_correction", "cfg4_full", "cut_front_tail", "trim_fixed",
                 "all_cuts", "filters", "no_filters", "fasta_adapters", "tid_nonzero", "short_adapter"]
 # option sets for the one-gap overlap passes; run on synthetic profile 2 (reads with single-base indels)
+MERGE_CONFIG_NAMES = ["merge_default", "merge_cfg4_full", "mergeu_cfg3_overlap_correction", "merge_filters", "mergeu_all_cuts", "merge_trim_fixed",
+                      "mergeu_gap_cfg4_full"]
 GAP_CONFIG_NAMES = ["gap_default", "gap_cfg3_overlap_correction", "gap_cfg4_full", "gap_all_cuts", "tight_overlap"]
 
 

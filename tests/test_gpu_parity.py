@@ -287,3 +287,30 @@ def test_pack2bit_rejects_other_bytes(gpu):
     arrs["seq1"][1234, 7] = ord("R")
     with pytest.raises(Exception):
         gpu.run_gpu(p, arrs, 160, mode="host_pack2bit")
+
+
+@pytest.mark.parametrize("L,S", [(150, 160), (100, 112)])
+@pytest.mark.parametrize("name", T.MERGE_CONFIG_NAMES)
+def test_merge_mode(gpu, name, L, S):
+    """--merge / --include_unmerged on the device (src/peprocessor.cpp:519-560, OverlapAnalysis::merge src/overlapanalysis.cpp:148-179):
+    records (FP_F_MERGED, the merged read's verdict), the second overlap analysis, mMergedPairs and the post-filter Stats over merged reads
+    up to two rows long (counter block sized 2 x stride) equal the oracle's"""
+    p = T.config_params(name, 1)
+    _, arrs = T.synth_host(20000, S, 1, 700, 78, 1, L)
+    want = T.run_cpu("oracle", p, arrs, 2 * S)
+    got = gpu.run_gpu(p, arrs, 2 * S)
+    T.assert_results_equal(got, want, 1, what=name)
+    assert int(got["counters"].filter[107]) > 0
+
+
+def test_merge_mode_with_other_bytes(gpu):
+    """merge mode on rows holding bytes outside {A,C,G,T,N} (byte paths of the analysis, complement of an unknown base = N)"""
+    p = T.config_params("merge_cfg4_full", 1)
+    _, arrs = T.synth_host(6000, 160, 1, 0, 79, 1, 150)
+    rng = np.random.default_rng(5)
+    for k in ("seq1", "seq2"):
+        rows = rng.integers(0, 6000, 600); cols = rng.integers(0, 150, 600)
+        arrs[k][rows, cols] = rng.choice(np.frombuffer(b"acgtnRYK.", np.uint8), 600)
+    want = T.run_cpu("oracle", p, arrs, 320)
+    got = gpu.run_gpu(p, arrs, 320)
+    T.assert_results_equal(got, want, 1, what="merge other bytes")

@@ -27,6 +27,9 @@ CASES = {
     "default": [],
     "full": ["--cut_right", "-g", "-x", "-c", "-a", T.TRUSEQ_R1, "--adapter_sequence_r2", T.TRUSEQ_R2],
     "cuts_failed_out": ["--cut_front", "--cut_tail", "-f", "2", "-T", "3", "-y", "-l", "30", "--failed_out", "failed.fq"],
+    # merging mode (PE only): merged reads built by the reference's own OverlapAnalysis::merge from the device's records
+    "merge": ["-m", "--merged_out", "m.fq", "--cut_right", "-g", "-a", T.TRUSEQ_R1, "--adapter_sequence_r2", T.TRUSEQ_R2],
+    "merge_include_unmerged": ["-m", "--merged_out", "m.fq", "--include_unmerged"],
 }
 
 
@@ -35,8 +38,10 @@ CASES = {
 @pytest.mark.parametrize("paired", [1, 0])
 @pytest.mark.parametrize("case", list(CASES))
 def test_bound_cli_equals_unmodified_cli(tmp_path, case, paired, n):
-    if n > 3000 and case == "cuts_failed_out":
+    if n > 3000 and case in ("cuts_failed_out", "merge_include_unmerged"):
         pytest.skip("large input covered by the other option sets")
+    if case.startswith("merge") and not paired:
+        pytest.skip("merging mode is paired-end only")
     flags = list(CASES[case])
     if not paired:
         for f2 in ("--adapter_sequence_r2", "-T"):
@@ -52,9 +57,11 @@ def test_bound_cli_equals_unmodified_cli(tmp_path, case, paired, n):
     for tag, cli in (("ref", T.REF_CLI), ("gpu", GPU_CLI)):
         d = tmp_path / tag
         os.makedirs(d)
-        cmd = [cli, "-i", str(tmp_path / "r1.fq"), "-o", "o1.fq", "-w", "1", "-j", "t.json", "-h", "t.html"] + flags
+        cmd = [cli, "-i", str(tmp_path / "r1.fq"), "-w", "1", "-j", "t.json", "-h", "t.html"] + flags
+        if case != "merge_include_unmerged":          # (--include_unmerged ignores --out1 / --out2, options.cpp:127-134)
+            cmd += ["-o", "o1.fq"]
         if paired:
-            cmd += ["-I", str(tmp_path / "r2.fq"), "-O", "o2.fq"]
+            cmd += ["-I", str(tmp_path / "r2.fq")] + (["-O", "o2.fq"] if case != "merge_include_unmerged" else [])
         r = subprocess.run(cmd, capture_output=True, text=True, cwd=d, env=dict(os.environ, FASTP_B200_TRACE="1"), timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         if tag == "gpu":

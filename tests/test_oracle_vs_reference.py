@@ -36,6 +36,21 @@ def test_port_equals_reference_gap_overlap(name, L, stride):
 
 
 @needs_ref
+@pytest.mark.parametrize("L,stride", [(150, 160), (100, 112)])
+@pytest.mark.parametrize("name", T.MERGE_CONFIG_NAMES)
+def test_port_equals_reference_merge_mode(name, L, stride):
+    """--merge / --include_unmerged (src/peprocessor.cpp:519-560, OverlapAnalysis::merge src/overlapanalysis.cpp:148-179): the second
+    overlap analysis on the trimmed reads, the merged read's verdict (weight 2), post-filter Stats of read 1 over merged reads up to two
+    rows long (counter block sized 2 x stride), mMergedPairs."""
+    p = T.config_params(name, 1)
+    _, arrs = T.synth_host(8000, stride, 1, 700, 77, 1, L)
+    x = T.run_cpu("oracle", p, arrs, 2 * stride)
+    y = T.run_cpu("ref", p, arrs, 2 * stride)
+    T.assert_results_equal(x, y, 1, skip=("adapter_pos",), what=name)
+    assert int(x["counters"].filter[107]) > 0, "no pair merged"
+
+
+@needs_ref
 @pytest.mark.parametrize("L,stride", [(250, 256), (100, 112), (36, 48)])
 def test_port_equals_reference_other_lengths(L, stride):
     p = T.config_params("cfg4_full", 1)

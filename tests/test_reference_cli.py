@@ -99,3 +99,65 @@ def test_harness_order_matches_cli(tmp_path, case, paired):
             s = bytes(res["arrs"]["seq" + side][i, r["front"]: r["front"] + r["len"]]).decode()
             q = bytes(res["arrs"]["qual" + side][i, r["front"]: r["front"] + r["len"]]).decode()
             assert (s, q) == want[j], (side, i)
+
+
+_COMP = bytes.maketrans(b"ACGTacgt", b"TGCATGCA")
+
+
+def _revcomp(s):
+    return "".join(chr(c) if chr(c) in "ACGT" else "N" for c in s.encode().translate(_COMP)[::-1])
+
+
+@needs_ref
+@pytest.mark.parametrize("include_unmerged", [0, 1])
+def test_merge_mode_matches_cli(tmp_path, include_unmerged):
+    """--merge [--include_unmerged] of the unmodified CLI against the harness / records: merged reads rebuilt from the per-read records and
+    fp_ov_result (fp_merged_lens) are byte-identical to --merged_out, the unmerged passing pairs to --out1/--out2, and the JSON's
+    after-filtering totals are the post-filter Stats of read 1 alone (src/peprocessor.cpp:519-591)."""
+    n, L = 3000, 150
+    _, arrs = T.synth_host(n, 160, 1, 0, 33, 1, L)
+    p = capi.default_params(1, lib=T.oracle(), seq_len1=L, seq_len2=L, merge_enabled=1, correction_enabled=1, merge_include_unmerged=include_unmerged)
+    res = T.run_cpu("ref", p, arrs, 320)
+    write_fastq(tmp_path / "r1.fq", arrs["seq1"], arrs["qual1"], arrs["len1"], "1:N:0")
+    write_fastq(tmp_path / "r2.fq", arrs["seq2"], arrs["qual2"], arrs["len2"], "2:N:0")
+    cmd = [T.REF_CLI, "-i", str(tmp_path / "r1.fq"), "-I", str(tmp_path / "r2.fq"), "-m", "--merged_out", str(tmp_path / "m.fq"), "-w", "1",
+           "--dont_eval_duplication", "-j", str(tmp_path / "t.json"), "-h", str(tmp_path / "t.html")]
+    cmd += ["--include_unmerged"] if include_unmerged else ["-o", str(tmp_path / "o1.fq"), "-O", str(tmp_path / "o2.fq")]
+    subprocess.run(cmd, check=True, capture_output=True, cwd=tmp_path)
+    js = json.load(open(tmp_path / "t.json"))
+    c = res["counters"]
+    af = js["summary"]["after_filtering"]
+    for key, field in (("reads", "total_reads"), ("bases", "total_bases"), ("q20", "q20_bases"), ("q30", "q30_bases")):
+        assert c.summary(capi.STATS_POST1)[key] == af[field], key
+        assert c.summary(capi.STATS_POST2)[key] == 0
+    fr = js["filtering_result"]
+    assert c.filter[capi.PASS_FILTER] == fr["passed_filter_reads"]
+    assert c.filter[capi.FAIL_QUALITY] == fr["low_quality_reads"]
+    assert c.filter[capi.FAIL_LENGTH] == fr["too_short_reads"]
+    o1, o2, ov, a = res["out1"], res["out2"], res["ov"], res["arrs"]
+
+    def window(side, i, lo, ln):
+        r = (o1 if side == "1" else o2)[i]
+        return (bytes(a["seq" + side][i, r["front"] + lo: r["front"] + lo + ln]).decode(), bytes(a["qual" + side][i, r["front"] + lo: r["front"] + lo + ln]).decode())
+    want_m, want_1, want_2 = [], [], []
+    for i in range(n):
+        if o1["flags"][i] & 0x80:                                   # FP_F_MERGED
+            if o1["verdict"][i] != 0:
+                continue
+            len1 = int(ov["overlap_len"][i]) + max(0, int(ov["offset"][i]))
+            len2 = int(o2["len"][i]) - int(ov["overlap_len"][i]) if ov["offset"][i] > 0 else 0
+            s1, q1 = window("1", i, 0, len1)
+            s2, q2 = window("2", i, 0, len2)
+            want_m.append((s1 + _revcomp(s2), q1 + q2[::-1]))
+        elif include_unmerged:
+            if o1["verdict"][i] == 0 and not (o1["flags"][i] & 1):
+                want_m.append(window("1", i, 0, int(o1["len"][i])))
+            if o2["verdict"][i] == 0 and not (o2["flags"][i] & 1):
+                want_m.append(window("2", i, 0, int(o2["len"][i])))
+        elif o1["pair_verdict"][i] == 0:
+            want_1.append(window("1", i, 0, int(o1["len"][i]))); want_2.append(window("2", i, 0, int(o2["len"][i])))
+    assert len(want_m) > 100
+    assert read_fastq(tmp_path / "m.fq") == want_m
+    assert int(c.filter[capi.FR_MERGED_PAIRS] if hasattr(capi, "FR_MERGED_PAIRS") else c.filter[107]) == sum(1 for i in range(n) if (o1["flags"][i] & 0x80) and o1["verdict"][i] == 0)
+    if not include_unmerged:
+        assert read_fastq(tmp_path / "o1.fq") == want_1 and read_fastq(tmp_path / "o2.fq") == want_2
