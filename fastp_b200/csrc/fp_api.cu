@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,8 @@ struct fp_ctx {
     fp_dev_params dp{};
     fp_dev_params* d_dp = nullptr;      /* device copy of dp, source of the per-launch constant refresh */
     void* d_cp_sym = nullptr;           /* global address of the __constant__ block */
+    cudaEvent_t params_ev = nullptr, last_chain_ev = nullptr;   /* block written by this ctx / its latest chain kernel done */
+    bool chain_launched = false;
     fp_counter_layout L{};
     int64_t max_batch = 0;
     int stride = 0, cycles = 0, tile = 0, grid_max = 0, num_sms = 0;
@@ -92,8 +95,8 @@ struct fp_ctx {
     fp_ov_result* d_ov[2] = {nullptr, nullptr};
     fp_patch* d_patch[2] = {nullptr, nullptr};
     unsigned int* d_npatch[2] = {nullptr, nullptr};
-    fp_patch* h_patch[2] = {nullptr, nullptr};
-    unsigned int* h_npatch[2] = {nullptr, nullptr};
+    fp_patch* h_patch[4] = {nullptr, nullptr, nullptr, nullptr};      /* host side: 4 rotating buffers (chunk % 4), see process_host */
+    unsigned int* h_npatch[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t patch_cap = 0;
     uint8_t* d_pk[2][4] = {{nullptr}};          /* packed staging per chunk slot: bases1 qual1 bases2 qual2 */
     fp_npos* d_npos[2] = {nullptr, nullptr};
@@ -154,6 +157,10 @@ static void build_luts(const fp_params* p, int stride, std::vector<int16_t>& ov,
         mind[len] = (int16_t)d;
     }
 }
+
+struct fp_ctx;
+struct ParamOwner { std::mutex mu; fp_ctx* owner = nullptr; };
+static ParamOwner g_param_owner[64];     /* per device ordinal: which context's parameters the __constant__ block holds */
 
 __global__ void fp_set_params_kernel(uint32_t* dst, const uint32_t* src, int nwords) {
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
@@ -422,10 +429,10 @@ static void free_staging(fp_ctx* c) {
         cudaFree(c->d_ev[i]); c->d_ev[i] = nullptr; cudaFree(c->d_nev[i]); c->d_nev[i] = nullptr;
         if (c->h_ev[i]) cudaFreeHost(c->h_ev[i]); c->h_ev[i] = nullptr;
         if (c->h_nev[i]) cudaFreeHost(c->h_nev[i]); c->h_nev[i] = nullptr;
-        if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
-        if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
     }
     for (int i = 0; i < 4; i++) {
+        if (c->h_patch[i]) cudaFreeHost(c->h_patch[i]); c->h_patch[i] = nullptr;
+        if (c->h_npatch[i]) cudaFreeHost(c->h_npatch[i]); c->h_npatch[i] = nullptr;
         for (int k = 0; k < 2; k++) { if (c->h_pkb[i][k]) cudaFreeHost(c->h_pkb[i][k]); c->h_pkb[i][k] = nullptr; }
         if (c->h_np[i]) cudaFreeHost(c->h_np[i]);
         c->h_np[i] = nullptr;
@@ -438,6 +445,9 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    { ParamOwner& po = g_param_owner[c->device & 63]; std::lock_guard<std::mutex> lk(po.mu); if (po.owner == c) po.owner = nullptr; }
+    if (c->params_ev) cudaEventDestroy(c->params_ev);
+    if (c->last_chain_ev) cudaEventDestroy(c->last_chain_ev);
     free_staging(c);
     {
         fp_ctx::Buf* all[] = {&c->fq_term, &c->fq_bcnt, &c->fq_agg, &c->fq_bstate, &c->fq_brec, &c->fq_recline, &c->fq_recend, &c->fq_info, &c->fq_bsum,
@@ -533,15 +543,28 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     a.n_tiles = (b->n + c->tile - 1) / c->tile;
     a.sl = c->sl;
     int grid = (int)std::min<long long>((a.n_tiles + c->groups - 1) / c->groups, c->grid_max);
-    /* The operator parameters live in one __constant__ block per device; it is refreshed before every launch BY A KERNEL from the
-       context's device copy (stream-ordered, no copy engine: a cudaMemcpyToSymbolAsync would queue behind bulk text / batch
-       transfers).  Contexts running concurrently on one device must therefore share the same fp_params. */
+    /* The operator parameters live in ONE __constant__ block per device, owned by the context that launched last.  A launch by the owner
+       costs nothing; a launch by another context first waits -- on the device, in its own stream -- for the owner's last chain kernel
+       (the only reader of the block), then rewrites the block from its device copy with a small kernel (stream-ordered, no copy engine:
+       a cudaMemcpyToSymbolAsync would queue behind bulk transfers).  Contexts with different parameters therefore alternate correctly
+       on one device; they just do not overlap each other's chain kernels. */
     if (!c->d_dp) {
         CK(cudaMalloc(&c->d_dp, sizeof(fp_dev_params)));
         CK(cudaMemcpy(c->d_dp, &c->dp, sizeof(fp_dev_params), cudaMemcpyHostToDevice));
         CK(cudaGetSymbolAddress((void**)&c->d_cp_sym, c_p));
+        CK(cudaEventCreateWithFlags(&c->params_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->last_chain_ev, cudaEventDisableTiming));
     }
-    fp_set_params_kernel<<<1, 128, 0, st>>>(reinterpret_cast<uint32_t*>(c->d_cp_sym), reinterpret_cast<const uint32_t*>(c->d_dp), (int)(sizeof(fp_dev_params) / 4));
+    ParamOwner& po = g_param_owner[c->device & 63];
+    std::unique_lock<std::mutex> plk(po.mu);
+    if (po.owner != c) {
+        if (po.owner && po.owner->last_chain_ev && po.owner->chain_launched) CK(cudaStreamWaitEvent(st, po.owner->last_chain_ev, 0));
+        fp_set_params_kernel<<<1, 128, 0, st>>>(reinterpret_cast<uint32_t*>(c->d_cp_sym), reinterpret_cast<const uint32_t*>(c->d_dp), (int)(sizeof(fp_dev_params) / 4));
+        CK(cudaEventRecord(c->params_ev, st));
+        po.owner = c;
+    } else {
+        CK(cudaStreamWaitEvent(st, c->params_ev, 0));          /* the block was written in another of this context's streams */
+    }
     fp_overrep_args oa;
     const bool ovr = c->p.overrep_enabled && (c->ovr_side[0].K > 0 || c->ovr_side[1].K > 0);
     if (ovr) {
@@ -566,6 +589,9 @@ static int launch_chain(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         CK(cudaLaunchKernel(chain_kernel(c->p.paired != 0, c->groups, c->group_threads), dim3(grid), dim3(c->group_threads * c->groups), kargs, (size_t)c->sl.total, st));
     }
     CK(cudaEventRecord(ev.b, st));
+    CK(cudaEventRecord(c->last_chain_ev, st));
+    c->chain_launched = true;
+    plk.unlock();
     c->evs.push_back(ev);
     CK(cudaGetLastError());
     if (ovr) {
@@ -814,10 +840,13 @@ static int ensure_staging(fp_ctx* c) {
             CK(cudaMalloc(&c->d_ov[i], (size_t)chunk * sizeof(fp_ov_result)));
             CK(cudaMalloc(&c->d_patch[i], (size_t)c->patch_cap * sizeof(fp_patch)));
             CK(cudaMalloc(&c->d_npatch[i], 4));
+        }
+    }
+    if (c->p.paired)
+        for (int i = 0; i < 4; i++) {
             CK(cudaMallocHost(&c->h_patch[i], (size_t)c->patch_cap * sizeof(fp_patch)));
             CK(cudaMallocHost(&c->h_npatch[i], 4));
         }
-    }
     return FP_OK;
 }
 
@@ -873,7 +902,7 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     const int S = c->stride;
     const int64_t n = b->n, CH = c->chunk;
     const int64_t nchunks = (n + CH - 1) / CH;
-    struct Pending { int64_t lo, cnt; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    struct Pending { int64_t lo, cnt; bool active; } pend[4] = {{0, 0, false}, {0, 0, false}, {0, 0, false}, {0, 0, false}};   /* by chunk % 4 */
     const bool want_ev = c->ev_host_n != nullptr;
     if (want_ev) {
         *c->ev_host_n = 0;
@@ -889,25 +918,28 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     fp_adapter_event* const saved_dev = c->ev_dev; const uint32_t saved_cap = c->ev_cap; uint32_t* const saved_cnt = c->ev_count;
     struct Restore { fp_ctx* c; fp_adapter_event* d; uint32_t cap; uint32_t* n; ~Restore() { c->ev_dev = d; c->ev_cap = cap; c->ev_count = n; } } restore{c, saved_dev, saved_cap, saved_cnt};
     if (!want_ev) { c->ev_dev = nullptr; c->ev_cap = 0; c->ev_count = nullptr; }
-    auto finish = [&](int slot) -> int {
-        if (!pend[slot].active) return FP_OK;
+    /* finish(k): host side of chunk k.  Device buffers belong to slot k & 1, the host patch buffers and `pend` to k % 4: the device slot
+       is handed to chunk k + 2 as soon as the chunk's event has fired, while its patches are still being written back here. */
+    auto finish = [&](int64_t k) -> int {
+        const int slot = (int)(k & 1), hs = (int)(k & 3);
+        if (!pend[hs].active) return FP_OK;
         CK(cudaEventSynchronize(c->chunk_done[slot]));           /* blocking-sync event: the waiting thread sleeps instead of spinning */
         if (want_ev) {
             const uint32_t ne = *c->h_nev[slot];
             const uint32_t have = std::min(ne, c->ev_chunk_cap);
             if (have > 0) CK(cudaMemcpy(c->h_ev[slot], c->d_ev[slot], (size_t)have * sizeof(fp_adapter_event), cudaMemcpyDeviceToHost));
-            for (uint32_t k = 0; k < have; k++) {
-                if (*c->ev_host_n < c->ev_host_cap) { c->ev_host[*c->ev_host_n] = c->h_ev[slot][k]; c->ev_host[*c->ev_host_n].unit = (uint32_t)(pend[slot].lo + c->h_ev[slot][k].unit); }
+            for (uint32_t i = 0; i < have; i++) {
+                if (*c->ev_host_n < c->ev_host_cap) { c->ev_host[*c->ev_host_n] = c->h_ev[slot][i]; c->ev_host[*c->ev_host_n].unit = (uint32_t)(pend[hs].lo + c->h_ev[slot][i].unit); }
                 (*c->ev_host_n)++;
             }
             if (ne > have) *c->ev_host_n += ne - have;           /* more events than the chunk buffer holds: counted, not listed */
         }
         if (pe && c->p.correction_enabled) {
-            uint32_t np = *c->h_npatch[slot];
-            const int64_t lo = pend[slot].lo;
+            uint32_t np = *c->h_npatch[hs];
+            const int64_t lo = pend[hs].lo;
             if (np <= c->patch_cap) {
-                for (uint32_t k = 0; k < np; k++) {
-                    const fp_patch& pt = c->h_patch[slot][k];
+                for (uint32_t i = 0; i < np; i++) {
+                    const fp_patch& pt = c->h_patch[hs][i];
                     if (!pk) {
                         uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * HP;
                         uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * HP;
@@ -920,14 +952,15 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 }
             } else if (pk) {
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
-            } else {   /* patch list overflow: take the corrected rows wholesale (row by row when the host pitch differs) */
+            } else {   /* patch list overflow: take the corrected rows wholesale (row by row when the host pitch differs); the issuing loop
+                          keeps the device slot until this is done (it sees the same count) */
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
                 uint8_t* dst[4] = {b->seq1, b->qual1, b->seq2, b->qual2};
-                for (int k = 0; k < 4; k++)
-                    CK(cudaMemcpy2D(dst[k] + lo * HP, (size_t)HP, c->d_stage[slot][k], (size_t)S, (size_t)HP, (size_t)pend[slot].cnt, cudaMemcpyDeviceToHost));
+                for (int a4 = 0; a4 < 4; a4++)
+                    CK(cudaMemcpy2D(dst[a4] + lo * HP, (size_t)HP, c->d_stage[slot][a4], (size_t)S, (size_t)HP, (size_t)pend[hs].cnt, cudaMemcpyDeviceToHost));
             }
         }
-        pend[slot].active = false;
+        pend[hs].active = false;
         return FP_OK;
     };
     /* FP_B_PACK2BIT: a team of host threads packs the bases of chunk k into pinned slot k % NS, up to two chunks ahead of the chunk whose
@@ -973,9 +1006,56 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 }
             });
     }
+    /* Completion work of a chunk (waiting for its stream, corrected bases written back into the caller's rows, event / patch lists) runs
+       on a helper thread when there are enough chunks, so that it overlaps the issue of the following chunks instead of delaying them:
+       with 0.7 corrections per pair the write-back alone is a couple of milliseconds per chunk. */
+    struct Fin {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        int64_t issued = 0, finished = 0;
+        bool stop = false;
+        int rc = FP_OK;
+        std::string err;
+        ~Fin() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+    } fin;
+    const bool use_fin = nchunks > 2;
+    if (use_fin)
+        fin.th = std::thread([&]() {
+            cudaSetDevice(c->device);
+            for (int64_t k = 0; k < nchunks; k++) {
+                {
+                    std::unique_lock<std::mutex> lk(fin.mu);
+                    fin.cv.wait(lk, [&] { return fin.stop || fin.issued > k; });
+                    if (fin.issued <= k) return;
+                }
+                const int r = finish(k);
+                {
+                    std::lock_guard<std::mutex> lk(fin.mu);
+                    if (r && !fin.rc) { fin.rc = r; fin.err = g_err; }
+                    fin.finished = k + 1;
+                }
+                fin.cv.notify_all();
+            }
+        });
+    auto fin_wait = [&](int64_t need) -> int {                 /* until `need` chunks are finished (or the helper failed) */
+        std::unique_lock<std::mutex> lk(fin.mu);
+        fin.cv.wait(lk, [&] { return fin.finished >= need || fin.rc; });
+        if (fin.rc) return set_err(fin.rc, "%s", fin.err.c_str());
+        return FP_OK;
+    };
     for (int64_t ci = 0; ci < nchunks; ci++) {
         const int slot = (int)(ci & 1);
-        rc = finish(slot);
+        if (!use_fin) rc = ci >= 2 ? finish(ci - 2) : FP_OK;    /* the slot's previous chunk is through */
+        else if (ci >= 2) {
+            /* the device slot is free once chunk ci - 2 has left the GPU; its host-side work may still be running on the helper -- unless
+               that work needs the device buffers (adapter events, a patch list that overflowed): then wait for it.  The host buffers
+               rotate over four chunks. */
+            const int64_t k2 = ci - 2;
+            CK(cudaEventSynchronize(c->chunk_done[slot]));
+            const bool needs_dev = want_ev || (pe && c->p.correction_enabled && *c->h_npatch[k2 & 3] > c->patch_cap);
+            rc = fin_wait(needs_dev ? ci - 1 : std::max<int64_t>(ci - 3, 0));
+        }
         if (rc) return rc;
         if (packfly) {
             { std::lock_guard<std::mutex> lk(team.mu); team.allowed = ci + 2; }
@@ -1101,14 +1181,16 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             CK(cudaMemcpyAsync(out2 + lo, c->d_out[slot][1], (size_t)cnt * sizeof(fp_read_result), cudaMemcpyDeviceToHost, st));
             if (ov) CK(cudaMemcpyAsync(ov + lo, c->d_ov[slot], (size_t)cnt * sizeof(fp_ov_result), cudaMemcpyDeviceToHost, st));
             if (c->p.correction_enabled) {
-                CK(cudaMemcpyAsync(c->h_npatch[slot], c->d_npatch[slot], 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(c->h_patch[slot], c->d_patch[slot], (size_t)c->patch_cap * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(c->h_npatch[ci & 3], c->d_npatch[slot], 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(c->h_patch[ci & 3], c->d_patch[slot], (size_t)c->patch_cap * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
             }
         }
         CK(cudaEventRecord(c->chunk_done[slot], st));
-        pend[slot].lo = lo; pend[slot].cnt = cnt; pend[slot].active = true;
+        pend[ci & 3].lo = lo; pend[ci & 3].cnt = cnt; pend[ci & 3].active = true;
+        if (use_fin) { { std::lock_guard<std::mutex> lk(fin.mu); fin.issued = ci + 1; } fin.cv.notify_all(); }
     }
-    for (int s = 0; s < 2; s++) { rc = finish(s); if (rc) return rc; }
+    if (use_fin) { rc = fin_wait(nchunks); if (rc) return rc; }
+    else for (int64_t k = std::max<int64_t>(nchunks - 2, 0); k < nchunks; k++) { rc = finish(k); if (rc) return rc; }
     return FP_OK;
 }
 

@@ -1204,9 +1204,10 @@ __device__ __noinline__ void dense_masked_step(ColAcc2& acc, const uint8_t* ts, 
 }
 
 /* Dense column pass over one tile for one thread's two cycles (w4 + 2*my_half, +1) of one side: Stats::statRead's per-cycle
- * counters (stats.cpp:204-227), exact for any byte.  A function of its own (accumulators in and out BY VALUE, once per tile) so
- * that the 40 accumulators get registers of their own inside the hot loop whatever the rest of the kernel keeps live. */
-__device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* ts, const uint8_t* tq, const uint16_t* lens, int rows, int S, int w4, int my_half,
+ * counters (stats.cpp:204-227), exact for any byte.  A function of its own so that the 40 accumulators get registers of their own
+ * inside the hot loop whatever the rest of the kernel keeps live; between tiles they rest in the caller's frame and are loaded /
+ * stored here ONCE per tile through the reference (by value they crossed local memory four times: 2 KB of L2 traffic per pair). */
+__device__ __noinline__ void dense_tile(ColAcc2& acc_io, const uint8_t* ts, const uint8_t* tq, const uint16_t* lens, int rows, int S, int w4, int my_half,
                                            int rfirst, int rstep, unsigned long long* G, int my_side) {
     FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(lens);
     unsigned int acc[2][NB][4];                      /* element-wise copies: the accumulators must live in registers in the loop */
@@ -1215,7 +1216,7 @@ __device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* 
         #pragma unroll
         for (int b = 0; b < NB; b++)
             #pragma unroll
-            for (int k = 0; k < 4; k++) acc[c][b][k] = acc_in.v[c][b][k];
+            for (int k = 0; k < 4; k++) acc[c][b][k] = acc_io.v[c][b][k];
     const int j0 = my_half * 2;
     const unsigned sel = my_half ? 0x7362u : 0x5140u;
     #pragma unroll (kDenseUnroll)
@@ -1256,14 +1257,12 @@ __device__ __noinline__ ColAcc2 dense_tile(const ColAcc2 acc_in, const uint8_t* 
                     for (int k = 0; k < 4; k++) acc[c][b][k] = tmp.v[c][b][k];
         }
     }
-    ColAcc2 out;
     #pragma unroll
     for (int c = 0; c < 2; c++)
         #pragma unroll
         for (int b = 0; b < NB; b++)
             #pragma unroll
-            for (int k = 0; k < 4; k++) out.v[c][b][k] = acc[c][b][k];
-    return out;
+            for (int k = 0; k < 4; k++) acc_io.v[c][b][k] = acc[c][b][k];
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1529,7 +1528,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
         if (col_active)           /* dense column pass: pre-filter stats of every row of the tile, two cycles per thread */
-            acc = dense_tile(acc, tile_seq[my_side], tile_qual[my_side], s_len + my_side * T, rows, S, my_w * 4, my_half, 4 * my_part, 4 * nsplit, G, my_side);
+            dense_tile(acc, tile_seq[my_side], tile_qual[my_side], s_len + my_side * T, rows, S, my_w * 4, my_half, 4 * my_part, 4 * nsplit, G, my_side);
         {   /* bit planes + validation: 32-item batches claimed dynamically -- warps without columns start at once, the dense warps join */
             const int nwords = (S + 31) >> 5;
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;

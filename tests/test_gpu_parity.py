@@ -314,3 +314,42 @@ def test_merge_mode_with_other_bytes(gpu):
     want = T.run_cpu("oracle", p, arrs, 320)
     got = gpu.run_gpu(p, arrs, 320)
     T.assert_results_equal(got, want, 1, what="merge other bytes")
+
+
+def test_two_contexts_with_different_params_on_one_device(gpu):
+    """The operator parameters sit in one __constant__ block per device: contexts with DIFFERENT fp_params that take turns on the device
+    (each on its own stream, no host synchronisation in between) must each see their own parameters in every launch."""
+    import ctypes as C
+    torch = gpu._torch()
+    pa, pb = T.config_params("cfg3_overlap_correction", 1), T.config_params("all_cuts", 1)
+    n, S = 60000, 160
+    _, arrs = T.synth_host(n, S, 1, 5, 91, 1, 150)
+    want = {k: T.run_cpu("oracle", p, arrs, S) for k, p in (("a", pa), ("b", pb))}
+    ctx = {"a": gpu.GpuCtx(pa, n, S, S), "b": gpu.GpuCtx(pb, n, S, S)}
+    st = {k: torch.cuda.Stream() for k in ctx}
+    dev, outs = {}, {}
+    for k in ctx:
+        _, t = gpu.device_batch({kk: v.copy() for kk, v in arrs.items()})
+        dev[k] = t
+        outs[k] = [torch.zeros(n * 16, dtype=torch.uint8, device="cuda:0") for _ in range(2)] + [torch.zeros(n * 8, dtype=torch.uint8, device="cuda:0")]
+        outs[k] += [torch.zeros((4 * n + 16) * 12, dtype=torch.uint8, device="cuda:0"), torch.zeros(1, dtype=torch.int32, device="cuda:0")]
+    torch.cuda.synchronize()
+    parts = 12
+    bounds = [n * i // parts for i in range(parts + 1)]
+    lib = ctx["a"].lib
+    for lo, hi in zip(bounds[:-1], bounds[1:]):              # a, b, a, b ... slices of the same rows, no sync between the launches
+        for k in ("a", "b"):
+            sb = capi.Batch(); sb.n, sb.stride = hi - lo, S
+            for kk, v in dev[k].items():
+                setattr(sb, kk, v.data_ptr() + lo * (2 if kk.startswith("len") else S))
+            o = outs[k]
+            # patch indices are batch-local: give every slice its own region of the patch buffer (only the counters / records are compared)
+            capi.check(lib.fp_process_pe(ctx[k].h, C.byref(sb), o[0].data_ptr() + lo * 16, o[1].data_ptr() + lo * 16, o[2].data_ptr() + lo * 8,
+                                         None, 0, None, C.c_void_p(st[k].cuda_stream)), lib)
+    torch.cuda.synchronize()
+    for k in ctx:
+        got = {"out1": outs[k][0].cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n], "out2": outs[k][1].cpu().numpy().view(capi.READ_RESULT_DTYPE)[:n],
+               "ov": outs[k][2].cpu().numpy().view(capi.OV_RESULT_DTYPE)[:n], "counters": ctx[k].counters(),
+               "arrs": {kk: v.cpu().numpy() for kk, v in dev[k].items()}, "layout": ctx[k].L}
+        T.assert_results_equal(got, want[k], 1, what=f"context {k}")
+        ctx[k].close()
