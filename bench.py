@@ -786,7 +786,7 @@ def gpu_workload(name, args, env, units, steps, warmup, with_e2e=False):
         #      (packing inside the clock, overlapped); qualities go up from the caller's rows as they are ----
         p2 = None
         try:
-            nthr2 = max(1, min(cpu_resources()["usable"] // max(world, 1) - 1, 32))
+            nthr2 = int(os.environ.get("FP_BENCH_PACK_THREADS", "0")) or max(1, min(cpu_resources()["usable"] // max(world, 1) - 1, 32))
             capi.check(lib.fp_set_host_threads(h, nthr2), lib)
             hbt.flags = 1 | capi.FP_B_PACK2BIT
             for _ in range(2):
@@ -915,8 +915,20 @@ def main():
     torch.cuda.set_device(local_rank)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-        comm = sharding.NcclComm(world, rank)       # raw ncclComm_t for the C-ABI collective fp_counters_allreduce
+        # NCCL may print a version banner on stdout (NCCL_DEBUG=VERSION in the environment): keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_out = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            comm = sharding.NcclComm(world, rank)   # raw ncclComm_t for the C-ABI collective fp_counters_allreduce
+            tt0 = torch.zeros(1, device=f"cuda:{local_rank}")
+            dist.all_reduce(tt0)                    # first collective (lazy communicator setup) while stdout is parked
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_out, 1)
+            os.close(saved_out)
     dev = f"cuda:{local_rank}"
     lib = capi.load()
     env = dict(torch=torch, dist=dist, capi=capi, lib=lib, world=world, rank=rank, local_rank=local_rank, dev=dev, comm=comm, cpu={})

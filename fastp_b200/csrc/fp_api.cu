@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -106,7 +107,7 @@ struct fp_ctx {
     fp_npos* h_np[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_pkb_cap = 0, h_np_cap = 0;
     int host_threads = 0;                       /* 0 = default_host_threads() */
-    cudaEvent_t chunk_done[2] = {nullptr, nullptr};   /* end of a host chunk's work on its stream (cudaEventBlockingSync) */
+    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};   /* end of host chunk k's work on its stream, by k % 4 (cudaEventBlockingSync) */
     /* FASTQ codec workspaces (grown on demand) and the buffers of fp_fastq_process_host */
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf fq_term, fq_bcnt, fq_agg, fq_bstate, fq_brec, fq_recline, fq_recend, fq_info, fq_bsum;
@@ -288,7 +289,8 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    for (int i = 0; i < 2; i++) { CK(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventBlockingSync | cudaEventDisableTiming)); }
+    for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventBlockingSync | cudaEventDisableTiming));
 
     /* LUTs */
     std::vector<int16_t> ov, lowq, mind;
@@ -470,7 +472,8 @@ extern "C" void fp_ctx_destroy(fp_ctx* c) {
     if (c->ovr_ev) cudaEventDestroy(c->ovr_ev);
     for (auto& e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 2; i++) { if (c->stream[i]) cudaStreamDestroy(c->stream[i]); if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]); }
+    for (int i = 0; i < 2; i++) if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    for (int i = 0; i < 4; i++) if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]);
     delete c;
 }
 
@@ -923,7 +926,8 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
     auto finish = [&](int64_t k) -> int {
         const int slot = (int)(k & 1), hs = (int)(k & 3);
         if (!pend[hs].active) return FP_OK;
-        CK(cudaEventSynchronize(c->chunk_done[slot]));           /* blocking-sync event: the waiting thread sleeps instead of spinning */
+        CK(cudaEventSynchronize(c->chunk_done[hs]));             /* blocking-sync event: the waiting thread sleeps instead of spinning.  One event per
+                                                                    chunk in flight on the HOST side (k % 4): the slot's next chunk records its own */
         if (want_ev) {
             const uint32_t ne = *c->h_nev[slot];
             const uint32_t have = std::min(ne, c->ev_chunk_cap);
@@ -938,18 +942,35 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
             uint32_t np = *c->h_npatch[hs];
             const int64_t lo = pend[hs].lo;
             if (np <= c->patch_cap) {
-                for (uint32_t i = 0; i < np; i++) {
-                    const fp_patch& pt = c->h_patch[hs][i];
-                    if (!pk) {
-                        uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * HP;
-                        uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * HP;
-                        sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
-                    }
-                    if (hp_n) {                                  /* caller's list: pair index relative to the whole host batch */
-                        if (*hp_n < hp_cap) { hp_out[*hp_n] = pt; hp_out[*hp_n].pair = (uint32_t)(lo + pt.pair); }
+                /* the write-back touches two random cache lines per correction: memory-latency bound (16 ns per patch on one core, 3 ms per
+                   chunk -- more than the chunk's transfer).  The lines of the patch 24 entries ahead are requested while this one is
+                   applied, and a large list is split over four threads (no two patches touch the same byte). */
+                const fp_patch* const P = c->h_patch[hs];
+                if (!pk) {
+                    auto apply_range = [&](uint32_t a0, uint32_t a1) {
+                        for (uint32_t i = a0; i < a1; i++) {
+                            const fp_patch& pt = P[i];
+                            if (i + 24 < a1) {
+                                const fp_patch& nx = P[i + 24];
+                                __builtin_prefetch((nx.which ? b->seq2 : b->seq1) + (lo + nx.pair) * HP + nx.pos, 1, 0);
+                                __builtin_prefetch((nx.which ? b->qual2 : b->qual1) + (lo + nx.pair) * HP + nx.pos, 1, 0);
+                            }
+                            uint8_t* sq = (pt.which ? b->seq2 : b->seq1) + (lo + pt.pair) * HP;
+                            uint8_t* ql = (pt.which ? b->qual2 : b->qual1) + (lo + pt.pair) * HP;
+                            sq[pt.pos] = pt.base; ql[pt.pos] = pt.qual;
+                        }
+                    };
+                    const uint32_t nt = np >= 65536 ? 4u : 1u;
+                    std::thread extra[3];
+                    for (uint32_t t = 1; t < nt; t++) extra[t - 1] = std::thread(apply_range, (uint32_t)((uint64_t)np * t / nt), (uint32_t)((uint64_t)np * (t + 1) / nt));
+                    apply_range(0, (uint32_t)((uint64_t)np / nt));
+                    for (uint32_t t = 1; t < nt; t++) extra[t - 1].join();
+                }
+                if (hp_n)                                        /* caller's list: pair index relative to the whole host batch */
+                    for (uint32_t i = 0; i < np; i++) {
+                        if (*hp_n < hp_cap) { hp_out[*hp_n] = P[i]; hp_out[*hp_n].pair = (uint32_t)(lo + P[i].pair); }
                         (*hp_n)++;
                     }
-                }
             } else if (pk) {
                 if (hp_n) *hp_n = ~(uint64_t)0 >> 1;             /* the caller's list cannot be complete */
             } else {   /* patch list overflow: take the corrected rows wholesale (row by row when the host pitch differs); the issuing loop
@@ -1044,23 +1065,32 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
         if (fin.rc) return set_err(fin.rc, "%s", fin.err.c_str());
         return FP_OK;
     };
+    const bool trace = getenv("FP_TRACE_HOST") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    double t_slot = 0, t_fin = 0, t_pack = 0, t_issue = 0;
+    const auto t_begin = now();
     for (int64_t ci = 0; ci < nchunks; ci++) {
         const int slot = (int)(ci & 1);
+        auto tp = now();
         if (!use_fin) rc = ci >= 2 ? finish(ci - 2) : FP_OK;    /* the slot's previous chunk is through */
         else if (ci >= 2) {
             /* the device slot is free once chunk ci - 2 has left the GPU; its host-side work may still be running on the helper -- unless
                that work needs the device buffers (adapter events, a patch list that overflowed): then wait for it.  The host buffers
                rotate over four chunks. */
             const int64_t k2 = ci - 2;
-            CK(cudaEventSynchronize(c->chunk_done[slot]));
+            CK(cudaEventSynchronize(c->chunk_done[k2 & 3]));
+            t_slot += ms_since(tp); tp = now();
             const bool needs_dev = want_ev || (pe && c->p.correction_enabled && *c->h_npatch[k2 & 3] > c->patch_cap);
             rc = fin_wait(needs_dev ? ci - 1 : std::max<int64_t>(ci - 3, 0));
+            t_fin += ms_since(tp); tp = now();
         }
         if (rc) return rc;
         if (packfly) {
             { std::lock_guard<std::mutex> lk(team.mu); team.allowed = ci + 2; }
             team.cv_allowed.notify_all();
             { std::unique_lock<std::mutex> lk(team.mu); team.cv_done.wait(lk, [&] { return team.done[(size_t)ci] >= NT; }); }
+            t_pack += ms_since(tp); tp = now();
             if (team.bad.load() == 1) return set_err(FP_E_UNSUPPORTED, "a base outside {A,C,G,T,N}: not representable in packed rows (FP_B_PACK2BIT)");
             if (team.bad.load() == 2) return set_err(FP_E_INVAL, "a read is longer than the host row pitch");
         }
@@ -1185,12 +1215,17 @@ static int process_host(fp_ctx* c, const fp_batch* b, fp_read_result* out1, fp_r
                 CK(cudaMemcpyAsync(c->h_patch[ci & 3], c->d_patch[slot], (size_t)c->patch_cap * sizeof(fp_patch), cudaMemcpyDeviceToHost, st));
             }
         }
-        CK(cudaEventRecord(c->chunk_done[slot], st));
+        CK(cudaEventRecord(c->chunk_done[ci & 3], st));
         pend[ci & 3].lo = lo; pend[ci & 3].cnt = cnt; pend[ci & 3].active = true;
         if (use_fin) { { std::lock_guard<std::mutex> lk(fin.mu); fin.issued = ci + 1; } fin.cv.notify_all(); }
+        t_issue += ms_since(tp);
     }
+    const double t_loop = ms_since(t_begin);
     if (use_fin) { rc = fin_wait(nchunks); if (rc) return rc; }
     else for (int64_t k = std::max<int64_t>(nchunks - 2, 0); k < nchunks; k++) { rc = finish(k); if (rc) return rc; }
+    if (trace)
+        fprintf(stderr, "[fastp_b200 host] %lld units, %lld chunks, mode %s: issue loop %.2f ms (waiting: device slot %.2f, helper %.2f, packers %.2f; issuing %.2f), drain %.2f ms\n",
+                (long long)n, (long long)nchunks, pk ? "packed" : packfly ? "pack2bit" : repitch ? "tight" : "rows", t_loop, t_slot, t_fin, t_pack, t_issue, ms_since(t_begin) - t_loop);
     return FP_OK;
 }
 
