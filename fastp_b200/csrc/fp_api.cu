@@ -239,6 +239,9 @@ static void make_smem_layout(fp_ctx* c) {
     smem_layout_for_tile(c, T, c->sl);
 }
 
+static int ctx_init(fp_ctx* c, const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles);
+extern "C" void fp_ctx_destroy(fp_ctx* c);
+
 extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles, fp_ctx** out) {
     if (!p || !out) return set_err(FP_E_INVAL, "null argument");
     if (stride <= 0 || stride % 16 || stride > FP_MAX_STRIDE) return set_err(FP_E_INVAL, "stride must be a multiple of 16 and <= FP_MAX_STRIDE");
@@ -255,18 +258,31 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
     CK(cudaSetDevice(device));
     fp_ctx* c = new fp_ctx();
     c->device = device;
+    const int rc = ctx_init(c, p, device, max_batch, stride, cycles);
+    if (rc != FP_OK) {                                         /* nothing of a partly built context survives (device memory, streams, events) */
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        fp_ctx_destroy(c);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = c;
+    return FP_OK;
+}
+
+static int ctx_init(fp_ctx* c, const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles) {
     c->p = *p;
     if (p->has_seq_r1 && p->adapter_seq_r1) c->ad1 = p->adapter_seq_r1;
     if (p->has_seq_r2 && p->adapter_seq_r2) c->ad2 = p->adapter_seq_r2;
     for (int i = 0; i < p->n_fasta_adapters; i++) c->fasta.push_back(p->fasta_adapters[i]);
     c->p.adapter_seq_r1 = c->ad1.c_str(); c->p.adapter_seq_r2 = c->ad2.c_str(); c->p.fasta_adapters = nullptr;
-    if ((int)c->fasta.size() > FP_MAX_ADAPTERS) { delete c; return set_err(FP_E_INVAL, "too many adapters"); }
-    for (auto& s : c->fasta) if (s.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
-    if (c->ad1.size() > FP_MAX_ADAPTER_LEN || c->ad2.size() > FP_MAX_ADAPTER_LEN) { delete c; return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
+    if ((int)c->fasta.size() > FP_MAX_ADAPTERS) { return set_err(FP_E_INVAL, "too many adapters"); }
+    for (auto& s : c->fasta) if (s.size() > FP_MAX_ADAPTER_LEN) { return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
+    if (c->ad1.size() > FP_MAX_ADAPTER_LEN || c->ad2.size() > FP_MAX_ADAPTER_LEN) { return set_err(FP_E_INVAL, "adapter longer than FP_MAX_ADAPTER_LEN"); }
     c->max_batch = max_batch; c->stride = stride; c->cycles = cycles;
-    if (p->merge_enabled && p->paired && p->overrep_enabled) { delete c; return set_err(FP_E_UNSUPPORTED, "merge mode together with over-representation analysis is not built"); }
+    if (p->merge_enabled && p->paired && p->overrep_enabled) { return set_err(FP_E_UNSUPPORTED, "merge mode together with over-representation analysis is not built"); }
     if (p->overrep_enabled) {
-        if (p->overrep_sampling < 1) { delete c; return set_err(FP_E_INVAL, "overrep_sampling must be >= 1"); }
+        if (p->overrep_sampling < 1) { return set_err(FP_E_INVAL, "overrep_sampling must be >= 1"); }
         for (int i = 0; i < p->n_overrep1; i++) c->overrep[0].push_back(p->overrep_seqs1[i]);
         if (p->paired) for (int i = 0; i < p->n_overrep2; i++) c->overrep[1].push_back(p->overrep_seqs2[i]);
     }
@@ -410,10 +426,9 @@ extern "C" int fp_ctx_create(const fp_params* p, int device, int64_t max_batch, 
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sl.total));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, c->group_threads * c->groups, c->sl.total));
     }
-    if (occ < 1) { fp_ctx_destroy(c); return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)"); }
+    if (occ < 1) return set_err(FP_E_CUDA, "kernel cannot be resident (shared memory / registers)");
     c->grid_max = occ * c->num_sms;
     if (getenv("FP_TRACE")) fprintf(stderr, "[fastp_b200] groups %d x %d threads, tile %d rows, smem %d B (shared %d + %d per group), %d CTA/SM\n", c->groups, c->group_threads, c->tile, c->sl.total, c->sl.off_group, c->sl.group_stride, occ);
-    *out = c;
     return FP_OK;
 }
 

@@ -422,6 +422,8 @@ def random_params(rng, paired, lib=None):
                   allow_gap_overlap_trimming=int(coin(0.3)), insert_size_max=R(300, 600) if coin(0.3) else 512)
         if coin(0.5):
             kw["adapter_seq_r2"] = TRUSEQ_R2[: R(6, len(TRUSEQ_R2))]
+        if coin(0.25):                                    # merging mode (drawn last: the earlier knobs keep their streams)
+            kw.update(merge_enabled=1, merge_include_unmerged=int(coin()))
     return capi.default_params(paired, lib=lib or oracle(), **kw), kw
 
 

@@ -353,3 +353,23 @@ def test_two_contexts_with_different_params_on_one_device(gpu):
                "arrs": {kk: v.cpu().numpy() for kk, v in dev[k].items()}, "layout": ctx[k].L}
         T.assert_results_equal(got, want[k], 1, what=f"context {k}")
         ctx[k].close()
+
+
+def test_failed_ctx_create_leaves_nothing_behind(gpu):
+    """a context that fails half-way through its construction is torn down (fp_ctx_create unwinds through fp_ctx_destroy): many failures
+    in a row neither exhaust the device nor disturb a following context"""
+    import ctypes as C
+    torch = gpu._torch()
+    lib = capi.load()
+    free0 = torch.cuda.mem_get_info()[0]
+    bad = T.config_params("default", 1)
+    capi.set_params(bad, adapter_seq_r1="A" * 300)                      # longer than FP_MAX_ADAPTER_LEN: rejected inside the construction
+    for _ in range(50):
+        h = C.c_void_p()
+        rc = lib.fp_ctx_create(C.byref(bad), 0, 1 << 20, 160, 160, C.byref(h))
+        assert rc != 0 and not h.value
+        assert b"adapter" in lib.fp_last_error()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20
+    p = T.config_params("cfg3_overlap_correction", 1)
+    _, arrs = T.synth_host(3000, 160, 1, 5, 3, 1, 150)
+    T.assert_results_equal(gpu.run_gpu(p, arrs, 160), T.run_cpu("oracle", p, arrs, 160), 1, what="after failed creates")
