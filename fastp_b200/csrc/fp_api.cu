@@ -237,6 +237,10 @@ static void make_smem_layout(fp_ctx* c) {
     while (T > 16 && smem_layout_for_tile(c, T, c->sl) > budget) T -= 8;
     c->tile = T;
     smem_layout_for_tile(c, T, c->sl);
+    /* kernel variants that stay selectable for measurements (profiles/README.md): bit 0 = base correction on per-warp work lists behind ONE
+       group barrier, bit 1 = L2 prefetch of the CTA's next tile */
+    c->sl.xflags = 2;
+    if (const char* e = getenv("FP_XFLAGS")) c->sl.xflags = atoi(e);
 }
 
 static int ctx_init(fp_ctx* c, const fp_params* p, int device, int64_t max_batch, int32_t stride, int32_t cycles);

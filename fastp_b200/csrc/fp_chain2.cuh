@@ -713,7 +713,7 @@ __device__ __noinline__ int t_correct(const TRead r1, const TRead r2, uint32_t* 
  * ------------------------------------------------------------------------------------------------ */
 #define FP_CORR_CAP 1024               /* corrections of one tile; more go the sequential way */
 __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, int PW, const fp_ov_result ov, int row, int sub, int g,
-                                              uint32_t* list, int* nlist, uint32_t* cm1, uint32_t* cm2) {
+                                              uint32_t* list, int* nlist, int cap, uint32_t* cm1, uint32_t* cm2) {
     FP_SMEM(r1.qual);    FP_SMEM(r2.qual);    FP_SMEM(r1.pl);    FP_SMEM(r2.pl);    FP_SMEM(list);    FP_SMEM(nlist);    FP_SMEM(cm1);    FP_SMEM(cm2);
     bool overflow = false;
     const int ol = ov.overlap_len;
@@ -744,7 +744,7 @@ __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, in
             else continue;
             const int P1 = r1.front + p1, P2 = r2.front + p2;
             const int slot = atomicAdd(nlist, 1);
-            if (slot >= FP_CORR_CAP) { overflow = true; continue; }            /* left to the sequential path after the distributed one */
+            if (slot >= cap) { overflow = true; continue; }            /* left to the sequential path after the distributed one */
             list[slot] = (uint32_t)row | ((uint32_t)which << 7) | ((uint32_t)(which ? P2 : P1) << 8) | ((uint32_t)(which ? P1 : P2) << 18);
             if (which) atomicOr(&cm2[P2 >> 5], 1u << (P2 & 31)); else atomicOr(&cm1[P1 >> 5], 1u << (P1 & 31));
         }
@@ -1045,6 +1045,59 @@ __device__ __noinline__ int t_pass_filter(const TRead r, int PW, const int16_t* 
             if (i + 1 < rlen) adj += (s[i] != s[i + 1]);
         }
     }
+    if (c_p.qual_filter) {
+        if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
+        if (c_p.avg_qual_req > 0) {
+            const uint8_t* q = r.qual + r.front;
+            int tq = 0;
+            for (int i = 0; i < rlen; i++) tq += (int)q[i] - 33;
+            if ((tq / rlen) < c_p.avg_qual_req) return FP_FAIL_QUALITY;
+        }
+        if (nb > c_p.n_base_limit) return FP_FAIL_N_BASE;
+    }
+    if (c_p.length_filter) {
+        if (rlen < c_p.length_required) return FP_FAIL_LENGTH;
+        if (c_p.length_limit > 0 && rlen > c_p.length_limit) return FP_FAIL_TOO_LONG;
+    }
+    if (c_p.complexity_filter) {
+        if (rlen <= 1) return FP_FAIL_COMPLEXITY;
+        if (adj < (int)lut[2 * (c_p.stride + 2) + rlen]) return FP_FAIL_COMPLEXITY;
+    }
+    return FP_PASS_FILTER;
+}
+
+/* Filter::passFilter shared by the lanes of a group: lane `half` (0 / 1) of a lane PAIR counts the plane words k = half, half + 2, ...
+ * of the pair's read, the two partial counts meet by one shuffle and both lanes hold the verdict.  PE groups give lanes 0, 1 to read 1
+ * and lanes 2, 3 to read 2 (the caller exchanges the verdicts); every lane of the group must call. */
+__device__ __noinline__ int t_pass_filter_pair(const TRead r, int PW, const int16_t* lut, int half, unsigned gm) {
+    FP_SMEM(r.pl);    FP_SMEM(r.seq);    FP_SMEM(r.qual);    FP_SMEM(lut);
+    const int rlen = (r.null || r.len == 0) ? 0 : r.len;
+    int lowq = 0, nb = 0, adj = 0;
+    if (r.clean) {
+        const uint32_t *plo = r.pl, *phi = r.pl + PW, *pnn = r.pl + 2 * PW, *plq = r.pl + 3 * PW;
+        for (int k = half; k * 32 < rlen; k += 2) {
+            const int bit = r.front + 32 * k;
+            const uint32_t m = low_mask(rlen - 32 * k);
+            const uint32_t nn = tp_bits(pnn, bit);
+            lowq += __popc(tp_bits(plq, bit) & m);
+            nb += __popc(nn & m);
+            if (c_p.complexity_filter) {
+                const uint32_t d = (tp_bits(plo, bit) ^ tp_bits(plo, bit + 1)) | (tp_bits(phi, bit) ^ tp_bits(phi, bit + 1)) | (nn ^ tp_bits(pnn, bit + 1));
+                adj += __popc(d & low_mask(rlen - 1 - 32 * k));
+            }
+        }
+    } else if (half == 0) {
+        const uint8_t* s = r.seq + r.front; const uint8_t* q = r.qual + r.front;
+        const uint8_t qq = (uint8_t)c_p.qualified_qual;
+        for (int i = 0; i < rlen; i++) {
+            lowq += (q[i] < qq); nb += (s[i] == 'N');
+            if (i + 1 < rlen) adj += (s[i] != s[i + 1]);
+        }
+    }
+    int packed = lowq | (nb << 10) | (adj << 20);                          /* each count <= 1023 (row length) */
+    packed += __shfl_xor_sync(gm, packed, 1);
+    lowq = packed & 1023; nb = (packed >> 10) & 1023; adj = packed >> 20;
+    if (rlen == 0) return FP_FAIL_LENGTH;
     if (c_p.qual_filter) {
         if (lowq > (int)lut[(c_p.stride + 2) + rlen]) return FP_FAIL_QUALITY;
         if (c_p.avg_qual_req > 0) {
@@ -1458,6 +1511,11 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
     for (int i = ctid; i < (int)(sizeof(BlockCounters) / 4); i += CT * NG) reinterpret_cast<unsigned int*>(bc)[i] = 0;
     for (int i = ctid; i < S + 2; i += CT * NG) { s_lut[i] = c_p.lut_ovlimit[i]; s_lut[(S + 2) + i] = c_p.lut_lowq[i]; s_lut[2 * (S + 2) + i] = c_p.lut_mindiff[i]; }
     if (tid == 0) { mbar_init(mbar, 1); s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    /* base correction work lists: ONE list per group (xflags bit 0 clear), or one per warp: region w = s_corr[w * WR .. (w+1) * WR), its
+       length in word 0 -- then nothing about a correction leaves the warp that decided it */
+    constexpr int WR = FP_CORR_CAP / (CT / 32);
+    const bool warp_lists = PAIRED && (sl.xflags & 1);
+    if (PAIRED) for (int i = tid; i < FP_CORR_CAP; i += CT) s_corr[i] = 0;
 
     /* column-pass ownership: thread = (side, half-word column): cycles 2*hc, 2*hc+1 */
     const int HPR = S >> 1;
@@ -1517,6 +1575,13 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 tma_bulk_g2s(tile_qual[1], a.b.qual2 + row0 * S, bytes, mbar);
             }
             s_qn[0] = 0; s_qn[1] = 0; s_qn[3] = 0;     /* request queue / removal items: next used after the phase-A barrier */
+            const long long tnext = tix + (long long)gridDim.x * NG;               /* the tile this group loads next: into L2 while this one is worked on */
+            if ((sl.xflags & 2) && tnext < a.n_tiles) {
+                const long long rn0 = tnext * T;
+                const uint32_t nb = (uint32_t)min((long long)T, a.b.n - rn0) * (uint32_t)S;
+                l2_prefetch(a.b.seq1 + rn0 * S, nb); l2_prefetch(a.b.qual1 + rn0 * S, nb);
+                if (PAIRED) { l2_prefetch(a.b.seq2 + rn0 * S, nb); l2_prefetch(a.b.qual2 + rn0 * S, nb); }
+            }
             if (PAIRED && c_p.correction) *s_ncorr = 0;
         }
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
@@ -1534,6 +1599,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
             const uint32_t qq4 = (uint32_t)(c_p.qualified_qual & 0x7F) * 0x01010101u;
             const uint32_t cq4 = (uint32_t)(min(max(c_p.cr_q, 0), 127)) * 0x01010101u;      /* plane 4: quality below cut_right's per-base threshold */
             const int total = SIDES * T * nwords;              /* pad words of the planes stay zero (cleared once at kernel start) */
+            const bool want_cq = c_p.cut_right != 0;           /* plane 4 has one reader: cut_right */
             /* item order.  Word-major: the lanes of a warp hold the SAME word index of 32 different rows, so with reads of one length the
                row-end word (partial steps, predicated counts) is taken by whole warps instead of one lane in five.  The lanes then read
                shared memory one row pitch apart: not when the pitch is a multiple of 16 words (the 256-byte rows of 250 bp reads would
@@ -1571,7 +1637,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                             for (int k = 0; k < 4; k++) {
                                 const uint2 sw = *reinterpret_cast<const uint2*>(sp + 8 * k), qw = *reinterpret_cast<const uint2*>(qp + 8 * k);
                                 uint32_t f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, f_cq;
-                                plane_pair(sw.x, sw.y, qw.x, qw.y, qq4, f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, cq4, f_cq);
+                                plane_pair(sw.x, sw.y, qw.x, qw.y, qq4, f_lo, f_hi, f_nn, f_lq, f_ok, f_bad, cq4, f_cq, want_cq);
                                 cqw = __byte_perm(cqw, f_cq, 0x7321);
                                 lo = __byte_perm(lo, f_lo, 0x7321); hi = __byte_perm(hi, f_hi, 0x7321); nn = __byte_perm(nn, f_nn, 0x7321);
                                 lq = __byte_perm(lq, f_lq, 0x7321); okm = __byte_perm(okm, f_ok, 0x7321); bad = __byte_perm(bad, f_bad, 0x7321);
@@ -1626,13 +1692,14 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                             for (int g8 = 0; g8 < 4; g8++) {               /* 8 windows per step: W = Z bits [16*g8, 16*g8 + 32) */
                                 const uint32_t W = __funnelshift_r(g8 < 2 ? Z0 : Z1, g8 < 2 ? Z1 : Z2, (g8 & 1) * 16);
                                 const uint32_t v8 = (vwin >> (8 * g8)) & 0xFFu;
-                                if (v8 == 0xFFu) {                         /* the usual step: eight countable windows, no selects */
+                                /* one path per warp step: lanes with and without uncountable windows would otherwise run both in turn */
+                                if (__all_sync(__activemask(), v8 == 0xFFu)) {      /* the usual step: eight countable windows, no selects */
                                     #pragma unroll
                                     for (int pp = 0; pp < 8; pp++) {       /* byte offset of the bin = field*4 | side*4096 */
                                         const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
                                         smem_inc(kaddr | (f4 & 0xFFCu));
                                     }
-                                } else if (v8) {
+                                } else if (__any_sync(__activemask(), v8 != 0u)) {
                                     #pragma unroll
                                     for (int pp = 0; pp < 8; pp++) {
                                         const uint32_t f4 = pp == 0 ? (W << 2) : (W >> (2 * pp - 2));
@@ -1687,7 +1754,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                         }
                     }
                     if (!r1.null && c_p.max_len1 > 0 && c_p.max_len1 < r1.len) r1.len = c_p.max_len1;   /* :268-271 */
-                    result = t_pass_filter(r1, PW, s_lut);                                        /* :273 */
+                    result = t_pass_filter_pair(r1, PW, s_lut, sub, gmask);                       /* :273 */
                     if (dimer) { result = FP_FAIL_ADAPTER_DIMER; flags |= FP_F_ADAPTER_DIMER; }
                     const bool dupout = a.is_dup && a.is_dup[gi];                                 /* dedupOut :280 */
                     if (dupout) flags |= FP_F_DUPLICATE;
@@ -1750,21 +1817,43 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 bool corr_overflow = false;
                 const bool distributed = need_correct && clean1 && clean2;
                 if (PAIRED && c_p.correction) {
+                    uint32_t* const wlist = warp_lists ? s_corr + warp * WR + 1 : s_corr;
+                    int* const wn = warp_lists ? reinterpret_cast<int*>(s_corr + warp * WR) : s_ncorr;
+                    const int wcap = warp_lists ? WR - 1 : FP_CORR_CAP;
                     if (distributed)
-                        corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, s_corr, s_ncorr, s_cm + rr * CMW, s_cm + (T + rr) * CMW);
+                        corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, wlist, wn, wcap, s_cm + rr * CMW, s_cm + (T + rr) * CMW);
+                    /* the one barrier that stays: the warps leave the overlap analysis at very different times, and behind it they run the
+                       correction code TOGETHER (one hot region of the instruction cache) */
                     GSYNC();
-                    const int ncorr = min(*s_ncorr, FP_CORR_CAP);
-                    for (int i = tid; i < ncorr; i += CT)
-                        t_correct_item(s_corr[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (s_corr[i] & 0x7F)));
-                    GSYNC();
-                    for (int i = tid; i < ncorr; i += CT) {
-                        const uint32_t en = s_corr[i];
-                        const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
-                        t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
-                                        (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
+                    if (warp_lists) {
+                        /* a pair's rows, masks and planes belong to the warp that holds the pair: warp-level syncs order item -> apply -> chain */
+                        const int ncorr = min(*wn, wcap);
+                        for (int i = lane; i < ncorr; i += 32)
+                            t_correct_item(wlist[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (wlist[i] & 0x7F)));
+                        __syncwarp();
+                        for (int i = lane; i < ncorr; i += 32) {
+                            const uint32_t en = wlist[i];
+                            const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
+                            t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
+                                            (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
+                        }
+                        __syncwarp();
+                        if (lane == 0) *wn = 0;
+                        __syncwarp();
+                    } else {
+                        const int ncorr = min(*s_ncorr, FP_CORR_CAP);
+                        for (int i = tid; i < ncorr; i += CT)
+                            t_correct_item(s_corr[i], tile_seq[0], sl.tile_array_bytes, S, T, s_len, s_cm, CMW, D, bc, a.sink, (unsigned int)(row0 + (s_corr[i] & 0x7F)));
+                        GSYNC();
+                        for (int i = tid; i < ncorr; i += CT) {
+                            const uint32_t en = s_corr[i];
+                            const int erow = en & 0x7F, ewhich = (en >> 7) & 1;
+                            t_correct_apply(en, tile_seq[0], sl.tile_array_bytes, S, T, tile_planes, PSTR, PW,
+                                            (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
+                        }
+                        GSYNC();
+                        if (tid == 0) *s_ncorr = 0;                /* (a PE tile is one round of this loop: 8 warps x 8 pairs >= T) */
                     }
-                    GSYNC();
-                    if (tid == 0) *s_ncorr = 0;                /* (a PE tile is one round of this loop: 8 warps x 8 pairs >= T) */
                 }
                 int res1 = FP_FAIL_LENGTH, res2 = FP_FAIL_LENGTH;
                 bool counted = false;
@@ -1866,7 +1955,10 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                         }
                     }
                     if (!merge_done) {
-                        res1 = t_pass_filter(r1, PW, s_lut); res2 = t_pass_filter(r2, PW, s_lut);  /* :565-566 */
+                        {   /* :565-566: lanes 0, 1 filter read 1, lanes 2, 3 read 2 */
+                            const int mine = t_pass_filter_pair(sub < 2 ? r1 : r2, PW, s_lut, sub & 1, gmask);
+                            res1 = __shfl_sync(gmask, mine, glead); res2 = __shfl_sync(gmask, mine, glead + 2);
+                        }
                         if (dimer) { res1 = res2 = FP_FAIL_ADAPTER_DIMER; flags1 |= FP_F_ADAPTER_DIMER; flags2 |= FP_F_ADAPTER_DIMER; }
                         pv = max(res1, res2);
                         /* merging mode keeps the post-filter Stats for merged (and --include_unmerged) reads only (:588-591) */

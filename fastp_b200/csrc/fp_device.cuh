@@ -131,7 +131,7 @@ __device__ __forceinline__ uint32_t gather_top4(uint32_t m0, uint32_t m1, uint32
 /* flags of 8 bases (even word a, odd word b; qualities qa, qb): each f_* holds the 8 flags in its TOP byte
  * (bit 24+i = base i of a, bit 28+i = base i of b).  f_bad: byte outside {A,C,G,T,N} or quality bit 7 set. */
 __device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, uint32_t qb, uint32_t qq4,
-                                           uint32_t& f_lo, uint32_t& f_hi, uint32_t& f_nn, uint32_t& f_lq, uint32_t& f_ok, uint32_t& f_bad, uint32_t cq4, uint32_t& f_cq) {
+                                           uint32_t& f_lo, uint32_t& f_hi, uint32_t& f_nn, uint32_t& f_lq, uint32_t& f_ok, uint32_t& f_bad, uint32_t cq4, uint32_t& f_cq, bool want_cq = true) {
     const uint32_t K = 0x01010101u, K4 = 0x10101010u, M = 0x01020408u;
     /* even word: bit j of every byte moved to bit 0 */
     const uint32_t a1 = a >> 1, a2 = a >> 2, a3 = a >> 3, a4 = a >> 4;
@@ -151,7 +151,8 @@ __device__ __forceinline__ void plane_pair(uint32_t a, uint32_t b, uint32_t qa, 
     f_nn = np * M;
     f_ok = okp * M;                                                                   /* exact: byte is one of 'A','C','G','T' */
     f_lq = (((ta >> 7) & K) | ((tb >> 3) & K4)) * M;
-    {   /* q < cut_right's per-base threshold 33+Q (filter.cpp:159): a window without such a base cannot fall below w*(33+Q) */
+    f_cq = 0;
+    if (want_cq) {   /* q < cut_right's per-base threshold 33+Q (filter.cpp:159): a window without such a base cannot fall below w*(33+Q) */
         const uint32_t ca = ~((qa | 0x80808080u) - cq4), cb = ~((qb | 0x80808080u) - cq4);
         f_cq = (((ca >> 7) & K) | ((cb >> 3) & K4)) * M;
     }
@@ -370,7 +371,7 @@ __device__ __noinline__ void dev_stat_positions_smem(const DeltaAcc D, int side,
 struct fp_smem_layout {
     int off_dummy, off_mbar, off_next, off_tile, tile_array_bytes, off_len, off_clean, off_kmer, off_qhist, off_bc, off_lut, off_delta,
         off_dkmer, off_dqh, off_rm, off_planes, off_queue, plane_words, plane_stride, total,
-        off_group, group_stride, off_corr, off_cm, cm_words;     /* off_mbar, off_next, off_len, off_clean, off_tile, off_rm, off_planes, off_queue are relative to a group's region */
+        off_group, group_stride, off_corr, off_cm, cm_words, xflags;     /* off_mbar, off_next, off_len, off_clean, off_tile, off_rm, off_planes, off_queue are relative to a group's region */
 };
 
 struct fp_launch_args {
@@ -400,6 +401,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 /* TMA bulk copy global -> shared (1-D), completion signalled on the mbarrier */
+/* bulk prefetch of a global span into L2 (bytes: a multiple of 16) */
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
