@@ -210,7 +210,11 @@ static size_t smem_layout_for_tile(fp_ctx* c, int T, fp_smem_layout& sl) {
     g = align_up(g, 128);
     sl.off_tile = (int)g; sl.tile_array_bytes = T * S; g += (size_t)sides * 2 * T * S + 32;   /* + slack for 32-byte plane reads */
     g = align_up(g, 16);
-    sl.off_rm = (int)g; g += (size_t)sides * (T + 4) * 4 + 16;             /* removal lists (one per side, padded to 4 entries) + their lengths */
+    {   /* removal lists (one per side, padded to 4 entries) + their lengths (4 words), then the same entries in buckets by lo >> 5
+           (per-cycle part of phase C) + their lengths; one region, see DeltaSinks */
+        const size_t nbk = (size_t)(S + 31) / 32;
+        sl.off_rm = (int)g; g += (size_t)sides * (T + 4) * 4 + 16 + sides * nbk * (size_t)(T + 4) * 4 + sides * nbk * 4;
+    }
     sl.plane_words = (S + 31) / 32 + 2;
     sl.plane_stride = (5 * sl.plane_words) | 1;                            /* odd: one lane group per row without bank conflicts */
     g = align_up(g, 16);

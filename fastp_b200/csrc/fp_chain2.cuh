@@ -723,12 +723,26 @@ __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, in
     const signed char GOOD = 33 + 30, BAD = 33 + 14;                          /* basecorrector.cpp:26-27 */
     const uint32_t *pl1 = r1.pl, *pl2 = r2.pl;
     const int e = r2.front + r2.len - 1, jb = r2.len - 1 - start2;           /* rc(r2) index of overlap position 0 */
+    /* mismatching positions of the overlap, 32 per word: lane `sub` of the group compares the words k = sub, sub + g, ... (three plane
+       fields of each read per word) and the group passes them round by shuffle, instead of every lane comparing every word */
+    const unsigned gm = group_mask(g);
+    const int nw = (ol + 31) >> 5;
+    uint32_t mine[2] = {0u, 0u};                                               /* 2 g = 8 words: a PE row has at most 256 bases (fp_ctx_create) */
+    #pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+        const int k = sub + g * kk;
+        if (k < nw) {
+            const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
+            const uint32_t rn = __brev(tp_bits_z(pl2 + 2 * PW, s0));
+            const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
+            mine[kk] = ((tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn)) & low_mask(ol - 32 * k);
+        }
+    }
     #pragma unroll 1
-    for (int k = 0; k * 32 < ol; k++) {
-        const int s0 = e - (jb + 32 * k) - 31, abit = r1.front + start1 + 32 * k;
-        const uint32_t rn = __brev(tp_bits_z(pl2 + 2 * PW, s0));
-        const uint32_t rl_ = __brev(tp_bits_z(pl2, s0)), rh = ~__brev(tp_bits_z(pl2 + PW, s0)) & ~rn;
-        uint32_t todo = ((tp_bits(pl1, abit) ^ rl_) | (tp_bits(pl1 + PW, abit) ^ rh) | (tp_bits(pl1 + 2 * PW, abit) ^ rn)) & low_mask(ol - 32 * k);
+    for (int k = 0; k < nw; k++) {
+        const int kk = k / g;
+        const uint32_t w = kk == 0 ? mine[0] : mine[1];
+        uint32_t todo = __shfl_sync(gm, w, (lane_id() & ~(g - 1)) + (k % g));
         /* a low-quality tail puts its mismatches side by side: the group's lanes take the positions i with i % g == sub, so one
            bad tail is shared by all of them */
         todo &= (g == 4 ? 0x11111111u : g == 2 ? 0x55555555u : 0xFFFFFFFFu) << sub;
@@ -744,7 +758,7 @@ __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, in
             else continue;
             const int P1 = r1.front + p1, P2 = r2.front + p2;
             const int slot = atomicAdd(nlist, 1);
-            if (slot >= cap) { overflow = true; continue; }            /* left to the sequential path after the distributed one */
+            if (slot >= cap) { overflow = true; continue; }                    /* left to the sequential path after the distributed one */
             list[slot] = (uint32_t)row | ((uint32_t)which << 7) | ((uint32_t)(which ? P2 : P1) << 8) | ((uint32_t)(which ? P1 : P2) << 18);
             if (which) atomicOr(&cm2[P2 >> 5], 1u << (P2 & 31)); else atomicOr(&cm1[P1 >> 5], 1u << (P1 & 31));
         }
@@ -752,8 +766,9 @@ __device__ __noinline__ bool t_correct_decide(const TRead r1, const TRead r2, in
     return overflow;
 }
 
-/* one correction: statistics deltas (post-filter), patch entry, correction matrix.  Rows are still unmodified. */
-__device__ __noinline__ void t_correct_item(uint32_t entry, const uint8_t* tile0, int tile_array_bytes, int S, int T, const uint16_t* s_len, const uint32_t* cm,
+/* one correction: statistics deltas (post-filter), patch entry (unless the caller writes it: sink.count == nullptr), correction matrix.
+   Rows are still unmodified.  Returns old base | old quality << 8 | new base << 16 | new quality << 24. */
+__device__ __noinline__ uint32_t t_correct_item(uint32_t entry, const uint8_t* tile0, int tile_array_bytes, int S, int T, const uint16_t* s_len, const uint32_t* cm,
                                             int CMW, const DeltaAcc D, BlockCounters* bc, const PatchSink& sink, unsigned int pair_index) {
     FP_SMEM(tile0);    FP_SMEM(s_len);    FP_SMEM(cm);    FP_SMEM(D.cyc);    FP_SMEM(D.kmer);    FP_SMEM(D.qh);    FP_SMEM(bc);
     const int row = entry & 0x7F, which = (entry >> 7) & 1, P = (entry >> 8) & 0x3FF, Pp = (entry >> 18) & 0x3FF;
@@ -802,15 +817,17 @@ __device__ __noinline__ void t_correct_item(uint32_t entry, const uint8_t* tile0
         const unsigned int slot = atomicAdd(sink.count, 1u);
         if (slot < sink.cap) { fp_patch pt; pt.pair = pair_index; pt.pos = (uint16_t)P; pt.which = (uint8_t)which; pt.base = nb; pt.qual = nq; pt.old_base = ob; pt.old_qual = oq; pt._pad = 0; sink.patches[slot] = pt; }
     }
+    return (uint32_t)ob | ((uint32_t)oq << 8) | ((uint32_t)nb << 16) | ((uint32_t)nq << 24);
 }
 
 /* the rewrite itself: shared-memory row, HBM row, bit planes (other lanes may touch the same plane words: atomics) */
-__device__ __forceinline__ void t_correct_apply(uint32_t entry, uint8_t* tile0, int tile_array_bytes, int S, int T, uint32_t* planes, int PSTR, int PW,
+__device__ __forceinline__ uint32_t t_correct_apply(uint32_t entry, uint8_t* tile0, int tile_array_bytes, int S, int T, uint32_t* planes, int PSTR, int PW,
                                                 uint8_t* gseq, uint8_t* gqual) {
     const int row = entry & 0x7F, which = (entry >> 7) & 1, P = (entry >> 8) & 0x3FF, Pp = (entry >> 18) & 0x3FF;
     uint8_t* mseq = tile0 + (which * 2) * tile_array_bytes + row * S; uint8_t* mqual = mseq + tile_array_bytes;
     const uint8_t* pseq = tile0 + ((which ^ 1) * 2) * tile_array_bytes + row * S; const uint8_t* pqual = pseq + tile_array_bytes;
     const uint8_t nb = comp_clean(pseq[Pp]), nq = pqual[Pp];
+    const uint32_t old = (uint32_t)mseq[P] | ((uint32_t)mqual[P] << 8);      /* returned: old base | old quality << 8 */
     mseq[P] = nb; mqual[P] = nq; gseq[P] = nb; gqual[P] = nq;
     uint32_t* pl = planes + (which * T + row) * PSTR + (P >> 5);
     const uint32_t m = 1u << (P & 31);
@@ -819,6 +836,7 @@ __device__ __forceinline__ void t_correct_apply(uint32_t entry, uint8_t* tile0, 
     if (!n && (c2 & 2)) atomicOr(&pl[PW], m); else atomicAnd(&pl[PW], ~m);
     if (n) atomicOr(&pl[2 * PW], m); else atomicAnd(&pl[2 * PW], ~m);
     if (nq < (uint8_t)c_p.qualified_qual) atomicOr(&pl[3 * PW], m); else atomicAnd(&pl[3 * PW], ~m);
+    return old;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1328,9 +1346,13 @@ __device__ __noinline__ void dense_tile(ColAcc2& acc_io, const uint8_t* ts, cons
  * ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ uint32_t rm_pack(int row, int lo, int hi) { return (uint32_t)row | ((uint32_t)lo << 8) | ((uint32_t)hi << 20); }
 
-__device__ __noinline__ void dense_remove(const uint32_t* list, int n, int ifirst, int istep, const uint8_t* ts, const uint8_t* tq, int S, int w4, int my_half,
+/* The side's entries are kept in BUCKETS by lo >> 5 (bk: [nbk][bstride] entries, nb: their lengths): a removal [lo, hi) touches the word
+ * column at w4 only if lo < w4 + 4, i.e. only if its bucket is <= (w4 + 3) >> 5 -- the column threads of the early cycles, where only
+ * failed reads reach, skip the tail trims altogether.  The quads of four entries (buckets are zero-padded to quads) are dealt
+ * round-robin to the `nsplit` threads of a column over all buckets together. */
+__device__ __noinline__ void dense_remove(const uint32_t* bk, const int* nb, int nbk, int bstride, int part, int nsplit, const uint8_t* ts, const uint8_t* tq, int S, int w4, int my_half,
                                           int* dc, int cycles) {
-    FP_SMEM(list); FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(dc);
+    FP_SMEM(bk); FP_SMEM(nb); FP_SMEM(ts); FP_SMEM(tq); FP_SMEM(dc);
     unsigned int acc[2][NB][4];
     #pragma unroll
     for (int c = 0; c < 2; c++)
@@ -1341,9 +1363,16 @@ __device__ __noinline__ void dense_remove(const uint32_t* list, int n, int ifirs
     const int j0 = my_half * 2;
     const unsigned sel = my_half ? 0x7362u : 0x5140u;
     bool any = false;
+    const int bmax = min(nbk - 1, (w4 + 3) >> 5);
+    int qskip = part;                                 /* quads to pass over before my next one */
     #pragma unroll 1
-    for (int i = ifirst; i < n; i += istep) {
-        const uint4 e4 = *reinterpret_cast<const uint4*>(list + i);
+    for (int b = 0; b <= bmax; b++) {
+      const int nq = (nb[b] + 3) >> 2;
+      const uint32_t* list = bk + b * bstride;
+      int qi = qskip;
+      #pragma unroll 1
+      for (; qi < nq; qi += nsplit) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(list + 4 * qi);
         const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
         uint32_t xs[4], xq[4], anym = 0;
         #pragma unroll
@@ -1363,6 +1392,8 @@ __device__ __noinline__ void dense_remove(const uint32_t* list, int n, int ifirs
         const uint32_t u0 = __byte_perm(xq[0], xq[1], sel), u1 = __byte_perm(xq[2], xq[3], sel);
         acc_cycle(acc[0], __byte_perm(t0, t1, 0x5410), __byte_perm(u0, u1, 0x5410));
         acc_cycle(acc[1], __byte_perm(t0, t1, 0x7632), __byte_perm(u0, u1, 0x7632));
+      }
+      qskip = qi - nq;                                /* my next quad of the concatenation lies this far into the next bucket */
     }
     if (!any) return;
     #pragma unroll
@@ -1432,13 +1463,20 @@ __device__ __noinline__ void hist_remove_chunk(const uint8_t* sp, const uint8_t*
 struct DeltaReq { uint32_t a, b; };        /* a = row | side<<8 | clean<<9 | (sign<0)<<10 | ctx0<<12;  b = lo | hi<<16 */
 
 struct DeltaSinks { DeltaReq* q; int* qn; uint32_t* rm; int* nrm; int T; };
+/* one region: flat lists [SIDES][T + 4], their lengths (4 words), bucket lists [SIDES][NBK][T + 4], their lengths [SIDES][NBK];
+   NBK = ceil(stride / 32) */
 /* removals from clean rows go to the side's removal list (fast engines); re-additions of front-shifted reads and everything on
    rows with bytes outside {A,C,G,T,N} go to the request queue (exact per-position engines) */
+template <int SIDES>
 __device__ __forceinline__ void push_delta(const DeltaSinks& K, bool want, bool clean, int side, int row, int ctx0, int lo, int hi, int sign) {
     if (want && hi > lo) {
         if (clean && sign < 0) {
             const int slot = atomicAdd(&K.nrm[side], 1);
-            K.rm[side * (K.T + 4) + slot] = rm_pack(row, lo, hi);
+            K.rm[side * (K.T + 4) + slot] = rm_pack(row, lo, hi);                  /* flat list: the histogram items of phase C */
+            const int nbuckets = (c_p.stride + 31) >> 5, b = side * nbuckets + (lo >> 5);    /* bucket list: the per-cycle counters (dense_remove) */
+            uint32_t* bk = K.rm + SIDES * (K.T + 4) + 4;
+            int* nbk = reinterpret_cast<int*>(bk + SIDES * nbuckets * (K.T + 4));
+            bk[b * (K.T + 4) + atomicAdd(&nbk[b], 1)] = rm_pack(row, lo, hi);
         } else {
             const int slot = atomicAdd(K.qn, 1);
             DeltaReq r; r.a = (uint32_t)row | ((uint32_t)side << 8) | ((clean ? 1u : 0u) << 9) | ((sign < 0 ? 1u : 0u) << 10) | ((uint32_t)ctx0 << 12); r.b = (uint32_t)lo | ((uint32_t)hi << 16);
@@ -1488,6 +1526,9 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
     D.qh = reinterpret_cast<int*>(smem + sl.off_dqh);
     uint32_t* s_rm = reinterpret_cast<uint32_t*>(gsm + sl.off_rm);          /* [SIDES][T + 4] removal lists */
     int* s_nrm = reinterpret_cast<int*>(s_rm + SIDES * (T + 4));             /* [SIDES] their lengths */
+    const int NBK = (S + 31) >> 5;                                           /* removal buckets per side: by lo >> 5 */
+    uint32_t* s_bk = s_rm + SIDES * (T + 4) + 4;                             /* [SIDES][NBK][T + 4] */
+    int* s_nbk = reinterpret_cast<int*>(s_bk + SIDES * NBK * (T + 4));       /* [SIDES][NBK] */
     DeltaSinks sinks; sinks.rm = s_rm; sinks.nrm = s_nrm; sinks.T = T;
     int16_t* s_lut = reinterpret_cast<int16_t*>(smem + sl.off_lut);
     const int PW = sl.plane_words, PSTR = sl.plane_stride;                  /* PSTR odd: conflict-free lane-group-per-row access */
@@ -1558,6 +1599,13 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
     fill_lens((long long)blockIdx.x * NG + gid);
     __syncthreads();
     uint32_t parity = 0;
+#ifdef FP_PHASE_TIMING
+    /* measurement build (scripts/gpu_phase_timing.sh): cycles each warp of CTA 0 spends up to every barrier of a tile, summed over the launch */
+    long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define FP_TP(k) do { const long long tn_ = clock64(); tph[k] += tn_ - tlast; tlast = tn_; } while (0)
+#else
+#define FP_TP(k) do { } while (0)
+#endif
 
     #pragma unroll 1
     for (long long tix = (long long)blockIdx.x * NG + gid; tix < a.n_tiles; tix += (long long)gridDim.x * NG) {
@@ -1587,8 +1635,9 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
         /* the read lengths of this tile were staged before the previous tile's last barrier (fill_lens), the bytes arrive through the
            mbarrier every thread waits on itself: no CTA barrier here */
         mbar_wait(mbar, parity);
+        FP_TP(0);
         parity ^= 1;
-        for (int i = tid; i < SIDES * (T + 4) + SIDES; i += CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
+        for (int i = tid; i < SIDES * (T + 4) + 4 + SIDES * NBK * (T + 4) + SIDES * NBK; i += CT) s_rm[i] = 0;      /* removal lists + lengths: filled in phase B */
         if (PAIRED && c_p.correction) for (int i = tid; i < SIDES * T * CMW; i += CT) s_cm[i] = 0;
 
         /* ---------------- phase A: dense pass (column warps) || bit planes + validation (other warps) ---------------- */
@@ -1714,7 +1763,9 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 }
             }
         }
+        FP_TP(1);
         GSYNC();
+        FP_TP(2);
 
         /* ---------------- phase B: operator chain, one lane GROUP per read / pair ---------------- */
         #pragma unroll 1
@@ -1767,8 +1818,8 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 }
                 /* post stats as a delta against pre (warp-cooperative): drop what was trimmed / failed, re-add shifted windows */
                 const bool keep_tail = counted && r1.front == 0;
-                push_delta(sinks, active && lead, clean, 0, rr, 0, keep_tail ? r1.len : 0, len0, -1);
-                push_delta(sinks, active && lead && counted && !keep_tail, clean, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
+                push_delta<SIDES>(sinks, active && lead, clean, 0, rr, 0, keep_tail ? r1.len : 0, len0, -1);
+                push_delta<SIDES>(sinks, active && lead && counted && !keep_tail, clean, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
             } else {
                 /* PairEndProcessor::processPairEnd loop body  peprocessor.cpp:383-643 */
                 uint8_t* rs1 = tile_seq[0] + rr * S; uint8_t* rq1 = tile_qual[0] + rr * S;
@@ -1824,7 +1875,9 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                         corr_overflow = t_correct_decide(r1, r2, PW, ovA, rr, sub, GL, wlist, wn, wcap, s_cm + rr * CMW, s_cm + (T + rr) * CMW);
                     /* the one barrier that stays: the warps leave the overlap analysis at very different times, and behind it they run the
                        correction code TOGETHER (one hot region of the instruction cache) */
+                    FP_TP(3);
                     GSYNC();
+                    FP_TP(4);
                     if (warp_lists) {
                         /* a pair's rows, masks and planes belong to the warp that holds the pair: warp-level syncs order item -> apply -> chain */
                         const int ncorr = min(*wn, wcap);
@@ -1852,6 +1905,7 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                                             (ewhich ? a.b.seq2 : a.b.seq1) + (row0 + erow) * S, (ewhich ? a.b.qual2 : a.b.qual1) + (row0 + erow) * S);
                         }
                         GSYNC();
+                        FP_TP(5);
                         if (tid == 0) *s_ncorr = 0;                /* (a PE tile is one round of this loop: 8 warps x 8 pairs >= T) */
                     }
                 }
@@ -1976,23 +2030,25 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
                 {
                     const bool removed = false;        /* corrections were folded into the accumulators base by base (t_patch_delta) */
                     const bool keep1 = counted && r1.front == 0 && !removed;
-                    push_delta(sinks, active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
-                    push_delta(sinks, active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
+                    push_delta<SIDES>(sinks, active && lead && !removed, clean1, 0, rr, 0, keep1 ? r1.len : 0, l1, -1);
+                    push_delta<SIDES>(sinks, active && lead && counted && !keep1, clean1, 0, rr, r1.front, r1.front, r1.front + r1.len, +1);
                     const bool keep2 = counted && r2.front == 0 && !removed;
-                    push_delta(sinks, active && lead && !removed, clean2, 1, rr, 0, keep2 ? r2.len : 0, l2, -1);
-                    push_delta(sinks, active && lead && counted && !keep2, clean2, 1, rr, r2.front, r2.front, r2.front + r2.len, +1);
+                    push_delta<SIDES>(sinks, active && lead && !removed, clean2, 1, rr, 0, keep2 ? r2.len : 0, l2, -1);
+                    push_delta<SIDES>(sinks, active && lead && counted && !keep2, clean2, 1, rr, r2.front, r2.front, r2.front + r2.len, +1);
                 }
             }
         }
 
+        FP_TP(6);
         GSYNC();
+        FP_TP(7);
 
         /* ---------------- phase C: post-filter statistics of what the chain removed / shifted (all warps) ---------------- */
         {
             /* (1) per-cycle counters of the removal lists: the column threads, transposed dp4a pass like phase A's */
             if (col_active) {
                 const int nr = s_nrm[my_side];
-                if (nr > 0) dense_remove(s_rm + my_side * (T + 4), nr, 4 * my_part, 4 * nsplit, tile_seq[my_side], tile_qual[my_side], S, my_w * 4, my_half,
+                if (nr > 0) dense_remove(s_bk + my_side * NBK * (T + 4), s_nbk + my_side * NBK, NBK, T + 4, my_part, nsplit, tile_seq[my_side], tile_qual[my_side], S, my_w * 4, my_half,
                                          D.cyc + my_side * S * 20, S);
             }
             /* (2) qualities and 5-mers of the removal lists: one lane per (entry, 32-base chunk), claimed 32 at a time */
@@ -2044,9 +2100,16 @@ __global__ void __launch_bounds__(CT * NG, (NG == 1 && CT == 256) ? 2 : 1) fp_ch
         }
         fill_lens(tix + (long long)gridDim.x * NG);
         if (tid == 0) s_qn[2] = 0;                     /* item counter of phase A: idle since the phase-A barrier */
+        FP_TP(8);
         GSYNC();
+        FP_TP(9);
     }
 
+#ifdef FP_PHASE_TIMING
+    if (blockIdx.x == 0 && lane == 0)
+        printf("PHASE warp %2d tma %lld busyA %lld totA %lld busyB1 %lld totB1 %lld corr %lld busyB2 %lld totB2 %lld busyC %lld totC %lld\n", warp,
+               tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7], tph[8], tph[9]);
+#endif
     __syncthreads();                               /* every group is done with the shared tables */
     /* ---------------- flush block-level accumulators ---------------- */
     const int BIN_SLOT[NB] = {1, 3, 4, 6, 7};      /* base & 7 of A C T N G */
