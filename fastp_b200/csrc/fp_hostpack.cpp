@@ -3,6 +3,7 @@
  * cross the link at 2 bits each; this is the code that has to keep up with the link (about 40 GB/s of bases for a Gen5 x16 slot).
  */
 #include "fp_hostpack.h"
+#include <stdlib.h>
 #include <string.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -88,20 +89,63 @@ int pack_avx2(const uint8_t* s, int L, uint8_t* d, uint32_t unit, int which, std
 }
 #endif
 
-bool have_avx2() {
 #if defined(__x86_64__)
-    static const bool v = __builtin_cpu_supports("avx2");
-    return v;
-#else
-    return false;
+/* 64 bases per step (AVX-512 BW + VL): the same arithmetic on a zmm register; VPMOVDB takes the sixteen packed bytes out of the 32-bit lanes
+ * in one instruction, and byte-masked loads / stores do the row's tail (a 150-base row is 64 + 64 + 22, no scalar remainder, no copy). */
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+int pack_avx512(const uint8_t* s, int L, uint8_t* d, uint32_t unit, int which, std::vector<fp_npos>& nl) {
+    const __m512i tbl = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i m3 = _mm512_set1_epi8(3);
+    const __m512i w1 = _mm512_set1_epi16(0x0401);
+    const __m512i w2 = _mm512_set1_epi32(0x00100001);
+    const __m512i isN = _mm512_set1_epi8('N');
+    const __m512i padA = _mm512_set1_epi8('A');                            /* bases past the row pack as code 0, like the other paths */
+    for (int k = 0; k < L; k += 64) {
+        const int n = L - k < 64 ? L - k : 64;
+        const __mmask64 lm = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+        const __m512i x = _mm512_mask_loadu_epi8(padA, lm, s + k);        /* masked-off bytes are not touched (no read past the row) */
+        __m512i c = _mm512_and_si512(_mm512_srli_epi16(x, 1), m3);
+        const __mmask64 okm = _mm512_cmpeq_epi8_mask(x, _mm512_shuffle_epi8(tbl, c));
+        if (okm != ~0ull) {
+            /* 'N' bases pack as code 0 and go on the list (in position order, like the byte-wise paths); any other byte: not representable */
+            __mmask64 nm = _mm512_cmpeq_epi8_mask(x, isN);
+            if ((okm | nm) != ~0ull) return 1;
+            c = _mm512_maskz_mov_epi8(~nm, c);
+            for (; nm; nm &= nm - 1) nl.push_back(fp_npos{unit, (uint16_t)(k + __builtin_ctzll(nm)), (uint8_t)which, 0});
+        }
+        const __m128i r = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(c, w1), w2));
+        if (n == 64) _mm_storeu_si128(reinterpret_cast<__m128i*>(d + (k >> 2)), r);
+        else _mm_mask_storeu_epi8(d + (k >> 2), (__mmask16)((1u << ((n + 3) >> 2)) - 1u), r);
+    }
+    return 0;
+}
+
 #endif
+
+/* 3 = AVX-512 BW + VL, 2 = AVX2, 1 = SWAR; FP_HOSTPACK_ISA=avx2 | swar lowers it (tests run every path on one machine) */
+int isa_level() {
+    static const int v = []() {
+        int lv = 1;
+#if defined(__x86_64__)
+        if (__builtin_cpu_supports("avx2")) lv = 2;
+        if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")) lv = 3;
+#endif
+        if (const char* e = getenv("FP_HOSTPACK_ISA")) {
+            if (!strcmp(e, "swar")) lv = 1;
+            else if (!strcmp(e, "avx2") && lv > 2) lv = 2;
+        }
+        return lv;
+    }();
+    return v;
 }
 
 }  // namespace
 
 int fp_pack_bases_row(const uint8_t* s, int L, uint8_t* d, uint32_t unit, int which, std::vector<fp_npos>& nl) {
 #if defined(__x86_64__)
-    if (have_avx2()) return pack_avx2(s, L, d, unit, which, nl);
+    const int lv = isa_level();
+    if (lv == 3) return pack_avx512(s, L, d, unit, which, nl);
+    if (lv == 2) return pack_avx2(s, L, d, unit, which, nl);
 #endif
     return pack_swar(s, 0, L, d, unit, which, nl);
 }

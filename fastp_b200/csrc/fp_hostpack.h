@@ -1,6 +1,6 @@
 /*
  * fp_hostpack.h -- host-side 2-bit packing of the bases of one read row (the host half of fp_packed_batch, include/fastp_b200.h).
- * Plain host C++ (built by g++, no CUDA): an AVX2 path picked at run time, a 64-bit SWAR path otherwise.
+ * Plain host C++ (built by g++, no CUDA): an AVX-512 (BW + VL) or AVX2 path picked at run time (FP_HOSTPACK_ISA=avx2 | swar forces a lower one), a 64-bit SWAR path otherwise.
  */
 #pragma once
 #include <stdint.h>

@@ -51,3 +51,60 @@ def test_pack_refuses_other_bytes():
     b = capi.batch_from_arrays(arrs)
     with pytest.raises(Exception):
         fp_gpu.pack_rows(lib, b, arrs, 0)
+
+
+_ISA_WORKER = r'''
+import ctypes as C, hashlib, sys
+import numpy as np
+sys.path.insert(0, "tests")
+import fp_testlib as T
+from fastp_b200 import capi
+import fp_gpu
+S = 208
+rng = np.random.default_rng(11)
+n = 6000
+seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (n, S))].copy()
+qual = rng.integers(33, 75, (n, S)).astype(np.uint8)
+ln = rng.integers(0, S + 1, n).astype(np.uint16)
+ln[:S + 1] = np.arange(S + 1)                          # every row length once, incl. 0 and the block edges 63 / 64 / 65 / 127 / 128 / 129
+for r in range(0, n, 9):                               # 'N's: at the block edges, at the row's last base, in runs
+    for p in (0, 31, 32, 63, 64, 127, 128, 191, 192, int(ln[r]) - 1):
+        if 0 <= p < ln[r]: seq[r, p] = ord("N")
+seq[7::197, 60:70] = ord("N")
+arrs = {"seq1": seq, "qual1": qual, "len1": ln, "seq2": seq[::-1].copy(), "qual2": qual[::-1].copy(), "len2": ln[::-1].copy()}
+lib = capi.load()
+b = capi.batch_from_arrays(arrs)
+pb, keep = fp_gpu.pack_rows(lib, b, arrs, 1, threads=3)
+h = hashlib.sha256()
+for k in ("bases1", "bases2", "len1", "len2"): h.update(keep[k].tobytes())
+h.update(keep["npos"][: pb.n_npos * 8].tobytes())
+bad = []
+for pos in (0, 63, 64, 100, 127, 128, 149):           # a byte outside {A,C,G,T,N} anywhere in a row is refused
+    a2 = {k: v.copy() for k, v in arrs.items()}
+    a2["len1"][:] = 150; a2["seq1"][1234, pos] = ord("R")
+    b2 = capi.batch_from_arrays(a2)
+    try:
+        fp_gpu.pack_rows(lib, b2, a2, 1, threads=2); bad.append(0)
+    except Exception:
+        bad.append(1)
+print("PACKHASH", h.hexdigest(), pb.n_npos, "".join(map(str, bad)))
+'''
+
+
+def test_every_isa_path_packs_the_same_bytes():
+    """AVX-512, AVX2 and SWAR packers (FP_HOSTPACK_ISA) on rows of every length with 'N's at the block edges: same packed bytes,
+    same 'N' list, same refusals."""
+    import os
+    import subprocess
+    import sys
+    outs = {}
+    for isa in ("native", "avx2", "swar"):
+        env = dict(os.environ)
+        env.pop("FP_HOSTPACK_ISA", None)
+        if isa != "native":
+            env["FP_HOSTPACK_ISA"] = isa
+        r = subprocess.run([sys.executable, "-c", _ISA_WORKER], cwd=T.ROOT, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[isa] = [l for l in r.stdout.splitlines() if l.startswith("PACKHASH")][0]
+    assert outs["native"] == outs["avx2"] == outs["swar"], outs
+    assert outs["swar"].split()[-1] == "1111111"
